@@ -1,0 +1,300 @@
+"""ctypes binding of libcge.so (include/cge.h) and the Python-side host helpers.
+
+The arithmetic all lives in the CUDA library; this module only marshals pointers.  There is
+no CPU fallback: if libcge.so is missing or no sm_100 device is present, calls raise.
+
+Reference mapping (paths relative to cpp/grid-algorithm/ of nablabits/cuda-grid-estimation):
+``Context.grid_posterior`` replaces the call sequence src/grid.cu:79-127; the ``linspace`` ...
+``expectation`` methods are the stage functions inc/cuda_functions.h:47-221 and
+inc/wrappers.h:95-121.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _build
+
+MODE_PRODUCT_F32 = 0
+MODE_LOGSPACE = 1
+
+OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_DEGENERATE, ERR_NCCL, ERR_SIZE = range(7)
+
+# every symbol include/cge.h declares (tests check the library exports each one)
+ABI_SYMBOLS = (
+    "cge_create", "cge_destroy", "cge_last_error", "cge_version", "cge_device_sm_count",
+    "cge_grid_posterior", "cge_likelihood_partials", "cge_partials", "cge_finalize",
+    "cge_results", "cge_read_results", "cge_posterior_dev", "cge_last_timing",
+    "cge_profile_begin", "cge_profile_end", "cge_launch_count", "cge_linspace", "cge_meshgrid3", "cge_densities", "cge_row_products",
+    "cge_normalize", "cge_marginalize", "cge_expectation", "cge_microbench",
+)
+
+
+class CgeError(RuntimeError):
+    def __init__(self, code: int, message: str):
+        super().__init__(f"libcge error {code}: {message}")
+        self.code = code
+
+
+class Params(C.Structure):
+    _fields_ = [("n_obs", C.c_int32), ("grid_size", C.c_int32), ("mu_start", C.c_float),
+                ("mu_end", C.c_float), ("sigma_start", C.c_float), ("sigma_end", C.c_float),
+                ("mode", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
+                ("reserved", C.c_int32)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("setup_ms", C.c_float), ("likelihood_ms", C.c_float), ("reduce_ms", C.c_float),
+                ("scale_ms", C.c_float), ("total_ms", C.c_float), ("h2d_ms", C.c_float),
+                ("d2h_ms", C.c_float)]
+
+    def as_dict(self):
+        return {k: float(getattr(self, k)) for k, _ in self._fields_}
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library(build_if_missing: bool = True) -> C.CDLL:
+    """Load cuda_grid_estimation_b200/libcge.so.  Raises if it cannot be built or loaded."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path):
+        if not build_if_missing:
+            raise FileNotFoundError(f"{path} is missing; run __graft_entry__.build()")
+        _build.build()
+    L = C.CDLL(path)
+    vp, i32, f32, sz = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+    PP = C.POINTER(Params)
+    sig = {
+        "cge_create": [i32, C.POINTER(vp)],
+        "cge_destroy": [vp],
+        "cge_version": [],
+        "cge_device_sm_count": [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)],
+        "cge_grid_posterior": [vp, PP, vp, vp, vp, vp, vp, C.POINTER(Timing)],
+        "cge_likelihood_partials": [vp, PP, vp, vp, vp],
+        "cge_partials": [vp, C.POINTER(vp), C.POINTER(sz)],
+        "cge_finalize": [vp, PP, vp, vp],
+        "cge_results": [vp, C.POINTER(vp), C.POINTER(sz)],
+        "cge_read_results": [vp, PP, vp, vp, vp, C.POINTER(C.c_double), vp],
+        "cge_posterior_dev": [vp, C.POINTER(vp), C.POINTER(sz)],
+        "cge_last_timing": [vp, C.POINTER(Timing)],
+        "cge_launch_count": [vp, C.POINTER(i32)],
+        "cge_profile_begin": [vp, i32],
+        "cge_profile_end": [vp, C.POINTER(Timing), C.POINTER(i32)],
+        "cge_linspace": [vp, vp, i32, f32, f32],
+        "cge_meshgrid3": [vp, vp, vp, vp, vp, vp, vp, i32, i32],
+        "cge_densities": [vp, vp, vp, vp, vp, sz],
+        "cge_row_products": [vp, vp, vp, sz, sz],
+        "cge_normalize": [vp, vp, vp, sz],
+        "cge_marginalize": [vp, vp, vp, i32, i32, i32],
+        "cge_expectation": [vp, vp, vp, i32, C.POINTER(C.c_double)],
+        "cge_microbench": [vp, i32, C.POINTER(C.c_double)],
+    }
+    for name, argtypes in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = argtypes
+        fn.restype = C.c_int
+    L.cge_last_error.argtypes = []
+    L.cge_last_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != OK:
+        raise CgeError(rc, load_library().cge_last_error().decode("utf-8", "replace"))
+
+
+def make_params(n_obs, grid_size, mu_range, sigma_range, mode=MODE_PRODUCT_F32, rows=None) -> Params:
+    rb, re = (0, 0) if rows is None else (int(rows[0]), int(rows[1]))
+    return Params(int(n_obs), int(grid_size), float(mu_range[0]), float(mu_range[1]),
+                  float(sigma_range[0]), float(sigma_range[1]), int(mode), rb, re, 0)
+
+
+@dataclass
+class GridResult:
+    expectations: np.ndarray            # [E[mu], E[sigma]]
+    marg_mu: np.ndarray                 # float64 [N]
+    marg_sigma: np.ndarray              # float64 [N]
+    posterior: Optional[np.ndarray]     # float32 [rows, N] or None (left on the device)
+    timing: dict
+    launches: int
+
+
+def _ptr(a) -> Optional[int]:
+    """Raw address of a numpy array or a torch tensor (None passes through)."""
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data
+    return int(a.data_ptr())
+
+
+class Context:
+    """One libcge context = one device, one stream, grow-only scratch.  Not thread-safe."""
+
+    def __init__(self, device: int = 0):
+        self._lib = load_library()
+        h = C.c_void_p()
+        _check(self._lib.cge_create(int(device), C.byref(h)))
+        self._h = h
+        self.device = int(device)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cge_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # ---- device info / peaks --------------------------------------------------------
+    def device_info(self):
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        _check(self._lib.cge_device_sm_count(self._h, C.byref(sm), C.byref(ma), C.byref(mi)))
+        return dict(sm_count=sm.value, cc=(ma.value, mi.value))
+
+    def microbench(self, kind: int) -> float:
+        """Measured pipe peak, lane-ops/s.  0 MUFU ex2, 1 FFMA, 2 DFMA, 3 FFMA2 (f32x2)."""
+        out = C.c_double()
+        _check(self._lib.cge_microbench(self._h, int(kind), C.byref(out)))
+        return out.value
+
+    # ---- fused path, synchronous, host or device buffers ---------------------------------
+    def grid_posterior(self, obs, grid_size, mu_range, sigma_range, mode=MODE_PRODUCT_F32,
+                       rows=None, posterior="host", want_timing=True) -> GridResult:
+        """The whole hot path in one call (replaces src/grid.cu:79-127).
+
+        obs        numpy float32 array (host) or CUDA torch tensor (device)
+        posterior  "host": return it as numpy; "device"/None: leave it in the context's device
+                   buffer; or a CUDA torch tensor / numpy array to write into.
+        """
+        if isinstance(obs, np.ndarray):
+            obs = np.ascontiguousarray(obs, np.float32)
+        n = int(obs.shape[0])
+        p = make_params(n, grid_size, mu_range, sigma_range, mode, rows)
+        nrows = grid_size if rows is None else rows[1] - rows[0]
+        post_arr = None
+        if isinstance(posterior, str) and posterior == "host":
+            post_arr = np.empty((nrows, grid_size), np.float32)
+            post_ptr = post_arr.ctypes.data
+        elif posterior is None or (isinstance(posterior, str) and posterior == "device"):
+            post_ptr = None
+        else:
+            post_ptr = _ptr(posterior)
+            post_arr = posterior if isinstance(posterior, np.ndarray) else None
+        mm = np.empty(grid_size, np.float64)
+        ms = np.empty(grid_size, np.float64)
+        ex = np.empty(2, np.float64)
+        tm = Timing()
+        _check(self._lib.cge_grid_posterior(self._h, C.byref(p), _ptr(obs), post_ptr, mm.ctypes.data,
+                                            ms.ctypes.data, ex.ctypes.data,
+                                            C.byref(tm) if want_timing else None))
+        return GridResult(ex, mm, ms, post_arr, tm.as_dict() if want_timing else {},
+                          self.launch_count())
+
+    # ---- phase API (device pointers, asynchronous on `stream`) -------------------------
+    def likelihood_partials(self, params: Params, obs_dev, posterior_dev, stream=None):
+        _check(self._lib.cge_likelihood_partials(self._h, C.byref(params), _ptr(obs_dev),
+                                                 _ptr(posterior_dev), stream))
+
+    def finalize(self, params: Params, posterior_dev, stream=None):
+        _check(self._lib.cge_finalize(self._h, C.byref(params), _ptr(posterior_dev), stream))
+
+    def partials_ptr(self):
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        _check(self._lib.cge_partials(self._h, C.byref(ptr), C.byref(cnt)))
+        return ptr.value, cnt.value
+
+    def results_ptr(self):
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        _check(self._lib.cge_results(self._h, C.byref(ptr), C.byref(cnt)))
+        return ptr.value, cnt.value
+
+    def posterior_ptr(self):
+        ptr, cnt = C.c_void_p(), C.c_size_t()
+        _check(self._lib.cge_posterior_dev(self._h, C.byref(ptr), C.byref(cnt)))
+        return ptr.value, cnt.value
+
+    def read_results(self, params: Params, stream=None):
+        N = params.grid_size
+        mm = np.empty(N, np.float64)
+        ms = np.empty(N, np.float64)
+        ex = np.empty(2, np.float64)
+        z = C.c_double()
+        _check(self._lib.cge_read_results(self._h, C.byref(params), ex.ctypes.data, mm.ctypes.data,
+                                          ms.ctypes.data, C.byref(z), stream))
+        return ex, mm, ms, z.value
+
+    def profile_begin(self, max_steps: int):
+        _check(self._lib.cge_profile_begin(self._h, int(max_steps)))
+
+    def profile_end(self):
+        """Mean per-phase device times (ms) over the captured steps, and how many there were."""
+        tm, n = Timing(), C.c_int()
+        _check(self._lib.cge_profile_end(self._h, C.byref(tm), C.byref(n)))
+        return tm.as_dict(), n.value
+
+    def launch_count(self) -> int:
+        n = C.c_int()
+        _check(self._lib.cge_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    # ---- stage API (device / managed pointers; torch CUDA tensors here) -----------------
+    def linspace(self, out_dev, size, start, end):
+        _check(self._lib.cge_linspace(self._h, _ptr(out_dev), int(size), float(start), float(end)))
+
+    def meshgrid3(self, vx, vy, vz, gx, gy, gz, nxy, nz):
+        _check(self._lib.cge_meshgrid3(self._h, _ptr(vx), _ptr(vy), _ptr(vz), _ptr(gx), _ptr(gy),
+                                       _ptr(gz), int(nxy), int(nz)))
+
+    def densities(self, dens, gx, gy, gz, count):
+        _check(self._lib.cge_densities(self._h, _ptr(dens), _ptr(gx), _ptr(gy), _ptr(gz), int(count)))
+
+    def row_products(self, dens, likes, densities_size, likes_size):
+        _check(self._lib.cge_row_products(self._h, _ptr(dens), _ptr(likes), int(densities_size),
+                                          int(likes_size)))
+
+    def normalize(self, likes, post, size):
+        _check(self._lib.cge_normalize(self._h, _ptr(likes), _ptr(post), int(size)))
+
+    def marginalize(self, marginal, matrix, rows, cols, axis):
+        _check(self._lib.cge_marginalize(self._h, _ptr(marginal), _ptr(matrix), int(rows), int(cols),
+                                         int(axis)))
+
+    def expectation(self, marginal, vector, size) -> float:
+        out = C.c_double()
+        _check(self._lib.cge_expectation(self._h, _ptr(marginal), _ptr(vector), int(size),
+                                         C.byref(out)))
+        return out.value
+
+
+class _DeviceView:
+    """Zero-copy view of a raw device pointer for torch (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2}
+
+
+def device_tensor(ptr: int, count: int, dtype: str, device_index: int):
+    """Wrap library-owned device memory as a torch tensor without copying."""
+    import torch
+    typestr = {"float64": "<f8", "float32": "<f4"}[dtype]
+    return torch.as_tensor(_DeviceView(ptr, count, typestr), device=torch.device("cuda", device_index))

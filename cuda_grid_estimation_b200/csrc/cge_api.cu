@@ -1,0 +1,721 @@
+// cge_api.cu -- the C ABI of libcge.so (include/cge.h) on top of the sm_100a kernels.
+// Host-side runtime: context (device, stream, grow-only scratch), launch planning, the fused
+// and phase entry points, the stage API, and the pipe-peak micro-benchmarks.
+// There is no CPU fallback anywhere in this file: every entry point needs the device.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/cge.h"
+#include "cge_kernels.cuh"
+
+#define CGE_EXPORT extern "C" __attribute__((visibility("default")))
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int set_error(int code, const char *fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+
+#define CK(call)                                                                        \
+  do {                                                                                  \
+    cudaError_t e_ = (call);                                                            \
+    if (e_ != cudaSuccess)                                                              \
+      return set_error(CGE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                       __FILE__, __LINE__);                                             \
+  } while (0)
+
+#define CKRC(expr)            \
+  do {                        \
+    int rc_ = (expr);         \
+    if (rc_ != CGE_OK) return rc_; \
+  } while (0)
+
+// grow-only device buffer
+template <class T>
+struct DevBuf {
+  T *ptr = nullptr;
+  size_t cap = 0;
+  int reserve(size_t count) {
+    if (count <= cap) return CGE_OK;
+    if (ptr) {
+      CK(cudaFree(ptr));
+      ptr = nullptr;
+      cap = 0;
+    }
+    size_t want = count + count / 8 + 64;
+    CK(cudaMalloc(&ptr, want * sizeof(T)));
+    cap = want;
+    return CGE_OK;
+  }
+  void release() {
+    if (ptr) cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
+struct Plan {
+  bool valid = false;
+  int N = 0, n = 0, n_pad = 0, mode = 0;
+  int row_begin = 0, row_end = 0, rows_local = 0;
+  int wm = 1, wn = 8;
+  int bands = 0, row_tiles = 0, tile_rows = 0;
+  int ncw = 0, ncolparts = 0;
+  int nb_col = 0, nb_row = 0;
+  bool vec4 = false;
+  size_t smem = 0;
+};
+
+}  // namespace
+
+struct cge_context {
+  int device = 0;
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[10] = {};
+  DevBuf<float> mu, sigma, obs_pad, obs_in, posterior;
+  DevBuf<double> ad, cd0, rowpart, colpart, partials, rowsum, zpart, smupart, results, tmp;
+  DevBuf<cge::ScaleInfo> scale;
+  DevBuf<float> sink;
+  Plan plan;
+  cge_timing timing = {};
+  int launches = 0;
+  // per-step event capture: 7 marks per step
+  //   0 before tables | 1 after setup | 2 after likelihood | 3 after fold |
+  //   4 before results | 5 after results | 6 after scale
+  std::vector<cudaEvent_t> prof_events;
+  int prof_cap = 0;       // steps that fit
+  int prof_step = 0;      // steps captured so far
+  bool prof_on = false;
+};
+
+namespace {
+
+int bind(cge_context *ctx) {
+  if (!ctx) return set_error(CGE_ERR_BAD_ARG, "context is NULL");
+  CK(cudaSetDevice(ctx->device));
+  return CGE_OK;
+}
+
+int check_params(const cge_params *p, int *rb, int *re) {
+  if (!p) return set_error(CGE_ERR_BAD_ARG, "params is NULL");
+  if (p->n_obs < 1) return set_error(CGE_ERR_BAD_ARG, "n_obs must be >= 1 (got %d)", p->n_obs);
+  if (p->grid_size < 1)
+    return set_error(CGE_ERR_BAD_ARG, "grid_size must be >= 1 (got %d)", p->grid_size);
+  if (!(p->sigma_start > 0.0f) || !(p->sigma_end > 0.0f))
+    return set_error(CGE_ERR_BAD_ARG, "sigma range must be > 0 (got [%g, %g])", p->sigma_start,
+                     p->sigma_end);
+  if (!std::isfinite(p->mu_start) || !std::isfinite(p->mu_end) || !std::isfinite(p->sigma_start) ||
+      !std::isfinite(p->sigma_end))
+    return set_error(CGE_ERR_BAD_ARG, "ranges must be finite");
+  if (p->mode != CGE_MODE_PRODUCT_F32 && p->mode != CGE_MODE_LOGSPACE)
+    return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
+  int b = p->row_begin, e = p->row_end;
+  if (b == 0 && e == 0) e = p->grid_size;
+  if (b < 0 || e > p->grid_size || b >= e)
+    return set_error(CGE_ERR_BAD_ARG, "row shard [%d, %d) outside grid of %d rows", b, e,
+                     p->grid_size);
+  *rb = b;
+  *re = e;
+  return CGE_OK;
+}
+
+// tile shape and grid for one shard
+void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, const float *post,
+               Plan *pl) {
+  pl->N = p->grid_size;
+  pl->n = p->n_obs;
+  pl->n_pad = (p->n_obs + 3) & ~3;
+  pl->mode = p->mode;
+  pl->row_begin = rb;
+  pl->row_end = re;
+  pl->rows_local = re - rb;
+  pl->ncw = (pl->N + cge::kWarpCols - 1) / cge::kWarpCols;
+  if (pl->ncw >= 8) { pl->wm = 1; pl->wn = 8; }
+  else if (pl->ncw >= 4) { pl->wm = 2; pl->wn = 4; }
+  else if (pl->ncw >= 2) { pl->wm = 4; pl->wn = 2; }
+  else { pl->wm = 8; pl->wn = 1; }
+  pl->bands = (pl->ncw + pl->wn - 1) / pl->wn;
+  const int unit = pl->wm * cge::kRM;
+  // aim for >= ~24 waves of 4 resident CTAs per SM, tiles of at most 128 rows
+  const long long want_ctas = (long long)ctx->sm_count * 4 * 24;
+  long long tr = ((long long)pl->rows_local * pl->bands) / want_ctas;
+  tr = (tr / unit) * unit;
+  if (tr < unit) tr = unit;
+  if (tr > 128) tr = (128 / unit) * unit;
+  pl->tile_rows = (int)tr;
+  pl->row_tiles = (pl->rows_local + pl->tile_rows - 1) / pl->tile_rows;
+  pl->ncolparts = pl->row_tiles * pl->wm;
+  pl->nb_col = (pl->N + 255) / 256;
+  pl->nb_row = (pl->rows_local + 7) / 8;
+  pl->vec4 = (pl->N % 4 == 0) && ((reinterpret_cast<uintptr_t>(post) & 15u) == 0);
+  const bool streamed = pl->n_pad > cge::kObsSingleMax;
+  pl->smem = 128 + (streamed ? 2 * (size_t)cge::kObsChunk * 4 : (size_t)pl->n_pad * 4);
+  pl->valid = true;
+}
+
+template <class Policy, int WM, int WN>
+int launch_like_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
+  dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
+  if (pl.vec4) {
+    auto k = cge::grid_likelihood_kernel<Policy, WM, WN, true>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    k<<<grid, block, pl.smem, st>>>(args);
+  } else {
+    auto k = cge::grid_likelihood_kernel<Policy, WM, WN, false>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    k<<<grid, block, pl.smem, st>>>(args);
+  }
+  CK(cudaGetLastError());
+  return CGE_OK;
+}
+
+template <class Policy>
+int launch_like(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
+  if (pl.wm == 1) return launch_like_shape<Policy, 1, 8>(pl, args, st);
+  if (pl.wm == 2) return launch_like_shape<Policy, 2, 4>(pl, args, st);
+  if (pl.wm == 4) return launch_like_shape<Policy, 4, 2>(pl, args, st);
+  return launch_like_shape<Policy, 8, 1>(pl, args, st);
+}
+
+// record profiling mark `k` of the current step (no-op unless capture is on and has room)
+int mark(cge_context *ctx, int k, cudaStream_t st) {
+  if (!ctx->prof_on || ctx->prof_step >= ctx->prof_cap) return CGE_OK;
+  CK(cudaEventRecord(ctx->prof_events[(size_t)ctx->prof_step * 7 + k], st));
+  return CGE_OK;
+}
+
+int prof_reserve(cge_context *ctx, int steps) {
+  while ((int)ctx->prof_events.size() < steps * 7) {
+    cudaEvent_t e;
+    CK(cudaEventCreate(&e));
+    ctx->prof_events.push_back(e);
+  }
+  ctx->prof_cap = steps;
+  ctx->prof_step = 0;
+  return CGE_OK;
+}
+
+// mean per-phase times over the captured steps (synchronises on the last mark)
+int prof_collect(cge_context *ctx, cge_timing *out, int *steps) {
+  cge_timing t = {};
+  const int n = ctx->prof_step;
+  if (n > 0) CK(cudaEventSynchronize(ctx->prof_events[(size_t)(n - 1) * 7 + 6]));
+  for (int s = 0; s < n; ++s) {
+    cudaEvent_t *e = &ctx->prof_events[(size_t)s * 7];
+    float a = 0, b = 0, c = 0, d = 0, f = 0, tot = 0;
+    CK(cudaEventElapsedTime(&a, e[0], e[1]));
+    CK(cudaEventElapsedTime(&b, e[1], e[2]));
+    CK(cudaEventElapsedTime(&c, e[2], e[3]));
+    CK(cudaEventElapsedTime(&d, e[4], e[5]));
+    CK(cudaEventElapsedTime(&f, e[5], e[6]));
+    CK(cudaEventElapsedTime(&tot, e[0], e[6]));
+    t.setup_ms += a; t.likelihood_ms += b; t.reduce_ms += c + d; t.scale_ms += f; t.total_ms += tot;
+  }
+  if (n > 0) {
+    t.setup_ms /= n; t.likelihood_ms /= n; t.reduce_ms /= n; t.scale_ms /= n; t.total_ms /= n;
+  }
+  if (out) *out = t;
+  if (steps) *steps = n;
+  return CGE_OK;
+}
+
+bool is_device_pointer(const void *p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------
+CGE_EXPORT int cge_version(void) { return CGE_VERSION; }
+
+CGE_EXPORT const char *cge_last_error(void) { return g_last_error.c_str(); }
+
+CGE_EXPORT int cge_create(int device, cge_context **out) {
+  if (!out) return set_error(CGE_ERR_BAD_ARG, "out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    cudaGetLastError();
+    return set_error(CGE_ERR_NO_DEVICE, "no CUDA device (%s); libcge has no CPU fallback",
+                     e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+  }
+  if (device < 0 || device >= count)
+    return set_error(CGE_ERR_BAD_ARG, "device %d out of range (have %d)", device, count);
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    return set_error(CGE_ERR_NO_DEVICE,
+                     "device %d is sm_%d%d; libcge is built for sm_100a (B200) only", device,
+                     prop.major, prop.minor);
+  CK(cudaSetDevice(device));
+  cge_context *ctx = new (std::nothrow) cge_context();
+  if (!ctx) return set_error(CGE_ERR_CUDA, "out of host memory");
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->cc_major = prop.major;
+  ctx->cc_minor = prop.minor;
+  cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+  if (se != cudaSuccess) {
+    delete ctx;
+    return set_error(CGE_ERR_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(se));
+  }
+  for (auto &ev : ctx->ev) {
+    cudaError_t ee = cudaEventCreate(&ev);
+    if (ee != cudaSuccess) {
+      delete ctx;
+      return set_error(CGE_ERR_CUDA, "cudaEventCreate failed: %s", cudaGetErrorString(ee));
+    }
+  }
+  *out = ctx;
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_destroy(cge_context *ctx) {
+  if (!ctx) return CGE_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ctx->mu.release(); ctx->sigma.release(); ctx->obs_pad.release(); ctx->obs_in.release();
+  ctx->posterior.release(); ctx->ad.release(); ctx->cd0.release(); ctx->rowpart.release();
+  ctx->colpart.release(); ctx->partials.release(); ctx->rowsum.release(); ctx->zpart.release();
+  ctx->smupart.release(); ctx->results.release(); ctx->tmp.release(); ctx->scale.release();
+  ctx->sink.release();
+  for (auto &ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  for (auto &ev : ctx->prof_events) cudaEventDestroy(ev);
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_device_sm_count(cge_context *ctx, int *sm_count, int *cc_major, int *cc_minor) {
+  if (!ctx) return set_error(CGE_ERR_BAD_ARG, "context is NULL");
+  if (sm_count) *sm_count = ctx->sm_count;
+  if (cc_major) *cc_major = ctx->cc_major;
+  if (cc_minor) *cc_minor = ctx->cc_minor;
+  return CGE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// phase 1: tables + scale + fused likelihood + local fold
+// ---------------------------------------------------------------------------------------
+CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, const float *obs_dev,
+                                       float *posterior_dev, void *stream) {
+  CKRC(bind(ctx));
+  int rb, re;
+  CKRC(check_params(p, &rb, &re));
+  if (!obs_dev || !posterior_dev)
+    return set_error(CGE_ERR_BAD_ARG, "obs_dev and posterior_dev must be device pointers");
+  cudaStream_t st = (cudaStream_t)stream;
+  Plan &pl = ctx->plan;
+  pl.valid = false;
+  make_plan(ctx, p, rb, re, posterior_dev, &pl);
+  const int N = pl.N;
+
+  CKRC(ctx->mu.reserve(N));
+  CKRC(ctx->sigma.reserve(N));
+  CKRC(ctx->ad.reserve(N));
+  CKRC(ctx->cd0.reserve(N));
+  CKRC(ctx->obs_pad.reserve(pl.n_pad));
+  CKRC(ctx->scale.reserve(1));
+  CKRC(ctx->rowpart.reserve((size_t)pl.rows_local * pl.ncw));
+  CKRC(ctx->colpart.reserve((size_t)pl.ncolparts * N));
+  CKRC(ctx->partials.reserve((size_t)N + 2));
+  CKRC(ctx->rowsum.reserve(pl.rows_local));
+  CKRC(ctx->zpart.reserve(pl.nb_row));
+  CKRC(ctx->smupart.reserve(pl.nb_row));
+  CKRC(ctx->results.reserve(4 + 2 * (size_t)N));
+
+  ctx->launches = 0;
+  CKRC(mark(ctx, 0, st));
+  cge::tables_kernel<<<(N + 255) / 256, 256, 0, st>>>(ctx->mu.ptr, ctx->sigma.ptr, ctx->ad.ptr,
+                                                       ctx->cd0.ptr, N, p->mu_start, p->mu_end,
+                                                       p->sigma_start, p->sigma_end);
+  CK(cudaGetLastError());
+  cge::scale_kernel<<<1, 1024, 0, st>>>(obs_dev, ctx->obs_pad.ptr, pl.n, pl.n_pad, ctx->mu.ptr,
+                                        ctx->ad.ptr, ctx->cd0.ptr, N, ctx->scale.ptr);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  CKRC(mark(ctx, 1, st));
+
+  cge::LikeArgs args;
+  args.obs_pad = ctx->obs_pad.ptr;
+  args.mu = ctx->mu.ptr;
+  args.ad = ctx->ad.ptr;
+  args.cd0 = ctx->cd0.ptr;
+  args.scale = ctx->scale.ptr;
+  args.post = posterior_dev;
+  args.rowpart = ctx->rowpart.ptr;
+  args.colpart = ctx->colpart.ptr;
+  args.n = pl.n;
+  args.n_pad = pl.n_pad;
+  args.N = N;
+  args.row_begin = rb;
+  args.row_end = re;
+  args.tile_rows = pl.tile_rows;
+  args.ncw = pl.ncw;
+  if (p->mode == CGE_MODE_PRODUCT_F32)
+    CKRC(launch_like<cge::ProductF32>(pl, args, st));
+  else
+    CKRC(launch_like<cge::LogSpaceF64>(pl, args, st));
+  ctx->launches += 1;
+  CKRC(mark(ctx, 2, st));
+
+  cge::fold_partials_kernel<<<pl.nb_col + pl.nb_row, 256, 0, st>>>(
+      ctx->colpart.ptr, pl.ncolparts, ctx->rowpart.ptr, pl.ncw, pl.rows_local, rb, N, ctx->mu.ptr,
+      ctx->partials.ptr, ctx->rowsum.ptr, ctx->zpart.ptr, ctx->smupart.ptr, pl.nb_col);
+  CK(cudaGetLastError());
+  cge::finish_partials_kernel<<<1, 1024, 0, st>>>(ctx->zpart.ptr, ctx->smupart.ptr, pl.nb_row,
+                                                  ctx->partials.ptr);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  CKRC(mark(ctx, 3, st));
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_partials(cge_context *ctx, double **partials_dev, size_t *count) {
+  if (!ctx) return set_error(CGE_ERR_BAD_ARG, "context is NULL");
+  if (!ctx->plan.valid) return set_error(CGE_ERR_BAD_ARG, "no likelihood call has been made");
+  if (partials_dev) *partials_dev = ctx->partials.ptr;
+  if (count) *count = (size_t)ctx->plan.N + 2;
+  return CGE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// phase 2: results + in-place scale
+// ---------------------------------------------------------------------------------------
+CGE_EXPORT int cge_finalize(cge_context *ctx, const cge_params *p, float *posterior_dev,
+                            void *stream) {
+  CKRC(bind(ctx));
+  int rb, re;
+  CKRC(check_params(p, &rb, &re));
+  const Plan &pl = ctx->plan;
+  if (!pl.valid || pl.N != p->grid_size || pl.row_begin != rb || pl.row_end != re)
+    return set_error(CGE_ERR_BAD_ARG, "cge_finalize does not match the last cge_likelihood_partials");
+  if (!posterior_dev) return set_error(CGE_ERR_BAD_ARG, "posterior_dev is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int N = pl.N;
+  CKRC(mark(ctx, 4, st));
+  cge::results_kernel<<<1, 1024, 0, st>>>(ctx->partials.ptr, ctx->rowsum.ptr, ctx->sigma.ptr, N, rb,
+                                          re, ctx->results.ptr);
+  CK(cudaGetLastError());
+  CKRC(mark(ctx, 5, st));
+  const size_t cells = (size_t)pl.rows_local * N;
+  const bool aligned = (reinterpret_cast<uintptr_t>(posterior_dev) & 15u) == 0;
+  // enough CTAs to keep every SM's memory pipeline full, capped so tiny grids stay tiny
+  size_t want = aligned ? (cells / 4 + 1023) / 1024 : (cells + 255) / 256;
+  size_t cap = (size_t)ctx->sm_count * 16;
+  int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
+  if (aligned)
+    cge::scale_posterior_kernel<<<blocks, 256, 0, st>>>(posterior_dev, cells, ctx->partials.ptr);
+  else
+    cge::scale_posterior_scalar_kernel<<<blocks, 256, 0, st>>>(posterior_dev, cells,
+                                                               ctx->partials.ptr);
+  CK(cudaGetLastError());
+  ctx->launches += 2;
+  CKRC(mark(ctx, 6, st));
+  if (ctx->prof_on && ctx->prof_step < ctx->prof_cap) ctx->prof_step++;
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_results(cge_context *ctx, double **results_dev, size_t *count) {
+  if (!ctx) return set_error(CGE_ERR_BAD_ARG, "context is NULL");
+  if (!ctx->plan.valid) return set_error(CGE_ERR_BAD_ARG, "no likelihood call has been made");
+  if (results_dev) *results_dev = ctx->results.ptr;
+  if (count) *count = 4 + 2 * (size_t)ctx->plan.N;
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_read_results(cge_context *ctx, const cge_params *p, double *expectations,
+                                double *marg_mu, double *marg_sigma, double *z, void *stream) {
+  CKRC(bind(ctx));
+  if (!ctx->plan.valid || !p || ctx->plan.N != p->grid_size)
+    return set_error(CGE_ERR_BAD_ARG, "cge_read_results does not match the last call");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t N = (size_t)ctx->plan.N;
+  double head[4];
+  CK(cudaMemcpyAsync(head, ctx->results.ptr, sizeof head, cudaMemcpyDeviceToHost, st));
+  if (marg_sigma)
+    CK(cudaMemcpyAsync(marg_sigma, ctx->results.ptr + 4, N * sizeof(double), cudaMemcpyDefault, st));
+  if (marg_mu)
+    CK(cudaMemcpyAsync(marg_mu, ctx->results.ptr + 4 + N, N * sizeof(double), cudaMemcpyDefault, st));
+  CK(cudaStreamSynchronize(st));
+  if (expectations) {
+    if (is_device_pointer(expectations))
+      CK(cudaMemcpy(expectations, head, 2 * sizeof(double), cudaMemcpyHostToDevice));
+    else {
+      expectations[0] = head[0];
+      expectations[1] = head[1];
+    }
+  }
+  if (z) *z = head[2];
+  if (!(head[2] > 0.0) || !std::isfinite(head[2]))
+    return set_error(CGE_ERR_DEGENERATE,
+                     "normaliser Z = %g: every cell underflowed or the inputs are not finite "
+                     "(use CGE_MODE_LOGSPACE for large n_obs)", head[2]);
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_last_timing(cge_context *ctx, cge_timing *timing) {
+  if (!ctx || !timing) return set_error(CGE_ERR_BAD_ARG, "NULL argument");
+  *timing = ctx->timing;
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_profile_begin(cge_context *ctx, int max_steps) {
+  CKRC(bind(ctx));
+  if (max_steps < 1 || max_steps > 65536) return set_error(CGE_ERR_BAD_ARG, "max_steps out of range");
+  CKRC(prof_reserve(ctx, max_steps));
+  ctx->prof_on = true;
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_profile_end(cge_context *ctx, cge_timing *mean, int *steps_captured) {
+  CKRC(bind(ctx));
+  int rc = prof_collect(ctx, mean, steps_captured);
+  ctx->prof_on = false;
+  return rc;
+}
+
+CGE_EXPORT int cge_launch_count(cge_context *ctx, int *launches) {
+  if (!ctx || !launches) return set_error(CGE_ERR_BAD_ARG, "NULL argument");
+  *launches = ctx->launches;
+  return CGE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// fused synchronous entry: host or device buffers
+// ---------------------------------------------------------------------------------------
+CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const float *obs,
+                                  float *posterior, double *marg_mu, double *marg_sigma,
+                                  double *expectations, cge_timing *timing) {
+  CKRC(bind(ctx));
+  int rb, re;
+  CKRC(check_params(p, &rb, &re));
+  if (!obs) return set_error(CGE_ERR_BAD_ARG, "obs is NULL");
+  cudaStream_t st = ctx->stream;
+  const size_t cells = (size_t)(re - rb) * p->grid_size;
+  ctx->timing = cge_timing{};
+  const bool was_on = ctx->prof_on;
+  if (timing && !was_on) {
+    CKRC(prof_reserve(ctx, 1));
+    ctx->prof_on = true;
+  }
+
+  const float *obs_dev = obs;
+  if (timing) CK(cudaEventRecord(ctx->ev[7], st));
+  if (!is_device_pointer(obs)) {
+    CKRC(ctx->obs_in.reserve(p->n_obs));
+    CK(cudaMemcpyAsync(ctx->obs_in.ptr, obs, (size_t)p->n_obs * sizeof(float),
+                       cudaMemcpyHostToDevice, st));
+    obs_dev = ctx->obs_in.ptr;
+  }
+  if (timing) CK(cudaEventRecord(ctx->ev[0], st));
+  float *post_dev = posterior;
+  const bool post_to_host = posterior && !is_device_pointer(posterior);
+  if (!posterior || post_to_host) {
+    CKRC(ctx->posterior.reserve(cells));
+    post_dev = ctx->posterior.ptr;
+  }
+  int rc = cge_likelihood_partials(ctx, p, obs_dev, post_dev, st);
+  if (rc == CGE_OK) rc = cge_finalize(ctx, p, post_dev, st);
+  if (rc != CGE_OK) {
+    if (!was_on) ctx->prof_on = false;
+    return rc;
+  }
+  if (timing) CK(cudaEventRecord(ctx->ev[1], st));
+  if (post_to_host)
+    CK(cudaMemcpyAsync(posterior, post_dev, cells * sizeof(float), cudaMemcpyDeviceToHost, st));
+  rc = cge_read_results(ctx, p, expectations, marg_mu, marg_sigma, nullptr, st);
+  if (timing) {
+    cudaEventRecord(ctx->ev[2], st);
+    cudaEventSynchronize(ctx->ev[2]);
+    cge_timing t = {};
+    if (!was_on) {
+      prof_collect(ctx, &t, nullptr);
+      ctx->prof_on = false;
+    }
+    cudaEventElapsedTime(&t.h2d_ms, ctx->ev[7], ctx->ev[0]);
+    cudaEventElapsedTime(&t.d2h_ms, ctx->ev[1], ctx->ev[2]);
+    cudaEventElapsedTime(&t.total_ms, ctx->ev[7], ctx->ev[2]);
+    ctx->timing = t;
+    *timing = t;
+  }
+  return rc;
+}
+
+// posterior kept by the context when cge_grid_posterior was called with posterior == NULL or a
+// host pointer
+CGE_EXPORT int cge_posterior_dev(cge_context *ctx, float **posterior_dev, size_t *count) {
+  if (!ctx) return set_error(CGE_ERR_BAD_ARG, "context is NULL");
+  if (posterior_dev) *posterior_dev = ctx->posterior.ptr;
+  if (count) *count = ctx->plan.valid ? (size_t)ctx->plan.rows_local * ctx->plan.N : 0;
+  return CGE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// stage API
+// ---------------------------------------------------------------------------------------
+static int grid_for(size_t count, int threads, int sm_count) {
+  size_t want = (count + threads - 1) / threads;
+  size_t cap = (size_t)sm_count * 32;
+  if (want < 1) want = 1;
+  return (int)(want > cap ? cap : want);
+}
+
+CGE_EXPORT int cge_linspace(cge_context *ctx, float *array_dev, int size, float start, float end) {
+  CKRC(bind(ctx));
+  if (!array_dev || size < 1) return set_error(CGE_ERR_BAD_ARG, "linspace: bad array/size");
+  cge::linspace_kernel<<<(size + 255) / 256, 256, 0, ctx->stream>>>(array_dev, size, start, end);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_meshgrid3(cge_context *ctx, const float *vec_x, const float *vec_y,
+                             const float *vec_z, float *grid_x, float *grid_y, float *grid_z,
+                             int vec_xy_size, int vec_z_size) {
+  CKRC(bind(ctx));
+  if (!vec_x || !vec_y || !vec_z || !grid_x || !grid_y || !grid_z || vec_xy_size < 1 ||
+      vec_z_size < 1)
+    return set_error(CGE_ERR_BAD_ARG, "meshgrid3: bad argument");
+  size_t total = (size_t)vec_xy_size * vec_xy_size * vec_z_size;
+  cge::meshgrid3_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+      vec_x, vec_y, vec_z, grid_x, grid_y, grid_z, vec_xy_size, vec_z_size);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_densities(cge_context *ctx, float *densities, const float *grid_x,
+                             const float *grid_y, const float *grid_z, size_t grid_size) {
+  CKRC(bind(ctx));
+  if (!densities || !grid_x || !grid_y || !grid_z || grid_size < 1)
+    return set_error(CGE_ERR_BAD_ARG, "densities: bad argument");
+  cge::densities_kernel<<<grid_for(grid_size, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+      densities, grid_x, grid_y, grid_z, grid_size);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_row_products(cge_context *ctx, const float *densities, double *likes,
+                                size_t densities_size, size_t likes_size) {
+  CKRC(bind(ctx));
+  if (!densities || !likes || likes_size < 1)
+    return set_error(CGE_ERR_BAD_ARG, "row_products: bad argument");
+  size_t cols = densities_size / likes_size;
+  if (cols * likes_size != densities_size || cols < 1 || cols > 0x7fffffff)
+    return set_error(CGE_ERR_SIZE, "likesSize != rows * cols (densities %zu, likes %zu)",
+                     densities_size, likes_size);
+  size_t blocks = (likes_size + 7) / 8;
+  if (blocks > 0x7fffffff) return set_error(CGE_ERR_BAD_ARG, "row_products: too many rows");
+  cge::row_products_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(densities, likes, likes_size,
+                                                                      (int)cols);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_normalize(cge_context *ctx, const double *likes, double *posterior, size_t size) {
+  CKRC(bind(ctx));
+  if (!likes || !posterior || size < 1) return set_error(CGE_ERR_BAD_ARG, "normalize: bad argument");
+  int nb = grid_for(size, 1024, ctx->sm_count);
+  if (nb > 1024) nb = 1024;
+  CKRC(ctx->tmp.reserve((size_t)nb + 1));
+  cge::block_sums_kernel<<<nb, 1024, 0, ctx->stream>>>(likes, size, ctx->tmp.ptr + 1);
+  CK(cudaGetLastError());
+  cge::final_sum_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->tmp.ptr + 1, nb, ctx->tmp.ptr);
+  CK(cudaGetLastError());
+  cge::scale_f64_kernel<<<grid_for(size, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+      likes, posterior, size, ctx->tmp.ptr);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_marginalize(cge_context *ctx, double *marginal, const double *matrix, int rows,
+                               int cols, int axis) {
+  CKRC(bind(ctx));
+  if (!marginal || !matrix || rows < 1 || cols < 1 || (axis != 0 && axis != 1))
+    return set_error(CGE_ERR_BAD_ARG, "marginalize: bad argument");
+  int blocks = axis == 1 ? (rows + 7) / 8 : (cols + 255) / 256;
+  cge::marginalize_kernel<<<blocks, 256, 0, ctx->stream>>>(marginal, matrix, rows, cols, axis);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_expectation(cge_context *ctx, const double *marginal, const float *vector,
+                               int size, double *expectation_host) {
+  CKRC(bind(ctx));
+  if (!marginal || !vector || size < 1 || !expectation_host)
+    return set_error(CGE_ERR_BAD_ARG, "expectation: bad argument");
+  CKRC(ctx->tmp.reserve(2));
+  cge::expectation_kernel<<<1, 1024, 0, ctx->stream>>>(marginal, vector, size, ctx->tmp.ptr);
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(expectation_host, ctx->tmp.ptr, sizeof(double), cudaMemcpyDeviceToHost,
+                     ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CGE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// pipe-peak micro-benchmarks
+// ---------------------------------------------------------------------------------------
+CGE_EXPORT int cge_microbench(cge_context *ctx, int kind, double *ops_per_second) {
+  CKRC(bind(ctx));
+  if (!ops_per_second || kind < 0 || kind > 3)
+    return set_error(CGE_ERR_BAD_ARG, "microbench: bad argument");
+  CKRC(ctx->sink.reserve(4));
+  const int iters = 4096, chains = 8;
+  const int blocks = ctx->sm_count * 8, threads = 256;
+  cudaStream_t st = ctx->stream;
+  auto launch = [&]() {
+    switch (kind) {
+      case 0: cge::microbench_kernel<0><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+      case 1: cge::microbench_kernel<1><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+      case 2: cge::microbench_kernel<2><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+      default: cge::microbench_kernel<3><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+    }
+  };
+  for (int w = 0; w < 3; ++w) launch();
+  CK(cudaGetLastError());
+  float best = 1e30f;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaEventRecord(ctx->ev[0], st));
+    launch();
+    CK(cudaEventRecord(ctx->ev[1], st));
+    CK(cudaEventSynchronize(ctx->ev[1]));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    if (ms < best) best = ms;
+  }
+  CK(cudaGetLastError());
+  double ops = (double)blocks * threads * (double)iters * chains * (kind == 3 ? 2.0 : 1.0);
+  *ops_per_second = ops / (best * 1e-3);
+  return CGE_OK;
+}

@@ -1,0 +1,147 @@
+// cge_device.cuh -- device-side helpers shared by the sm_100a kernels: PTX wrappers
+// (MUFU ex2, mbarrier, 1-D TMA bulk copy, streaming vector stores), the reference's range
+// formula, and fixed-order (deterministic) warp/block reductions.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace cge {
+
+// ---------------------------------------------------------------------------------------
+// arithmetic
+// ---------------------------------------------------------------------------------------
+// One MUFU.EX2 per call.  .ftz: subnormal results flush to +0, which is what lets far-tail
+// cells die quietly instead of dragging subnormal arithmetic through the product.
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Reference range formula, reference inc/kernels.h:63:  start + idx*(end-start)/(size-1)
+// evaluated in float32 with one rounding per operation (no FMA contraction, IEEE divide),
+// so mu_i / sigma_j are bit-identical to the reference's linspaceKernel output.
+// size == 1 would be 0/0 in the reference; here it yields `start`.
+__device__ __forceinline__ float range_value(int idx, int size, float start, float end) {
+  if (size <= 1) return start;
+  float span = __fsub_rn(end, start);
+  float num = __fmul_rn(__int2float_rn(idx), span);
+  float q = __fdiv_rn(num, __int2float_rn(size - 1));
+  return __fadd_rn(start, q);
+}
+
+// ---------------------------------------------------------------------------------------
+// shared-memory addressing, mbarrier and TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t arrivals) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(arrivals)
+               : "memory");
+}
+
+// make the barrier initialisation visible to the async (TMA) proxy
+__device__ __forceinline__ void mbar_init_fence() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra WAIT_DONE;\n\t"
+      "bra WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned; completion is
+// signalled on `bar` as `bytes` of transaction count.
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src,
+                                              uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// global stores / loads for streamed data
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_stream_f4(float *p, float a, float b, float c, float d) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c),
+               "f"(d)
+               : "memory");
+}
+
+__device__ __forceinline__ void st_stream_f1(float *p, float a) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------
+// fixed-order reductions: the combination tree depends only on lane / warp indices, never on
+// timing, so every run (and every shard layout with the same tiling) sums in the same order.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  return v;
+}
+
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+
+__device__ __forceinline__ double warp_min(double v) {
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, off));
+  return v;
+}
+
+// Block-wide sum, result valid in every thread.  `scratch` holds >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double *scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // scratch may still be read from a previous call
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double t = lane < nwarps ? scratch[lane] : 0.0;
+  return warp_sum(t);
+}
+
+__device__ __forceinline__ double block_max(double v, double *scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double t = lane < nwarps ? scratch[lane] : -1.0 / 0.0;
+  return warp_max(t);
+}
+
+__device__ __forceinline__ double block_min(double v, double *scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  v = warp_min(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  double t = lane < nwarps ? scratch[lane] : 1.0 / 0.0;
+  return warp_min(t);
+}
+
+}  // namespace cge

@@ -1,0 +1,174 @@
+/*
+ * cge.h -- C ABI of libcge.so: the B200-native (sm_100a) grid-estimation hot path.
+ *
+ * Drop-in boundary for the one data-parallel path of nablabits/cuda-grid-estimation
+ * (reference paths below are relative to cpp/grid-algorithm/ in that repository):
+ *
+ *     src/grid.cu:79-127   computeDensitiesWrapper -> computeLikesWrapper ->
+ *                          computePosteriorCuda -> computeExpectationsWrapper
+ *
+ * The reference has no FFI layer; its "API" is a set of header-defined C++ functions.
+ * This header is what an FFI for that path binds: plain C, plain pointers and sizes, an int
+ * status from every call, no C++ or torch types.  The C++ shim with the reference's own
+ * function names on top of this ABI is include/cge_compat.h.
+ *
+ * Conventions
+ *   - posterior layout is the reference's: posterior[i * grid_size + j] = P(mu_i, sigma_j)
+ *     (inc/kernels.h:92; pinned by src/tests.cu:93-95).
+ *   - ranges use the reference's float32 formula start + i*(end-start)/(size-1)
+ *     (inc/kernels.h:63), bit for bit.
+ *   - flat prior (src/grid.cu:97-101): the posterior is likes * (1/Z) (inc/utils.h:82-84).
+ *   - every `*_dev` pointer is device (or managed) memory on the context's device; `stream` is
+ *     a cudaStream_t passed as void*, with CUDA's own meaning of NULL (the legacy default
+ *     stream).  Calls that take a stream only enqueue work unless stated otherwise.  The
+ *     synchronous entry points run on a context-owned non-blocking stream: inputs produced
+ *     on another stream must be complete before they are called.
+ *   - there is NO CPU fallback: without a usable sm_100 device every call fails with
+ *     CGE_ERR_NO_DEVICE / CGE_ERR_CUDA.
+ */
+#ifndef CGE_H
+#define CGE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CGE_VERSION 1
+
+/* status codes (the reference returns void and prints; src/grid.cu:15-17 is its only check) */
+enum {
+  CGE_OK = 0,
+  CGE_ERR_BAD_ARG = 1,    /* NULL pointer, size < 1, sigma range not > 0, shard out of range */
+  CGE_ERR_NO_DEVICE = 2,  /* no CUDA device / not sm_100 */
+  CGE_ERR_CUDA = 3,       /* a CUDA runtime call failed; see cge_last_error() */
+  CGE_ERR_DEGENERATE = 4, /* normaliser Z is zero or not finite (all cells underflowed) */
+  CGE_ERR_NCCL = 5,       /* collective failed */
+  CGE_ERR_SIZE = 6        /* stage API: densitiesSize != rows*cols (inc/wrappers.h:110-113) */
+};
+
+/* arithmetic mode of the likelihood kernel */
+enum {
+  CGE_MODE_PRODUCT_F32 = 0, /* running float32 product of per-observation pdfs, MUFU ex2 per
+                               pdf-eval, one global per-factor rescale (posterior is
+                               scale-invariant) -- BASELINE.json "float32 product path" */
+  CGE_MODE_LOGSPACE = 1     /* float64 sum of log-pdf, log-sum-exp normalisation -- for
+                               observation counts where any product underflows */
+};
+
+typedef struct cge_context cge_context; /* opaque: device, stream, scratch, tables */
+
+typedef struct cge_params {
+  int32_t n_obs;        /* observations (reference: rvsSize, src/grid.cu:34) */
+  int32_t grid_size;    /* N: points per axis (reference: vecSize, src/grid.cu:65) */
+  float mu_start;       /* reference: startMu..endSigma, src/grid.cu:67-70 */
+  float mu_end;
+  float sigma_start;
+  float sigma_end;
+  int32_t mode;         /* CGE_MODE_* */
+  int32_t row_begin;    /* shard: this call owns mu rows [row_begin, row_end) of the global */
+  int32_t row_end;      /* grid; 0,0 means the whole grid (0, grid_size) */
+  int32_t reserved;
+} cge_params;
+
+/* per-phase device timings of the last synchronous call, milliseconds (CUDA events) */
+typedef struct cge_timing {
+  float setup_ms;       /* range/coefficient tables + scale statistics */
+  float likelihood_ms;  /* fused likelihood kernel */
+  float reduce_ms;      /* deterministic partial reduction (Z, marginals, expectations) */
+  float scale_ms;       /* posterior *= 1/Z */
+  float total_ms;
+  float h2d_ms;         /* host-buffer entry points only */
+  float d2h_ms;
+} cge_timing;
+
+/* ---- context ------------------------------------------------------------------------- */
+int cge_create(int device, cge_context **out);
+int cge_destroy(cge_context *ctx);
+const char *cge_last_error(void);       /* thread-local message of the last failing call */
+int cge_version(void);
+int cge_device_sm_count(cge_context *ctx, int *sm_count, int *cc_major, int *cc_minor);
+
+/* ---- the fused hot path: replaces src/grid.cu:79-127 in one call ------------------------
+ * cge_grid_posterior: host or device buffers (detected with cudaPointerGetAttributes), runs
+ * synchronously, returns when every requested output is written.
+ *   obs            n_obs float32                                  (reference: observations)
+ *   posterior      (row_end-row_begin) * grid_size float32, or NULL to keep it on device only
+ *   marg_mu        grid_size float64 (row sums; only [row_begin,row_end) are this shard's, the
+ *                  rest are written as 0), or NULL               (inc/wrappers.h:169)
+ *   marg_sigma     grid_size float64 (column sums of this shard), or NULL (inc/wrappers.h:170)
+ *   expectations   2 float64 {E[mu], E[sigma]}, or NULL          (inc/wrappers.h:173-176)
+ *   timing         optional
+ * With a shard (row_begin/row_end not covering the grid) the normaliser is the SHARD's unless
+ * the caller uses the phase API below and all-reduces the partials.
+ */
+int cge_grid_posterior(cge_context *ctx, const cge_params *p, const float *obs,
+                       float *posterior, double *marg_mu, double *marg_sigma,
+                       double *expectations, cge_timing *timing);
+
+/* ---- phase API (multi-GPU: one process per GPU, the caller owns the collective) ----------
+ * phase 1: tables + likelihood + local deterministic reduction.  Leaves the packed partial
+ *          vector {Z, sum_i mu_i*rowsum_i, colsum[0..N)} (N+2 float64) in a context-owned
+ *          device buffer (cge_partials) and the UNNORMALISED likelihoods in posterior_dev.
+ * ...      the caller sums the partial vector over ranks in place (ncclAllReduce / torch
+ *          all_reduce, float64 sum) -- nothing else crosses NVLink.
+ * phase 2: marginals, expectations and the in-place scale posterior_dev *= 1/Z.
+ *          Results stay on the device in the context's result block (cge_results).
+ */
+int cge_likelihood_partials(cge_context *ctx, const cge_params *p, const float *obs_dev,
+                            float *posterior_dev, void *stream);
+int cge_partials(cge_context *ctx, double **partials_dev, size_t *count);
+int cge_finalize(cge_context *ctx, const cge_params *p, float *posterior_dev, void *stream);
+/* result block on device: {E[mu], E[sigma], Z, 1/Z} then marg_sigma[N] then marg_mu[N]
+ * (marg_mu holds this shard's rows at their global index, 0 elsewhere) */
+int cge_results(cge_context *ctx, double **results_dev, size_t *count);
+/* blocking convenience: copies the result block pieces to host pointers (any may be NULL) */
+int cge_read_results(cge_context *ctx, const cge_params *p, double *expectations,
+                     double *marg_mu, double *marg_sigma, double *z, void *stream);
+/* device posterior the context keeps when cge_grid_posterior got posterior == NULL or a host pointer */
+int cge_posterior_dev(cge_context *ctx, float **posterior_dev, size_t *count);
+int cge_last_timing(cge_context *ctx, cge_timing *timing);
+/* per-step CUDA-event capture around every phase of the next `max_steps` phase-API steps (events
+ * are recorded on the stream the kernels are launched on); cge_profile_end synchronises and
+ * returns the mean per-phase device times.  h2d_ms/d2h_ms are not filled. */
+int cge_profile_begin(cge_context *ctx, int max_steps);
+int cge_profile_end(cge_context *ctx, cge_timing *mean, int *steps_captured);
+/* number of kernels the last cge_likelihood_partials + cge_finalize pair launched */
+int cge_launch_count(cge_context *ctx, int *launches);
+
+/* ---- stage API: the reference's L1 functions, one C entry each (device/managed pointers) --
+ * These exist so the reference's stage-by-stage callers and tests keep working; they
+ * materialise what the reference materialises and are meant for the reference's sizes.
+ */
+/* inc/cuda_functions.h:47-62 linspaceCuda */
+int cge_linspace(cge_context *ctx, float *array_dev, int size, float start, float end);
+/* inc/cuda_functions.h:65-92 create3dGridCuda */
+int cge_meshgrid3(cge_context *ctx, const float *vec_x, const float *vec_y, const float *vec_z,
+                  float *grid_x, float *grid_y, float *grid_z, int vec_xy_size, int vec_z_size);
+/* inc/cuda_functions.h:95-115 computeDensitiesCuda: densities[f] = pdf(grid_z[f]; grid_x[f], grid_y[f]) */
+int cge_densities(cge_context *ctx, float *densities, const float *grid_x, const float *grid_y,
+                  const float *grid_z, size_t grid_size);
+/* inc/wrappers.h:95-121 computeLikesWrapper: likes[r] = prod_k densities[r*cols+k], float64 */
+int cge_row_products(cge_context *ctx, const float *densities, double *likes,
+                     size_t densities_size, size_t likes_size);
+/* inc/cuda_functions.h:139-159 computePosteriorCuda: posterior = likes * (1/sum(likes)) */
+int cge_normalize(cge_context *ctx, const double *likes, double *posterior, size_t size);
+/* inc/cuda_functions.h:161-182 marginalizeCuda on a dense row-major rows x cols matrix;
+ * axis=1 -> row sums (mu marginal), axis=0 -> column sums (sigma marginal) */
+int cge_marginalize(cge_context *ctx, double *marginal, const double *matrix, int rows,
+                    int cols, int axis);
+/* inc/cuda_functions.h:185-221 computeExpectationsCuda */
+int cge_expectation(cge_context *ctx, const double *marginal, const float *vector, int size,
+                    double *expectation_host);
+
+/* ---- roofline micro-benchmarks (bench.py): measured pipe peaks on this device ------------
+ * kind: 0 = MUFU ex2.approx.ftz.f32, 1 = FFMA, 2 = DFMA, 3 = FFMA2 (fma.rn.f32x2).
+ * Returns operations per second (lane-ops; an FMA counts as one op). */
+int cge_microbench(cge_context *ctx, int kind, double *ops_per_second);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CGE_H */

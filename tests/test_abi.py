@@ -1,0 +1,79 @@
+"""CPU: the C-ABI library builds, loads, exports every symbol include/cge.h declares, and the
+product path fails loudly (no CPU fallback) when there is no sm_100 device."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+import cuda_grid_estimation_b200 as cge
+from cuda_grid_estimation_b200 import _build, api
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "cge.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(cge_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_builds_and_loads():
+    path = _build.build()
+    assert os.path.exists(path)
+    lib = cge.load_library()
+    assert lib.cge_version() == 1
+
+
+def test_every_declared_symbol_is_exported():
+    lib = cge.load_library()
+    declared = _header_symbols()
+    assert len(declared) >= 20
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in include/cge.h but not exported"
+    assert sorted(api.ABI_SYMBOLS) == declared, "api.ABI_SYMBOLS out of sync with include/cge.h"
+
+
+def test_exports_are_plain_c_and_sm100a_only():
+    out = subprocess.run(["nm", "-D", "--defined-only", _build.LIB_PATH], capture_output=True,
+                         text=True, check=True).stdout
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert set(_header_symbols()) <= exported
+    # nothing mangled leaks out of the boundary
+    assert not [s for s in exported if s.startswith("_Z")], "C++ symbols exported"
+    sass = subprocess.run(["cuobjdump", "-lelf", _build.LIB_PATH], capture_output=True, text=True)
+    if sass.returncode == 0:
+        archs = set(re.findall(r"sm_\d+a?", sass.stdout))
+        assert archs == {"sm_100a"}, archs
+
+
+def test_struct_layouts_match_header():
+    assert C.sizeof(api.Params) == 40
+    assert C.sizeof(api.Timing) == 28
+
+
+def test_no_cpu_fallback_without_device():
+    """In the build container there is no GPU: creating a context must fail with a clear error,
+    not silently compute on the host.  (On a GPU box this test checks a bad device index.)"""
+    import torch
+    if torch.cuda.is_available():
+        with pytest.raises(cge.CgeError) as ei:
+            cge.Context(10_000)
+        assert ei.value.code == api.ERR_BAD_ARG
+    else:
+        with pytest.raises(cge.CgeError) as ei:
+            cge.Context(0)
+        assert ei.value.code in (api.ERR_NO_DEVICE, api.ERR_CUDA)
+        assert "no CPU fallback" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_product_does_not_import_oracle():
+    """The product package must never reach into oracle/ (test infrastructure)."""
+    pkg = os.path.join(ROOT, "cuda_grid_estimation_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+                assert "liboracle" not in src, f

@@ -1,0 +1,407 @@
+"""GPU (-m gpu): parity of the CUDA hot path, called through the C ABI, against the CPU oracle,
+the committed golden fixtures and size-independent properties at BASELINE.json's full sizes.
+
+Tolerances (BASELINE.md section 2 / SURVEY section 8(d)):
+  |dE[mu]|, |dE[sigma]| <= 1e-5 (expected ~1e-8)
+  posterior: relative error <= 1e-4 on cells with P >= 1e-20 * P_max; below that floor the
+             absolute error is <= 1e-4 * 1e-20 * P_max (cells more than ~50 decades under the
+             peak flush to zero in float32)
+  marginals: abs <= 1e-7 * max or rel <= 1e-4
+  sum(posterior) = 1 +- 1e-6
+"""
+import os
+
+import numpy as np
+import pytest
+
+import cuda_grid_estimation_b200 as cge
+import oracle
+from cuda_grid_estimation_b200 import api
+
+pytestmark = pytest.mark.gpu
+
+E_TOL = 1e-5
+POST_REL = 1e-4
+FLOOR = 1e-20
+
+
+def check_against(res, ref, post_rel=POST_REL, e_tol=E_TOL, what=""):
+    d_e = np.abs(res.expectations - ref["expectations"]).max()
+    assert d_e <= e_tol, f"{what}: E {res.expectations} vs {ref['expectations']}"
+    for key, got in (("marg_mu", res.marg_mu), ("marg_sigma", res.marg_sigma)):
+        want = ref[key]
+        ok = (np.abs(got - want) <= 1e-7 * want.max()) | (np.abs(got - want) <= 1e-4 * np.abs(want))
+        assert ok.all(), f"{what}: {key} max abs {np.abs(got - want).max()}"
+    if res.posterior is not None and ref.get("posterior") is not None:
+        P, Q = res.posterior.astype(np.float64), ref["posterior"]
+        assert P.shape == Q.shape
+        big = Q >= FLOOR * Q.max()
+        rel = np.abs(P[big] - Q[big]) / Q[big]
+        assert rel.max() <= post_rel, f"{what}: posterior max rel err {rel.max():.3e}"
+        # below the floor: absolute, at the floor's own scale (flushed tail included)
+        assert np.abs(P[~big] - Q[~big]).max(initial=0.0) <= post_rel * FLOOR * Q.max()
+        assert abs(P.sum() - 1.0) <= 1e-6
+    return d_e
+
+
+# ---------------------------------------------------------------------------------------
+# config 1: README workload
+# ---------------------------------------------------------------------------------------
+def test_readme_product_vs_oracle(ctx, readme_obs):
+    res = ctx.grid_posterior(readme_obs, 101, (18, 22), (1, 3), mode=cge.MODE_PRODUCT_F32)
+    ref = oracle.grid_posterior(readme_obs, 101, 18, 22, 1, 3, oracle.NUM_REF)
+    d = check_against(res, ref, what="readme/product vs REF")
+    assert d < 1e-6  # expected ~1e-8
+    f64 = oracle.grid_posterior(readme_obs, 101, 18, 22, 1, 3, oracle.NUM_F64)
+    check_against(res, f64, what="readme/product vs F64")
+    assert res.launches == 7
+
+
+def test_readme_logspace_vs_oracle(ctx, readme_obs):
+    res = ctx.grid_posterior(readme_obs, 101, (18, 22), (1, 3), mode=cge.MODE_LOGSPACE)
+    f64 = oracle.grid_posterior(readme_obs, 101, 18, 22, 1, 3, oracle.NUM_F64)
+    d = check_against(res, f64, post_rel=2e-5, what="readme/log vs F64")
+    assert d < 1e-7
+
+
+def test_readme_vs_reference_python_golden(ctx, readme_obs, golden_dir):
+    """Reference's own numpy_estimator output (np.linspace ranges differ from the C++ formula by
+    <= 1.9e-6, which moves cells by up to ~7e-5 relative; expectations by ~4e-8)."""
+    g = np.load(os.path.join(golden_dir, "numpy_estimator_readme.npz"))
+    res = ctx.grid_posterior(g["observations"], 101, (18, 22), (1, 3))
+    assert np.abs(res.expectations - g["expectations_axis_correct"]).max() <= E_TOL
+    Q = g["posterior_sigma_mu"].T
+    big = Q >= 1e-12 * Q.max()
+    rel = np.abs(res.posterior.astype(np.float64)[big] - Q[big]) / Q[big]
+    assert rel.max() <= 2e-4
+
+
+def test_reference_cuda_golden(ctx, golden_dir):
+    """Outputs of the reference CUDA pipeline itself (oracle/ref_harness.cu run on a B200 by
+    tests/golden/make_ref_cuda_golden.py)."""
+    path = os.path.join(golden_dir, "ref_cuda_readme.npz")
+    if not os.path.exists(path):
+        pytest.skip("ref_cuda_readme.npz not generated yet (needs one GPU run of make_ref_cuda_golden.py)")
+    g = np.load(path)
+    N = int(g["N"])
+    res = ctx.grid_posterior(g["observations"], N, tuple(g["ranges"][:2]), tuple(g["ranges"][2:]))
+    ref = dict(expectations=g["expectations"], marg_mu=g["marg_mu"], marg_sigma=g["marg_sigma"],
+               posterior=g["posterior"].reshape(N, N))
+    check_against(res, ref, what="vs reference CUDA binary")
+
+
+# ---------------------------------------------------------------------------------------
+# edge cases: ragged sizes, tiny grids, single observation, grid missing the MLE
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N", [2, 3, 5, 100, 127, 128, 129, 255, 256, 257, 511, 513, 1000, 1023, 1025])
+def test_ragged_grid_sizes(ctx, readme_obs, N):
+    for mode, num in ((cge.MODE_PRODUCT_F32, oracle.NUM_REF), (cge.MODE_LOGSPACE, oracle.NUM_F64)):
+        res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), mode=mode)
+        ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, num)
+        check_against(res, ref, what=f"N={N} mode={mode}")
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 8, 49, 51, 64, 255, 256])
+def test_observation_counts(ctx, n):
+    obs = oracle.readme_observations(n=n, seed=7)
+    for mode, num in ((cge.MODE_PRODUCT_F32, oracle.NUM_REF), (cge.MODE_LOGSPACE, oracle.NUM_F64)):
+        res = ctx.grid_posterior(obs, 96, (18, 22), (1, 3), mode=mode)
+        ref = oracle.grid_posterior(obs, 96, 18, 22, 1, 3, num)
+        check_against(res, ref, what=f"n={n} mode={mode}")
+
+
+def test_grid_without_mle_and_small_sigma(ctx, readme_obs):
+    for mu_r, sg_r in (((25, 30), (1, 3)), ((18, 22), (0.25, 0.75)), ((-5, 5), (4, 9)), ((19, 20), (1.5, 2.5))):
+        for mode, num in ((cge.MODE_PRODUCT_F32, oracle.NUM_REF), (cge.MODE_LOGSPACE, oracle.NUM_F64)):
+            res = ctx.grid_posterior(readme_obs, 64, mu_r, sg_r, mode=mode)
+            ref = oracle.grid_posterior(readme_obs, 64, *mu_r, *sg_r, num)
+            check_against(res, ref, what=f"{mu_r} {sg_r} mode={mode}")
+
+
+def test_single_point_grid(ctx, readme_obs):
+    """N=1: the reference's range formula is 0/0; libcge defines the single point as `start`.
+    One cell => posterior is exactly 1."""
+    res = ctx.grid_posterior(readme_obs, 1, (20, 20), (2, 2))
+    assert res.posterior.shape == (1, 1) and res.posterior[0, 0] == pytest.approx(1.0, abs=1e-6)
+    assert res.expectations == pytest.approx([20.0, 2.0], abs=1e-5)
+
+
+def test_determinism_bitwise(ctx, readme_obs):
+    runs = [ctx.grid_posterior(readme_obs, 1000, (18, 22), (1, 3)) for _ in range(3)]
+    for r in runs[1:]:
+        assert r.posterior.tobytes() == runs[0].posterior.tobytes()
+        assert r.marg_mu.tobytes() == runs[0].marg_mu.tobytes()
+        assert r.marg_sigma.tobytes() == runs[0].marg_sigma.tobytes()
+        assert r.expectations.tobytes() == runs[0].expectations.tobytes()
+
+
+def test_many_observations_product_and_streamed_logspace(ctx):
+    # product path with a few hundred observations (beyond the reference's 256 limit)
+    obs = oracle.readme_observations(n=300, seed=3)
+    res = ctx.grid_posterior(obs, 128, (18, 22), (1, 3), mode=cge.MODE_PRODUCT_F32)
+    check_against(res, oracle.grid_posterior(obs, 128, 18, 22, 1, 3, oracle.NUM_LOG), what="n=300 product")
+    # one big shared-memory load (n <= 16384) and the double-buffered streamed path (n > 16384)
+    for n in (9001, 16384, 16385, 20000, 40003):
+        obs = oracle.readme_observations(n=n, seed=11)
+        res = ctx.grid_posterior(obs, 64, (19.9, 20.1), (1.9, 2.1), mode=cge.MODE_LOGSPACE)
+        ref = oracle.grid_posterior(obs, 64, 19.9, 20.1, 1.9, 2.1, oracle.NUM_LOG)
+        check_against(res, ref, what=f"log-space n={n}")
+
+
+def test_error_behaviour(ctx, readme_obs):
+    with pytest.raises(cge.CgeError) as ei:
+        ctx.grid_posterior(readme_obs, 0, (18, 22), (1, 3))
+    assert ei.value.code == api.ERR_BAD_ARG
+    with pytest.raises(cge.CgeError) as ei:
+        ctx.grid_posterior(readme_obs, 16, (18, 22), (0, 3))
+    assert ei.value.code == api.ERR_BAD_ARG
+    with pytest.raises(cge.CgeError) as ei:
+        ctx.grid_posterior(readme_obs, 16, (18, 22), (1, 3), rows=(8, 20))
+    assert ei.value.code == api.ERR_BAD_ARG
+    with pytest.raises(cge.CgeError) as ei:
+        ctx.grid_posterior(readme_obs, 16, (18, 22), (1, 3), mode=9)
+    assert ei.value.code == api.ERR_BAD_ARG
+    bad = readme_obs.copy()
+    bad[3] = np.nan
+    with pytest.raises(cge.CgeError) as ei:
+        ctx.grid_posterior(bad, 16, (18, 22), (1, 3))
+    assert ei.value.code == api.ERR_DEGENERATE
+    # the context survives errors
+    res = ctx.grid_posterior(readme_obs, 16, (18, 22), (1, 3))
+    assert abs(res.posterior.astype(np.float64).sum() - 1) < 1e-6
+
+
+# ---------------------------------------------------------------------------------------
+# device-pointer phase API + row shards on one GPU (the multi-GPU data path, minus NCCL)
+# ---------------------------------------------------------------------------------------
+def test_phase_api_with_row_shards(ctx, readme_obs):
+    import torch
+    N = 257
+    dev = torch.device("cuda", 0)
+    obs_t = torch.from_numpy(readme_obs).to(dev)
+    full = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
+    stream = torch.cuda.current_stream().cuda_stream
+    spans = [cge.shard_rows(N, 3, r) for r in range(3)]
+    ctxs = [cge.Context(0) for _ in spans]
+    try:
+        posts, parts = [], []
+        for c, (rb, re) in zip(ctxs, spans):
+            p = cge.make_params(50, N, (18, 22), (1, 3), cge.MODE_PRODUCT_F32, (rb, re))
+            post = torch.empty((re - rb, N), dtype=torch.float32, device=dev)
+            c.likelihood_partials(p, obs_t, post, stream)
+            ptr, cnt = c.partials_ptr()
+            assert cnt == N + 2
+            parts.append(cge.device_tensor(ptr, cnt, "float64", 0))
+            posts.append((p, post))
+        total = torch.stack(parts).sum(dim=0)      # stands in for the all-reduce
+        for part in parts:
+            part.copy_(total)
+        rows = []
+        for c, (p, post) in zip(ctxs, posts):
+            c.finalize(p, post, stream)
+            ex, mm, ms, z = c.read_results(p, stream)
+            assert np.abs(ex - full.expectations).max() < 1e-9
+            assert np.abs(ms - full.marg_sigma).max() < 1e-12
+            assert np.abs(mm[p.row_begin:p.row_end] - full.marg_mu[p.row_begin:p.row_end]).max() < 1e-12
+            assert mm[:p.row_begin].sum() == 0 and mm[p.row_end:].sum() == 0
+            rows.append(post.cpu().numpy())
+        got = np.concatenate(rows, axis=0)
+        rel = np.abs(got - full.posterior) / np.maximum(full.posterior, 1e-30)
+        assert rel[full.posterior > 0].max() < 1e-6
+    finally:
+        for c in ctxs:
+            c.close()
+
+
+def test_device_buffers_and_unaligned_posterior(ctx, readme_obs):
+    import torch
+    dev = torch.device("cuda", 0)
+    N = 128
+    obs_t = torch.from_numpy(readme_obs).to(dev)
+    backing = torch.zeros(N * N + 1, dtype=torch.float32, device=dev)
+    ref = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
+    torch.cuda.synchronize()  # the synchronous ABI runs on the context's own stream
+    for off in (0, 1):  # off=1 -> 4-byte aligned only: scalar store / scalar scale paths
+        post = backing[off:off + N * N]
+        res = ctx.grid_posterior(obs_t, N, (18, 22), (1, 3), posterior=post)
+        got = post.cpu().numpy().reshape(N, N)
+        assert got.tobytes() == ref.posterior.tobytes()
+        assert res.expectations.tobytes() == ref.expectations.tobytes()
+
+
+# ---------------------------------------------------------------------------------------
+# config 2: 4096 x 4096 x 50, whole posterior against the oracle
+# ---------------------------------------------------------------------------------------
+def test_4096_product_vs_oracle(ctx, readme_obs):
+    N = 4096
+    res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
+    ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_REF)
+    check_against(res, ref, what="4096^2 product vs REF")
+    cf = oracle.closed_form_posterior(readme_obs, N, 18, 22, 1, 3)
+    assert np.abs(res.expectations - cf["expectations"]).max() < 1e-6
+
+
+# ---------------------------------------------------------------------------------------
+# configs 3 and 5 at full size: size-independent properties + sampled rows
+# ---------------------------------------------------------------------------------------
+def _closed_form_logz(obs, N, ranges, chunk=1024):
+    """(log sum_ij exp(loglik_ij), max_ij loglik_ij) in float64, by row chunks (independent
+    closed form)."""
+    m = -np.inf
+    s = 0.0
+    for r0 in range(0, N, chunk):
+        ll = oracle.closed_form_loglik(obs, N, *ranges, rows=np.arange(r0, min(N, r0 + chunk)))
+        mc = ll.max()
+        if mc > m:
+            s = s * np.exp(m - mc) if np.isfinite(m) else 0.0
+            m = mc
+        s += np.exp(ll - m).sum()
+    return m + np.log(s), m
+
+
+def _full_size_properties(ctx, obs, N, mode, sample_rows):
+    import torch
+    ranges = (18.0, 22.0, 1.0, 3.0)
+    res = ctx.grid_posterior(obs, N, ranges[:2], ranges[2:], mode=mode, posterior="device")
+    ptr, cnt = ctx.posterior_ptr()
+    assert cnt == N * N
+    post = cge.device_tensor(ptr, cnt, "float32", 0).view(N, N)
+    # sum = 1, marginals are the row/column sums of what was written
+    total = post.sum(dtype=torch.float64).item()
+    assert abs(total - 1.0) <= 1e-6
+    rows = post.sum(dim=1, dtype=torch.float64).cpu().numpy()
+    cols = post.sum(dim=0, dtype=torch.float64).cpu().numpy()
+    assert np.abs(rows - res.marg_mu).max() <= 1e-7 * res.marg_mu.max()
+    assert np.abs(cols - res.marg_sigma).max() <= 1e-7 * res.marg_sigma.max()
+    assert abs(res.marg_mu.sum() - 1) < 1e-9 and abs(res.marg_sigma.sum() - 1) < 1e-9
+    # expectations against the independent closed form
+    mu = oracle.linspace(N, *ranges[:2]).astype(np.float64)
+    sg = oracle.linspace(N, *ranges[2:]).astype(np.float64)
+    logz, llmax = _closed_form_logz(obs, N, ranges)
+    e_mu = e_sg = 0.0
+    for r0 in range(0, N, 1024):
+        idx = np.arange(r0, min(N, r0 + 1024))
+        p = np.exp(oracle.closed_form_loglik(obs, N, *ranges, rows=idx) - logz)
+        e_mu += (p.sum(axis=1) * mu[idx]).sum()
+        e_sg += (p.sum(axis=0) * sg).sum()
+    assert abs(res.expectations[0] - e_mu) <= E_TOL and abs(res.expectations[1] - e_sg) <= E_TOL
+    # sampled rows, cell by cell
+    for i in sample_rows:
+        want = np.exp(oracle.closed_form_loglik(obs, N, *ranges, rows=np.array([i]))[0] - logz)
+        got = post[i].cpu().numpy().astype(np.float64)
+        pmax = np.exp(llmax - logz)
+        big = want >= FLOOR * pmax
+        if big.any():
+            rel = np.abs(got[big] - want[big]) / want[big]
+            assert rel.max() <= POST_REL, f"row {i}: {rel.max():.3e}"
+    return res
+
+
+def test_16384_product_properties(ctx, readme_obs):
+    N = 16384
+    peak_row = int(round((19.549 - 18) / 4 * (N - 1)))
+    _full_size_properties(ctx, readme_obs, N, cge.MODE_PRODUCT_F32,
+                          [0, 1, peak_row - 1500, peak_row, peak_row + 1, peak_row + 2000, N - 1])
+
+
+def test_16384_logspace_10k_observations(ctx):
+    N = 16384
+    obs = oracle.readme_observations(n=10000)
+    peak_row = int(round((float(obs.astype(np.float64).mean()) - 18) / 4 * (N - 1)))
+    _full_size_properties(ctx, obs, N, cge.MODE_LOGSPACE,
+                          [0, peak_row - 300, peak_row - 40, peak_row, peak_row + 7, peak_row + 250, N - 1])
+
+
+# ---------------------------------------------------------------------------------------
+# stage API through the C ABI: the reference's own known answers (src/tests.cu)
+# ---------------------------------------------------------------------------------------
+def test_stage_api_known_answers(ctx):
+    import torch
+    dev = torch.device("cuda", 0)
+    f32 = lambda n: torch.empty(n, dtype=torch.float32, device=dev)
+    f64 = lambda n: torch.empty(n, dtype=torch.float64, device=dev)
+    # Linspaces (tests.cu:49-67) and the checkArrays values (utils.h:16-30)
+    v = f32(3)
+    ctx.linspace(v, 3, 1.0, 2.0)
+    assert v.cpu().tolist() == [1.0, 1.5, 2.0]
+    mu, sg = f32(101), f32(101)
+    ctx.linspace(mu, 101, 18.0, 22.0)
+    ctx.linspace(sg, 101, 1.0, 3.0)
+    assert np.array_equal(mu.cpu().numpy(), oracle.linspace(101, 18, 22))
+    assert np.array_equal(sg.cpu().numpy(), oracle.linspace(101, 1, 3))
+    assert mu[50].item() == 20.0 and mu[49].item() == np.float32(19.96)
+    # GenerateGrids (tests.cu:70-108)
+    vx, vy, vz = f32(3), f32(3), f32(2)
+    ctx.linspace(vx, 3, 1, 3); ctx.linspace(vy, 3, 1, 3); ctx.linspace(vz, 2, 4, 5)
+    gx, gy, gz = f32(18), f32(18), f32(18)
+    ctx.meshgrid3(vx, vy, vz, gx, gy, gz, 3, 2)
+    assert gx.cpu().tolist() == [1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 3, 3, 3, 3, 3, 3]
+    assert gy.cpu().tolist() == [1, 1, 2, 2, 3, 3, 1, 1, 2, 2, 3, 3, 1, 1, 2, 2, 3, 3]
+    assert gz.cpu().tolist() == [4, 5, 4, 5, 4, 5, 4, 5, 4, 5, 4, 5, 4, 5, 4, 5, 4, 5]
+    # ComputeDensities (tests.cu:111-135)
+    a, b, c, d = f32(3), f32(3), f32(3), f32(3)
+    ctx.linspace(a, 3, 20, 22); ctx.linspace(b, 3, 1, 3); ctx.linspace(c, 3, 20, 21)
+    ctx.densities(d, a, b, c, 3)
+    assert d.cpu().tolist() == pytest.approx([0.39894228, 0.19333406, 0.12579441], abs=1e-5)
+    # ComputeLikes (tests.cu:163-194)
+    dens, likes = f32(10), f64(2)
+    ctx.linspace(dens, 10, 1.0, 10.0)
+    ctx.row_products(dens, likes, 10, 2)
+    assert likes.cpu().tolist() == [120.0, 30240.0]
+    with pytest.raises(cge.CgeError) as ei:
+        ctx.row_products(dens, likes, 10, 3)  # wrappers.h:110-113 "likesSize != rows * cols"
+    assert ei.value.code == api.ERR_SIZE
+    # ComputePosterior (tests.cu:196-209)
+    lv = torch.tensor([1.0, 2.0, 3.0], dtype=torch.float64, device=dev)
+    pv = f64(3)
+    ctx.normalize(lv, pv, 3)
+    got = pv.cpu().tolist()
+    assert got[0] == pytest.approx(1 / 6, abs=1e-5) and got[1] == pytest.approx(2 / 6, abs=1e-5)
+    assert got[2] == 0.5
+    # ComputeExpectations (tests.cu:211-245)
+    post = torch.full((9,), 0.1, dtype=torch.float64, device=dev)
+    post[4] = 0.2
+    mm, ms = f64(3), f64(3)
+    ctx.marginalize(mm, post, 3, 3, 1)
+    ctx.marginalize(ms, post, 3, 3, 0)
+    vmu, vsg = f32(3), f32(3)
+    ctx.linspace(vmu, 3, 1.0, 3.0); ctx.linspace(vsg, 3, 4.0, 6.0)
+    assert ctx.expectation(mm, vmu, 3) == 2.0
+    assert ctx.expectation(ms, vsg, 3) == 5.0
+
+
+def test_stage_api_pipeline_matches_fused(ctx, readme_obs):
+    """The reference's stage-by-stage pipeline (src/grid.cu:79-127) through the stage ABI gives
+    the same answer as the fused entry point and the oracle."""
+    import torch
+    dev = torch.device("cuda", 0)
+    N, n = 101, 50
+    obs = torch.from_numpy(readme_obs).to(dev)
+    mu = torch.empty(N, dtype=torch.float32, device=dev)
+    sg = torch.empty(N, dtype=torch.float32, device=dev)
+    ctx.linspace(mu, N, 18.0, 22.0)
+    ctx.linspace(sg, N, 1.0, 3.0)
+    g = [torch.empty(N * N * n, dtype=torch.float32, device=dev) for _ in range(4)]
+    ctx.meshgrid3(mu, sg, obs, g[0], g[1], g[2], N, n)
+    ctx.densities(g[3], g[0], g[1], g[2], N * N * n)
+    likes = torch.empty(N * N, dtype=torch.float64, device=dev)
+    ctx.row_products(g[3], likes, N * N * n, N * N)
+    post = torch.empty_like(likes)
+    ctx.normalize(likes, post, N * N)
+    mm = torch.empty(N, dtype=torch.float64, device=dev)
+    ms = torch.empty(N, dtype=torch.float64, device=dev)
+    ctx.marginalize(mm, post, N, N, 1)
+    ctx.marginalize(ms, post, N, N, 0)
+    e = np.array([ctx.expectation(mm, mu, N), ctx.expectation(ms, sg, N)])
+    ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_REF)
+    assert np.abs(e - ref["expectations"]).max() < 1e-8
+    P = post.cpu().numpy().reshape(N, N)
+    big = ref["posterior"] >= FLOOR * ref["posterior"].max()
+    assert (np.abs(P[big] - ref["posterior"][big]) / ref["posterior"][big]).max() < 1e-5
+    # densities: a3's value to f32 accuracy
+    dens_ref = oracle.densities(g[0].cpu().numpy(), g[1].cpu().numpy(), g[2].cpu().numpy())
+    dens = g[3].cpu().numpy()
+    assert np.abs(dens - dens_ref).max() <= 1e-5
+    assert (np.abs(dens - dens_ref) / dens_ref).max() < 1e-5
+    fused = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
+    assert np.abs(fused.expectations - e).max() < 1e-6
