@@ -76,18 +76,26 @@ def test_readme_vs_reference_python_golden(ctx, readme_obs, golden_dir):
     assert rel.max() <= 2e-4
 
 
-def test_reference_cuda_golden(ctx, golden_dir):
+@pytest.mark.parametrize("name", ["readme", "small", "max256"])
+def test_reference_cuda_golden(ctx, golden_dir, name):
     """Outputs of the reference CUDA pipeline itself (oracle/ref_harness.cu run on a B200 by
-    tests/golden/make_ref_cuda_golden.py)."""
-    path = os.path.join(golden_dir, "ref_cuda_readme.npz")
-    if not os.path.exists(path):
-        pytest.skip("ref_cuda_readme.npz not generated yet (needs one GPU run of make_ref_cuda_golden.py)")
-    g = np.load(path)
+    tests/golden/make_ref_cuda_golden.py): the reference's result on the same inputs."""
+    g = np.load(os.path.join(golden_dir, f"ref_cuda_{name}.npz"))
     N = int(g["N"])
-    res = ctx.grid_posterior(g["observations"], N, tuple(g["ranges"][:2]), tuple(g["ranges"][2:]))
-    ref = dict(expectations=g["expectations"], marg_mu=g["marg_mu"], marg_sigma=g["marg_sigma"],
-               posterior=g["posterior"].reshape(N, N))
-    check_against(res, ref, what="vs reference CUDA binary")
+    rng = [float(x) for x in g["ranges"]]
+    for mode in (cge.MODE_PRODUCT_F32, cge.MODE_LOGSPACE):
+        res = ctx.grid_posterior(g["observations"], N, rng[:2], rng[2:], mode=mode)
+        if "posterior" in g:
+            ref = dict(expectations=g["expectations"], marg_mu=g["marg_mu"],
+                       marg_sigma=g["marg_sigma"], posterior=g["posterior"].reshape(N, N))
+            check_against(res, ref, what=f"{name} mode={mode} vs reference CUDA binary")
+        else:
+            ref = dict(expectations=g["expectations"], marg_mu=g["marg_mu"], marg_sigma=g["marg_sigma"])
+            check_against(res, ref, what=f"{name} mode={mode} vs reference CUDA binary")
+            rows, Q = g["sample_rows"], g["posterior_rows"]
+            P = res.posterior.astype(np.float64)[rows]
+            big = Q >= FLOOR * g["marg_mu"].max() / N
+            assert (np.abs(P[big] - Q[big]) / Q[big]).max() <= POST_REL
 
 
 # ---------------------------------------------------------------------------------------
