@@ -21,6 +21,8 @@ from . import _build
 
 MODE_PRODUCT_F32 = 0
 MODE_LOGSPACE = 1
+VARIANT_DEFAULT = 0
+VARIANT_MUFU_ONLY = 1
 
 OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_DEGENERATE, ERR_NCCL, ERR_SIZE = range(7)
 
@@ -44,7 +46,7 @@ class Params(C.Structure):
     _fields_ = [("n_obs", C.c_int32), ("grid_size", C.c_int32), ("mu_start", C.c_float),
                 ("mu_end", C.c_float), ("sigma_start", C.c_float), ("sigma_end", C.c_float),
                 ("mode", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("variant", C.c_int32)]
 
 
 class Timing(C.Structure):
@@ -112,10 +114,11 @@ def _check(rc: int):
         raise CgeError(rc, load_library().cge_last_error().decode("utf-8", "replace"))
 
 
-def make_params(n_obs, grid_size, mu_range, sigma_range, mode=MODE_PRODUCT_F32, rows=None) -> Params:
+def make_params(n_obs, grid_size, mu_range, sigma_range, mode=MODE_PRODUCT_F32, rows=None,
+                variant=0) -> Params:
     rb, re = (0, 0) if rows is None else (int(rows[0]), int(rows[1]))
     return Params(int(n_obs), int(grid_size), float(mu_range[0]), float(mu_range[1]),
-                  float(sigma_range[0]), float(sigma_range[1]), int(mode), rb, re, 0)
+                  float(sigma_range[0]), float(sigma_range[1]), int(mode), rb, re, int(variant))
 
 
 @dataclass
@@ -178,7 +181,7 @@ class Context:
 
     # ---- fused path, synchronous, host or device buffers ---------------------------------
     def grid_posterior(self, obs, grid_size, mu_range, sigma_range, mode=MODE_PRODUCT_F32,
-                       rows=None, posterior="host", want_timing=True) -> GridResult:
+                       rows=None, posterior="host", want_timing=True, variant=0) -> GridResult:
         """The whole hot path in one call (replaces src/grid.cu:79-127).
 
         obs        numpy float32 array (host) or CUDA torch tensor (device)
@@ -188,7 +191,7 @@ class Context:
         if isinstance(obs, np.ndarray):
             obs = np.ascontiguousarray(obs, np.float32)
         n = int(obs.shape[0])
-        p = make_params(n, grid_size, mu_range, sigma_range, mode, rows)
+        p = make_params(n, grid_size, mu_range, sigma_range, mode, rows, variant)
         nrows = grid_size if rows is None else rows[1] - rows[0]
         post_arr = None
         if isinstance(posterior, str) and posterior == "host":

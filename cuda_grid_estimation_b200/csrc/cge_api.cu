@@ -71,7 +71,7 @@ struct DevBuf {
 
 struct Plan {
   bool valid = false;
-  int N = 0, n = 0, n_pad = 0, mode = 0;
+  int N = 0, n = 0, n_pad = 0, mode = 0, variant = 0;
   int row_begin = 0, row_end = 0, rows_local = 0;
   int wm = 1, wn = 8;
   int bands = 0, row_tiles = 0, tile_rows = 0;
@@ -89,7 +89,8 @@ struct cge_context {
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[10] = {};
   DevBuf<float> mu, sigma, obs_pad, obs_in, posterior;
-  DevBuf<double> ad, cd0, rowpart, colpart, partials, rowsum, zpart, smupart, results, tmp;
+  DevBuf<double> ad, cd0, rowpart, colpart, partials, rowsum, zpart, smupart, espart, results, tmp;
+  DevBuf<unsigned int> tickets;  // [0] fold, [1] results; zero between launches
   DevBuf<cge::ScaleInfo> scale;
   DevBuf<float> sink;
   Plan plan;
@@ -125,6 +126,11 @@ int check_params(const cge_params *p, int *rb, int *re) {
     return set_error(CGE_ERR_BAD_ARG, "ranges must be finite");
   if (p->mode != CGE_MODE_PRODUCT_F32 && p->mode != CGE_MODE_LOGSPACE)
     return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
+  switch (p->variant) {
+    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 100: case 112: case 122: case 123:
+    case 133: case 134: break;
+    default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
+  }
   int b = p->row_begin, e = p->row_end;
   if (b == 0 && e == 0) e = p->grid_size;
   if (b < 0 || e > p->grid_size || b >= e)
@@ -142,6 +148,7 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->n = p->n_obs;
   pl->n_pad = (p->n_obs + 3) & ~3;
   pl->mode = p->mode;
+  pl->variant = p->variant;
   pl->row_begin = rb;
   pl->row_end = re;
   pl->rows_local = re - rb;
@@ -154,14 +161,15 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   const int unit = pl->wm * cge::kRM;
   // aim for >= ~24 waves of 4 resident CTAs per SM, tiles of at most 128 rows
   const long long want_ctas = (long long)ctx->sm_count * 4 * 24;
-  long long tr = ((long long)pl->rows_local * pl->bands) / want_ctas;
+  const int span = re - (rb & ~(cge::kRM - 1));  // tiles start at a multiple of kRM (see kernel)
+  long long tr = ((long long)span * pl->bands) / want_ctas;
   tr = (tr / unit) * unit;
   if (tr < unit) tr = unit;
   if (tr > 128) tr = (128 / unit) * unit;
   pl->tile_rows = (int)tr;
-  pl->row_tiles = (pl->rows_local + pl->tile_rows - 1) / pl->tile_rows;
+  pl->row_tiles = (span + pl->tile_rows - 1) / pl->tile_rows;
   pl->ncolparts = pl->row_tiles * pl->wm;
-  pl->nb_col = (pl->N + 255) / 256;
+  pl->nb_col = (pl->N + 31) / 32;
   pl->nb_row = (pl->rows_local + 7) / 8;
   pl->vec4 = (pl->N % 4 == 0) && ((reinterpret_cast<uintptr_t>(post) & 15u) == 0);
   const bool streamed = pl->n_pad > cge::kObsSingleMax;
@@ -191,6 +199,23 @@ int launch_like(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   if (pl.wm == 2) return launch_like_shape<Policy, 2, 4>(pl, args, st);
   if (pl.wm == 4) return launch_like_shape<Policy, 4, 2>(pl, args, st);
   return launch_like_shape<Policy, 8, 1>(pl, args, st);
+}
+
+// product path: the default is the hybrid MUFU + FMA-polynomial kernel; the other variants exist
+// for tuning and for the MUFU-only roofline measurement (wide shape only, else the default)
+int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
+  if (pl.variant == CGE_VARIANT_MUFU_ONLY) return launch_like<cge::ProductF32>(pl, args, st);
+  if (pl.wm == 1) {
+    switch (pl.variant) {
+      case 100: return launch_like_shape<cge::ProductHybrid<0, 0>, 1, 8>(pl, args, st);
+      case 112: return launch_like_shape<cge::ProductHybrid<1, 2>, 1, 8>(pl, args, st);
+      case 122: return launch_like_shape<cge::ProductHybrid<2, 2>, 1, 8>(pl, args, st);
+      case 133: return launch_like_shape<cge::ProductHybrid<3, 3>, 1, 8>(pl, args, st);
+      case 134: return launch_like_shape<cge::ProductHybrid<3, 4>, 1, 8>(pl, args, st);
+      default: break;
+    }
+  }
+  return launch_like<cge::ProductHybrid<2, 3>>(pl, args, st);
 }
 
 // record profiling mark `k` of the current step (no-op unless capture is on and has room)
@@ -298,7 +323,8 @@ CGE_EXPORT int cge_destroy(cge_context *ctx) {
   if (!ctx) return CGE_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  ctx->mu.release(); ctx->sigma.release(); ctx->obs_pad.release(); ctx->obs_in.release();
+  ctx->mu.release(); ctx->sigma.release(); ctx->obs_pad.release();
+  ctx->obs_in.release(); ctx->espart.release(); ctx->tickets.release();
   ctx->posterior.release(); ctx->ad.release(); ctx->cd0.release(); ctx->rowpart.release();
   ctx->colpart.release(); ctx->partials.release(); ctx->rowsum.release(); ctx->zpart.release();
   ctx->smupart.release(); ctx->results.release(); ctx->tmp.release(); ctx->scale.release();
@@ -341,6 +367,11 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   CKRC(ctx->cd0.reserve(N));
   CKRC(ctx->obs_pad.reserve(pl.n_pad));
   CKRC(ctx->scale.reserve(1));
+  CKRC(ctx->espart.reserve((size_t)(N + 255) / 256));
+  if (!ctx->tickets.ptr) {
+    CKRC(ctx->tickets.reserve(2));
+    CK(cudaMemsetAsync(ctx->tickets.ptr, 0, 2 * sizeof(unsigned int), st));
+  }
   CKRC(ctx->rowpart.reserve((size_t)pl.rows_local * pl.ncw));
   CKRC(ctx->colpart.reserve((size_t)pl.ncolparts * N));
   CKRC(ctx->partials.reserve((size_t)N + 2));
@@ -351,14 +382,11 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
 
   ctx->launches = 0;
   CKRC(mark(ctx, 0, st));
-  cge::tables_kernel<<<(N + 255) / 256, 256, 0, st>>>(ctx->mu.ptr, ctx->sigma.ptr, ctx->ad.ptr,
-                                                       ctx->cd0.ptr, N, p->mu_start, p->mu_end,
-                                                       p->sigma_start, p->sigma_end);
+  cge::setup_kernel<<<(N + 255) / 256, 256, 0, st>>>(
+      ctx->mu.ptr, ctx->sigma.ptr, ctx->ad.ptr, ctx->cd0.ptr, N, p->mu_start, p->mu_end,
+      p->sigma_start, p->sigma_end, obs_dev, ctx->obs_pad.ptr, pl.n, pl.n_pad, ctx->scale.ptr);
   CK(cudaGetLastError());
-  cge::scale_kernel<<<1, 1024, 0, st>>>(obs_dev, ctx->obs_pad.ptr, pl.n, pl.n_pad, ctx->mu.ptr,
-                                        ctx->ad.ptr, ctx->cd0.ptr, N, ctx->scale.ptr);
-  CK(cudaGetLastError());
-  ctx->launches += 2;
+  ctx->launches += 1;
   CKRC(mark(ctx, 1, st));
 
   cge::LikeArgs args;
@@ -378,7 +406,7 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   args.tile_rows = pl.tile_rows;
   args.ncw = pl.ncw;
   if (p->mode == CGE_MODE_PRODUCT_F32)
-    CKRC(launch_like<cge::ProductF32>(pl, args, st));
+    CKRC(launch_product(pl, args, st));
   else
     CKRC(launch_like<cge::LogSpaceF64>(pl, args, st));
   ctx->launches += 1;
@@ -386,12 +414,10 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
 
   cge::fold_partials_kernel<<<pl.nb_col + pl.nb_row, 256, 0, st>>>(
       ctx->colpart.ptr, pl.ncolparts, ctx->rowpart.ptr, pl.ncw, pl.rows_local, rb, N, ctx->mu.ptr,
-      ctx->partials.ptr, ctx->rowsum.ptr, ctx->zpart.ptr, ctx->smupart.ptr, pl.nb_col);
+      ctx->partials.ptr, ctx->rowsum.ptr, ctx->zpart.ptr, ctx->smupart.ptr, pl.nb_col, pl.nb_row,
+      ctx->tickets.ptr);
   CK(cudaGetLastError());
-  cge::finish_partials_kernel<<<1, 1024, 0, st>>>(ctx->zpart.ptr, ctx->smupart.ptr, pl.nb_row,
-                                                  ctx->partials.ptr);
-  CK(cudaGetLastError());
-  ctx->launches += 2;
+  ctx->launches += 1;
   CKRC(mark(ctx, 3, st));
   return CGE_OK;
 }
@@ -419,8 +445,9 @@ CGE_EXPORT int cge_finalize(cge_context *ctx, const cge_params *p, float *poster
   cudaStream_t st = (cudaStream_t)stream;
   const int N = pl.N;
   CKRC(mark(ctx, 4, st));
-  cge::results_kernel<<<1, 1024, 0, st>>>(ctx->partials.ptr, ctx->rowsum.ptr, ctx->sigma.ptr, N, rb,
-                                          re, ctx->results.ptr);
+  cge::results_kernel<<<(N + 255) / 256, 256, 0, st>>>(ctx->partials.ptr, ctx->rowsum.ptr,
+                                                       ctx->sigma.ptr, N, rb, re, ctx->results.ptr,
+                                                       ctx->espart.ptr, ctx->tickets.ptr + 1);
   CK(cudaGetLastError());
   CKRC(mark(ctx, 5, st));
   const size_t cells = (size_t)pl.rows_local * N;

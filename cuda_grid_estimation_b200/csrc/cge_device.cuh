@@ -31,6 +31,78 @@ __device__ __forceinline__ float range_value(int idx, int size, float start, flo
 }
 
 // ---------------------------------------------------------------------------------------
+// packed float32x2 arithmetic (sm_100 FADD2 / FMUL2 / FFMA2): two lanes per issue slot.
+// A packed value lives in an aligned 64-bit register pair; lo = first element.
+// ---------------------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 v;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+  return v;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float &lo, float &hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+
+// 2^t on the MUFU pipe for both lanes
+__device__ __forceinline__ f32x2 ex2_mufu2(f32x2 t) {
+  float lo, hi;
+  unpack2(t, lo, hi);
+  return pack2(ex2_approx(lo), ex2_approx(hi));
+}
+
+// 2^t on the FMA pipe for both lanes: Cody-Waite split t = n + f, f in [-0.5, 0.5] by the
+// 1.5*2^23 magic-number round, degree-5 minimax polynomial for 2^f (max relative error 7.5e-8
+// exact, ~2.3e-7 after float32 Horner rounding -- the same class as ex2.approx's 2^-22.5), and
+// n added straight into the exponent field.  t is clamped at -125 so the exponent cannot
+// wrap: a factor that would have flushed to zero becomes ~2^-125 instead, 165 binades below the
+// rescaled peak.
+__device__ __forceinline__ f32x2 ex2_poly2(f32x2 t) {
+  float tl, th;
+  unpack2(t, tl, th);
+  tl = fmaxf(tl, -125.0f);
+  th = fmaxf(th, -125.0f);
+  const f32x2 tc = pack2(tl, th);
+  const f32x2 magic = pack2(12582912.0f, 12582912.0f);
+  const f32x2 r = add2(tc, magic);   // low mantissa bits of r hold round(t)
+  const f32x2 n = sub2(r, magic);
+  const f32x2 f = sub2(tc, n);
+  f32x2 q = fma2(f, pack2(0.0013276472454890609f, 0.0013276472454890609f),
+                 pack2(0.009675540961325169f, 0.009675540961325169f));
+  q = fma2(q, f, pack2(0.05550713092088699f, 0.05550713092088699f));
+  q = fma2(q, f, pack2(0.24022120237350464f, 0.24022120237350464f));
+  q = fma2(q, f, pack2(0.6931469440460205f, 0.6931469440460205f));
+  q = fma2(q, f, pack2(1.0000001192092896f, 1.0000001192092896f));
+  float ql, qh, rl, rh;
+  unpack2(q, ql, qh);
+  unpack2(r, rl, rh);
+  const float el = __int_as_float(__float_as_int(ql) + (__float_as_int(rl) << 23));
+  const float eh = __int_as_float(__float_as_int(qh) + (__float_as_int(rh) << 23));
+  return pack2(el, eh);
+}
+
+// ---------------------------------------------------------------------------------------
 // shared-memory addressing, mbarrier and TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP)
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) {

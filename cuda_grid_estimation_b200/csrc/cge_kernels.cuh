@@ -7,8 +7,8 @@
 //   (inc/kernels.h:208-259), K8 computeExpectationsCuda (inc/cuda_functions.h:185-221).
 //
 // Here K1-K5 are ONE fused kernel (grid_likelihood_kernel) that never materialises the
-// N*N*n tensors, and K6-K8 are a fixed-order partial reduction (three tiny kernels) plus one
-// HBM-bound in-place scale pass.
+// N*N*n tensors, and K6-K8 are a fixed-order partial reduction (two small kernels) plus one
+// HBM-bound in-place scale pass.  A step is 5 launches: setup, likelihood, fold, results, scale.
 //
 // Data layout in HBM
 //   posterior  float32 [rows_local][N], sigma fastest (the reference layout, kernels.h:92)
@@ -54,84 +54,107 @@ struct LikeArgs {
   float *post;      // shard base (row `row_begin` at offset 0)
   double *rowpart;  // [rows_local][ncw]
   double *colpart;  // [ncolparts][N]
-  int n, n_pad, N;
+  int n, n_pad, N;  // n observations; n_pad staged floats (multiple of 4)
   int row_begin, row_end;
   int tile_rows;    // rows per CTA tile, multiple of WM*kRM
   int ncw;          // ceil(N / 128)
 };
 
 // ---------------------------------------------------------------------------------------
-// tables_kernel: K1 twice + the per-sigma coefficients.  float64 math once per grid point.
+// setup_kernel: K1 twice + the per-sigma coefficients (every block), and in block 0 the
+// observation staging and the global rescale.
+//
+// The rescale only positions the float32 dynamic range; it cancels in the posterior.  It needs
+// max_ij log2 L_ij = max_j (a_j * S_min + n*c0_j) with S_min = min_i [SS + n (xbar - mu_i)^2].
+// S(mu) is a parabola and f(sigma) = a(sigma) S + n c0(sigma) is unimodal (peak at
+// sigma^2 = S/n), so the grid maxima sit next to the continuous ones: a handful of candidate
+// grid points (the neighbours of the continuous optimum plus both ends) is exact, O(1).
 // ---------------------------------------------------------------------------------------
-__global__ void tables_kernel(float *__restrict__ mu, float *__restrict__ sigma,
-                              double *__restrict__ ad, double *__restrict__ cd0, int N,
-                              float mu0, float mu1, float sg0, float sg1) {
-  int idx = blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= N) return;
-  mu[idx] = range_value(idx, N, mu0, mu1);
-  float s = range_value(idx, N, sg0, sg1);
-  sigma[idx] = s;
-  double sd = (double)s;
-  const double kLog2e = 1.4426950408889634074;
-  const double kSqrt2Pi = 2.5066282746310005024;
-  ad[idx] = -0.5 * kLog2e / (sd * sd);
-  cd0[idx] = -log2(sd * kSqrt2Pi);
-}
+__device__ __forceinline__ double coef_a(double sd) { return -0.5 * 1.4426950408889634074 / (sd * sd); }
+__device__ __forceinline__ double coef_c0(double sd) { return -log2(sd * 2.5066282746310005024); }
 
-// ---------------------------------------------------------------------------------------
-// scale_kernel (one CTA): stages the observations into the padded buffer and picks the global
-// rescale from closed-form statistics.  The scale cancels in the posterior; it only positions
-// the float32 dynamic range.  max_ij log2 L_ij = max_j (a_j * S_min + n*c0_j) with
-// S_min = min_i sum_k (x_k - mu_i)^2 = min_i [SS + n (xbar - mu_i)^2]  (a_j < 0 for all j).
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) scale_kernel(const float *__restrict__ obs,
-                                                      float *__restrict__ obs_pad, int n, int n_pad,
-                                                      const float *__restrict__ mu,
-                                                      const double *__restrict__ ad,
-                                                      const double *__restrict__ cd0, int N,
-                                                      ScaleInfo *__restrict__ out) {
-  __shared__ double scratch[32];
-  const int tid = threadIdx.x, nt = blockDim.x;
-  double s = 0.0;
-  for (int k = tid; k < n_pad; k += nt) {
-    float x = k < n ? obs[k] : 0.0f;
-    obs_pad[k] = x;
-    s += (double)x;
+__global__ void __launch_bounds__(256)
+    setup_kernel(float *__restrict__ mu, float *__restrict__ sigma, double *__restrict__ ad,
+                 double *__restrict__ cd0, int N, float mu0, float mu1, float sg0, float sg1,
+                 const float *__restrict__ obs, float *__restrict__ obs_pad, int n, int n_pad,
+                 ScaleInfo *__restrict__ out) {
+  const int tid = threadIdx.x;
+  const int idx = blockIdx.x * blockDim.x + tid;
+  if (idx < N) {
+    mu[idx] = range_value(idx, N, mu0, mu1);
+    const float s = range_value(idx, N, sg0, sg1);
+    sigma[idx] = s;
+    ad[idx] = coef_a((double)s);
+    cd0[idx] = coef_c0((double)s);
   }
-  const double xbar = block_sum(s, scratch) / (double)n;
+  if (blockIdx.x != 0) return;
+
+  __shared__ double scratch[32];
+  const int nt = blockDim.x;
+  double sum = 0.0;
+  for (int k = tid; k < n_pad; k += nt) {
+    const float x = k < n ? obs[k] : 0.0f;
+    obs_pad[k] = x;
+    sum += (double)x;
+  }
+  const double xbar = block_sum(sum, scratch) / (double)n;
   double q = 0.0;
   for (int k = tid; k < n; k += nt) {
-    double d = (double)obs[k] - xbar;
+    const double d = (double)obs[k] - xbar;
     q += d * d;
   }
   const double ss = block_sum(q, scratch);
+  if (tid != 0) return;
+
+  auto candidates = [N](double pos, int (&c)[6]) {
+    if (!(pos == pos) || pos < 0.0) pos = 0.0;          // NaN / below range
+    if (pos > (double)(N - 1)) pos = (double)(N - 1);
+    const int f = (int)pos;
+    c[0] = 0;
+    c[1] = N - 1;
+    for (int t = 0; t < 4; ++t) c[2 + t] = min(max(f - 1 + t, 0), N - 1);
+  };
+  int cand[6];
+  const double mspan = (double)mu1 - (double)mu0;
+  candidates(mspan != 0.0 ? (xbar - (double)mu0) / mspan * (double)(N - 1) : 0.0, cand);
   double smin = 1.0 / 0.0;
-  for (int i = tid; i < N; i += nt) {
-    double d = xbar - (double)mu[i];
+  for (int t = 0; t < 6; ++t) {
+    const double d = xbar - (double)range_value(cand[t], N, mu0, mu1);
     smin = fmin(smin, ss + (double)n * d * d);
   }
-  smin = block_min(smin, scratch);
+  const double sspan = (double)sg1 - (double)sg0;
+  candidates(sspan != 0.0 ? (sqrt(smin / (double)n) - (double)sg0) / sspan * (double)(N - 1) : 0.0,
+             cand);
   double m2 = -1.0 / 0.0;
-  for (int j = tid; j < N; j += nt) m2 = fmax(m2, ad[j] * smin + (double)n * cd0[j]);
-  m2 = block_max(m2, scratch);
-  if (tid == 0) {
-    out->log2s = (kPeakLog2 - m2) / (double)n;
-    out->shift = kPeakLog2 - m2;
-    out->m2 = m2;
-    out->xbar = xbar;
-    out->ss = ss;
-    out->smin = smin;
+  for (int t = 0; t < 6; ++t) {
+    const double sd = (double)range_value(cand[t], N, sg0, sg1);
+    m2 = fmax(m2, coef_a(sd) * smin + (double)n * coef_c0(sd));
   }
+  out->log2s = (kPeakLog2 - m2) / (double)n;
+  out->shift = kPeakLog2 - m2;
+  out->m2 = m2;
+  out->xbar = xbar;
+  out->ss = ss;
+  out->smin = smin;
 }
 
 // ---------------------------------------------------------------------------------------
 // Arithmetic policies of the fused likelihood kernel.  Each owns the per-thread state for a
 // kRM x kRN patch of cells and consumes one observation at a time.
 // ---------------------------------------------------------------------------------------
+template <class Policy>
+__device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs, int count,
+                                                   const float (&mu)[kRM]);
+
 // float32 product path: per pdf-eval one FFMA (exponent), one MUFU.EX2, one FMUL (running
 // product); the subtract and square are shared by the kRN columns of a row.
 //   factor_k = 2^(a_j*(x_k-mu_i)^2 + c_j),  c_j = c0_j + log2 s   (constants FMA-folded)
 struct ProductF32 {
+  static constexpr int kObsStride = 1;  // floats of shared memory per observation
+  static __device__ __forceinline__ void consume(ProductF32 &pol, const float *xs, int count,
+                                                 const float (&mu)[kRM]) {
+    consume_scalar_obs(pol, xs, count, mu);
+  }
   float a[kRN], c[kRN];
   float p[kRM][kRN];
 
@@ -174,6 +197,11 @@ struct ProductF32 {
 // log-space path: float64 sum of log2-pdf terms (one DFMA per pdf-eval), then a single
 // exponential per cell against the global maximum: L_ij = 2^(sum_k a_j d_ik^2 + n c0_j + shift).
 struct LogSpaceF64 {
+  static constexpr int kObsStride = 1;
+  static __device__ __forceinline__ void consume(LogSpaceF64 &pol, const float *xs, int count,
+                                                 const float (&mu)[kRM]) {
+    consume_scalar_obs(pol, xs, count, mu);
+  }
   double a[kRN], cshift[kRN];
   double acc[kRM][kRN];
 
@@ -216,8 +244,8 @@ struct LogSpaceF64 {
 
 // consume `count` observations from shared memory (16-byte aligned), four per LDS.128 broadcast
 template <class Policy>
-__device__ __forceinline__ void consume_obs(Policy &pol, const float *xs, int count,
-                                            const float (&mu)[kRM]) {
+__device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs, int count,
+                                                   const float (&mu)[kRM]) {
   const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
   const int n4 = count >> 2;
 #pragma unroll 2
@@ -230,6 +258,87 @@ __device__ __forceinline__ void consume_obs(Policy &pol, const float *xs, int co
   }
   for (int k = n4 << 2; k < count; ++k) pol.step(xs[k], mu);
 }
+
+// ---------------------------------------------------------------------------------------
+// float32 product path, hybrid exponential: the same per-pdf-eval work as ProductF32
+// (exponent FMA, 2^t, running product) but
+//   * the per-cell arithmetic runs as packed f32x2 (FFMA2/FMUL2): a thread's 4 columns are two
+//     register pairs; the per-row (x - mu)^2 stays scalar and enters FFMA2 as a broadcast operand;
+//   * of the 8 column pairs a thread updates per observation, NPA (even observations) or NPB
+//     (odd observations) pairs take 2^t from the degree-5 FMA-pipe polynomial (ex2_poly2)
+//     instead of MUFU.EX2.  With MUFU-only code the XU pipe is 96 % busy while the FMA pipe
+//     idles at 30 % and half the issue slots are free (profiles/r01_ncu_full_16384x50.csv);
+//     moving ~5/16 of the exponentials over balances the two pipes.
+// Which cells use which pipe is fixed at compile time, so results stay bit-reproducible.
+// ---------------------------------------------------------------------------------------
+template <int NPA, int NPB>
+struct ProductHybrid {
+  static constexpr int kObsStride = 1;
+  f32x2 a2[kRN / 2], c2[kRN / 2];
+  f32x2 p2[kRM][kRN / 2];
+
+  __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, double log2s,
+                                               double /*shift*/) {
+#pragma unroll
+    for (int h = 0; h < kRN / 2; ++h) {
+      float av[2], cv[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = j0 + 2 * h + e;
+        av[e] = j < g.N ? (float)g.ad[j] : 0.0f;
+        cv[e] = j < g.N ? (float)(g.cd0[j] + log2s) : 0.0f;
+      }
+      a2[h] = pack2(av[0], av[1]);
+      c2[h] = pack2(cv[0], cv[1]);
+    }
+  }
+  __device__ __forceinline__ void begin_rows() {
+    const f32x2 one = pack2(1.0f, 1.0f);
+#pragma unroll
+    for (int r = 0; r < kRM; ++r)
+#pragma unroll
+      for (int h = 0; h < kRN / 2; ++h) p2[r][h] = one;
+  }
+  // one observation; the first NP (row, pair) slots take 2^t from the polynomial
+  template <int NP>
+  __device__ __forceinline__ void step_np(float x, const float (&mu)[kRM]) {
+#pragma unroll
+    for (int r = 0; r < kRM; ++r) {
+      const float d = x - mu[r];  // same f32 rounding as the reference's (x - mu), kernels.h:111
+      const float dd = d * d;
+      const f32x2 dd2 = pack2(dd, dd);  // becomes a scalar-broadcast operand of FFMA2
+#pragma unroll
+      for (int h = 0; h < kRN / 2; ++h) {
+        const f32x2 t2 = fma2(dd2, a2[h], c2[h]);
+        // spread the polynomial slots over the rows: (r, h) = (0,0),(1,1),(2,0),(3,1), then the rest
+        const int slot = ((h + r) & 1) * kRM + r;
+        const f32x2 e2 = slot < NP ? ex2_poly2(t2) : ex2_mufu2(t2);
+        p2[r][h] = mul2(p2[r][h], e2);
+      }
+    }
+  }
+  __device__ __forceinline__ float value(int r, int cidx) const {
+    float lo, hi;
+    unpack2(p2[r][cidx >> 1], lo, hi);
+    return (cidx & 1) ? hi : lo;
+  }
+  static __device__ __forceinline__ void consume(ProductHybrid &pol, const float *xs, int count,
+                                                 const float (&mu)[kRM]) {
+    const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
+    const int n4 = count >> 2;
+    for (int q = 0; q < n4; ++q) {
+      const float4 x = xs4[q];
+      pol.template step_np<NPA>(x.x, mu);
+      pol.template step_np<NPB>(x.y, mu);
+      pol.template step_np<NPA>(x.z, mu);
+      pol.template step_np<NPB>(x.w, mu);
+    }
+    for (int k = n4 << 2; k < count; ++k) {
+      if (k & 1) pol.template step_np<NPB>(xs[k], mu);
+      else pol.template step_np<NPA>(xs[k], mu);
+    }
+  }
+};
 
 // ---------------------------------------------------------------------------------------
 // grid_likelihood_kernel: K1-K5 fused.
@@ -253,9 +362,14 @@ __global__ void __launch_bounds__(WM *WN * 32)
   const int wn = warp % WN, wm = warp / WN;
   const int cw = blockIdx.x * WN + wn;            // global 128-column strip index
   const int j0 = cw * kWarpCols + lane * kRN;     // first of this thread's 4 columns
-  const int tile_row0 = g.row_begin + blockIdx.y * g.tile_rows;
+  // tiles start at a multiple of kRM below row_begin, so a cell's position inside the register
+  // patch (hence which exponential path it takes) depends on its GLOBAL row only: a row shard
+  // computes bit-identical unnormalised cells to the single-GPU run
+  const int tile_row0 = (g.row_begin & ~(kRM - 1)) + blockIdx.y * g.tile_rows;
   const int groups = g.tile_rows / (WM * kRM);    // row groups this warp walks
-  const bool streamed = g.n_pad > kObsSingleMax;
+  constexpr int kStride = Policy::kObsStride;        // staged floats per observation
+  constexpr int kChunkObs = kObsChunk / kStride;     // observations per streamed chunk
+  const bool streamed = g.n_pad > kObsSingleMax;      // n_pad counts staged floats
   const int nchunks = streamed ? (g.n_pad + kObsChunk - 1) / kObsChunk : 1;
 
   if (tid == 0) {
@@ -289,9 +403,9 @@ __global__ void __launch_bounds__(WM *WN * 32)
 
   auto begin_group = [&](int grp) {
     row = tile_row0 + (grp * WM + wm) * kRM;
-    rows_any = row < g.row_end;
+    rows_any = row < g.row_end && row + kRM > g.row_begin;
 #pragma unroll
-    for (int r = 0; r < kRM; ++r) mu[r] = g.mu[min(row + r, g.N - 1)];
+    for (int r = 0; r < kRM; ++r) mu[r] = g.mu[min(row + r, g.N - 1)];  // row >= 0 always
     pol.begin_rows();
   };
 
@@ -299,7 +413,7 @@ __global__ void __launch_bounds__(WM *WN * 32)
     if (!rows_any) return;  // warp-uniform
 #pragma unroll
     for (int r = 0; r < kRM; ++r) {
-      const bool rv = row + r < g.row_end;
+      const bool rv = row + r >= g.row_begin && row + r < g.row_end;
       float v[kRN];
       double rs = 0.0;
 #pragma unroll
@@ -329,7 +443,7 @@ __global__ void __launch_bounds__(WM *WN * 32)
     mbar_wait(&bars[0], 0);
     for (int grp = 0; grp < groups; ++grp) {
       begin_group(grp);
-      if (rows_any && col_any) consume_obs(pol, obs_s, g.n, mu);
+      if (rows_any && col_any) Policy::consume(pol, obs_s, g.n, mu);
       end_group();
     }
   } else {
@@ -339,8 +453,9 @@ __global__ void __launch_bounds__(WM *WN * 32)
       mbar_wait(&bars[seq & 1], (seq >> 1) & 1);
       const int ch = seq % nchunks;
       if (ch == 0) begin_group(seq / nchunks);
-      const int count = min(kObsChunk, g.n - ch * kObsChunk);
-      if (rows_any && col_any) consume_obs(pol, obs_s + (size_t)(seq & 1) * kObsChunk, count, mu);
+      const int count = min(kChunkObs, g.n - ch * kChunkObs);
+      if (rows_any && col_any)
+        Policy::consume(pol, obs_s + (size_t)(seq & 1) * kObsChunk, count, mu);
       if (ch == nchunks - 1) end_group();
       __syncthreads();  // every warp is done with this stage before it is refilled
     }
@@ -357,97 +472,146 @@ __global__ void __launch_bounds__(WM *WN * 32)
 
 // ---------------------------------------------------------------------------------------
 // K6-K8 replacement, stage 1: fold the partial buffers in a fixed order.
-//   blocks [0, nb_col): thread per column, sequential sum over the ncolparts slots -> colsum
-//   blocks [nb_col, ..): warp per row, lanes stride the ncw strips, shuffle tree -> rowsum;
-//                        block partials of Z and sum mu_i*rowsum_i
+//   blocks [0, nb_col): 32 columns each; 8 slot groups stride the ncolparts slots (4 loads in
+//                       flight per thread), then the groups are summed 0..7       -> colsum
+//   blocks [nb_col, ..): warp per row, lanes stride the ncw strips, shuffle tree  -> rowsum;
+//                        per-block partials of Z and sum mu_i*rowsum_i
+//   the last block to finish (threadfence + ticket) adds the block partials in index order:
+//                        partials[0] = Z, partials[1] = sum_i mu_i*rowsum_i
+// The ticket only decides WHO does the final sum, never its order: bit-reproducible.
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
     fold_partials_kernel(const double *__restrict__ colpart, int ncolparts,
                          const double *__restrict__ rowpart, int ncw, int rows_local,
                          int row_begin, int N, const float *__restrict__ mu,
                          double *__restrict__ partials, double *__restrict__ rowsum,
-                         double *__restrict__ zpart, double *__restrict__ smupart, int nb_col) {
+                         double *__restrict__ zpart, double *__restrict__ smupart, int nb_col,
+                         int nb_row, unsigned int *__restrict__ ticket) {
+  __shared__ double sh[8][33];
+  __shared__ bool is_last;
   const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
   if ((int)blockIdx.x < nb_col) {
-    const int j = blockIdx.x * 256 + tid;
+    const int j = blockIdx.x * 32 + lane;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
     if (j < N) {
+      const double *src = colpart + j;
+      int t = warp;
+      for (; t + 24 < ncolparts; t += 32) {
+        s0 += src[(size_t)t * N];
+        s1 += src[(size_t)(t + 8) * N];
+        s2 += src[(size_t)(t + 16) * N];
+        s3 += src[(size_t)(t + 24) * N];
+      }
+      for (; t < ncolparts; t += 8) s0 += src[(size_t)t * N];
+    }
+    sh[warp][lane] = (s0 + s1) + (s2 + s3);
+    __syncthreads();
+    if (warp == 0 && j < N) {
       double s = 0.0;
-      for (int t = 0; t < ncolparts; ++t) s += colpart[(size_t)t * N + j];
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += sh[w][lane];
       partials[2 + j] = s;
     }
-    return;
+  } else {
+    const int rb = blockIdx.x - nb_col;
+    const int il = rb * 8 + warp;
+    double s = 0.0;
+    if (il < rows_local) {
+      const double *src = rowpart + (size_t)il * ncw;
+      for (int w = lane; w < ncw; w += 32) s += src[w];
+    }
+    s = warp_sum(s);
+    if (lane == 0) {
+      if (il < rows_local) rowsum[il] = s;
+      sh[0][warp] = s;
+      sh[1][warp] = il < rows_local ? s * (double)mu[row_begin + il] : 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      double z = 0.0, m = 0.0;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) {
+        z += sh[0][w];
+        m += sh[1][w];
+      }
+      zpart[rb] = z;
+      smupart[rb] = m;
+    }
   }
-  __shared__ double zs[8], ms[8];
-  const int lane = tid & 31, warp = tid >> 5;
-  const int rb = blockIdx.x - nb_col;
-  const int il = rb * 8 + warp;
-  double s = 0.0;
-  if (il < rows_local) {
-    const double *src = rowpart + (size_t)il * ncw;
-    for (int w = lane; w < ncw; w += 32) s += src[w];
+  // ---- last block: Z and sum mu*rowsum over the row-block partials, in index order
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double z = 0.0, m = 0.0;
+  for (int b = tid; b < nb_row; b += 256) {
+    z += __ldcg(zpart + b);
+    m += __ldcg(smupart + b);
   }
-  s = warp_sum(s);
+  z = warp_sum(z);
+  m = warp_sum(m);
+  __syncthreads();
   if (lane == 0) {
-    if (il < rows_local) rowsum[il] = s;
-    zs[warp] = s;
-    ms[warp] = il < rows_local ? s * (double)mu[row_begin + il] : 0.0;
+    sh[2][warp] = z;
+    sh[3][warp] = m;
   }
   __syncthreads();
   if (tid == 0) {
-    double z = 0.0, m = 0.0;
+    double zt = 0.0, mt = 0.0;
 #pragma unroll
     for (int w = 0; w < 8; ++w) {
-      z += zs[w];
-      m += ms[w];
+      zt += sh[2][w];
+      mt += sh[3][w];
     }
-    zpart[rb] = z;
-    smupart[rb] = m;
+    partials[0] = zt;
+    partials[1] = mt;
+    *ticket = 0u;  // ready for the next launch on this stream
   }
 }
 
-// stage 2 (one CTA): Z and sum_i mu_i*rowsum_i of this shard -> partials[0..1]
-__global__ void __launch_bounds__(1024)
-    finish_partials_kernel(const double *__restrict__ zpart, const double *__restrict__ smupart,
-                           int nb_row, double *__restrict__ partials) {
-  __shared__ double scratch[32];
-  double z = 0.0, m = 0.0;
-  for (int b = threadIdx.x; b < nb_row; b += blockDim.x) {
-    z += zpart[b];
-    m += smupart[b];
-  }
-  z = block_sum(z, scratch);
-  m = block_sum(m, scratch);
-  if (threadIdx.x == 0) {
-    partials[0] = z;
-    partials[1] = m;
-  }
-}
-
-// stage 3 (one CTA), after the cross-rank sum of `partials`: marginals and expectations.
+// stage 2, after the cross-rank sum of `partials`: marginals and expectations.
 //   marg_sigma_j = colsum_j * (1/Z)   E[sigma] = sum_j marg_sigma_j * sigma_j   (cuda_functions.h:201-218)
 //   marg_mu_i    = rowsum_i * (1/Z)   E[mu]    = (sum_i mu_i*rowsum_i) * (1/Z)
-__global__ void __launch_bounds__(1024)
+// 256 grid points per block; the last block adds the per-block E[sigma] partials in index order.
+__global__ void __launch_bounds__(256)
     results_kernel(const double *__restrict__ partials, const double *__restrict__ rowsum,
                    const float *__restrict__ sigma, int N, int row_begin, int row_end,
-                   double *__restrict__ results) {
+                   double *__restrict__ results, double *__restrict__ espart,
+                   unsigned int *__restrict__ ticket) {
   __shared__ double scratch[32];
+  __shared__ bool is_last;
+  const int tid = threadIdx.x;
   const double z = partials[0];
   const double inv = 1 / z;  // reciprocal multiply, as inc/utils.h:82-84
   double *marg_sigma = results + 4, *marg_mu = results + 4 + N;
+  const int idx = blockIdx.x * 256 + tid;
   double es = 0.0;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) {
-    double m = partials[2 + j] * inv;
-    marg_sigma[j] = m;
-    es += m * (double)sigma[j];
+  if (idx < N) {
+    const double m = partials[2 + idx] * inv;
+    marg_sigma[idx] = m;
+    es = m * (double)sigma[idx];
+    marg_mu[idx] = (idx >= row_begin && idx < row_end) ? rowsum[idx - row_begin] * inv : 0.0;
   }
   es = block_sum(es, scratch);
-  for (int i = threadIdx.x; i < N; i += blockDim.x)
-    marg_mu[i] = (i >= row_begin && i < row_end) ? rowsum[i - row_begin] * inv : 0.0;
-  if (threadIdx.x == 0) {
+  if (tid == 0) espart[blockIdx.x] = es;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double e = 0.0;
+  for (int b = tid; b < (int)gridDim.x; b += 256) e += __ldcg(espart + b);
+  e = block_sum(e, scratch);
+  if (tid == 0) {
     results[0] = partials[1] * inv;
-    results[1] = es;
+    results[1] = e;
     results[2] = z;
     results[3] = inv;
+    *ticket = 0u;
   }
 }
 

@@ -58,7 +58,7 @@ class ShardedGridPosterior:
     likelihood + local fold  ->  all_reduce(P)  ->  results + in-place scale of the local rows.
     With world_size == 1 the all-reduce is skipped."""
 
-    def __init__(self, ctx, grid_size, mu_range, sigma_range, n_obs, mode=0, group=None):
+    def __init__(self, ctx, grid_size, mu_range, sigma_range, n_obs, mode=0, group=None, variant=0):
         import torch
         import torch.distributed as dist
         from .api import make_params
@@ -71,7 +71,7 @@ class ShardedGridPosterior:
         else:
             self.world, self.rank = 1, 0
         self.rows = shard_rows(grid_size, self.world, self.rank)
-        self.params = make_params(n_obs, grid_size, mu_range, sigma_range, mode, self.rows)
+        self.params = make_params(n_obs, grid_size, mu_range, sigma_range, mode, self.rows, variant)
         self.grid_size = grid_size
         self._partials = None
 

@@ -70,8 +70,18 @@ typedef struct cge_params {
   int32_t mode;         /* CGE_MODE_* */
   int32_t row_begin;    /* shard: this call owns mu rows [row_begin, row_end) of the global */
   int32_t row_end;      /* grid; 0,0 means the whole grid (0, grid_size) */
-  int32_t reserved;
+  int32_t variant;      /* CGE_VARIANT_*: 0 = library default; other values pick a tuning variant
+                           of the likelihood kernel (same results within tolerance) */
 } cge_params;
+
+/* likelihood-kernel variants for cge_params.variant (product mode; ignored in log-space) */
+enum {
+  CGE_VARIANT_DEFAULT = 0,   /* hybrid: packed f32x2 arithmetic, 2^t split between MUFU.EX2 and
+                                an FMA-pipe degree-5 polynomial (5 of every 16 evaluations) */
+  CGE_VARIANT_MUFU_ONLY = 1  /* scalar arithmetic, every 2^t on MUFU.EX2 (the MUFU roofline case) */
+  /* 100 + 10*a + b: hybrid with a / b polynomial column pairs (of 8) on even / odd observations;
+     instantiated: 100, 112, 122, 123 (= default), 133, 134 */
+};
 
 /* per-phase device timings of the last synchronous call, milliseconds (CUDA events) */
 typedef struct cge_timing {
