@@ -46,3 +46,36 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         print(res.stderr)
     return LIB_PATH
+
+
+# ---- host-side programs on top of the C ABI (C++/CUDA, like the reference's own binaries) ----
+BIN_DIR = os.path.join(PKG_DIR, "bin")
+ROOT = os.path.dirname(PKG_DIR)
+HOST_PROGRAMS = {
+    # the reference's main() equivalent on the fused path
+    "grid": os.path.join(PKG_DIR, "host", "grid_main.cu"),
+    # the reference's unit tests restated against include/cge_compat.h
+    "test_compat": os.path.join(ROOT, "tests", "cpp", "test_compat.cu"),
+}
+
+
+def build_host_programs(force: bool = False) -> dict:
+    """nvcc the host programs against libcge.so (rpath = the package directory)."""
+    build()
+    os.makedirs(BIN_DIR, exist_ok=True)
+    out = {}
+    for name, src in HOST_PROGRAMS.items():
+        exe = os.path.join(BIN_DIR, name)
+        out[name] = exe
+        deps = [src, LIB_PATH, os.path.join(ROOT, "include", "cge.h"),
+                os.path.join(ROOT, "include", "cge_compat.h")]
+        if not force and os.path.exists(exe) and all(
+                os.path.getmtime(d) <= os.path.getmtime(exe) for d in deps):
+            continue
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-O2", "-std=c++17", "-w",
+               "-o", exe, src, "-L" + PKG_DIR, "-lcge", "-Xlinker", "-rpath," + PKG_DIR,
+               "-Xlinker", "-rpath,$ORIGIN/.."]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {name}:\n" + res.stdout + res.stderr)
+    return out

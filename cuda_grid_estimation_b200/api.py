@@ -31,7 +31,8 @@ ABI_SYMBOLS = (
     "cge_create", "cge_destroy", "cge_last_error", "cge_version", "cge_device_sm_count",
     "cge_grid_posterior", "cge_likelihood_partials", "cge_partials", "cge_finalize",
     "cge_results", "cge_read_results", "cge_posterior_dev", "cge_last_timing",
-    "cge_profile_begin", "cge_profile_end", "cge_launch_count", "cge_linspace", "cge_meshgrid3", "cge_densities", "cge_row_products",
+    "cge_profile_begin", "cge_profile_end", "cge_launch_count", "cge_linspace", "cge_meshgrid3", "cge_densities", "cge_densities_grid",
+    "cge_row_products_rows", "cge_marginalize_rows", "cge_row_products",
     "cge_normalize", "cge_marginalize", "cge_expectation", "cge_microbench",
 )
 
@@ -93,6 +94,9 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "cge_linspace": [vp, vp, i32, f32, f32],
         "cge_meshgrid3": [vp, vp, vp, vp, vp, vp, vp, i32, i32],
         "cge_densities": [vp, vp, vp, vp, vp, sz],
+        "cge_densities_grid": [vp, vp, vp, vp, vp, i32, i32],
+        "cge_row_products_rows": [vp, vp, vp, i32, i32],
+        "cge_marginalize_rows": [vp, vp, vp, i32, i32, i32],
         "cge_row_products": [vp, vp, vp, sz, sz],
         "cge_normalize": [vp, vp, vp, sz],
         "cge_marginalize": [vp, vp, vp, i32, i32, i32],

@@ -127,8 +127,8 @@ int check_params(const cge_params *p, int *rb, int *re) {
   if (p->mode != CGE_MODE_PRODUCT_F32 && p->mode != CGE_MODE_LOGSPACE)
     return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
   switch (p->variant) {
-    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 100: case 112: case 122: case 123:
-    case 133: case 134: break;
+    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 100: case 122: case 123: case 133:
+    case 222: case 322: case 522: case 523: case 611: case 633: case 722: break;
     default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
   }
   int b = p->row_begin, e = p->row_end;
@@ -177,11 +177,11 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->valid = true;
 }
 
-template <class Policy, int WM, int WN>
+template <class Policy, int WM, int WN, int MINB = 1>
 int launch_like_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
   if (pl.vec4) {
-    auto k = cge::grid_likelihood_kernel<Policy, WM, WN, true>;
+    auto k = cge::grid_likelihood_kernel<Policy, WM, WN, true, MINB>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     k<<<grid, block, pl.smem, st>>>(args);
   } else {
@@ -201,21 +201,30 @@ int launch_like(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   return launch_like_shape<Policy, 8, 1>(pl, args, st);
 }
 
-// product path: the default is the hybrid MUFU + FMA-polynomial kernel; the other variants exist
-// for tuning and for the MUFU-only roofline measurement (wide shape only, else the default)
+// product path: the default is the hybrid MUFU + FMA-polynomial kernel with a one-observation
+// loop body (ProductHybrid<2, 2, false, 1>): 4 of every 16 exponentials per thread come from the
+// FMA-pipe polynomial.  The other variants are kept for the roofline measurement (MUFU-only) and
+// to document the tuning sweep (profiles/r01_variant_sweep.md); they are only built for the
+// wide tile shape and fall back to the default elsewhere.
 int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   if (pl.variant == CGE_VARIANT_MUFU_ONLY) return launch_like<cge::ProductF32>(pl, args, st);
   if (pl.wm == 1) {
     switch (pl.variant) {
       case 100: return launch_like_shape<cge::ProductHybrid<0, 0>, 1, 8>(pl, args, st);
-      case 112: return launch_like_shape<cge::ProductHybrid<1, 2>, 1, 8>(pl, args, st);
       case 122: return launch_like_shape<cge::ProductHybrid<2, 2>, 1, 8>(pl, args, st);
+      case 123: return launch_like_shape<cge::ProductHybrid<2, 3>, 1, 8>(pl, args, st);
       case 133: return launch_like_shape<cge::ProductHybrid<3, 3>, 1, 8>(pl, args, st);
-      case 134: return launch_like_shape<cge::ProductHybrid<3, 4>, 1, 8>(pl, args, st);
+      case 222: return launch_like_shape<cge::ProductHybrid<2, 2, true>, 1, 8>(pl, args, st);
+      case 322: return launch_like_shape<cge::ProductHybrid<2, 2>, 1, 8, 4>(pl, args, st);
+      case 522: return launch_like_shape<cge::ProductHybrid<2, 2, false, 2>, 1, 8>(pl, args, st);
+      case 523: return launch_like_shape<cge::ProductHybrid<2, 3, false, 2>, 1, 8>(pl, args, st);
+      case 611: return launch_like_shape<cge::ProductHybrid<1, 1, false, 1>, 1, 8>(pl, args, st);
+      case 633: return launch_like_shape<cge::ProductHybrid<3, 3, false, 1>, 1, 8>(pl, args, st);
+      case 722: return launch_like_shape<cge::ProductHybrid<2, 2, true, 1>, 1, 8>(pl, args, st);
       default: break;
     }
   }
-  return launch_like<cge::ProductHybrid<2, 3>>(pl, args, st);
+  return launch_like<cge::ProductHybrid<2, 2, false, 1>>(pl, args, st);
 }
 
 // record profiling mark `k` of the current step (no-op unless capture is on and has room)
@@ -644,6 +653,43 @@ CGE_EXPORT int cge_densities(cge_context *ctx, float *densities, const float *gr
     return set_error(CGE_ERR_BAD_ARG, "densities: bad argument");
   cge::densities_kernel<<<grid_for(grid_size, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
       densities, grid_x, grid_y, grid_z, grid_size);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_densities_grid(cge_context *ctx, float *densities, const float *mu,
+                                  const float *sigma, const float *obs, int grid_size, int n_obs) {
+  CKRC(bind(ctx));
+  if (!densities || !mu || !sigma || !obs || grid_size < 1 || n_obs < 1)
+    return set_error(CGE_ERR_BAD_ARG, "densities_grid: bad argument");
+  size_t total = (size_t)grid_size * grid_size * n_obs;
+  cge::densities_grid_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+      densities, mu, sigma, obs, grid_size, n_obs);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_row_products_rows(cge_context *ctx, double *likes, double *const *rows_ptr,
+                                     int rows, int cols) {
+  CKRC(bind(ctx));
+  if (!likes || !rows_ptr || rows < 1 || cols < 1)
+    return set_error(CGE_ERR_BAD_ARG, "row_products_rows: bad argument");
+  cge::row_products_pp_kernel<<<(rows + 7) / 8, 256, 0, ctx->stream>>>(likes, rows_ptr, rows, cols);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(ctx->stream));
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_marginalize_rows(cge_context *ctx, double *marginal, double *const *rows_ptr,
+                                    int rows, int cols, int axis) {
+  CKRC(bind(ctx));
+  if (!marginal || !rows_ptr || rows < 1 || cols < 1 || (axis != 0 && axis != 1))
+    return set_error(CGE_ERR_BAD_ARG, "marginalize_rows: bad argument");
+  const int outs = axis == 1 ? rows : cols;
+  cge::marginalize_pp_kernel<<<(outs + 7) / 8, 256, 0, ctx->stream>>>(marginal, rows_ptr, rows, cols,
+                                                                      axis);
   CK(cudaGetLastError());
   CK(cudaStreamSynchronize(ctx->stream));
   return CGE_OK;

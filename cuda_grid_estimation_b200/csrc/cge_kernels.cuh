@@ -271,7 +271,7 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 //     moving ~5/16 of the exponentials over balances the two pipes.
 // Which cells use which pipe is fixed at compile time, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------
-template <int NPA, int NPB>
+template <int NPA, int NPB, bool SCALAR_POLY = false, int OBS_PER_ITER = 4>
 struct ProductHybrid {
   static constexpr int kObsStride = 1;
   f32x2 a2[kRN / 2], c2[kRN / 2];
@@ -312,7 +312,8 @@ struct ProductHybrid {
         const f32x2 t2 = fma2(dd2, a2[h], c2[h]);
         // spread the polynomial slots over the rows: (r, h) = (0,0),(1,1),(2,0),(3,1), then the rest
         const int slot = ((h + r) & 1) * kRM + r;
-        const f32x2 e2 = slot < NP ? ex2_poly2(t2) : ex2_mufu2(t2);
+        const f32x2 e2 = slot < NP ? (SCALAR_POLY ? ex2_poly2_scalar(t2) : ex2_poly2(t2))
+                                   : ex2_mufu2(t2);
         p2[r][h] = mul2(p2[r][h], e2);
       }
     }
@@ -324,18 +325,33 @@ struct ProductHybrid {
   }
   static __device__ __forceinline__ void consume(ProductHybrid &pol, const float *xs, int count,
                                                  const float (&mu)[kRM]) {
-    const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
-    const int n4 = count >> 2;
-    for (int q = 0; q < n4; ++q) {
-      const float4 x = xs4[q];
-      pol.template step_np<NPA>(x.x, mu);
-      pol.template step_np<NPB>(x.y, mu);
-      pol.template step_np<NPA>(x.z, mu);
-      pol.template step_np<NPB>(x.w, mu);
-    }
-    for (int k = n4 << 2; k < count; ++k) {
-      if (k & 1) pol.template step_np<NPB>(xs[k], mu);
-      else pol.template step_np<NPA>(xs[k], mu);
+    if (OBS_PER_ITER == 4) {
+      const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
+      const int n4 = count >> 2;
+      for (int q = 0; q < n4; ++q) {
+        const float4 x = xs4[q];
+        pol.template step_np<NPA>(x.x, mu);
+        pol.template step_np<NPB>(x.y, mu);
+        pol.template step_np<NPA>(x.z, mu);
+        pol.template step_np<NPB>(x.w, mu);
+      }
+      for (int k = n4 << 2; k < count; ++k) {
+        if (k & 1) pol.template step_np<NPB>(xs[k], mu);
+        else pol.template step_np<NPA>(xs[k], mu);
+      }
+    } else if (OBS_PER_ITER == 2) {
+      const float2 *xs2 = reinterpret_cast<const float2 *>(xs);
+      const int n2 = count >> 1;
+#pragma unroll 1
+      for (int q = 0; q < n2; ++q) {
+        const float2 x = xs2[q];
+        pol.template step_np<NPA>(x.x, mu);
+        pol.template step_np<NPB>(x.y, mu);
+      }
+      if (count & 1) pol.template step_np<NPA>(xs[count - 1], mu);
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < count; ++k) pol.template step_np<NPA>(xs[k], mu);
     }
   }
 };
@@ -350,8 +366,8 @@ struct ProductHybrid {
 //   Per row group the warp emits its partial row sums (fixed-order shuffle tree) and keeps
 //   float64 column sums in registers until the tile ends: no atomics anywhere.
 // ---------------------------------------------------------------------------------------
-template <class Policy, int WM, int WN, bool VEC4>
-__global__ void __launch_bounds__(WM *WN * 32)
+template <class Policy, int WM, int WN, bool VEC4, int MINB = 1>
+__global__ void __launch_bounds__(WM *WN * 32, MINB)
     grid_likelihood_kernel(const LikeArgs g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);         // 2 mbarriers
@@ -709,6 +725,58 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) p *= __shfl_xor_sync(0xffffffffu, p, off);
   if (lane == 0) likes[r] = p;
+}
+
+// a2+a4 fused for the stage wrapper (inc/wrappers.h:19-92): densities[(i*N + j)*n + k] =
+// pdf(obs_k; mu_i, sigma_j) straight from the three vectors -- the reference's three N*N*n
+// meshgrid copies are never built.
+__global__ void densities_grid_kernel(float *__restrict__ dens, const float *__restrict__ mu,
+                                      const float *__restrict__ sigma,
+                                      const float *__restrict__ obs, int N, int n) {
+  const size_t total = (size_t)N * N * n;
+  for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < total;
+       f += (size_t)gridDim.x * blockDim.x) {
+    const int k = (int)(f % n);
+    const size_t ij = f / n;
+    const float x = obs[k], m = mu[ij / N], s = sigma[ij % N];
+    const float z = __fdiv_rn(__fsub_rn(x, m), s);
+    const float e = expf(__fmul_rn(-0.5f, __fmul_rn(z, z)));
+    dens[f] = (float)((double)e / ((double)s * 2.5066282746310002));
+  }
+}
+
+// the reference's row-pointer matrices (double**, one allocation per row: inc/utils.h:53-63):
+// K5 / K7 on that layout, warp per output element, fixed-order shuffle tree.
+__global__ void __launch_bounds__(256)
+    row_products_pp_kernel(double *__restrict__ likes, double *const *__restrict__ rows_ptr,
+                           int rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  const double *src = rows_ptr[r];
+  double p = 1.0;
+  for (int k = lane; k < cols; k += 32) p *= src[k];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) p *= __shfl_xor_sync(0xffffffffu, p, off);
+  if (lane == 0) likes[r] = p;
+}
+
+__global__ void __launch_bounds__(256)
+    marginalize_pp_kernel(double *__restrict__ marginal, double *const *__restrict__ rows_ptr,
+                          int rows, int cols, int axis) {
+  const int lane = threadIdx.x & 31;
+  const int o = blockIdx.x * 8 + (threadIdx.x >> 5);
+  double s = 0.0;
+  if (axis == 1) {  // row sums
+    if (o >= rows) return;
+    const double *src = rows_ptr[o];
+    for (int j = lane; j < cols; j += 32) s += src[j];
+  } else {          // column sums
+    if (o >= cols) return;
+    for (int i = lane; i < rows; i += 32) s += rows_ptr[i][o];
+  }
+  s = warp_sum(s);
+  if (lane == 0) marginal[o] = s;
 }
 
 // K6: two-level fixed-order sum, then the reciprocal multiply

@@ -76,11 +76,14 @@ typedef struct cge_params {
 
 /* likelihood-kernel variants for cge_params.variant (product mode; ignored in log-space) */
 enum {
-  CGE_VARIANT_DEFAULT = 0,   /* hybrid: packed f32x2 arithmetic, 2^t split between MUFU.EX2 and
-                                an FMA-pipe degree-5 polynomial (5 of every 16 evaluations) */
+  CGE_VARIANT_DEFAULT = 0,   /* hybrid: packed f32x2 arithmetic; of the 16 exponentials a thread
+                                evaluates per observation, 12 use MUFU.EX2 and 4 an FMA-pipe
+                                degree-5 polynomial; one observation per loop iteration */
   CGE_VARIANT_MUFU_ONLY = 1  /* scalar arithmetic, every 2^t on MUFU.EX2 (the MUFU roofline case) */
-  /* 100 + 10*a + b: hybrid with a / b polynomial column pairs (of 8) on even / odd observations;
-     instantiated: 100, 112, 122, 123 (= default), 133, 134 */
+  /* tuning variants kept for the record (wide tile shape only, see cge_api.cu launch_product):
+     100 packed, MUFU only; 1ab / 5ab / 6ab hybrid with a / b polynomial column pairs (of 8) on
+     even / odd observations and 4 / 2 / 1 observations per loop iteration; 2ab, 7ab scalar
+     polynomial; 3ab capped at 64 registers */
 };
 
 /* per-phase device timings of the last synchronous call, milliseconds (CUDA events) */
@@ -160,6 +163,18 @@ int cge_meshgrid3(cge_context *ctx, const float *vec_x, const float *vec_y, cons
 /* inc/cuda_functions.h:95-115 computeDensitiesCuda: densities[f] = pdf(grid_z[f]; grid_x[f], grid_y[f]) */
 int cge_densities(cge_context *ctx, float *densities, const float *grid_x, const float *grid_y,
                   const float *grid_z, size_t grid_size);
+/* inc/wrappers.h:19-92 computeDensitiesWrapper minus its two linspace calls: densities straight
+ * from the three vectors, densities[(i*N + j)*n + k] = pdf(obs[k]; mu[i], sigma[j]); the three
+ * N*N*n meshgrid temporaries of the reference are never built */
+int cge_densities_grid(cge_context *ctx, float *densities, const float *mu, const float *sigma,
+                       const float *obs, int grid_size, int n_obs);
+/* inc/cuda_functions.h:118-136 computeLikesCuda on the reference's row-pointer matrix (double**,
+ * inc/utils.h:53-63): likes[r] = prod_k rows_ptr[r][k]; the matrix is left untouched */
+int cge_row_products_rows(cge_context *ctx, double *likes, double *const *rows_ptr, int rows,
+                          int cols);
+/* inc/cuda_functions.h:161-182 marginalizeCuda on a row-pointer matrix, same axis meaning */
+int cge_marginalize_rows(cge_context *ctx, double *marginal, double *const *rows_ptr, int rows,
+                         int cols, int axis);
 /* inc/wrappers.h:95-121 computeLikesWrapper: likes[r] = prod_k densities[r*cols+k], float64 */
 int cge_row_products(cge_context *ctx, const float *densities, double *likes,
                      size_t densities_size, size_t likes_size);

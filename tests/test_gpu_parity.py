@@ -57,7 +57,7 @@ def test_readme_product_vs_oracle(ctx, readme_obs):
     assert res.launches == 5  # setup, likelihood, fold, results, scale
 
 
-@pytest.mark.parametrize("variant", [1, 100, 112, 122, 123, 133, 134])
+@pytest.mark.parametrize("variant", [1, 100, 122, 123, 133, 222, 322, 522, 523, 611, 633, 722])
 def test_product_kernel_variants(ctx, readme_obs, variant):
     """Every instantiated likelihood-kernel variant (MUFU-only scalar, packed, hybrid MUFU + FMA
     polynomial at several splits) meets the same tolerances; N=1024 uses the wide tile shape the
@@ -429,3 +429,47 @@ def test_stage_api_pipeline_matches_fused(ctx, readme_obs):
     assert (np.abs(dens - dens_ref) / dens_ref).max() < 1e-5
     fused = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
     assert np.abs(fused.expectations - e).max() < 1e-6
+
+
+# ---------------------------------------------------------------------------------------
+# the C++ host side: reference's own tests against include/cge_compat.h, and the grid CLI
+# ---------------------------------------------------------------------------------------
+def _bin(name):
+    from cuda_grid_estimation_b200 import _build
+    path = os.path.join(_build.BIN_DIR, name)
+    assert os.path.exists(path), f"{path} missing: run __graft_entry__.build()"
+    return path
+
+
+def test_cpp_compat_shim_reference_tests(tmp_path, readme_obs):
+    """cpp/grid-algorithm/src/tests.cu restated (tests/cpp/test_compat.cu) + src/grid.cu's call
+    sequence through the reference's own function names, compiled against the shim."""
+    import subprocess
+    obs_file = tmp_path / "obs.bin"
+    readme_obs.tofile(obs_file)
+    res = subprocess.run([_bin("test_compat"), str(obs_file)], capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "ALL PASSED" in res.stdout
+    line = [l for l in res.stdout.splitlines() if l.startswith("PIPELINE")][0].split()
+    got = np.array([float(line[1]), float(line[2])])
+    ref = oracle.grid_posterior(readme_obs, 101, 18, 22, 1, 3, oracle.NUM_REF)
+    assert np.abs(got - ref["expectations"]).max() < 1e-8
+
+
+def test_cpp_grid_cli(tmp_path, readme_obs):
+    """bin/grid equivalent (src/grid.cu:129-132 output format) on the fused path."""
+    import subprocess
+    obs_file = tmp_path / "obs.bin"
+    readme_obs.tofile(obs_file)
+    res = subprocess.run([_bin("grid"), "--obs-file", str(obs_file), "--timing"],
+                         capture_output=True, text=True)
+    assert res.returncode == 0, res.stdout + res.stderr
+    lines = res.stdout.splitlines()
+    assert lines[0].startswith("Inferred mu: ") and lines[0].endswith("; Actual mu: 20")
+    assert lines[1].startswith("Inferred sigma: ") and lines[1].endswith("; Actual sigma: 2")
+    e_mu = float(lines[0].split()[2].rstrip(";"))
+    e_sg = float(lines[1].split()[2].rstrip(";"))
+    assert abs(e_mu - 19.549052475) < 1e-6 and abs(e_sg - 1.916762506) < 1e-6
+    # the reference's default run (no arguments) also works: 50 host-drawn observations
+    res = subprocess.run([_bin("grid")], capture_output=True, text=True)
+    assert res.returncode == 0 and "Inferred mu" in res.stdout

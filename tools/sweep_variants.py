@@ -3,6 +3,7 @@
 per-step capture) and report accuracy against the oracle on the README workload.
 usage: python tools/sweep_variants.py [N] [n_obs] [steps]"""
 import json
+import os
 import sys
 
 import numpy as np
@@ -22,7 +23,7 @@ out = []
 with cge.Context(0) as ctx:
     obs_t = torch.from_numpy(obs).to(dev)
     post = torch.empty((N, N), dtype=torch.float32, device=dev)
-    for variant in (1, 100, 112, 122, 0, 133, 134):
+    for variant in [int(v) for v in os.environ.get("CGE_VARIANTS", "1,100,112,122,0,133,134").split(",")]:
         p = cge.make_params(n, N, (18, 22), (1, 3), cge.MODE_PRODUCT_F32, None, variant)
         for _ in range(3):
             ctx.likelihood_partials(p, obs_t, post, None)
