@@ -127,8 +127,9 @@ int check_params(const cge_params *p, int *rb, int *re) {
   if (p->mode != CGE_MODE_PRODUCT_F32 && p->mode != CGE_MODE_LOGSPACE)
     return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
   switch (p->variant) {
-    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 100: case 122: case 123: case 133:
-    case 222: case 322: case 522: case 523: case 611: case 633: case 722: break;
+    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 2: case 100: case 122: case 123: case 133:
+    case 222: case 322: case 522: case 523: case 611: case 633: case 722: case 822: case 833:
+    case 922: case 933: break;
     default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
   }
   int b = p->row_begin, e = p->row_end;
@@ -152,7 +153,9 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->row_begin = rb;
   pl->row_end = re;
   pl->rows_local = re - rb;
-  pl->ncw = (pl->N + cge::kWarpCols - 1) / cge::kWarpCols;
+  // columns per warp strip: 32 lanes x Policy::kCols (log-space keeps 8 columns per thread)
+  const int strip = 32 * (p->mode == CGE_MODE_LOGSPACE ? cge::LogSpaceF64::kCols : 4);
+  pl->ncw = (pl->N + strip - 1) / strip;
   if (pl->ncw >= 8) { pl->wm = 1; pl->wn = 8; }
   else if (pl->ncw >= 4) { pl->wm = 2; pl->wn = 4; }
   else if (pl->ncw >= 2) { pl->wm = 4; pl->wn = 2; }
@@ -185,7 +188,7 @@ int launch_like_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     k<<<grid, block, pl.smem, st>>>(args);
   } else {
-    auto k = cge::grid_likelihood_kernel<Policy, WM, WN, false>;
+    auto k = cge::grid_likelihood_kernel<Policy, WM, WN, false, MINB>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     k<<<grid, block, pl.smem, st>>>(args);
   }
@@ -193,12 +196,12 @@ int launch_like_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st
   return CGE_OK;
 }
 
-template <class Policy>
+template <class Policy, int MINB = 1>
 int launch_like(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
-  if (pl.wm == 1) return launch_like_shape<Policy, 1, 8>(pl, args, st);
-  if (pl.wm == 2) return launch_like_shape<Policy, 2, 4>(pl, args, st);
-  if (pl.wm == 4) return launch_like_shape<Policy, 4, 2>(pl, args, st);
-  return launch_like_shape<Policy, 8, 1>(pl, args, st);
+  if (pl.wm == 1) return launch_like_shape<Policy, 1, 8, MINB>(pl, args, st);
+  if (pl.wm == 2) return launch_like_shape<Policy, 2, 4, MINB>(pl, args, st);
+  if (pl.wm == 4) return launch_like_shape<Policy, 4, 2, MINB>(pl, args, st);
+  return launch_like_shape<Policy, 8, 1, MINB>(pl, args, st);
 }
 
 // product path: the default is the hybrid MUFU + FMA-polynomial kernel with a one-observation
@@ -221,6 +224,11 @@ int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
       case 611: return launch_like_shape<cge::ProductHybrid<1, 1, false, 1>, 1, 8>(pl, args, st);
       case 633: return launch_like_shape<cge::ProductHybrid<3, 3, false, 1>, 1, 8>(pl, args, st);
       case 722: return launch_like_shape<cge::ProductHybrid<2, 2, true, 1>, 1, 8>(pl, args, st);
+      // 8ab / 9ab: one observation per iteration, capped for 3 / 4 CTAs per SM
+      case 822: return launch_like_shape<cge::ProductHybrid<2, 2, false, 1>, 1, 8, 3>(pl, args, st);
+      case 833: return launch_like_shape<cge::ProductHybrid<3, 3, false, 1>, 1, 8, 3>(pl, args, st);
+      case 922: return launch_like_shape<cge::ProductHybrid<2, 2, false, 1>, 1, 8, 4>(pl, args, st);
+      case 933: return launch_like_shape<cge::ProductHybrid<3, 3, false, 1>, 1, 8, 4>(pl, args, st);
       default: break;
     }
   }
@@ -417,7 +425,11 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   if (p->mode == CGE_MODE_PRODUCT_F32)
     CKRC(launch_product(pl, args, st));
   else
-    CKRC(launch_like<cge::LogSpaceF64>(pl, args, st));
+  {
+    // variant 2: capped at 128 registers (2 CTAs per SM, small spills); default: uncapped
+    if (p->variant == 2) CKRC((launch_like<cge::LogSpaceF64, 2>(pl, args, st)));
+    else CKRC((launch_like<cge::LogSpaceF64, 1>(pl, args, st)));
+  }
   ctx->launches += 1;
   CKRC(mark(ctx, 2, st));
 

@@ -16,7 +16,7 @@
 //   ad         float64 [N]      a_j  = -0.5*log2(e)/sigma_j^2
 //   cd0        float64 [N]      c0_j = -log2(sigma_j*sqrt(2*pi))
 //   obs_pad    float32 [n_pad]  observations, zero-padded to a multiple of 4, 16 B aligned
-//   rowpart    float64 [rows_local][ncw]   per (row, 128-column warp strip) partial row sums
+//   rowpart    float64 [rows_local][ncw]   per (row, warp column strip) partial row sums
 //   colpart    float64 [ncolparts][N]      per (row tile x warp row) partial column sums
 //   partials   float64 [N+2]    {Z, sum_i mu_i*rowsum_i, colsum[0..N)}  <- the all-reduce payload
 //   results    float64 [4+2N]   {E[mu], E[sigma], Z, 1/Z}, marg_sigma[N], marg_mu[N]
@@ -31,8 +31,15 @@ namespace cge {
 constexpr double kPeakLog2 = 40.0;
 
 constexpr int kRM = 4;            // register patch: rows (mu) per thread
-constexpr int kRN = 4;            // register patch: columns (sigma) per thread, one float4 store
-constexpr int kWarpCols = 32 * kRN;  // 128 columns per warp
+constexpr int kRN = 4;            // columns (sigma) per thread and float4 store; a policy owns
+                                  // Policy::kCols = 4 or 8 columns = 1 or 2 such groups
+constexpr int kGroupCols = 32 * kRN;  // 128 columns: one float4 per lane across a warp
+
+// column of patch element `cidx` for a thread whose first column is jbase: groups of 4 adjacent
+// columns, successive groups 128 columns apart (so every float4 store of a warp is one 512-byte run)
+__device__ __forceinline__ int patch_col(int jbase, int cidx) {
+  return jbase + (cidx >> 2) * kGroupCols + (cidx & 3);
+}
 constexpr int kObsChunk = 8192;   // floats per streamed observation chunk (32 KB)
 constexpr int kObsSingleMax = 16384;  // up to this many (padded) observations live in smem at once
 
@@ -57,7 +64,7 @@ struct LikeArgs {
   int n, n_pad, N;  // n observations; n_pad staged floats (multiple of 4)
   int row_begin, row_end;
   int tile_rows;    // rows per CTA tile, multiple of WM*kRM
-  int ncw;          // ceil(N / 128)
+  int ncw;          // column strips per row: ceil(N / (32 * Policy::kCols))
 };
 
 // ---------------------------------------------------------------------------------------
@@ -150,6 +157,7 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 // product); the subtract and square are shared by the kRN columns of a row.
 //   factor_k = 2^(a_j*(x_k-mu_i)^2 + c_j),  c_j = c0_j + log2 s   (constants FMA-folded)
 struct ProductF32 {
+  static constexpr int kCols = 4;
   static constexpr int kObsStride = 1;  // floats of shared memory per observation
   static __device__ __forceinline__ void consume(ProductF32 &pol, const float *xs, int count,
                                                  const float (&mu)[kRM]) {
@@ -191,54 +199,72 @@ struct ProductF32 {
       for (int cidx = 0; cidx < kRN; ++cidx)
         p[r][cidx] *= ex2_approx(fmaf(dd[r], a[cidx], c[cidx]));
   }
-  __device__ __forceinline__ float value(int r, int cidx) const { return p[r][cidx]; }
+  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx) const {
+    return p[r][cidx];
+  }
 };
 
 // log-space path: float64 sum of log2-pdf terms (one DFMA per pdf-eval), then a single
 // exponential per cell against the global maximum: L_ij = 2^(sum_k a_j d_ik^2 + n c0_j + shift).
+// The FP64 pipe is the bound, so everything that is not the per-eval DFMA is kept off it:
+// (x - mu)^2 is formed in float32 (2^-24 relative rounding per term, random: ~1e-6 relative on a
+// cell after 10^4 observations) and widened once per (row, observation); 8 columns per thread
+// amortise that widening over 8 evaluations.
 struct LogSpaceF64 {
+  static constexpr int kCols = 8;
   static constexpr int kObsStride = 1;
   static __device__ __forceinline__ void consume(LogSpaceF64 &pol, const float *xs, int count,
                                                  const float (&mu)[kRM]) {
-    consume_scalar_obs(pol, xs, count, mu);
+    const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
+    const int n4 = count >> 2;
+#pragma unroll 1
+    for (int q = 0; q < n4; ++q) {  // 4 observations x 32 independent DFMA chains per iteration
+      const float4 x = xs4[q];
+      pol.step(x.x, mu);
+      pol.step(x.y, mu);
+      pol.step(x.z, mu);
+      pol.step(x.w, mu);
+    }
+    for (int k = n4 << 2; k < count; ++k) pol.step(xs[k], mu);
   }
-  double a[kRN], cshift[kRN];
-  double acc[kRM][kRN];
+  double a[kCols];
+  double acc[kRM][kCols];
+  double shift_;
+  int jbase_;
 
-  __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, double /*log2s*/,
+  __device__ __forceinline__ void load_columns(const LikeArgs &g, int jbase, double /*log2s*/,
                                                double shift) {
+    jbase_ = jbase;
+    shift_ = shift;
 #pragma unroll
-    for (int cidx = 0; cidx < kRN; ++cidx) {
-      int j = j0 + cidx;
-      if (j < g.N) {
-        a[cidx] = g.ad[j];
-        cshift[cidx] = (double)g.n * g.cd0[j] + shift;
-      } else {
-        a[cidx] = 0.0;
-        cshift[cidx] = 0.0;
-      }
+    for (int cidx = 0; cidx < kCols; ++cidx) {
+      const int j = patch_col(jbase, cidx);
+      a[cidx] = j < g.N ? g.ad[j] : 0.0;
     }
   }
   __device__ __forceinline__ void begin_rows() {
 #pragma unroll
     for (int r = 0; r < kRM; ++r)
 #pragma unroll
-      for (int cidx = 0; cidx < kRN; ++cidx) acc[r][cidx] = 0.0;
+      for (int cidx = 0; cidx < kCols; ++cidx) acc[r][cidx] = 0.0;
   }
   __device__ __forceinline__ void step(float x, const float (&mu)[kRM]) {
     double dd[kRM];
 #pragma unroll
     for (int r = 0; r < kRM; ++r) {
-      double d = (double)(x - mu[r]);
-      dd[r] = d * d;
+      const float d = x - mu[r];
+      dd[r] = (double)(d * d);
     }
 #pragma unroll
     for (int r = 0; r < kRM; ++r)
 #pragma unroll
-      for (int cidx = 0; cidx < kRN; ++cidx) acc[r][cidx] = fma(dd[r], a[cidx], acc[r][cidx]);
+      for (int cidx = 0; cidx < kCols; ++cidx) acc[r][cidx] = fma(dd[r], a[cidx], acc[r][cidx]);
   }
-  __device__ __forceinline__ float value(int r, int cidx) const {
-    return ex2_approx((float)(acc[r][cidx] + cshift[cidx]));
+  // n*c0_j + shift is only needed here, once per cell: read c0_j back instead of holding it
+  __device__ __forceinline__ float value(const LikeArgs &g, int r, int cidx) const {
+    const int j = patch_col(jbase_, cidx);
+    const double c = j < g.N ? (double)g.n * g.cd0[j] + shift_ : 0.0;
+    return ex2_approx((float)(acc[r][cidx] + c));
   }
 };
 
@@ -273,6 +299,7 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 // ---------------------------------------------------------------------------------------
 template <int NPA, int NPB, bool SCALAR_POLY = false, int OBS_PER_ITER = 4>
 struct ProductHybrid {
+  static constexpr int kCols = 4;
   static constexpr int kObsStride = 1;
   f32x2 a2[kRN / 2], c2[kRN / 2];
   f32x2 p2[kRM][kRN / 2];
@@ -318,7 +345,7 @@ struct ProductHybrid {
       }
     }
   }
-  __device__ __forceinline__ float value(int r, int cidx) const {
+  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx) const {
     float lo, hi;
     unpack2(p2[r][cidx >> 1], lo, hi);
     return (cidx & 1) ? hi : lo;
@@ -358,9 +385,9 @@ struct ProductHybrid {
 
 // ---------------------------------------------------------------------------------------
 // grid_likelihood_kernel: K1-K5 fused.
-//   CTA = WM x WN warps.  A warp owns a strip of 128 sigma columns (lane -> 4 adjacent
-//   columns, one 16-byte store per row) and walks down its rows kRM at a time.
-//   blockIdx.x = column band (WN*128 columns), blockIdx.y = row tile (tile_rows rows).
+//   CTA = WM x WN warps.  A warp owns a strip of 32*kCols sigma columns (lane -> kCols/4 groups
+//   of 4 adjacent columns, one 16-byte store per group and row) and walks down its rows kRM at
+//   a time.  blockIdx.x = column band (WN strips), blockIdx.y = row tile (tile_rows rows).
 //   Observations reach shared memory by TMA bulk copy (cp.async.bulk + mbarrier): once per CTA
 //   when they fit, else streamed in double-buffered 32 KB chunks.
 //   Per row group the warp emits its partial row sums (fixed-order shuffle tree) and keeps
@@ -376,8 +403,10 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int wn = warp % WN, wm = warp / WN;
-  const int cw = blockIdx.x * WN + wn;            // global 128-column strip index
-  const int j0 = cw * kWarpCols + lane * kRN;     // first of this thread's 4 columns
+  constexpr int kCols = Policy::kCols;            // columns per thread: 4 or 8
+  constexpr int kGroups = kCols / kRN;            // float4 groups per thread
+  const int cw = blockIdx.x * WN + wn;            // global column-strip index (32*kCols columns)
+  const int j0 = cw * (32 * kCols) + lane * kRN;  // first column; group g starts 128*g further
   // tiles start at a multiple of kRM below row_begin, so a cell's position inside the register
   // patch (hence which exponential path it takes) depends on its GLOBAL row only: a row shard
   // computes bit-identical unnormalised cells to the single-GPU run
@@ -408,10 +437,10 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
   const ScaleInfo sc = *g.scale;
   Policy pol;
   pol.load_columns(g, j0, sc.log2s, sc.shift);
-  double colacc[kRN];
+  double colacc[kCols];
 #pragma unroll
-  for (int cidx = 0; cidx < kRN; ++cidx) colacc[cidx] = 0.0;
-  const bool col_any = j0 < g.N;
+  for (int cidx = 0; cidx < kCols; ++cidx) colacc[cidx] = 0.0;
+  const bool col_any = j0 < g.N;  // columns only grow with cidx
 
   float mu[kRM];
   int row = 0;
@@ -430,23 +459,28 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
 #pragma unroll
     for (int r = 0; r < kRM; ++r) {
       const bool rv = row + r >= g.row_begin && row + r < g.row_end;
-      float v[kRN];
+      float v[kCols];
       double rs = 0.0;
 #pragma unroll
-      for (int cidx = 0; cidx < kRN; ++cidx) {
-        const bool ok = rv && (j0 + cidx < g.N);
-        v[cidx] = ok ? pol.value(r, cidx) : 0.0f;
+      for (int cidx = 0; cidx < kCols; ++cidx) {
+        const bool ok = rv && (patch_col(j0, cidx) < g.N);
+        v[cidx] = ok ? pol.value(g, r, cidx) : 0.0f;
         rs += (double)v[cidx];
         colacc[cidx] += (double)v[cidx];
       }
-      if (rv && col_any) {
-        float *dst = g.post + (size_t)(row + r - g.row_begin) * (size_t)g.N + j0;
-        if (VEC4) {
-          st_stream_f4(dst, v[0], v[1], v[2], v[3]);
-        } else {
+      if (rv) {
+        float *rowp = g.post + (size_t)(row + r - g.row_begin) * (size_t)g.N;
 #pragma unroll
-          for (int cidx = 0; cidx < kRN; ++cidx)
-            if (j0 + cidx < g.N) st_stream_f1(dst + cidx, v[cidx]);
+        for (int grp4 = 0; grp4 < kGroups; ++grp4) {
+          const int jg = j0 + grp4 * kGroupCols;
+          if (jg >= g.N) continue;
+          if (VEC4) {
+            st_stream_f4(rowp + jg, v[4 * grp4], v[4 * grp4 + 1], v[4 * grp4 + 2], v[4 * grp4 + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < kRN; ++e)
+              if (jg + e < g.N) st_stream_f1(rowp + jg + e, v[4 * grp4 + e]);
+          }
         }
       }
       rs = warp_sum(rs);
@@ -479,10 +513,12 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
 
   // partial column sums of this warp's rows: one slot per (row tile, warp row)
   if (col_any) {
-    double *dst = g.colpart + (size_t)(blockIdx.y * WM + wm) * (size_t)g.N + j0;
+    double *dst = g.colpart + (size_t)(blockIdx.y * WM + wm) * (size_t)g.N;
 #pragma unroll
-    for (int cidx = 0; cidx < kRN; ++cidx)
-      if (j0 + cidx < g.N) dst[cidx] = colacc[cidx];
+    for (int cidx = 0; cidx < kCols; ++cidx) {
+      const int j = patch_col(j0, cidx);
+      if (j < g.N) dst[j] = colacc[cidx];
+    }
   }
 }
 
