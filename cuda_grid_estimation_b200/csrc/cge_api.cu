@@ -127,9 +127,8 @@ int check_params(const cge_params *p, int *rb, int *re) {
   if (p->mode != CGE_MODE_PRODUCT_F32 && p->mode != CGE_MODE_LOGSPACE)
     return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
   switch (p->variant) {
-    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 2: case 100: case 122: case 123: case 133:
-    case 222: case 322: case 522: case 523: case 611: case 633: case 722: case 822: case 833:
-    case 922: case 933: break;
+    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 2: case 100: case 122: case 133:
+    case 222: case 522: case 523: case 633: case 822: break;
     default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
   }
   int b = p->row_begin, e = p->row_end;
@@ -207,7 +206,7 @@ int launch_like(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
 // product path: the default is the hybrid MUFU + FMA-polynomial kernel with a one-observation
 // loop body (ProductHybrid<2, 2, false, 1>): 4 of every 16 exponentials per thread come from the
 // FMA-pipe polynomial.  The other variants are kept for the roofline measurement (MUFU-only) and
-// to document the tuning sweep (profiles/r01_variant_sweep.md); they are only built for the
+// to document the tuning sweep (profiles/r01_variant_sweep_*.jsonl); they are only built for the
 // wide tile shape and fall back to the default elsewhere.
 int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   if (pl.variant == CGE_VARIANT_MUFU_ONLY) return launch_like<cge::ProductF32>(pl, args, st);
@@ -215,20 +214,12 @@ int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
     switch (pl.variant) {
       case 100: return launch_like_shape<cge::ProductHybrid<0, 0>, 1, 8>(pl, args, st);
       case 122: return launch_like_shape<cge::ProductHybrid<2, 2>, 1, 8>(pl, args, st);
-      case 123: return launch_like_shape<cge::ProductHybrid<2, 3>, 1, 8>(pl, args, st);
       case 133: return launch_like_shape<cge::ProductHybrid<3, 3>, 1, 8>(pl, args, st);
       case 222: return launch_like_shape<cge::ProductHybrid<2, 2, true>, 1, 8>(pl, args, st);
-      case 322: return launch_like_shape<cge::ProductHybrid<2, 2>, 1, 8, 4>(pl, args, st);
       case 522: return launch_like_shape<cge::ProductHybrid<2, 2, false, 2>, 1, 8>(pl, args, st);
       case 523: return launch_like_shape<cge::ProductHybrid<2, 3, false, 2>, 1, 8>(pl, args, st);
-      case 611: return launch_like_shape<cge::ProductHybrid<1, 1, false, 1>, 1, 8>(pl, args, st);
       case 633: return launch_like_shape<cge::ProductHybrid<3, 3, false, 1>, 1, 8>(pl, args, st);
-      case 722: return launch_like_shape<cge::ProductHybrid<2, 2, true, 1>, 1, 8>(pl, args, st);
-      // 8ab / 9ab: one observation per iteration, capped for 3 / 4 CTAs per SM
       case 822: return launch_like_shape<cge::ProductHybrid<2, 2, false, 1>, 1, 8, 3>(pl, args, st);
-      case 833: return launch_like_shape<cge::ProductHybrid<3, 3, false, 1>, 1, 8, 3>(pl, args, st);
-      case 922: return launch_like_shape<cge::ProductHybrid<2, 2, false, 1>, 1, 8, 4>(pl, args, st);
-      case 933: return launch_like_shape<cge::ProductHybrid<3, 3, false, 1>, 1, 8, 4>(pl, args, st);
       default: break;
     }
   }

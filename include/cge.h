@@ -80,10 +80,12 @@ enum {
                                 evaluates per observation, 12 use MUFU.EX2 and 4 an FMA-pipe
                                 degree-5 polynomial; one observation per loop iteration */
   CGE_VARIANT_MUFU_ONLY = 1  /* scalar arithmetic, every 2^t on MUFU.EX2 (the MUFU roofline case) */
-  /* tuning variants kept for the record (wide tile shape only, see cge_api.cu launch_product):
+  /* tuning variants kept for the record (wide tile shape only, see cge_api.cu launch_product;
+     the full sweep incl. variants since removed is in profiles/r01_variant_sweep_*.jsonl):
      100 packed, MUFU only; 1ab / 5ab / 6ab hybrid with a / b polynomial column pairs (of 8) on
-     even / odd observations and 4 / 2 / 1 observations per loop iteration; 2ab, 7ab scalar
-     polynomial; 3ab capped at 64 registers */
+     even / odd observations and 4 / 2 / 1 observations per loop iteration; 222 scalar
+     polynomial; 822 = default capped at 80 registers.  In log-space mode variant 2 caps the
+     kernel at 128 registers. */
 };
 
 /* per-phase device timings of the last synchronous call, milliseconds (CUDA events) */

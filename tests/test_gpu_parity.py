@@ -57,7 +57,7 @@ def test_readme_product_vs_oracle(ctx, readme_obs):
     assert res.launches == 5  # setup, likelihood, fold, results, scale
 
 
-@pytest.mark.parametrize("variant", [1, 100, 122, 123, 133, 222, 322, 522, 523, 611, 633, 722])
+@pytest.mark.parametrize("variant", [1, 100, 122, 133, 222, 522, 523, 633, 822])
 def test_product_kernel_variants(ctx, readme_obs, variant):
     """Every instantiated likelihood-kernel variant (MUFU-only scalar, packed, hybrid MUFU + FMA
     polynomial at several splits) meets the same tolerances; N=1024 uses the wide tile shape the
