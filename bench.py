@@ -8,8 +8,9 @@ hot path (BASELINE.json: "G pdf-evals/s ... at 1/2/4/8 B200").
            --master-port P bench.py --gpus N --steps K --warmup W
 
 A "step" is one full pass of the hot path over one batch of synthetic observations:
-tables + rescale statistics, the fused likelihood kernel, the deterministic fold, (N>1: one
-all-reduce of N+2 float64), marginals/expectations and the in-place 1/Z scale.  The default
+tables + rescale statistics, the fused likelihood kernel, the deterministic fold, (N>1: the sum of
+N+2 float64 over ranks, by peer loads inside the results kernel or NCCL), marginals/expectations
+and the in-place 1/Z scale.  The default
 workload is BASELINE.json configs[2] -- 16384 x 16384 grid x 50 observations, float32 product
 path -- the configuration the headline target (>= 60 % of MUFU peak on one GPU) is quoted on;
 with --gpus N the same grid is row-sharded (strong scaling, as configs[2] states).
@@ -254,7 +255,7 @@ def run_ours(args):
     info = ctx.device_info()
     obs_host = torch.from_numpy(observations(n)).pin_memory()
     obs_dev = obs_host.to(dev)
-    sh = cge.ShardedGridPosterior(ctx, N, MU_RANGE, SIGMA_RANGE, n, mode)
+    sh = cge.ShardedGridPosterior(ctx, N, MU_RANGE, SIGMA_RANGE, n, mode, exchange=args.exchange)
     post = sh.alloc_posterior()
     cells_local = sh.rows_local * N
     need_flush = cells_local * 4 <= 126e6
@@ -367,7 +368,10 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": elapsed_ms / steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64" if mode else "f32",
-            "data": "synthetic", "config": workload_config(args.workload, world),
+            "data": "synthetic", "config": dict(workload_config(args.workload, world),
+                           exchange=("none" if world == 1 else
+                                     "peer loads over NVLink fused into the results kernel (CUDA IPC)"
+                                     if sh.exchange == "p2p" else "NCCL all_reduce")),
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h, "steps": e2e_steps,
@@ -396,6 +400,7 @@ def run_ours(args):
             except Exception as e:  # the oracle is test infrastructure; never fail the GPU number on it
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
                                        "sample": f"unavailable: {e!r}"}
+    sh.close()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -415,6 +420,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-step-seconds", type=float, default=4.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", choices=["auto", "p2p", "nccl"], default="auto",
+                    help="N>1: how the N+2 float64 partial vector is summed over ranks")
     args = ap.parse_args()
     args.steps_defaulted = args.steps is None
     if args.steps is None:

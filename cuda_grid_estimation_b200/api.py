@@ -30,6 +30,7 @@ OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_DEGENERATE, ERR_NCCL, ERR_SIZE = r
 ABI_SYMBOLS = (
     "cge_create", "cge_destroy", "cge_last_error", "cge_version", "cge_device_sm_count",
     "cge_grid_posterior", "cge_likelihood_partials", "cge_partials", "cge_finalize",
+    "cge_peer_local_handle", "cge_peer_connect", "cge_peer_disconnect",
     "cge_results", "cge_read_results", "cge_posterior_dev", "cge_last_timing",
     "cge_profile_begin", "cge_profile_end", "cge_launch_count", "cge_linspace", "cge_meshgrid3", "cge_densities", "cge_densities_grid",
     "cge_row_products_rows", "cge_marginalize_rows", "cge_row_products",
@@ -84,6 +85,9 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "cge_likelihood_partials": [vp, PP, vp, vp, vp],
         "cge_partials": [vp, C.POINTER(vp), C.POINTER(sz)],
         "cge_finalize": [vp, PP, vp, vp],
+        "cge_peer_local_handle": [vp, vp, i32],
+        "cge_peer_connect": [vp, i32, i32, vp],
+        "cge_peer_disconnect": [vp],
         "cge_results": [vp, C.POINTER(vp), C.POINTER(sz)],
         "cge_read_results": [vp, PP, vp, vp, vp, C.POINTER(C.c_double), vp],
         "cge_posterior_dev": [vp, C.POINTER(vp), C.POINTER(sz)],
@@ -223,6 +227,21 @@ class Context:
 
     def finalize(self, params: Params, posterior_dev, stream=None):
         _check(self._lib.cge_finalize(self._h, C.byref(params), _ptr(posterior_dev), stream))
+
+    # ---- peer exchange over CUDA IPC -------------------------------------------------------
+    IPC_HANDLE_BYTES = 64
+
+    def peer_local_handle(self, max_grid_size: int) -> bytes:
+        buf = C.create_string_buffer(self.IPC_HANDLE_BYTES)
+        _check(self._lib.cge_peer_local_handle(self._h, buf, int(max_grid_size)))
+        return bytes(buf.raw)
+
+    def peer_connect(self, rank: int, world: int, handles: bytes):
+        assert len(handles) == world * self.IPC_HANDLE_BYTES
+        _check(self._lib.cge_peer_connect(self._h, int(rank), int(world), handles))
+
+    def peer_disconnect(self):
+        _check(self._lib.cge_peer_disconnect(self._h))
 
     def partials_ptr(self):
         ptr, cnt = C.c_void_p(), C.c_size_t()

@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -99,6 +100,12 @@ struct cge_context {
   // per-step event capture: 7 marks per step
   //   0 before tables | 1 after setup | 2 after likelihood | 3 after fold |
   //   4 before results | 5 after results | 6 after scale
+  // peer exchange (CUDA IPC): block = [flag word, padded to 256 B][buf 0: cap f64][buf 1: cap f64]
+  bool peer_on = false;
+  int peer_rank = 0, peer_world = 1;
+  size_t peer_cap = 0;                 // doubles per buffer
+  unsigned char *peer_block[cge::kMaxPeers] = {};  // [peer_rank] is this context's own allocation
+  unsigned long long peer_step = 0;    // steps completed; every rank advances in lockstep
   std::vector<cudaEvent_t> prof_events;
   int prof_cap = 0;       // steps that fit
   int prof_step = 0;      // steps captured so far
@@ -161,13 +168,21 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   else { pl->wm = 8; pl->wn = 1; }
   pl->bands = (pl->ncw + pl->wn - 1) / pl->wn;
   const int unit = pl->wm * cge::kRM;
-  // aim for >= ~24 waves of 4 resident CTAs per SM, tiles of at most 128 rows
-  const long long want_ctas = (long long)ctx->sm_count * 4 * 24;
+  // Tile height: tall enough that the per-tile column partials stay small (the fold kernel reads
+  // row_tiles*WM*N doubles) and the per-CTA prologue is amortised, short enough that the grid is
+  // still >= ~8 CTAs per resident slot.  Measured sweep: profiles/r01_tile_rows_sweep.jsonl
+  // (16..48 rows is flat for the likelihood kernel; the fold time falls with the height).
   const int span = re - (rb & ~(cge::kRM - 1));  // tiles start at a multiple of kRM (see kernel)
+  const long long want_ctas = (long long)ctx->sm_count * 2 * 8;
   long long tr = ((long long)span * pl->bands) / want_ctas;
-  tr = (tr / unit) * unit;
-  if (tr < unit) tr = unit;
-  if (tr > 128) tr = (128 / unit) * unit;
+  if (tr < 16) tr = 16;
+  if (tr > 48) tr = 48;
+  if (tr > span) tr = span;
+  tr = ((tr + unit - 1) / unit) * unit;
+  if (const char *ov = std::getenv("CGE_TILE_ROWS")) {  // tuning knob, not part of the ABI
+    long long v = std::atoll(ov);
+    if (v >= unit) tr = (v / unit) * unit;
+  }
   pl->tile_rows = (int)tr;
   pl->row_tiles = (span + pl->tile_rows - 1) / pl->tile_rows;
   pl->ncolparts = pl->row_tiles * pl->wm;
@@ -224,6 +239,15 @@ int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
     }
   }
   return launch_like<cge::ProductHybrid<2, 2, false, 1>>(pl, args, st);
+}
+
+int peer_release(cge_context *ctx);
+constexpr size_t kPeerHeader = 256;
+double *peer_buf(const cge_context *ctx, int rank, unsigned long long step) {
+  return reinterpret_cast<double *>(ctx->peer_block[rank] + kPeerHeader) + (step & 1) * ctx->peer_cap;
+}
+unsigned long long *peer_flag(const cge_context *ctx, int rank) {
+  return reinterpret_cast<unsigned long long *>(ctx->peer_block[rank]);
 }
 
 // record profiling mark `k` of the current step (no-op unless capture is on and has room)
@@ -331,6 +355,8 @@ CGE_EXPORT int cge_destroy(cge_context *ctx) {
   if (!ctx) return CGE_OK;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  cudaDeviceSynchronize();
+  peer_release(ctx);
   ctx->mu.release(); ctx->sigma.release(); ctx->obs_pad.release();
   ctx->obs_in.release(); ctx->espart.release(); ctx->tickets.release();
   ctx->posterior.release(); ctx->ad.release(); ctx->cd0.release(); ctx->rowpart.release();
@@ -424,10 +450,19 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   ctx->launches += 1;
   CKRC(mark(ctx, 2, st));
 
+  double *fold_out = ctx->partials.ptr;
+  unsigned long long *ready = nullptr;
+  if (ctx->peer_on) {  // this step's vector goes where the peers can read it
+    if ((size_t)N + 2 > ctx->peer_cap)
+      return set_error(CGE_ERR_BAD_ARG, "grid_size %d exceeds the peer exchange capacity %zu", N,
+                       ctx->peer_cap - 2);
+    fold_out = peer_buf(ctx, ctx->peer_rank, ctx->peer_step);
+    ready = peer_flag(ctx, ctx->peer_rank);
+  }
   cge::fold_partials_kernel<<<pl.nb_col + pl.nb_row, 256, 0, st>>>(
       ctx->colpart.ptr, pl.ncolparts, ctx->rowpart.ptr, pl.ncw, pl.rows_local, rb, N, ctx->mu.ptr,
-      ctx->partials.ptr, ctx->rowsum.ptr, ctx->zpart.ptr, ctx->smupart.ptr, pl.nb_col, pl.nb_row,
-      ctx->tickets.ptr);
+      fold_out, ctx->rowsum.ptr, ctx->zpart.ptr, ctx->smupart.ptr, pl.nb_col, pl.nb_row,
+      ctx->tickets.ptr, ready, ctx->peer_step + 1);
   CK(cudaGetLastError());
   ctx->launches += 1;
   CKRC(mark(ctx, 3, st));
@@ -457,9 +492,24 @@ CGE_EXPORT int cge_finalize(cge_context *ctx, const cge_params *p, float *poster
   cudaStream_t st = (cudaStream_t)stream;
   const int N = pl.N;
   CKRC(mark(ctx, 4, st));
-  cge::results_kernel<<<(N + 255) / 256, 256, 0, st>>>(ctx->partials.ptr, ctx->rowsum.ptr,
-                                                       ctx->sigma.ptr, N, rb, re, ctx->results.ptr,
-                                                       ctx->espart.ptr, ctx->tickets.ptr + 1);
+  if (ctx->peer_on) {
+    cge::PeerView pv = {};
+    pv.world = ctx->peer_world;
+    pv.want = ctx->peer_step + 1;
+    for (int r = 0; r < ctx->peer_world; ++r) {
+      pv.buf[r] = peer_buf(ctx, r, ctx->peer_step);
+      pv.flag[r] = peer_flag(ctx, r);
+    }
+    cge::results_peer_kernel<<<(N + 255) / 256, 256, 0, st>>>(
+        pv, ctx->partials.ptr, ctx->rowsum.ptr, ctx->sigma.ptr, N, rb, re, ctx->results.ptr,
+        ctx->espart.ptr, ctx->tickets.ptr + 1);
+    ctx->peer_step++;
+  } else {
+    cge::results_kernel<<<(N + 255) / 256, 256, 0, st>>>(ctx->partials.ptr, ctx->rowsum.ptr,
+                                                         ctx->sigma.ptr, N, rb, re,
+                                                         ctx->results.ptr, ctx->espart.ptr,
+                                                         ctx->tickets.ptr + 1);
+  }
   CK(cudaGetLastError());
   CKRC(mark(ctx, 5, st));
   const size_t cells = (size_t)pl.rows_local * N;
@@ -478,6 +528,83 @@ CGE_EXPORT int cge_finalize(cge_context *ctx, const cge_params *p, float *poster
   CKRC(mark(ctx, 6, st));
   if (ctx->prof_on && ctx->prof_step < ctx->prof_cap) ctx->prof_step++;
   return CGE_OK;
+}
+
+// ---------------------------------------------------------------------------------------
+// peer exchange over CUDA IPC (one process per GPU, one node)
+// ---------------------------------------------------------------------------------------
+namespace {
+int peer_release(cge_context *ctx) {
+  for (int r = 0; r < cge::kMaxPeers; ++r) {
+    if (!ctx->peer_block[r]) continue;
+    if (r == ctx->peer_rank) cudaFree(ctx->peer_block[r]);
+    else cudaIpcCloseMemHandle(ctx->peer_block[r]);
+    ctx->peer_block[r] = nullptr;
+  }
+  ctx->peer_on = false;
+  ctx->peer_world = 1;
+  ctx->peer_rank = 0;
+  ctx->peer_cap = 0;
+  ctx->peer_step = 0;
+  return CGE_OK;
+}
+}  // namespace
+
+CGE_EXPORT int cge_peer_local_handle(cge_context *ctx, void *handle, int max_grid_size) {
+  CKRC(bind(ctx));
+  static_assert(sizeof(cudaIpcMemHandle_t) == CGE_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!handle || max_grid_size < 1) return set_error(CGE_ERR_BAD_ARG, "peer_local_handle: bad argument");
+  CK(cudaStreamSynchronize(ctx->stream));
+  peer_release(ctx);
+  ctx->peer_cap = (((size_t)max_grid_size + 2) + 31) & ~(size_t)31;
+  const size_t bytes = kPeerHeader + 2 * ctx->peer_cap * sizeof(double);
+  unsigned char *block = nullptr;
+  CK(cudaMalloc(&block, bytes));
+  CK(cudaMemset(block, 0, bytes));
+  CK(cudaDeviceSynchronize());
+  ctx->peer_block[0] = block;  // parked at slot 0 until cge_peer_connect tells us our rank
+  cudaIpcMemHandle_t h;
+  CK(cudaIpcGetMemHandle(&h, block));
+  std::memcpy(handle, &h, sizeof h);
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_peer_connect(cge_context *ctx, int rank, int world, const void *handles) {
+  CKRC(bind(ctx));
+  if (!handles || world < 2 || world > cge::kMaxPeers || rank < 0 || rank >= world)
+    return set_error(CGE_ERR_BAD_ARG, "peer_connect: need 2..%d ranks", cge::kMaxPeers);
+  if (!ctx->peer_block[0] || ctx->peer_on)
+    return set_error(CGE_ERR_BAD_ARG, "peer_connect: call cge_peer_local_handle first");
+  unsigned char *mine = ctx->peer_block[0];
+  ctx->peer_block[0] = nullptr;
+  ctx->peer_rank = rank;
+  ctx->peer_block[rank] = mine;
+  const unsigned char *hb = static_cast<const unsigned char *>(handles);
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) continue;
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, hb + (size_t)r * sizeof h, sizeof h);
+    void *p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      ctx->peer_world = world;
+      peer_release(ctx);
+      return set_error(CGE_ERR_CUDA, "cudaIpcOpenMemHandle for rank %d failed: %s", r,
+                       cudaGetErrorString(e));
+    }
+    ctx->peer_block[r] = static_cast<unsigned char *>(p);
+  }
+  ctx->peer_world = world;
+  ctx->peer_step = 0;
+  ctx->peer_on = true;
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_peer_disconnect(cge_context *ctx) {
+  CKRC(bind(ctx));
+  CK(cudaDeviceSynchronize());
+  return peer_release(ctx);
 }
 
 CGE_EXPORT int cge_results(cge_context *ctx, double **results_dev, size_t *count) {

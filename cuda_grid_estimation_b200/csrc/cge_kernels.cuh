@@ -111,32 +111,36 @@ __global__ void __launch_bounds__(256)
     q += d * d;
   }
   const double ss = block_sum(q, scratch);
-  if (tid != 0) return;
+  if (tid >= 32) return;
 
-  auto candidates = [N](double pos, int (&c)[6]) {
+  // candidate grid indices around a continuous optimum `pos`: both ends + 4 neighbours;
+  // lane t < 6 evaluates candidate t, the rest of warp 0 idles through the shuffles
+  auto candidate = [N](double pos, int t) {
     if (!(pos == pos) || pos < 0.0) pos = 0.0;          // NaN / below range
     if (pos > (double)(N - 1)) pos = (double)(N - 1);
     const int f = (int)pos;
-    c[0] = 0;
-    c[1] = N - 1;
-    for (int t = 0; t < 4; ++t) c[2 + t] = min(max(f - 1 + t, 0), N - 1);
+    if (t == 0) return 0;
+    if (t == 1) return N - 1;
+    return min(max(f - 3 + t, 0), N - 1);
   };
-  int cand[6];
   const double mspan = (double)mu1 - (double)mu0;
-  candidates(mspan != 0.0 ? (xbar - (double)mu0) / mspan * (double)(N - 1) : 0.0, cand);
+  const double mpos = mspan != 0.0 ? (xbar - (double)mu0) / mspan * (double)(N - 1) : 0.0;
   double smin = 1.0 / 0.0;
-  for (int t = 0; t < 6; ++t) {
-    const double d = xbar - (double)range_value(cand[t], N, mu0, mu1);
-    smin = fmin(smin, ss + (double)n * d * d);
+  if (tid < 6) {
+    const double d = xbar - (double)range_value(candidate(mpos, tid), N, mu0, mu1);
+    smin = ss + (double)n * d * d;
   }
+  smin = warp_min(smin);
   const double sspan = (double)sg1 - (double)sg0;
-  candidates(sspan != 0.0 ? (sqrt(smin / (double)n) - (double)sg0) / sspan * (double)(N - 1) : 0.0,
-             cand);
+  const double spos =
+      sspan != 0.0 ? (sqrt(smin / (double)n) - (double)sg0) / sspan * (double)(N - 1) : 0.0;
   double m2 = -1.0 / 0.0;
-  for (int t = 0; t < 6; ++t) {
-    const double sd = (double)range_value(cand[t], N, sg0, sg1);
-    m2 = fmax(m2, coef_a(sd) * smin + (double)n * coef_c0(sd));
+  if (tid < 6) {
+    const double sd = (double)range_value(candidate(spos, tid), N, sg0, sg1);
+    m2 = coef_a(sd) * smin + (double)n * coef_c0(sd);
   }
+  m2 = warp_max(m2);
+  if (tid != 0) return;
   out->log2s = (kPeakLog2 - m2) / (double)n;
   out->shift = kPeakLog2 - m2;
   out->m2 = m2;
@@ -538,7 +542,8 @@ __global__ void __launch_bounds__(256)
                          int row_begin, int N, const float *__restrict__ mu,
                          double *__restrict__ partials, double *__restrict__ rowsum,
                          double *__restrict__ zpart, double *__restrict__ smupart, int nb_col,
-                         int nb_row, unsigned int *__restrict__ ticket) {
+                         int nb_row, unsigned int *__restrict__ ticket,
+                         unsigned long long *ready_flag, unsigned long long ready_value) {
   __shared__ double sh[8][33];
   __shared__ bool is_last;
   const int tid = threadIdx.x;
@@ -621,6 +626,14 @@ __global__ void __launch_bounds__(256)
     partials[0] = zt;
     partials[1] = mt;
     *ticket = 0u;  // ready for the next launch on this stream
+    if (ready_flag) {
+      // peer exchange: every block's column sums are ordered before this point by the ticket
+      // (fence + atomic); publish "the partial vector of step `ready_value - 1` is complete"
+      // to the other GPUs, which poll this word over NVLink
+      __threadfence_system();
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ready_flag), "l"(ready_value)
+                   : "memory");
+    }
   }
 }
 
@@ -660,6 +673,97 @@ __global__ void __launch_bounds__(256)
   e = block_sum(e, scratch);
   if (tid == 0) {
     results[0] = partials[1] * inv;
+    results[1] = e;
+    results[2] = z;
+    results[3] = inv;
+    *ticket = 0u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------
+// stage 2 with the exchange fused in (one process per GPU, one node): instead of a library
+// all-reduce between the fold and this kernel, every rank reads the peers' partial vectors
+// straight out of their HBM over NVLink (CUDA IPC mappings) and adds them in RANK ORDER -- the
+// sum is bit-identical on every rank and independent of any collective algorithm.
+//   peers.buf[r]   rank r's partial vector for this step (N+2 f64; this rank's own included)
+//   peers.flag[r]  rank r's "step s complete" word; polled with ld.acquire.sys until >= want
+// A rank may overwrite its vector of step s at step s+2: by then it has itself waited for every
+// peer's step-(s+1) flag, which each peer raises only after its own step-s results kernel.
+// The poll gives up after ~4e9 cycles and poisons the result (Z = NaN -> CGE_ERR_DEGENERATE).
+// ---------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerView {
+  const double *buf[kMaxPeers];
+  const unsigned long long *flag[kMaxPeers];
+  int world;
+  unsigned long long want;
+};
+
+__device__ __forceinline__ double ld_peer(const double *p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(256)
+    results_peer_kernel(const PeerView peers, double *__restrict__ partials,
+                        const double *__restrict__ rowsum, const float *__restrict__ sigma, int N,
+                        int row_begin, int row_end, double *__restrict__ results,
+                        double *__restrict__ espart, unsigned int *__restrict__ ticket) {
+  __shared__ double scratch[32];
+  __shared__ bool is_last;
+  __shared__ int timed_out;
+  const int tid = threadIdx.x;
+  if (tid == 0) timed_out = 0;
+  __syncthreads();
+  if (tid < peers.world) {  // one lane per peer polls that peer's flag
+    const long long t0 = clock64();
+    unsigned long long v;
+    do {
+      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(peers.flag[tid]) : "memory");
+      if (v >= peers.want) break;
+      if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }
+      __nanosleep(100);
+    } while (true);
+  }
+  __syncthreads();
+  __threadfence_system();
+  double z = 0.0, smu = 0.0;
+  for (int r = 0; r < peers.world; ++r) {  // rank order: same bits on every rank
+    z += ld_peer(peers.buf[r]);
+    smu += ld_peer(peers.buf[r] + 1);
+  }
+  if (timed_out) z = __longlong_as_double(0x7ff8000000000000LL);
+  const double inv = 1 / z;
+  double *marg_sigma = results + 4, *marg_mu = results + 4 + N;
+  const int idx = blockIdx.x * 256 + tid;
+  double es = 0.0;
+  if (idx < N) {
+    double c = 0.0;
+    for (int r = 0; r < peers.world; ++r) c += ld_peer(peers.buf[r] + 2 + idx);
+    partials[2 + idx] = c;  // the summed vector, for callers that read cge_partials afterwards
+    const double m = c * inv;
+    marg_sigma[idx] = m;
+    es = m * (double)sigma[idx];
+    marg_mu[idx] = (idx >= row_begin && idx < row_end) ? rowsum[idx - row_begin] * inv : 0.0;
+  }
+  if (blockIdx.x == 0 && tid == 0) {
+    partials[0] = z;  // the scale pass reads Z from here
+    partials[1] = smu;
+  }
+  es = block_sum(es, scratch);
+  if (tid == 0) espart[blockIdx.x] = es;
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+  double e = 0.0;
+  for (int b = tid; b < (int)gridDim.x; b += 256) e += __ldcg(espart + b);
+  e = block_sum(e, scratch);
+  if (tid == 0) {
+    results[0] = smu * inv;
     results[1] = e;
     results[2] = z;
     results[3] = inv;

@@ -55,10 +55,16 @@ def finalize_from_partials(partials: np.ndarray, rowsum_local: np.ndarray, sigma
 
 class ShardedGridPosterior:
     """One process per GPU.  Each call enqueues, on torch's current stream:
-    likelihood + local fold  ->  all_reduce(P)  ->  results + in-place scale of the local rows.
-    With world_size == 1 the all-reduce is skipped."""
+    likelihood + local fold  ->  exchange of P  ->  results + in-place scale of the local rows.
 
-    def __init__(self, ctx, grid_size, mu_range, sigma_range, n_obs, mode=0, group=None, variant=0):
+    exchange="p2p" (default for world_size > 1): the ranks swap CUDA IPC handles once (through
+    torch.distributed), after which the results kernel reads the peers' partial vectors over
+    NVLink and adds them in rank order itself -- no collective launch in the step.
+    exchange="nccl": torch.distributed.all_reduce of P between the two phases.
+    With world_size == 1 there is no exchange."""
+
+    def __init__(self, ctx, grid_size, mu_range, sigma_range, n_obs, mode=0, group=None, variant=0,
+                 exchange="p2p"):
         import torch
         import torch.distributed as dist
         from .api import make_params
@@ -74,6 +80,50 @@ class ShardedGridPosterior:
         self.params = make_params(n_obs, grid_size, mu_range, sigma_range, mode, self.rows, variant)
         self.grid_size = grid_size
         self._partials = None
+        if exchange not in ("p2p", "nccl", "auto"):
+            raise ValueError(f"unknown exchange {exchange!r}")
+        self.exchange = exchange if self.world > 1 else "none"
+        if self.exchange in ("p2p", "auto"):
+            self.exchange = self._connect_peers(exchange == "auto")
+
+    def _connect_peers(self, may_fall_back: bool) -> str:
+        """CUDA IPC handshake through torch.distributed.  With may_fall_back the ranks agree
+        (all-reduce of a success flag) to use the NCCL exchange if any of them could not map a
+        peer -- both are GPU paths; there is no CPU path to fall back to."""
+        from .api import CgeError
+        dist, ctx, torch = self.dist, self.ctx, self.torch
+        err = None
+        try:
+            mine = ctx.peer_local_handle(self.grid_size)
+        except CgeError as e:
+            mine, err = b"\0" * ctx.IPC_HANDLE_BYTES, e
+        gathered = [None] * self.world
+        dist.all_gather_object(gathered, mine, group=self.group)
+        if err is None:
+            try:
+                ctx.peer_connect(self.rank, self.world, b"".join(gathered))
+            except CgeError as e:
+                err = e
+        ok = torch.tensor([0 if err else 1], dtype=torch.int32,
+                          device=torch.device("cuda", ctx.device))
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)
+        if int(ok.item()) == 1:
+            return "p2p"
+        try:
+            ctx.peer_disconnect()
+        except CgeError:
+            pass
+        if not may_fall_back:
+            raise err if err else RuntimeError("a peer rank could not set up the CUDA IPC exchange")
+        return "nccl"
+
+    def close(self):
+        """Collective: every rank must call it before its context is destroyed."""
+        if self.exchange == "p2p":
+            self.torch.cuda.synchronize()
+            self.dist.barrier(group=self.group)
+            self.ctx.peer_disconnect()
+            self.exchange = "none"
 
     @property
     def rows_local(self) -> int:
@@ -88,7 +138,7 @@ class ShardedGridPosterior:
         from .api import device_tensor
         stream = self.torch.cuda.current_stream().cuda_stream
         self.ctx.likelihood_partials(self.params, obs_dev, posterior_dev, stream)
-        if self.world > 1:
+        if self.exchange == "nccl":
             ptr, cnt = self.ctx.partials_ptr()
             if self._partials is None or self._partials.data_ptr() != ptr:
                 self._partials = device_tensor(ptr, cnt, "float64", self.ctx.device)

@@ -132,6 +132,21 @@ int cge_grid_posterior(cge_context *ctx, const cge_params *p, const float *obs,
  * phase 2: marginals, expectations and the in-place scale posterior_dev *= 1/Z.
  *          Results stay on the device in the context's result block (cge_results).
  */
+/* Peer exchange (optional; one process per GPU on ONE node): replaces "the caller sums the partial
+ * vector" by peer loads over NVLink fused into phase 2.  Each rank allocates an exchange block and
+ * exports its CUDA IPC handle (cge_peer_local_handle), the caller gathers the handles of all ranks
+ * (any transport) and hands the concatenation, in rank order, to cge_peer_connect.  From then on
+ * cge_likelihood_partials publishes this rank's vector to the peers and cge_finalize waits for
+ * theirs and adds all of them in rank order inside the results kernel -- no library collective,
+ * bit-identical totals on every rank.  Every rank must make the same sequence of phase calls.
+ * Ranks must not destroy/disconnect while a peer may still be reading (barrier first). */
+#define CGE_IPC_HANDLE_BYTES 64
+int cge_peer_local_handle(cge_context *ctx, void *handle /* CGE_IPC_HANDLE_BYTES out */,
+                          int max_grid_size);
+int cge_peer_connect(cge_context *ctx, int rank, int world,
+                     const void *handles /* world * CGE_IPC_HANDLE_BYTES, rank order */);
+int cge_peer_disconnect(cge_context *ctx);
+
 int cge_likelihood_partials(cge_context *ctx, const cge_params *p, const float *obs_dev,
                             float *posterior_dev, void *stream);
 int cge_partials(cge_context *ctx, double **partials_dev, size_t *count);
