@@ -167,7 +167,10 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   else if (pl->ncw >= 2) { pl->wm = 4; pl->wn = 2; }
   else { pl->wm = 8; pl->wn = 1; }
   pl->bands = (pl->ncw + pl->wn - 1) / pl->wn;
-  const int unit = pl->wm * cge::kRM;
+  // tile heights are multiples of the patch rows of every warp row and of the global alignment
+  const int patch_rows = p->mode == CGE_MODE_LOGSPACE ? cge::LogSpaceF64::kRows : cge::kRM;
+  int unit = pl->wm * patch_rows;
+  if (unit % cge::kRM) unit *= cge::kRM / patch_rows;
   // Tile height: tall enough that the per-tile column partials stay small (the fold kernel reads
   // row_tiles*WM*N doubles) and the per-CTA prologue is amortised, short enough that the grid is
   // still >= ~8 CTAs per resident slot.  Measured sweep: profiles/r01_tile_rows_sweep.jsonl

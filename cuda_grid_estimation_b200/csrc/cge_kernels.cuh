@@ -30,7 +30,8 @@ namespace cge {
 // 166 bits (1e-50 relative to the peak) below it before a cell flushes to zero.
 constexpr double kPeakLog2 = 40.0;
 
-constexpr int kRM = 4;            // register patch: rows (mu) per thread
+constexpr int kRM = 4;            // register patch rows (mu) per thread for the product policies;
+                                  // also the row alignment of every tile (Policy::kRows divides it)
 constexpr int kRN = 4;            // columns (sigma) per thread and float4 store; a policy owns
                                   // Policy::kCols = 4 or 8 columns = 1 or 2 such groups
 constexpr int kGroupCols = 32 * kRN;  // 128 columns: one float4 per lane across a warp
@@ -63,7 +64,7 @@ struct LikeArgs {
   double *colpart;  // [ncolparts][N]
   int n, n_pad, N;  // n observations; n_pad staged floats (multiple of 4)
   int row_begin, row_end;
-  int tile_rows;    // rows per CTA tile, multiple of WM*kRM
+  int tile_rows;    // rows per CTA tile, multiple of WM*Policy::kRows and of kRM
   int ncw;          // column strips per row: ceil(N / (32 * Policy::kCols))
 };
 
@@ -155,12 +156,13 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------
 template <class Policy>
 __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs, int count,
-                                                   const float (&mu)[kRM]);
+                                                   const float (&mu)[Policy::kRows]);
 
 // float32 product path: per pdf-eval one FFMA (exponent), one MUFU.EX2, one FMUL (running
 // product); the subtract and square are shared by the kRN columns of a row.
 //   factor_k = 2^(a_j*(x_k-mu_i)^2 + c_j),  c_j = c0_j + log2 s   (constants FMA-folded)
 struct ProductF32 {
+  static constexpr int kRows = kRM;
   static constexpr int kCols = 4;
   static constexpr int kObsStride = 1;  // floats of shared memory per observation
   static __device__ __forceinline__ void consume(ProductF32 &pol, const float *xs, int count,
@@ -215,10 +217,12 @@ struct ProductF32 {
 // cell after 10^4 observations) and widened once per (row, observation); 8 columns per thread
 // amortise that widening over 8 evaluations.
 struct LogSpaceF64 {
+  static constexpr int kRows = 4;   // 4 x 8 patch (a 2 x 8 patch measured 4 % slower: the bound is
+                                    // the FP64 pipe's operand bandwidth, not occupancy)
   static constexpr int kCols = 8;
   static constexpr int kObsStride = 1;
   static __device__ __forceinline__ void consume(LogSpaceF64 &pol, const float *xs, int count,
-                                                 const float (&mu)[kRM]) {
+                                                 const float (&mu)[kRows]) {
     const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
     const int n4 = count >> 2;
 #pragma unroll 1
@@ -232,7 +236,7 @@ struct LogSpaceF64 {
     for (int k = n4 << 2; k < count; ++k) pol.step(xs[k], mu);
   }
   double a[kCols];
-  double acc[kRM][kCols];
+  double acc[kRows][kCols];
   double shift_;
   int jbase_;
 
@@ -248,19 +252,19 @@ struct LogSpaceF64 {
   }
   __device__ __forceinline__ void begin_rows() {
 #pragma unroll
-    for (int r = 0; r < kRM; ++r)
+    for (int r = 0; r < kRows; ++r)
 #pragma unroll
       for (int cidx = 0; cidx < kCols; ++cidx) acc[r][cidx] = 0.0;
   }
-  __device__ __forceinline__ void step(float x, const float (&mu)[kRM]) {
-    double dd[kRM];
+  __device__ __forceinline__ void step(float x, const float (&mu)[kRows]) {
+    double dd[kRows];
 #pragma unroll
-    for (int r = 0; r < kRM; ++r) {
+    for (int r = 0; r < kRows; ++r) {
       const float d = x - mu[r];
       dd[r] = (double)(d * d);
     }
 #pragma unroll
-    for (int r = 0; r < kRM; ++r)
+    for (int r = 0; r < kRows; ++r)
 #pragma unroll
       for (int cidx = 0; cidx < kCols; ++cidx) acc[r][cidx] = fma(dd[r], a[cidx], acc[r][cidx]);
   }
@@ -275,7 +279,7 @@ struct LogSpaceF64 {
 // consume `count` observations from shared memory (16-byte aligned), four per LDS.128 broadcast
 template <class Policy>
 __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs, int count,
-                                                   const float (&mu)[kRM]) {
+                                                   const float (&mu)[Policy::kRows]) {
   const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
   const int n4 = count >> 2;
 #pragma unroll 2
@@ -303,6 +307,7 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 // ---------------------------------------------------------------------------------------
 template <int NPA, int NPB, bool SCALAR_POLY = false, int OBS_PER_ITER = 4>
 struct ProductHybrid {
+  static constexpr int kRows = kRM;
   static constexpr int kCols = 4;
   static constexpr int kObsStride = 1;
   f32x2 a2[kRN / 2], c2[kRN / 2];
@@ -407,6 +412,7 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int wn = warp % WN, wm = warp / WN;
+  constexpr int kRows = Policy::kRows;            // rows per thread: 4 or 2
   constexpr int kCols = Policy::kCols;            // columns per thread: 4 or 8
   constexpr int kGroups = kCols / kRN;            // float4 groups per thread
   const int cw = blockIdx.x * WN + wn;            // global column-strip index (32*kCols columns)
@@ -415,7 +421,7 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
   // patch (hence which exponential path it takes) depends on its GLOBAL row only: a row shard
   // computes bit-identical unnormalised cells to the single-GPU run
   const int tile_row0 = (g.row_begin & ~(kRM - 1)) + blockIdx.y * g.tile_rows;
-  const int groups = g.tile_rows / (WM * kRM);    // row groups this warp walks
+  const int groups = g.tile_rows / (WM * kRows);    // row groups this warp walks
   constexpr int kStride = Policy::kObsStride;        // staged floats per observation
   constexpr int kChunkObs = kObsChunk / kStride;     // observations per streamed chunk
   const bool streamed = g.n_pad > kObsSingleMax;      // n_pad counts staged floats
@@ -446,22 +452,22 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
   for (int cidx = 0; cidx < kCols; ++cidx) colacc[cidx] = 0.0;
   const bool col_any = j0 < g.N;  // columns only grow with cidx
 
-  float mu[kRM];
+  float mu[kRows];
   int row = 0;
   bool rows_any = false;
 
   auto begin_group = [&](int grp) {
-    row = tile_row0 + (grp * WM + wm) * kRM;
-    rows_any = row < g.row_end && row + kRM > g.row_begin;
+    row = tile_row0 + (grp * WM + wm) * kRows;
+    rows_any = row < g.row_end && row + kRows > g.row_begin;
 #pragma unroll
-    for (int r = 0; r < kRM; ++r) mu[r] = g.mu[min(row + r, g.N - 1)];  // row >= 0 always
+    for (int r = 0; r < kRows; ++r) mu[r] = g.mu[min(row + r, g.N - 1)];  // row >= 0 always
     pol.begin_rows();
   };
 
   auto end_group = [&]() {
     if (!rows_any) return;  // warp-uniform
 #pragma unroll
-    for (int r = 0; r < kRM; ++r) {
+    for (int r = 0; r < kRows; ++r) {
       const bool rv = row + r >= g.row_begin && row + r < g.row_end;
       float v[kCols];
       double rs = 0.0;
