@@ -8,7 +8,7 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcge.so")
-SOURCES = ["cge_api.cu"]
+SOURCES = ["cge_api.cu", "cge_extras.cu"]
 HEADERS = ["cge_kernels.cuh", "cge_device.cuh", os.path.join("..", "..", "include", "cge.h")]
 
 NVCC_FLAGS = [

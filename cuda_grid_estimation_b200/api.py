@@ -35,6 +35,7 @@ ABI_SYMBOLS = (
     "cge_profile_begin", "cge_profile_end", "cge_launch_count", "cge_linspace", "cge_meshgrid3", "cge_densities", "cge_densities_grid",
     "cge_row_products_rows", "cge_marginalize_rows", "cge_row_products",
     "cge_normalize", "cge_marginalize", "cge_expectation", "cge_microbench",
+    "cge_generate_normal", "cge_quantiles", "cge_set_prior",
 )
 
 
@@ -106,6 +107,9 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "cge_marginalize": [vp, vp, vp, i32, i32, i32],
         "cge_expectation": [vp, vp, vp, i32, C.POINTER(C.c_double)],
         "cge_microbench": [vp, i32, C.POINTER(C.c_double)],
+        "cge_generate_normal": [vp, vp, i32, f32, f32, C.c_ulonglong, i32],
+        "cge_quantiles": [vp, vp, i32, vp, i32, vp, vp],
+        "cge_set_prior": [vp, vp, vp, i32, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -309,6 +313,37 @@ class Context:
         _check(self._lib.cge_expectation(self._h, _ptr(marginal), _ptr(vector), int(size),
                                          C.byref(out)))
         return out.value
+
+
+    # -- methods appended for the "next" rows (bound late to keep Context readable) --
+
+
+def _generate_normal(self, out_dev, n, mu, sigma, seed=42, zero_state=False):
+    """Reference observation generator (cuRAND XORWOW); out_dev is a CUDA float32 tensor."""
+    _check(self._lib.cge_generate_normal(self._h, _ptr(out_dev), int(n), float(mu), float(sigma),
+                                         int(seed), 1 if zero_state else 0))
+
+
+def _quantiles(self, marginal_dev, n, probs, cdf_dev=None):
+    """First index whose cumulative mass exceeds each p; marginal_dev is a CUDA float64 tensor."""
+    probs = np.ascontiguousarray(probs, np.float64)
+    idx = np.empty(probs.size, np.int32)
+    _check(self._lib.cge_quantiles(self._h, _ptr(marginal_dev), int(n), probs.ctypes.data,
+                                   probs.size, idx.ctypes.data, _ptr(cdf_dev)))
+    return idx
+
+
+def _set_prior(self, prior_mu=None, prior_sigma=None, grid_size=0, prior_full=None):
+    """Non-flat prior for the following calls; all None restores the flat prior."""
+    keep = [np.ascontiguousarray(a, np.float32) if isinstance(a, (np.ndarray, list, tuple)) else a
+            for a in (prior_mu, prior_sigma)]
+    _check(self._lib.cge_set_prior(self._h, _ptr(keep[0]), _ptr(keep[1]), int(grid_size),
+                                   _ptr(prior_full)))
+
+
+Context.set_prior = _set_prior
+Context.generate_normal = _generate_normal
+Context.quantiles = _quantiles
 
 
 class _DeviceView:

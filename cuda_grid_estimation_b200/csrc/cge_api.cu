@@ -92,6 +92,10 @@ struct cge_context {
   DevBuf<float> mu, sigma, obs_pad, obs_in, posterior;
   DevBuf<double> ad, cd0, rowpart, colpart, partials, rowsum, zpart, smupart, espart, results, tmp;
   DevBuf<unsigned int> tickets;  // [0] fold, [1] results; zero between launches
+  DevBuf<float> prior_mu, prior_sigma;   // owned copies of the separable prior factors
+  bool has_prior_mu = false, has_prior_sigma = false;
+  int prior_n = 0;
+  const float *prior_full = nullptr;     // caller-owned device table, shard layout
   DevBuf<cge::ScaleInfo> scale;
   DevBuf<float> sink;
   Plan plan;
@@ -361,7 +365,7 @@ CGE_EXPORT int cge_destroy(cge_context *ctx) {
   cudaDeviceSynchronize();
   peer_release(ctx);
   ctx->mu.release(); ctx->sigma.release(); ctx->obs_pad.release();
-  ctx->obs_in.release(); ctx->espart.release(); ctx->tickets.release();
+  ctx->obs_in.release(); ctx->espart.release(); ctx->tickets.release(); ctx->prior_mu.release(); ctx->prior_sigma.release();
   ctx->posterior.release(); ctx->ad.release(); ctx->cd0.release(); ctx->rowpart.release();
   ctx->colpart.release(); ctx->partials.release(); ctx->rowsum.release(); ctx->zpart.release();
   ctx->smupart.release(); ctx->results.release(); ctx->tmp.release(); ctx->scale.release();
@@ -432,6 +436,11 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   args.ad = ctx->ad.ptr;
   args.cd0 = ctx->cd0.ptr;
   args.scale = ctx->scale.ptr;
+  if ((ctx->has_prior_mu || ctx->has_prior_sigma) && ctx->prior_n != N)
+    return set_error(CGE_ERR_BAD_ARG, "prior was set for grid_size %d, call has %d", ctx->prior_n, N);
+  args.prior_mu = ctx->has_prior_mu ? ctx->prior_mu.ptr : nullptr;
+  args.prior_sigma = ctx->has_prior_sigma ? ctx->prior_sigma.ptr : nullptr;
+  args.prior_full = ctx->prior_full;
   args.post = posterior_dev;
   args.rowpart = ctx->rowpart.ptr;
   args.colpart = ctx->colpart.ptr;
@@ -469,6 +478,32 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   CK(cudaGetLastError());
   ctx->launches += 1;
   CKRC(mark(ctx, 3, st));
+  return CGE_OK;
+}
+
+// optional non-flat prior for the following calls (NULL, NULL, n, NULL restores the flat prior)
+CGE_EXPORT int cge_set_prior(cge_context *ctx, const float *prior_mu, const float *prior_sigma,
+                             int grid_size, const float *prior_full_dev) {
+  CKRC(bind(ctx));
+  if ((prior_mu || prior_sigma) && grid_size < 1)
+    return set_error(CGE_ERR_BAD_ARG, "set_prior: grid_size must be >= 1");
+  CK(cudaStreamSynchronize(ctx->stream));
+  ctx->has_prior_mu = ctx->has_prior_sigma = false;
+  ctx->prior_n = grid_size;
+  if (prior_mu) {
+    CKRC(ctx->prior_mu.reserve(grid_size));
+    CK(cudaMemcpy(ctx->prior_mu.ptr, prior_mu, (size_t)grid_size * sizeof(float), cudaMemcpyDefault));
+    ctx->has_prior_mu = true;
+  }
+  if (prior_sigma) {
+    CKRC(ctx->prior_sigma.reserve(grid_size));
+    CK(cudaMemcpy(ctx->prior_sigma.ptr, prior_sigma, (size_t)grid_size * sizeof(float),
+                  cudaMemcpyDefault));
+    ctx->has_prior_sigma = true;
+  }
+  if (prior_full_dev && !is_device_pointer(prior_full_dev))
+    return set_error(CGE_ERR_BAD_ARG, "set_prior: the full prior table must be device memory");
+  ctx->prior_full = prior_full_dev;
   return CGE_OK;
 }
 
@@ -888,6 +923,17 @@ CGE_EXPORT int cge_expectation(cge_context *ctx, const double *marginal, const f
   CK(cudaStreamSynchronize(ctx->stream));
   return CGE_OK;
 }
+
+// ---------------------------------------------------------------------------------------
+// hooks for the other translation unit (cge_extras.cu); not part of the public ABI
+// ---------------------------------------------------------------------------------------
+extern "C" int cge_internal_stream(cge_context *ctx, void **stream, int *sm_count) {
+  CKRC(bind(ctx));
+  if (stream) *stream = ctx->stream;
+  if (sm_count) *sm_count = ctx->sm_count;
+  return CGE_OK;
+}
+extern "C" int cge_internal_error(int code, const char *msg) { return set_error(code, "%s", msg); }
 
 // ---------------------------------------------------------------------------------------
 // pipe-peak micro-benchmarks

@@ -59,6 +59,11 @@ struct LikeArgs {
   const double *ad;
   const double *cd0;
   const ScaleInfo *scale;
+  // optional prior (NULL = flat, the reference's case): separable factors indexed by the global
+  // mu row / sigma column, and/or a full table laid out like this shard of the posterior
+  const float *prior_mu;
+  const float *prior_sigma;
+  const float *prior_full;
   float *post;      // shard base (row `row_begin` at offset 0)
   double *rowpart;  // [rows_local][ncw]
   double *colpart;  // [ncolparts][N]
@@ -451,6 +456,7 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
 #pragma unroll
   for (int cidx = 0; cidx < kCols; ++cidx) colacc[cidx] = 0.0;
   const bool col_any = j0 < g.N;  // columns only grow with cidx
+  const bool has_prior = g.prior_mu || g.prior_sigma || g.prior_full;
 
   float mu[kRows];
   int row = 0;
@@ -473,8 +479,15 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
       double rs = 0.0;
 #pragma unroll
       for (int cidx = 0; cidx < kCols; ++cidx) {
-        const bool ok = rv && (patch_col(j0, cidx) < g.N);
+        const int j = patch_col(j0, cidx);
+        const bool ok = rv && (j < g.N);
         v[cidx] = ok ? pol.value(g, r, cidx) : 0.0f;
+        if (has_prior && ok) {  // likelihood x prior before normalisation (cuda_functions.h:145-148)
+          if (g.prior_mu) v[cidx] *= g.prior_mu[row + r];
+          if (g.prior_sigma) v[cidx] *= g.prior_sigma[j];
+          if (g.prior_full)
+            v[cidx] *= g.prior_full[(size_t)(row + r - g.row_begin) * (size_t)g.N + j];
+        }
         rs += (double)v[cidx];
         colacc[cidx] += (double)v[cidx];
       }

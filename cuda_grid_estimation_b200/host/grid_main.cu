@@ -6,7 +6,10 @@
 // src/grid.cu:129-132.
 //
 //   grid [--grid N] [--obs n] [--mu a b] [--sigma a b] [--true-mu m] [--true-sigma s]
-//        [--mode product|log] [--obs-file path] [--seed k] [--timing]
+//        [--mode product|log] [--obs-file path] [--seed k] [--curand] [--timing]
+//   --curand draws the observations on the device exactly like the reference's
+//   generateNormalCuda (cuRAND XORWOW, seed 42): with no other argument the program then
+//   reproduces bin/grid's run, observation for observation.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,13 +17,15 @@
 #include <random>
 #include <vector>
 
+#include <cuda_runtime.h>
+
 #include "../../include/cge.h"
 
 int main(int argc, char **argv) {
   int N = 101, n = 50, mode = CGE_MODE_PRODUCT_F32, seed = 42;
   float mu = 20.0f, sigma = 2.0f;
   float mu0 = mu - 2, mu1 = mu + 2, sg0 = sigma - 1, sg1 = sigma + 1;  // src/grid.cu:67-70
-  bool ranges_set = false, timing = false;
+  bool ranges_set = false, timing = false, use_curand = false;
   const char *obs_file = nullptr;
   for (int i = 1; i < argc; ++i) {
     auto need = [&](int k) { if (i + k >= argc) { std::fprintf(stderr, "missing value for %s\n", argv[i]); std::exit(2); } };
@@ -34,12 +39,29 @@ int main(int argc, char **argv) {
     else if (!std::strcmp(argv[i], "--obs-file")) { need(1); obs_file = argv[++i]; }
     else if (!std::strcmp(argv[i], "--seed")) { need(1); seed = std::atoi(argv[++i]); }
     else if (!std::strcmp(argv[i], "--timing")) timing = true;
+    else if (!std::strcmp(argv[i], "--curand")) use_curand = true;
     else { std::fprintf(stderr, "unknown argument %s\n", argv[i]); return 2; }
   }
   if (!ranges_set) { mu0 = mu - 2; mu1 = mu + 2; sg0 = sigma - 1; sg1 = sigma + 1; }
 
+  cge_context *ctx = nullptr;
+  if (cge_create(0, &ctx) != CGE_OK) {
+    std::fprintf(stderr, "Error: %s\n", cge_last_error());
+    return EXIT_FAILURE;
+  }
   std::vector<float> obs;
-  if (obs_file) {
+  if (use_curand) {
+    float *dev = nullptr;
+    cudaMalloc(&dev, n * sizeof(float));
+    if (cge_generate_normal(ctx, dev, n, mu, sigma, (unsigned long long)seed, 0) != CGE_OK) {
+      std::fprintf(stderr, "Error: %s\n", cge_last_error());
+      return EXIT_FAILURE;
+    }
+    obs.resize(n);
+    cudaMemcpy(obs.data(), dev, n * sizeof(float), cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    std::printf("observations[0] = %.4f\n", obs[0]);  // the reference checks 18.5689 (grid.cu:41-47)
+  } else if (obs_file) {
     FILE *f = std::fopen(obs_file, "rb");
     if (!f) { std::fprintf(stderr, "cannot open %s\n", obs_file); return 2; }
     float v;
@@ -53,11 +75,6 @@ int main(int argc, char **argv) {
     for (auto &x : obs) x = dist(gen);
   }
 
-  cge_context *ctx = nullptr;
-  if (cge_create(0, &ctx) != CGE_OK) {
-    std::fprintf(stderr, "Error: %s\n", cge_last_error());
-    return EXIT_FAILURE;
-  }
   cge_params p = {};
   p.n_obs = n; p.grid_size = N; p.mu_start = mu0; p.mu_end = mu1;
   p.sigma_start = sg0; p.sigma_end = sg1; p.mode = mode;

@@ -205,6 +205,32 @@ int cge_marginalize(cge_context *ctx, double *marginal, const double *matrix, in
 int cge_expectation(cge_context *ctx, const double *marginal, const float *vector, int size,
                     double *expectation_host);
 
+/* ---- non-flat prior -------------------------------------------------
+ * The reference only ever uses a flat prior and says a custom one "would have needed" the joint
+ * product before normalisation (inc/cuda_functions.h:145-148; notebook cell 4: posterior =
+ * likes * prior).  cge_set_prior installs, for the calls that follow on this context, separable
+ * factors prior_mu[grid_size], prior_sigma[grid_size] (host or device; copied) and/or a full
+ * device table laid out like the posterior shard ([rows][grid_size]; not copied, must stay
+ * alive).  posterior = likes * prior / sum(likes * prior).  All-NULL restores the flat prior.
+ * Prior values should be O(1): they multiply a float32 likelihood rescaled to peak at 2^40. */
+int cge_set_prior(cge_context *ctx, const float *prior_mu, const float *prior_sigma, int grid_size,
+                  const float *prior_full_dev);
+
+/* ---- around the path (SURVEY section 8(f) "next" rows) ---------------------------------------
+ * cge_generate_normal: the reference's observation generator -- cuRAND XORWOW, curand_init(seed,
+ * i, 0) per observation i, out[i] = fma(sigma, curand_normal, mu) -- inc/kernels.h:7-49 with the
+ * launch shape of inc/cuda_functions.h:13-44 (seed 42 there).  flags & 1: draw from an all-zero
+ * generator state instead, which is what src/tests.cu:21-46 exercises (expects 0.00459315).
+ * Input synthesis, not part of the hot path; provided so the reference binary's own observations
+ * (obs[0] = 18.5689, src/grid.cu:41-47) can be reproduced bit for bit. */
+int cge_generate_normal(cge_context *ctx, float *out_dev, int n, float mu, float sigma,
+                        unsigned long long seed, int flags);
+/* cge_quantiles: for each probability p, the first index whose cumulative marginal mass exceeds p
+ * (fixed-order device prefix sum) -- the credible-interval step the notebook suggests
+ * (notebooks/quick-prototyping.ipynb cell 5).  cdf_dev (n float64) is optional. */
+int cge_quantiles(cge_context *ctx, const double *marginal_dev, int n, const double *probs_host,
+                  int nprobs, int *indices_host, double *cdf_dev);
+
 /* ---- roofline micro-benchmarks (bench.py): measured pipe peaks on this device ------------
  * kind: 0 = MUFU ex2.approx.ftz.f32, 1 = FFMA, 2 = DFMA, 3 = FFMA2 (fma.rn.f32x2).
  * Returns operations per second (lane-ops; an FMA counts as one op). */
