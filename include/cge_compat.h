@@ -88,6 +88,13 @@ inline void freeMatrix(double **matrix, int rows) {
 
 /* ---- inc/cuda_functions.h --------------------------------------------------------------- */
 
+/* inc/cuda_functions.h:13-44 -- observation synthesis with the reference's generator (cuRAND
+ * XORWOW, seed 42 as in inc/kernels.h:18, one subsequence per observation).  Not part of the
+ * hot path; here so the reference's main() links without its own kernels.h. */
+inline void generateNormalCuda(unsigned int n, float mu, float sigma, float *observations) {
+  cge_compat::ok(cge_generate_normal(cge_compat::context(), observations, (int)n, mu, sigma, 42ULL, 0));
+}
+
 /* inc/cuda_functions.h:47-62 */
 inline void linspaceCuda(float *array, int size, float start, float end) {
   cge_compat::ok(cge_linspace(cge_compat::context(), array, size, start, end));

@@ -142,3 +142,18 @@ def test_quantiles_credible_interval(ctx, readme_obs):
     one = torch.zeros(10, dtype=torch.float64, device="cuda")
     one[7] = 1.0
     assert ctx.quantiles(one, 10, [0.05, 0.95, 1.0]).tolist() == [7, 7, 10]
+
+
+def test_reference_main_unchanged_on_libcge():
+    """The reference's src/grid.cu, byte for byte, compiled against include/compat/inc/*.h ->
+    cge_compat.h -> libcge.so (oracle/Makefile target grid_on_libcge) prints what the reference's
+    own build of the same file prints."""
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "grid")
+    ours = os.path.join(ROOT, "oracle", "_ref", "grid_on_libcge")
+    if not (os.path.exists(ref_bin) and os.path.exists(ours)):
+        pytest.skip("oracle/_ref binaries not built (need the reference checkout at build time)")
+    a = subprocess.run([ref_bin], capture_output=True, text=True, timeout=300)
+    b = subprocess.run([ours], capture_output=True, text=True, timeout=300)
+    assert a.returncode == 0 and b.returncode == 0, (a.stdout, a.stderr, b.stdout, b.stderr)
+    assert "Inferred mu" in a.stdout
+    assert a.stdout.strip().splitlines()[-2:] == b.stdout.strip().splitlines()[-2:], (a.stdout, b.stdout)
