@@ -138,8 +138,9 @@ int check_params(const cge_params *p, int *rb, int *re) {
   if (p->mode != CGE_MODE_PRODUCT_F32 && p->mode != CGE_MODE_LOGSPACE)
     return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
   switch (p->variant) {
-    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 2: case 100: case 122: case 133:
-    case 222: case 522: case 523: case 633: case 822: break;
+    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 2: case CGE_VARIANT_PAIRED:
+    case CGE_VARIANT_HYBRID: case 100: case 122: case 133: case 222: case 522: case 523: case 633:
+    case 822: case 1322: case 31: case 33: case 34: case 35: case 381: case 382: case 384: break;
     default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
   }
   int b = p->row_begin, e = p->row_end;
@@ -164,7 +165,8 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->row_end = re;
   pl->rows_local = re - rb;
   // columns per warp strip: 32 lanes x Policy::kCols (log-space keeps 8 columns per thread)
-  const int strip = 32 * (p->mode == CGE_MODE_LOGSPACE ? cge::LogSpaceF64::kCols : 4);
+  const bool wide_patch = p->mode == CGE_MODE_PRODUCT_F32 && p->variant >= 381 && p->variant <= 384;
+  const int strip = 32 * (p->mode == CGE_MODE_LOGSPACE ? cge::LogSpaceF64::kCols : wide_patch ? 8 : 4);
   pl->ncw = (pl->N + strip - 1) / strip;
   if (pl->ncw >= 8) { pl->wm = 1; pl->wn = 8; }
   else if (pl->ncw >= 4) { pl->wm = 2; pl->wn = 4; }
@@ -225,13 +227,47 @@ int launch_like(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   return launch_like_shape<Policy, 8, 1, MINB>(pl, args, st);
 }
 
-// product path: the default is the hybrid MUFU + FMA-polynomial kernel with a one-observation
-// loop body (ProductHybrid<2, 2, false, 1>): 4 of every 16 exponentials per thread come from the
-// FMA-pipe polynomial.  The other variants are kept for the roofline measurement (MUFU-only) and
-// to document the tuning sweep (profiles/r01_variant_sweep_*.jsonl); they are only built for the
-// wide tile shape and fall back to the default elsewhere.
+template <class Fine, class Coarse, int WM, int WN>
+int launch_dual_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
+  dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
+  if (pl.vec4) {
+    auto k = cge::grid_likelihood_dual_kernel<Fine, Coarse, WM, WN, true>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    k<<<grid, block, pl.smem, st>>>(args);
+  } else {
+    auto k = cge::grid_likelihood_dual_kernel<Fine, Coarse, WM, WN, false>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    k<<<grid, block, pl.smem, st>>>(args);
+  }
+  CK(cudaGetLastError());
+  return CGE_OK;
+}
+
+template <class Fine, class Coarse>
+int launch_dual(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
+  if (pl.wm == 1) return launch_dual_shape<Fine, Coarse, 1, 8>(pl, args, st);
+  if (pl.wm == 2) return launch_dual_shape<Fine, Coarse, 2, 4>(pl, args, st);
+  if (pl.wm == 4) return launch_dual_shape<Fine, Coarse, 4, 2>(pl, args, st);
+  return launch_dual_shape<Fine, Coarse, 8, 1>(pl, args, st);
+}
+
+// product path.  Default: grid_likelihood_dual_kernel -- ProductPaired (half the exponentials
+// from MUFU.EX2, the other half derived from the row above by a degree-2 FMA-pipe polynomial)
+// when the grid is fine enough (ScaleInfo::umax <= kPairedUmax, decided on the device), else
+// ProductHybrid<2, 2, false, 1> (12 of 16 exponentials from MUFU.EX2, 4 from a degree-5
+// polynomial).  CGE_VARIANT_PAIRED / _HYBRID force one of the two, CGE_VARIANT_MUFU_ONLY is the
+// roofline case; the numbered variants document the tuning sweeps
+// (profiles/r01_variant_sweep_*.jsonl) and are only built for the wide tile shape.
+using DefaultFine = cge::ProductPaired<4, 2>;
+using DefaultCoarse = cge::ProductHybrid<2, 2, false, 1>;
+
 int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
-  if (pl.variant == CGE_VARIANT_MUFU_ONLY) return launch_like<cge::ProductF32>(pl, args, st);
+  switch (pl.variant) {
+    case CGE_VARIANT_MUFU_ONLY: return launch_like<cge::ProductF32>(pl, args, st);
+    case CGE_VARIANT_PAIRED: return launch_like<DefaultFine>(pl, args, st);
+    case CGE_VARIANT_HYBRID: return launch_like<DefaultCoarse>(pl, args, st);
+    default: break;
+  }
   if (pl.wm == 1) {
     switch (pl.variant) {
       case 100: return launch_like_shape<cge::ProductHybrid<0, 0>, 1, 8>(pl, args, st);
@@ -242,10 +278,24 @@ int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
       case 523: return launch_like_shape<cge::ProductHybrid<2, 3, false, 2>, 1, 8>(pl, args, st);
       case 633: return launch_like_shape<cge::ProductHybrid<3, 3, false, 1>, 1, 8>(pl, args, st);
       case 822: return launch_like_shape<cge::ProductHybrid<2, 2, false, 1>, 1, 8, 3>(pl, args, st);
+      // 1322: exponent FMA as two scalar FFMAs, 1 observation per iteration
+      case 1322: return launch_like_shape<cge::ProductHybrid<2, 2, false, 1, true>, 1, 8>(pl, args, st);
+      // paired rows (CGE_VARIANT_PAIRED = 4 columns per thread, 2 observations per iteration):
+      // 31 / 34 = 1 / 4 observations per iteration; 33 = capped at 80 registers (3 CTAs per SM);
+      // 35 = 4 observations, capped at 128 registers; 38x = 8 columns per thread
+      case 31: return launch_like_shape<cge::ProductPaired<4, 1>, 1, 8>(pl, args, st);
+      case 33: return launch_like_shape<cge::ProductPaired<4, 2>, 1, 8, 3>(pl, args, st);
+      case 35: return launch_like_shape<cge::ProductPaired<4, 4>, 1, 8, 2>(pl, args, st);
+      case 34: return launch_like_shape<cge::ProductPaired<4, 4>, 1, 8>(pl, args, st);
+      case 381: return launch_like_shape<cge::ProductPaired<8, 1>, 1, 8>(pl, args, st);
+      case 382: return launch_like_shape<cge::ProductPaired<8, 2>, 1, 8>(pl, args, st);
+      case 384: return launch_like_shape<cge::ProductPaired<8, 4>, 1, 8>(pl, args, st);
       default: break;
     }
   }
-  return launch_like<cge::ProductHybrid<2, 2, false, 1>>(pl, args, st);
+  if (pl.variant >= 381 && pl.variant <= 384)
+    return set_error(CGE_ERR_BAD_ARG, "variant %d needs grid_size >= 2048", pl.variant);
+  return launch_dual<DefaultFine, DefaultCoarse>(pl, args, st);
 }
 
 int peer_release(cge_context *ctx);
@@ -402,7 +452,7 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   make_plan(ctx, p, rb, re, posterior_dev, &pl);
   const int N = pl.N;
 
-  CKRC(ctx->mu.reserve(N));
+  CKRC(ctx->mu.reserve((size_t)N + 4));
   CKRC(ctx->sigma.reserve(N));
   CKRC(ctx->ad.reserve(N));
   CKRC(ctx->cd0.reserve(N));
@@ -423,7 +473,7 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
 
   ctx->launches = 0;
   CKRC(mark(ctx, 0, st));
-  cge::setup_kernel<<<(N + 255) / 256, 256, 0, st>>>(
+  cge::setup_kernel<<<(N + 3 + 255) / 256, 256, 0, st>>>(
       ctx->mu.ptr, ctx->sigma.ptr, ctx->ad.ptr, ctx->cd0.ptr, N, p->mu_start, p->mu_end,
       p->sigma_start, p->sigma_end, obs_dev, ctx->obs_pad.ptr, pl.n, pl.n_pad, ctx->scale.ptr);
   CK(cudaGetLastError());
@@ -940,7 +990,7 @@ extern "C" int cge_internal_error(int code, const char *msg) { return set_error(
 // ---------------------------------------------------------------------------------------
 CGE_EXPORT int cge_microbench(cge_context *ctx, int kind, double *ops_per_second) {
   CKRC(bind(ctx));
-  if (!ops_per_second || kind < 0 || kind > 3)
+  if (!ops_per_second || kind < 0 || kind > 7)
     return set_error(CGE_ERR_BAD_ARG, "microbench: bad argument");
   CKRC(ctx->sink.reserve(4));
   const int iters = 4096, chains = 8;
@@ -951,7 +1001,11 @@ CGE_EXPORT int cge_microbench(cge_context *ctx, int kind, double *ops_per_second
       case 0: cge::microbench_kernel<0><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
       case 1: cge::microbench_kernel<1><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
       case 2: cge::microbench_kernel<2><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
-      default: cge::microbench_kernel<3><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+      case 3: cge::microbench_kernel<3><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+      case 4: cge::microbench_kernel<4><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+      case 5: cge::microbench_kernel<5><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+      case 6: cge::microbench_kernel<6><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+      default: cge::microbench_kernel<7><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
     }
   };
   for (int w = 0; w < 3; ++w) launch();
@@ -967,7 +1021,11 @@ CGE_EXPORT int cge_microbench(cge_context *ctx, int kind, double *ops_per_second
     if (ms < best) best = ms;
   }
   CK(cudaGetLastError());
-  double ops = (double)blocks * threads * (double)iters * chains * (kind == 3 ? 2.0 : 1.0);
+  // kinds 0-3: one instruction class, 8 chains; kinds 4-7: FMA lane-ops of the mix per iteration
+  // (packed count as 2; the MUFU chains' bounding FFMA counts as 1; MUFU ops are not counted)
+  static const double per_iter[8] = {8, 8, 8, 16, 4 * 2 + 4, 4 * 2 + 8, 6 * 2 + 2, 4 * 2 + 4 + 2};
+  (void)chains;
+  double ops = (double)blocks * threads * (double)iters * per_iter[kind];
   *ops_per_second = ops / (best * 1e-3);
   return CGE_OK;
 }

@@ -51,6 +51,7 @@ struct ScaleInfo {
   double xbar;
   double ss;
   double smin;
+  double umax;   // bound on |t_(i+1,j,k) - t_(i,j,k)| over adjacent mu rows (ProductPaired eligibility)
 };
 
 struct LikeArgs {
@@ -73,6 +74,26 @@ struct LikeArgs {
   int ncw;          // column strips per row: ceil(N / (32 * Policy::kCols))
 };
 
+// per-thread column coefficients, fetched before the policy is known (dual kernel)
+template <int KC>
+struct ColumnCoefs {
+  double a[KC], c0[KC];
+  __device__ __forceinline__ void load(const LikeArgs &g, int j0) {
+#pragma unroll
+    for (int cidx = 0; cidx < KC; ++cidx) {
+      const int j = patch_col(j0, cidx);
+      a[cidx] = j < g.N ? g.ad[j] : 0.0;
+      c0[cidx] = j < g.N ? g.cd0[j] : 0.0;
+    }
+  }
+};
+
+template <int WN>
+__device__ __forceinline__ int first_column(int kcols) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  return (blockIdx.x * WN + warp % WN) * (32 * kcols) + lane * kRN;
+}
+
 // ---------------------------------------------------------------------------------------
 // setup_kernel: K1 twice + the per-sigma coefficients (every block), and in block 0 the
 // observation staging and the global rescale.
@@ -93,6 +114,7 @@ __global__ void __launch_bounds__(256)
                  ScaleInfo *__restrict__ out) {
   const int tid = threadIdx.x;
   const int idx = blockIdx.x * blockDim.x + tid;
+  if (idx >= N && idx < N + 3) mu[idx] = range_value(N - 1, N, mu0, mu1);  // float4 row loads
   if (idx < N) {
     mu[idx] = range_value(idx, N, mu0, mu1);
     const float s = range_value(idx, N, sg0, sg1);
@@ -104,13 +126,19 @@ __global__ void __launch_bounds__(256)
 
   __shared__ double scratch[32];
   const int nt = blockDim.x;
-  double sum = 0.0;
+  double sum = 0.0, xlo = 1.0 / 0.0, xhi = -1.0 / 0.0;
   for (int k = tid; k < n_pad; k += nt) {
     const float x = k < n ? obs[k] : 0.0f;
     obs_pad[k] = x;
     sum += (double)x;
+    if (k < n) {
+      xlo = fmin(xlo, (double)x);
+      xhi = fmax(xhi, (double)x);
+    }
   }
   const double xbar = block_sum(sum, scratch) / (double)n;
+  xlo = block_min(xlo, scratch);
+  xhi = block_max(xhi, scratch);
   double q = 0.0;
   for (int k = tid; k < n; k += nt) {
     const double d = (double)obs[k] - xbar;
@@ -153,6 +181,17 @@ __global__ void __launch_bounds__(256)
   out->xbar = xbar;
   out->ss = ss;
   out->smin = smin;
+  // Largest exponent step between vertically adjacent cells,
+  //   |t_(i+1,j,k) - t_(i,j,k)| = |a_j| |mu_(i+1) - mu_i| |mu_i + mu_(i+1) - 2 x_k|,
+  // bounded over the whole grid and every observation.  The row spacing gets 2 ulp of slack for
+  // the float32 rounding of the range values.  ProductPaired is only used below kPairedUmax.
+  {
+    const double mlo = fmin((double)mu0, (double)mu1), mhi = fmax((double)mu0, (double)mu1);
+    const double reach = fmax(fmax(fabs(xhi - mlo), fabs(xlo - mlo)), fmax(fabs(xhi - mhi), fabs(xlo - mhi)));
+    const double dmu = N > 1 ? (mhi - mlo) / (double)(N - 1) + 2.4e-7 * fmax(fabs(mlo), fabs(mhi)) : 0.0;
+    const double sdmin = fmin((double)sg0, (double)sg1);
+    out->umax = fabs(coef_a(sdmin)) * dmu * 2.0 * reach;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -177,18 +216,13 @@ struct ProductF32 {
   float a[kRN], c[kRN];
   float p[kRM][kRN];
 
-  __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, double log2s,
-                                               double /*shift*/) {
+  __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
+                                               const ColumnCoefs<kCols> &cf) {
 #pragma unroll
     for (int cidx = 0; cidx < kRN; ++cidx) {
-      int j = j0 + cidx;
-      if (j < g.N) {
-        a[cidx] = (float)g.ad[j];
-        c[cidx] = (float)(g.cd0[j] + log2s);
-      } else {
-        a[cidx] = 0.0f;
-        c[cidx] = 0.0f;
-      }
+      const bool ok = j0 + cidx < g.N;
+      a[cidx] = (float)cf.a[cidx];
+      c[cidx] = ok ? (float)(cf.c0[cidx] + sc.log2s) : 0.0f;
     }
   }
   __device__ __forceinline__ void begin_rows() {
@@ -245,15 +279,12 @@ struct LogSpaceF64 {
   double shift_;
   int jbase_;
 
-  __device__ __forceinline__ void load_columns(const LikeArgs &g, int jbase, double /*log2s*/,
-                                               double shift) {
+  __device__ __forceinline__ void load_columns(const LikeArgs &, int jbase, const ScaleInfo &sc,
+                                               const ColumnCoefs<kCols> &cf) {
     jbase_ = jbase;
-    shift_ = shift;
+    shift_ = sc.shift;
 #pragma unroll
-    for (int cidx = 0; cidx < kCols; ++cidx) {
-      const int j = patch_col(jbase, cidx);
-      a[cidx] = j < g.N ? g.ad[j] : 0.0;
-    }
+    for (int cidx = 0; cidx < kCols; ++cidx) a[cidx] = cf.a[cidx];
   }
   __device__ __forceinline__ void begin_rows() {
 #pragma unroll
@@ -310,7 +341,7 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 //     moving ~5/16 of the exponentials over balances the two pipes.
 // Which cells use which pipe is fixed at compile time, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------
-template <int NPA, int NPB, bool SCALAR_POLY = false, int OBS_PER_ITER = 4>
+template <int NPA, int NPB, bool SCALAR_POLY = false, int OBS_PER_ITER = 4, bool SCALAR_T = false>
 struct ProductHybrid {
   static constexpr int kRows = kRM;
   static constexpr int kCols = 4;
@@ -318,16 +349,16 @@ struct ProductHybrid {
   f32x2 a2[kRN / 2], c2[kRN / 2];
   f32x2 p2[kRM][kRN / 2];
 
-  __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, double log2s,
-                                               double /*shift*/) {
+  __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
+                                               const ColumnCoefs<kCols> &cf) {
 #pragma unroll
     for (int h = 0; h < kRN / 2; ++h) {
       float av[2], cv[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = j0 + 2 * h + e;
-        av[e] = j < g.N ? (float)g.ad[j] : 0.0f;
-        cv[e] = j < g.N ? (float)(g.cd0[j] + log2s) : 0.0f;
+        av[e] = (float)cf.a[2 * h + e];
+        cv[e] = j < g.N ? (float)(cf.c0[2 * h + e] + sc.log2s) : 0.0f;
       }
       a2[h] = pack2(av[0], av[1]);
       c2[h] = pack2(cv[0], cv[1]);
@@ -350,7 +381,15 @@ struct ProductHybrid {
       const f32x2 dd2 = pack2(dd, dd);  // becomes a scalar-broadcast operand of FFMA2
 #pragma unroll
       for (int h = 0; h < kRN / 2; ++h) {
-        const f32x2 t2 = fma2(dd2, a2[h], c2[h]);
+        f32x2 t2;
+        if (SCALAR_T) {  // exponent as two scalar FFMAs (either FMA half-pipe) instead of one FFMA2
+          float al, ah, cl, ch;
+          unpack2(a2[h], al, ah);
+          unpack2(c2[h], cl, ch);
+          t2 = pack2(fmaf(dd, al, cl), fmaf(dd, ah, ch));
+        } else {
+          t2 = fma2(dd2, a2[h], c2[h]);
+        }
         // spread the polynomial slots over the rows: (r, h) = (0,0),(1,1),(2,0),(3,1), then the rest
         const int slot = ((h + r) & 1) * kRM + r;
         const f32x2 e2 = slot < NP ? (SCALAR_POLY ? ex2_poly2_scalar(t2) : ex2_poly2(t2))
@@ -398,6 +437,130 @@ struct ProductHybrid {
 };
 
 // ---------------------------------------------------------------------------------------
+// float32 product path, paired rows: of every two vertically adjacent cells (mu_i, mu_(i+1) at
+// the same sigma_j) one takes its factor from MUFU.EX2 and the other derives its own from it,
+//   pdf(x_k; mu_(i+1), sigma_j) = pdf(x_k; mu_i, sigma_j) * 2^u,
+//   u = a_j * g_ik,   g_ik = (mu_(i+1) - mu_i) * (mu_i + mu_(i+1) - 2 x_k)      (exact identity)
+// with 2^u - 1 from a degree-2 polynomial on the FMA pipe: on a fine grid |u| is tiny (6e-3 at
+// 16384 rows for the README ranges), so no range reduction is needed.  Every pdf-eval still forms
+// its own factor and multiplies it into its own running product; what changes is the pipe mix:
+//   MUFU row   : FFMA2 (exponent), 2 MUFU.EX2, FMUL2 (product)            per column pair
+//   derived row: FFMA2 (a_j k1 + g a_j^2 k2), FMUL2 (* g), FFMA2 (e + e v), FMUL2 (product)
+// i.e. half the MUFU work of ProductF32 for ~3 packed FMA-pipe instructions more per 4 evals;
+// ncu showed the MUFU-only kernel with the XU pipe 97 % busy and the FMA pipe at 30 %.
+// Polynomial: 2^u = 1 + u (k1 + k2 u) with k2 = ln(2)^2/2 and the cubic term folded into
+// k1 = ln 2 + (ln(2)^3/6)(3/4) U^2 (Chebyshev economisation on [-U, U], U = ScaleInfo::umax):
+// error <= 0.0139 U^3 = 1.8e-8 at the eligibility bound kPairedUmax, below the float32 rounding
+// of the factor itself.  The derived factor is e*(1+v) evaluated as fma(e, v, e): one rounding.
+// Grids too coarse for that bound run ProductHybrid instead (chosen on the device, see
+// grid_likelihood_dual_kernel); which rows are MUFU rows depends on the global row index only.
+// ---------------------------------------------------------------------------------------
+constexpr double kPairedUmax = 0.011;
+
+template <int KC = 4, int OBS_PER_ITER = 1>
+struct ProductPaired {
+  static constexpr int kRows = kRM;
+  static constexpr int kCols = KC;
+  static constexpr int kObsStride = 1;
+  static constexpr int kPairs = KC / 2;
+  f32x2 a2[kPairs], c2[kPairs];    // exponent coefficients of the MUFU rows
+  f32x2 k1a[kPairs], k2a[kPairs];  // a_j k1, a_j^2 k2 of the derived rows
+  f32x2 p2[kRM][kPairs];
+
+  __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
+                                               const ColumnCoefs<kCols> &cf) {
+    const double U = sc.umax;
+    const double k1 = 0.69314718055994530942 + 0.0555041086648215799 * 0.75 * U * U;
+    const double k2 = 0.24022650695910071233;
+#pragma unroll
+    for (int h = 0; h < kPairs; ++h) {
+      float av[2], cv[2], k1v[2], k2v[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = patch_col(j0, 2 * h + e);
+        const double a = cf.a[2 * h + e];
+        av[e] = (float)a;
+        cv[e] = j < g.N ? (float)(cf.c0[2 * h + e] + sc.log2s) : 0.0f;
+        k1v[e] = (float)(a * k1);
+        k2v[e] = (float)(a * a * k2);
+      }
+      a2[h] = pack2(av[0], av[1]);
+      c2[h] = pack2(cv[0], cv[1]);
+      k1a[h] = pack2(k1v[0], k1v[1]);
+      k2a[h] = pack2(k2v[0], k2v[1]);
+    }
+  }
+  __device__ __forceinline__ void begin_rows() {
+    const f32x2 one = pack2(1.0f, 1.0f);
+#pragma unroll
+    for (int r = 0; r < kRM; ++r)
+#pragma unroll
+      for (int h = 0; h < kPairs; ++h) p2[r][h] = one;
+  }
+  // one observation: rows (0,1) and (2,3) of the patch are the pairs; gm/gb give g = x*gm + gb
+  __device__ __forceinline__ void step(float x, const float (&mu)[kRM], const float (&gm)[kRM / 2],
+                                       const float (&gb)[kRM / 2]) {
+#pragma unroll
+    for (int rp = 0; rp < kRM / 2; ++rp) {
+      const float d = x - mu[2 * rp];  // same f32 rounding as the reference's (x - mu), kernels.h:111
+      const float dd = d * d;
+      const float gg = fmaf(x, gm[rp], gb[rp]);
+      const f32x2 dd2 = pack2(dd, dd);
+      const f32x2 g2 = pack2(gg, gg);
+#pragma unroll
+      for (int h = 0; h < kPairs; ++h) {
+        const f32x2 e2 = ex2_mufu2(fma2(dd2, a2[h], c2[h]));
+        p2[2 * rp][h] = mul2(p2[2 * rp][h], e2);
+        const f32x2 v2 = mul2(g2, fma2(g2, k2a[h], k1a[h]));  // 2^u - 1
+        const f32x2 f2 = fma2(e2, v2, e2);                    // neighbour's factor
+        p2[2 * rp + 1][h] = mul2(p2[2 * rp + 1][h], f2);
+      }
+    }
+  }
+  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx) const {
+    float lo, hi;
+    unpack2(p2[r][cidx >> 1], lo, hi);
+    return (cidx & 1) ? hi : lo;
+  }
+  static __device__ __forceinline__ void consume(ProductPaired &pol, const float *xs, int count,
+                                                 const float (&mu)[kRM]) {
+    float gm[kRM / 2], gb[kRM / 2];
+#pragma unroll
+    for (int rp = 0; rp < kRM / 2; ++rp) {
+      const float delta = __fsub_rn(mu[2 * rp + 1], mu[2 * rp]);  // exact (adjacent range values)
+      gm[rp] = -2.0f * delta;
+      gb[rp] = __fmul_rn(delta, __fadd_rn(mu[2 * rp], mu[2 * rp + 1]));
+    }
+    if (OBS_PER_ITER == 4) {
+      const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
+      const int n4 = count >> 2;
+#pragma unroll 1
+      for (int q = 0; q < n4; ++q) {
+        const float4 x = xs4[q];
+        pol.step(x.x, mu, gm, gb);
+        pol.step(x.y, mu, gm, gb);
+        pol.step(x.z, mu, gm, gb);
+        pol.step(x.w, mu, gm, gb);
+      }
+      for (int k = n4 << 2; k < count; ++k) pol.step(xs[k], mu, gm, gb);
+    } else if (OBS_PER_ITER == 2) {
+      const float2 *xs2 = reinterpret_cast<const float2 *>(xs);
+      const int n2 = count >> 1;
+#pragma unroll 1
+      for (int q = 0; q < n2; ++q) {
+        const float2 x = xs2[q];
+        pol.step(x.x, mu, gm, gb);
+        pol.step(x.y, mu, gm, gb);
+      }
+      if (count & 1) pol.step(xs[count - 1], mu, gm, gb);
+    } else {
+#pragma unroll 1
+      for (int k = 0; k < count; ++k) pol.step(xs[k], mu, gm, gb);
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------
 // grid_likelihood_kernel: K1-K5 fused.
 //   CTA = WM x WN warps.  A warp owns a strip of 32*kCols sigma columns (lane -> kCols/4 groups
 //   of 4 adjacent columns, one 16-byte store per group and row) and walks down its rows kRM at
@@ -407,10 +570,10 @@ struct ProductHybrid {
 //   Per row group the warp emits its partial row sums (fixed-order shuffle tree) and keeps
 //   float64 column sums in registers until the tile ends: no atomics anywhere.
 // ---------------------------------------------------------------------------------------
-template <class Policy, int WM, int WN, bool VEC4, int MINB = 1>
-__global__ void __launch_bounds__(WM *WN * 32, MINB)
-    grid_likelihood_kernel(const LikeArgs g) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+template <class Policy, int WM, int WN, bool VEC4>
+__device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleInfo &sc,
+                                                const ColumnCoefs<Policy::kCols> &cf,
+                                                unsigned char *smem_raw) {
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);         // 2 mbarriers
   float *obs_s = reinterpret_cast<float *>(smem_raw + 128);         // stage 0 (and 1 if streamed)
 
@@ -449,9 +612,8 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
   };
   if (tid == 0) issue(0);
 
-  const ScaleInfo sc = *g.scale;
   Policy pol;
-  pol.load_columns(g, j0, sc.log2s, sc.shift);
+  pol.load_columns(g, j0, sc, cf);
   double colacc[kCols];
 #pragma unroll
   for (int cidx = 0; cidx < kCols; ++cidx) colacc[cidx] = 0.0;
@@ -465,51 +627,91 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
   auto begin_group = [&](int grp) {
     row = tile_row0 + (grp * WM + wm) * kRows;
     rows_any = row < g.row_end && row + kRows > g.row_begin;
-#pragma unroll
-    for (int r = 0; r < kRows; ++r) mu[r] = g.mu[min(row + r, g.N - 1)];  // row >= 0 always
+    // `row` is a multiple of 4 and setup_kernel pads the table with 3 copies of its last value,
+    // so the 4 rows of the patch are one aligned 16-byte load
+    const float4 m4 = *reinterpret_cast<const float4 *>(g.mu + min(row, (g.N - 1) & ~3));
+    mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
     pol.begin_rows();
   };
 
+  // Epilogue of one row group: store the kRows x kCols patch, add it into the row / column sums.
+  // Within the patch the sums are float32 in a fixed pairwise order (4 or 8 terms); everything
+  // across threads, groups and tiles is float64 in a fixed order.  The kRows row sums of a warp
+  // are reduced together by a transposing butterfly (12 shuffles instead of 40): lane 8*q ends up
+  // with the total of row q.
   auto end_group = [&]() {
     if (!rows_any) return;  // warp-uniform
+    float v[kRows][kCols];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+#pragma unroll
+      for (int cidx = 0; cidx < kCols; ++cidx) v[r][cidx] = pol.value(g, r, cidx);
+    const bool interior =
+        row >= g.row_begin && row + kRows <= g.row_end && patch_col(j0, kCols - 1) < g.N;
+    if (!interior) {  // shard / grid edges: cells outside contribute exactly zero
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const bool rv = row + r >= g.row_begin && row + r < g.row_end;
+#pragma unroll
+        for (int cidx = 0; cidx < kCols; ++cidx)
+          if (!(rv && patch_col(j0, cidx) < g.N)) v[r][cidx] = 0.0f;
+      }
+    }
+    if (has_prior) {  // likelihood x prior before normalisation (cuda_functions.h:145-148)
+#pragma unroll
+      for (int r = 0; r < kRows; ++r) {
+        const bool rv = row + r >= g.row_begin && row + r < g.row_end;
+#pragma unroll
+        for (int cidx = 0; cidx < kCols; ++cidx) {
+          const int j = patch_col(j0, cidx);
+          if (!(rv && j < g.N)) continue;
+          if (g.prior_mu) v[r][cidx] *= g.prior_mu[row + r];
+          if (g.prior_sigma) v[r][cidx] *= g.prior_sigma[j];
+          if (g.prior_full)
+            v[r][cidx] *= g.prior_full[(size_t)(row + r - g.row_begin) * (size_t)g.N + j];
+        }
+      }
+    }
+    float *rowp = g.post + (ptrdiff_t)(row - g.row_begin) * (ptrdiff_t)g.N + j0;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r, rowp += g.N) {
+      if (!interior && !(row + r >= g.row_begin && row + r < g.row_end)) continue;
+#pragma unroll
+      for (int grp4 = 0; grp4 < kGroups; ++grp4) {
+        const int jg = j0 + grp4 * kGroupCols;
+        if (!interior && jg >= g.N) continue;
+        if (VEC4) {
+          st_stream_f4(rowp + grp4 * kGroupCols, v[r][4 * grp4], v[r][4 * grp4 + 1],
+                       v[r][4 * grp4 + 2], v[r][4 * grp4 + 3]);
+        } else {
+#pragma unroll
+          for (int e = 0; e < kRN; ++e)
+            if (jg + e < g.N) st_stream_f1(rowp + grp4 * kGroupCols + e, v[r][4 * grp4 + e]);
+        }
+      }
+    }
+    // column sums over the patch rows, row sums over the patch columns (float32, pairwise)
+    static_assert(kRows == 4, "the patch reductions below are written for 4 rows");
+#pragma unroll
+    for (int cidx = 0; cidx < kCols; ++cidx)
+      colacc[cidx] += (double)((v[0][cidx] + v[1][cidx]) + (v[2][cidx] + v[3][cidx]));
+    double rs[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
-      const bool rv = row + r >= g.row_begin && row + r < g.row_end;
-      float v[kCols];
-      double rs = 0.0;
-#pragma unroll
-      for (int cidx = 0; cidx < kCols; ++cidx) {
-        const int j = patch_col(j0, cidx);
-        const bool ok = rv && (j < g.N);
-        v[cidx] = ok ? pol.value(g, r, cidx) : 0.0f;
-        if (has_prior && ok) {  // likelihood x prior before normalisation (cuda_functions.h:145-148)
-          if (g.prior_mu) v[cidx] *= g.prior_mu[row + r];
-          if (g.prior_sigma) v[cidx] *= g.prior_sigma[j];
-          if (g.prior_full)
-            v[cidx] *= g.prior_full[(size_t)(row + r - g.row_begin) * (size_t)g.N + j];
-        }
-        rs += (double)v[cidx];
-        colacc[cidx] += (double)v[cidx];
-      }
-      if (rv) {
-        float *rowp = g.post + (size_t)(row + r - g.row_begin) * (size_t)g.N;
-#pragma unroll
-        for (int grp4 = 0; grp4 < kGroups; ++grp4) {
-          const int jg = j0 + grp4 * kGroupCols;
-          if (jg >= g.N) continue;
-          if (VEC4) {
-            st_stream_f4(rowp + jg, v[4 * grp4], v[4 * grp4 + 1], v[4 * grp4 + 2], v[4 * grp4 + 3]);
-          } else {
-#pragma unroll
-            for (int e = 0; e < kRN; ++e)
-              if (jg + e < g.N) st_stream_f1(rowp + jg + e, v[4 * grp4 + e]);
-          }
-        }
-      }
-      rs = warp_sum(rs);
-      if (lane == 0 && rv && cw < g.ncw)
-        g.rowpart[(size_t)(row + r - g.row_begin) * (size_t)g.ncw + cw] = rs;
+      float t = (v[r][0] + v[r][1]) + (v[r][2] + v[r][3]);
+      if (kCols == 8) t += (v[r][4] + v[r][5]) + (v[r][6] + v[r][7]);
+      rs[r] = (double)t;
     }
+    const bool up16 = lane & 16, up8 = lane & 8;
+    const double k0 = (up16 ? rs[2] : rs[0]) + __shfl_xor_sync(0xffffffffu, up16 ? rs[0] : rs[2], 16);
+    const double k1 = (up16 ? rs[3] : rs[1]) + __shfl_xor_sync(0xffffffffu, up16 ? rs[1] : rs[3], 16);
+    double tot = (up8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 2);
+    tot += __shfl_xor_sync(0xffffffffu, tot, 1);
+    const int rq = row + (lane >> 3);  // lanes 0, 8, 16, 24 publish rows 0..3 of the patch
+    if ((lane & 7) == 0 && rq >= g.row_begin && rq < g.row_end && cw < g.ncw)
+      g.rowpart[(size_t)(rq - g.row_begin) * (size_t)g.ncw + cw] = tot;
   };
 
   if (!streamed) {
@@ -543,6 +745,35 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
       if (j < g.N) dst[j] = colacc[cidx];
     }
   }
+}
+
+template <class Policy, int WM, int WN, bool VEC4, int MINB = 1>
+__global__ void __launch_bounds__(WM *WN * 32, MINB)
+    grid_likelihood_kernel(const LikeArgs g) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const ScaleInfo sc = *g.scale;
+  ColumnCoefs<Policy::kCols> cf;
+  cf.load(g, first_column<WN>(Policy::kCols));
+  likelihood_body<Policy, WM, WN, VEC4>(g, sc, cf, smem_raw);
+}
+
+// The default product kernel: ProductPaired where the grid is fine enough for its polynomial
+// (ScaleInfo::umax, computed by setup_kernel from the ranges and the observations that are
+// already on the device), ProductHybrid otherwise.  The choice is uniform over the launch and
+// depends on (ranges, N, observations) only -- never on the shard -- so every rank of a sharded
+// run takes the same path and results stay bit-reproducible.  Both policies share the tiling.
+template <class Fine, class Coarse, int WM, int WN, bool VEC4, int MINB = 1>
+__global__ void __launch_bounds__(WM *WN * 32, MINB)
+    grid_likelihood_dual_kernel(const LikeArgs g) {
+  static_assert(Fine::kCols == Coarse::kCols && Fine::kRows == Coarse::kRows, "same tiling");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const ScaleInfo sc = *g.scale;
+  ColumnCoefs<Fine::kCols> cf;  // in flight together with `sc`, before the path is known
+  cf.load(g, first_column<WN>(Fine::kCols));
+  if (sc.umax <= kPairedUmax)
+    likelihood_body<Fine, WM, WN, VEC4>(g, sc, cf, smem_raw);
+  else
+    likelihood_body<Coarse, WM, WN, VEC4>(g, sc, cf, smem_raw);
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1043,6 +1274,51 @@ __global__ void __launch_bounds__(256) microbench_kernel(float *out, int iters, 
 #pragma unroll
     for (int c = 0; c < C; ++c) s += v[c];
     if (s == 123.456) out[0] = (float)s;
+  } else if (KIND >= 4) {
+    // mixes: NP packed FFMA2 chains + NS scalar FFMA chains (+ NM MUFU chains) per iteration --
+    // do packed (heavy half of the FMA pipe only) and scalar (either half) instructions add up to
+    // more than either alone, and how much FMA work fits beside a saturated XU pipe?
+    //   4: 4 FFMA2 + 4 FFMA    5: 4 FFMA2 + 8 FFMA    6: 6 FFMA2 + 2 MUFU    7: 4 FFMA2 + 4 FFMA + 2 MUFU
+    constexpr int NP = KIND == 6 ? 6 : 4;
+    constexpr int NS = KIND == 4 ? 4 : KIND == 5 ? 8 : KIND == 7 ? 4 : 0;
+    constexpr int NM = KIND >= 6 ? 2 : 0;
+    unsigned long long v[NP];
+    float w[NS > 0 ? NS : 1], m[NM > 0 ? NM : 1];
+#pragma unroll
+    for (int c = 0; c < NP; ++c) {
+      float lo = seed + 0.001f * (threadIdx.x + c), hi = lo + 0.5f;
+      asm("mov.b64 %0, {%1, %2};" : "=l"(v[c]) : "f"(lo), "f"(hi));
+    }
+#pragma unroll
+    for (int c = 0; c < NS; ++c) w[c] = seed + 0.002f * (threadIdx.x + c);
+#pragma unroll
+    for (int c = 0; c < NM; ++c) m[c] = seed + 0.003f * (threadIdx.x + c);
+    unsigned long long a2, b2;
+    const float a = 0.999f + seed * 1e-6f, b = 0.001f;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(a2) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(b2) : "f"(b));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int c = 0; c < (NP > NS ? NP : NS); ++c) {
+        if (c < NP) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(v[c]) : "l"(a2), "l"(b2));
+        if (c < NS) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(w[c]) : "f"(a), "f"(b));
+        if (c < NM) asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(m[c]));
+      }
+#pragma unroll
+      for (int c = 0; c < NM; ++c) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(m[c]) : "f"(a), "f"(-1.0f));
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int c = 0; c < NP; ++c) {
+      float lo, hi;
+      asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v[c]));
+      s += lo + hi;
+    }
+#pragma unroll
+    for (int c = 0; c < NS; ++c) s += w[c];
+#pragma unroll
+    for (int c = 0; c < NM; ++c) s += m[c];
+    if (s == 123.456f) out[0] = s;
   } else {  // packed FFMA2: fma.rn.f32x2, two lanes-ops per instruction
     unsigned long long v[C];
 #pragma unroll

@@ -76,16 +76,23 @@ typedef struct cge_params {
 
 /* likelihood-kernel variants for cge_params.variant (product mode; ignored in log-space) */
 enum {
-  CGE_VARIANT_DEFAULT = 0,   /* hybrid: packed f32x2 arithmetic; of the 16 exponentials a thread
-                                evaluates per observation, 12 use MUFU.EX2 and 4 an FMA-pipe
-                                degree-5 polynomial; one observation per loop iteration */
-  CGE_VARIANT_MUFU_ONLY = 1  /* scalar arithmetic, every 2^t on MUFU.EX2 (the MUFU roofline case) */
+  CGE_VARIANT_DEFAULT = 0,   /* paired rows on fine grids (chosen on the device from the ranges and
+                                the observations), hybrid otherwise */
+  CGE_VARIANT_MUFU_ONLY = 1, /* scalar arithmetic, every 2^t on MUFU.EX2 (the MUFU roofline case) */
+  CGE_VARIANT_PAIRED = 3,    /* paired rows, forced: packed f32x2 arithmetic; of two vertically
+                                adjacent cells one factor is 2^t on MUFU.EX2, the other is derived
+                                from it, e * 2^u with 2^u - 1 a degree-2 FMA-pipe polynomial (only
+                                accurate while the row spacing keeps |u| <= 0.011) */
+  CGE_VARIANT_HYBRID = 4     /* hybrid, forced: packed f32x2 arithmetic; of the 16 exponentials a
+                                thread evaluates per observation, 12 use MUFU.EX2 and 4 an FMA-pipe
+                                degree-5 polynomial with Cody-Waite range reduction */
   /* tuning variants kept for the record (wide tile shape only, see cge_api.cu launch_product;
      the full sweep incl. variants since removed is in profiles/r01_variant_sweep_*.jsonl):
      100 packed, MUFU only; 1ab / 5ab / 6ab hybrid with a / b polynomial column pairs (of 8) on
      even / odd observations and 4 / 2 / 1 observations per loop iteration; 222 scalar
-     polynomial; 822 = default capped at 80 registers.  In log-space mode variant 2 caps the
-     kernel at 128 registers. */
+     polynomial; 822 = hybrid capped at 80 registers; 1322 = exponent FMAs scalar; 31 / 34 =
+     paired rows with 1 / 4 observations per loop iteration (CGE_VARIANT_PAIRED has 2); 33 / 35 =
+     paired rows capped at 80 / 128 registers; 38x = paired rows, 8 columns per thread.  In log-space mode variant 2 caps the kernel at 128 registers. */
 };
 
 /* per-phase device timings of the last synchronous call, milliseconds (CUDA events) */
@@ -232,8 +239,11 @@ int cge_quantiles(cge_context *ctx, const double *marginal_dev, int n, const dou
                   int nprobs, int *indices_host, double *cdf_dev);
 
 /* ---- roofline micro-benchmarks (bench.py): measured pipe peaks on this device ------------
- * kind: 0 = MUFU ex2.approx.ftz.f32, 1 = FFMA, 2 = DFMA, 3 = FFMA2 (fma.rn.f32x2).
- * Returns operations per second (lane-ops; an FMA counts as one op). */
+ * kind: 0 = MUFU ex2.approx.ftz.f32, 1 = FFMA, 2 = DFMA, 3 = FFMA2 (fma.rn.f32x2);
+ * 4-7 = instruction mixes per loop iteration: 4 FFMA2 + 4 FFMA, 4 FFMA2 + 8 FFMA,
+ * 6 FFMA2 + 2 MUFU, 4 FFMA2 + 4 FFMA + 2 MUFU (how packed, scalar and MUFU work overlap).
+ * Returns operations per second (FMA lane-ops; a packed FFMA2 counts as two; for the mixes the
+ * MUFU ops are not counted). */
 int cge_microbench(cge_context *ctx, int kind, double *ops_per_second);
 
 #ifdef __cplusplus

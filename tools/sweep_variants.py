@@ -16,14 +16,15 @@ import oracle  # noqa: E402
 N = int(sys.argv[1]) if len(sys.argv) > 1 else 16384
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 50
 steps = int(sys.argv[3]) if len(sys.argv) > 3 else 20
+NACC = int(os.environ.get("CGE_ACC_N", "4096"))  # accuracy is checked on the README workload at this N
 obs = oracle.readme_observations(n=n)
-ref = oracle.grid_posterior(oracle.readme_observations(), 1024, 18, 22, 1, 3, oracle.NUM_F64)
+ref = oracle.grid_posterior(oracle.readme_observations(), NACC, 18, 22, 1, 3, oracle.NUM_F64)
 dev = torch.device("cuda", 0)
 out = []
 with cge.Context(0) as ctx:
     obs_t = torch.from_numpy(obs).to(dev)
     post = torch.empty((N, N), dtype=torch.float32, device=dev)
-    for variant in [int(v) for v in os.environ.get("CGE_VARIANTS", "1,100,112,122,0,133,134").split(",")]:
+    for variant in [int(v) for v in os.environ.get("CGE_VARIANTS", "1,4,3,0,31,33,34,35,381,382,384").split(",")]:
         p = cge.make_params(n, N, (18, 22), (1, 3), cge.MODE_PRODUCT_F32, None, variant)
         for _ in range(3):
             ctx.likelihood_partials(p, obs_t, post, None)
@@ -34,7 +35,7 @@ with cge.Context(0) as ctx:
             ctx.likelihood_partials(p, obs_t, post, None)
             ctx.finalize(p, post, None)
         t, cap = ctx.profile_end()
-        r = ctx.grid_posterior(oracle.readme_observations(), 1024, (18, 22), (1, 3), variant=variant)
+        r = ctx.grid_posterior(oracle.readme_observations(), NACC, (18, 22), (1, 3), variant=variant)
         big = ref["posterior"] >= 1e-20 * ref["posterior"].max()
         rel = np.abs(r.posterior.astype(np.float64)[big] - ref["posterior"][big]) / ref["posterior"][big]
         row = dict(variant=variant, likelihood_ms=t["likelihood_ms"], total_ms=t["total_ms"],
