@@ -139,6 +139,7 @@ int check_params(const cge_params *p, int *rb, int *re) {
     return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
   switch (p->variant) {
     case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 2: case CGE_VARIANT_PAIRED:
+    case CGE_VARIANT_LOG_F64: case 6:
     case CGE_VARIANT_HYBRID: case 100: case 122: case 133: case 222: case 522: case 523: case 633:
     case 822: case 1322: case 31: case 33: case 34: case 35: case 381: case 382: case 384: break;
     default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
@@ -475,7 +476,9 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   CKRC(mark(ctx, 0, st));
   cge::setup_kernel<<<(N + 3 + 255) / 256, 256, 0, st>>>(
       ctx->mu.ptr, ctx->sigma.ptr, ctx->ad.ptr, ctx->cd0.ptr, N, p->mu_start, p->mu_end,
-      p->sigma_start, p->sigma_end, obs_dev, ctx->obs_pad.ptr, pl.n, pl.n_pad, ctx->scale.ptr);
+      p->sigma_start, p->sigma_end, obs_dev, ctx->obs_pad.ptr, pl.n, pl.n_pad,
+      (p->mode == CGE_MODE_LOGSPACE && p->variant != CGE_VARIANT_LOG_F64 && p->variant != 2) ? 1 : 0,
+      ctx->scale.ptr);
   CK(cudaGetLastError());
   ctx->launches += 1;
   CKRC(mark(ctx, 1, st));
@@ -505,9 +508,13 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
     CKRC(launch_product(pl, args, st));
   else
   {
-    // variant 2: capped at 128 registers (2 CTAs per SM, small spills); default: uncapped
-    if (p->variant == 2) CKRC((launch_like<cge::LogSpaceF64, 2>(pl, args, st)));
-    else CKRC((launch_like<cge::LogSpaceF64, 1>(pl, args, st)));
+    // default: float32x2 tile sums of centred terms folded into float64 (LogSpaceTiled);
+    // CGE_VARIANT_LOG_F64: one DFMA per pdf-eval (the first log-space kernel, kept as the
+    // FP64-pipe roofline case); 2: the same capped at 128 registers; 6: tiled capped at 128
+    if (p->variant == CGE_VARIANT_LOG_F64) CKRC((launch_like<cge::LogSpaceF64, 1>(pl, args, st)));
+    else if (p->variant == 2) CKRC((launch_like<cge::LogSpaceF64, 2>(pl, args, st)));
+    else if (p->variant == 6) CKRC((launch_like<cge::LogSpaceTiled, 2>(pl, args, st)));
+    else CKRC((launch_like<cge::LogSpaceTiled, 1>(pl, args, st)));
   }
   ctx->launches += 1;
   CKRC(mark(ctx, 2, st));

@@ -51,6 +51,8 @@ struct ScaleInfo {
   double xbar;
   double ss;
   double smin;
+  double mu_c;   // log-space: grid value nearest the sample mean; obs_pad holds x_k - mu_c
+  double s_c;    // log-space: sum_k (x_k - mu_c)^2
   double umax;   // bound on |t_(i+1,j,k) - t_(i,j,k)| over adjacent mu rows (ProductPaired eligibility)
 };
 
@@ -111,7 +113,7 @@ __global__ void __launch_bounds__(256)
     setup_kernel(float *__restrict__ mu, float *__restrict__ sigma, double *__restrict__ ad,
                  double *__restrict__ cd0, int N, float mu0, float mu1, float sg0, float sg1,
                  const float *__restrict__ obs, float *__restrict__ obs_pad, int n, int n_pad,
-                 ScaleInfo *__restrict__ out) {
+                 int centred, ScaleInfo *__restrict__ out) {
   const int tid = threadIdx.x;
   const int idx = blockIdx.x * blockDim.x + tid;
   if (idx >= N && idx < N + 3) mu[idx] = range_value(N - 1, N, mu0, mu1);  // float4 row loads
@@ -139,6 +141,21 @@ __global__ void __launch_bounds__(256)
   const double xbar = block_sum(sum, scratch) / (double)n;
   xlo = block_min(xlo, scratch);
   xhi = block_max(xhi, scratch);
+  // centre of the log-space kernel: the grid value nearest the sample mean (depends on the global
+  // grid only, so every shard uses the same one).  In that mode the staged observations are
+  // x_k - mu_c, rounded once to float32.
+  double mu_c = 0.0;
+  {
+    const double span = (double)mu1 - (double)mu0;
+    double pos = span != 0.0 ? (xbar - (double)mu0) / span * (double)(N - 1) : 0.0;
+    if (!(pos == pos) || pos < 0.0) pos = 0.0;
+    if (pos > (double)(N - 1)) pos = (double)(N - 1);
+    mu_c = (double)range_value((int)(pos + 0.5), N, mu0, mu1);
+  }
+  if (centred) {
+    __syncthreads();
+    for (int k = tid; k < n; k += nt) obs_pad[k] = (float)((double)obs[k] - mu_c);
+  }
   double q = 0.0;
   for (int k = tid; k < n; k += nt) {
     const double d = (double)obs[k] - xbar;
@@ -181,6 +198,8 @@ __global__ void __launch_bounds__(256)
   out->xbar = xbar;
   out->ss = ss;
   out->smin = smin;
+  out->mu_c = mu_c;
+  out->s_c = ss + (double)n * (xbar - mu_c) * (xbar - mu_c);
   // Largest exponent step between vertically adjacent cells,
   //   |t_(i+1,j,k) - t_(i,j,k)| = |a_j| |mu_(i+1) - mu_i| |mu_i + mu_(i+1) - 2 x_k|,
   // bounded over the whole grid and every observation.  The row spacing gets 2 ulp of slack for
@@ -309,6 +328,112 @@ struct LogSpaceF64 {
     const int j = patch_col(jbase_, cidx);
     const double c = j < g.N ? (double)g.n * g.cd0[j] + shift_ : 0.0;
     return ex2_approx((float)(acc[r][cidx] + c));
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// log-space path, float32x2 tiles: the same sum of log2-pdf terms, one FMA per pdf-eval, but on
+// the FP32 pipe (packed FFMA2, twice the FP64 pipe's rate) with the float64 work reduced to one
+// add per cell and 64 observations.  What makes float32 accumulation accurate enough is
+// centring: with mu_c the grid value nearest the sample mean, x' = x - mu_c, mu' = mu_i - mu_c,
+//   (x_k - mu_i)^2 = (x_k - mu_c)^2 + e_ik,    e_ik = mu'_i (mu'_i - 2 x'_k)      (exact identity)
+//   log2 L_ij = [a_j S_c + n c0_j] + sum_k a_j e_ik,        S_c = sum_k (x_k - mu_c)^2
+// The bracket is float64, once per cell (S_c from setup_kernel).  The per-eval terms a_j e_ik are
+// small wherever the posterior is not negligible (|mu'| <= ~sqrt(66 / (n |a|)) for cells within
+// 1e-20 of the peak), so 64-term float32 tile sums folded into float64 lose ~3e-6 relative on a
+// cell at n = 10^4 -- a plain float32 sum of a_j (x - mu)^2 would lose 1e-4.
+// Per (row, observation): one scalar FFMA (e = x' * (-2 mu') + mu'^2) shared by the 8 columns,
+// then 4 FFMA2.
+// ---------------------------------------------------------------------------------------
+struct LogSpaceTiled {
+  static constexpr int kRows = 4;
+  static constexpr int kCols = 8;
+  static constexpr int kObsStride = 1;
+  static constexpr int kTile = 64;  // observations per float32 tile sum
+  static constexpr int kPairs = kCols / 2;
+  f32x2 a2[kPairs];
+  double acc[kRows][kCols];
+  double s_c_, shift_, mu_c_;
+  int jbase_;
+
+  __device__ __forceinline__ void load_columns(const LikeArgs &, int jbase, const ScaleInfo &sc,
+                                               const ColumnCoefs<kCols> &cf) {
+    jbase_ = jbase;
+    s_c_ = sc.s_c;
+    shift_ = sc.shift;
+    mu_c_ = sc.mu_c;
+#pragma unroll
+    for (int h = 0; h < kPairs; ++h) a2[h] = pack2((float)cf.a[2 * h], (float)cf.a[2 * h + 1]);
+  }
+  __device__ __forceinline__ void begin_rows() {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+#pragma unroll
+      for (int cidx = 0; cidx < kCols; ++cidx) acc[r][cidx] = 0.0;
+  }
+  __device__ __forceinline__ void step(float xc, const float (&gm)[kRows], const float (&gb)[kRows],
+                                       f32x2 (&t2)[kRows][kPairs]) {
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const float e = fmaf(xc, gm[r], gb[r]);
+      const f32x2 e2 = pack2(e, e);
+#pragma unroll
+      for (int h = 0; h < kPairs; ++h) t2[r][h] = fma2(e2, a2[h], t2[r][h]);
+    }
+  }
+  __device__ __forceinline__ void fold(f32x2 (&t2)[kRows][kPairs]) {
+    const f32x2 zero = pack2(0.0f, 0.0f);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+#pragma unroll
+      for (int h = 0; h < kPairs; ++h) {
+        float lo, hi;
+        unpack2(t2[r][h], lo, hi);
+        acc[r][2 * h] += (double)lo;
+        acc[r][2 * h + 1] += (double)hi;
+        t2[r][h] = zero;
+      }
+  }
+  static __device__ __forceinline__ void consume(LogSpaceTiled &pol, const float *xs, int count,
+                                                 const float (&mu)[kRows]) {
+    float gm[kRows], gb[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const float m = (float)((double)mu[r] - pol.mu_c_);
+      gm[r] = -2.0f * m;
+      gb[r] = m * m;
+    }
+    f32x2 t2[kRows][kPairs];
+    const f32x2 zero = pack2(0.0f, 0.0f);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+#pragma unroll
+      for (int h = 0; h < kPairs; ++h) t2[r][h] = zero;
+    const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
+    const int ntiles = count / kTile;
+#pragma unroll 1
+    for (int tIdx = 0; tIdx < ntiles; ++tIdx) {
+#pragma unroll 1
+      for (int q = 0; q < kTile / 4; ++q) {  // 4 observations x 16 independent FFMA2 chains
+        const float4 x = xs4[tIdx * (kTile / 4) + q];
+        pol.step(x.x, gm, gb, t2);
+        pol.step(x.y, gm, gb, t2);
+        pol.step(x.z, gm, gb, t2);
+        pol.step(x.w, gm, gb, t2);
+      }
+      pol.fold(t2);
+    }
+    const int rest = ntiles * kTile;
+    if (rest < count) {
+      for (int k = rest; k < count; ++k) pol.step(xs[k], gm, gb, t2);
+      pol.fold(t2);
+    }
+  }
+  __device__ __forceinline__ float value(const LikeArgs &g, int r, int cidx) const {
+    const int j = patch_col(jbase_, cidx);
+    if (j >= g.N) return 0.0f;
+    const double base = g.ad[j] * s_c_ + (double)g.n * g.cd0[j] + shift_;
+    return ex2_approx((float)(acc[r][cidx] + base));
   }
 };
 

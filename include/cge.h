@@ -54,8 +54,9 @@ enum {
   CGE_MODE_PRODUCT_F32 = 0, /* running float32 product of per-observation pdfs, MUFU ex2 per
                                pdf-eval, one global per-factor rescale (posterior is
                                scale-invariant) -- BASELINE.json "float32 product path" */
-  CGE_MODE_LOGSPACE = 1     /* float64 sum of log-pdf, log-sum-exp normalisation -- for
-                               observation counts where any product underflows */
+  CGE_MODE_LOGSPACE = 1     /* sum of log-pdf (float32x2 tile sums of centred terms folded into
+                               float64), log-sum-exp normalisation -- for observation counts where
+                               any product underflows */
 };
 
 typedef struct cge_context cge_context; /* opaque: device, stream, scratch, tables */
@@ -83,6 +84,9 @@ enum {
                                 adjacent cells one factor is 2^t on MUFU.EX2, the other is derived
                                 from it, e * 2^u with 2^u - 1 a degree-2 FMA-pipe polynomial (only
                                 accurate while the row spacing keeps |u| <= 0.011) */
+  CGE_VARIANT_LOG_F64 = 5,   /* log-space mode only: float64 accumulation, one DFMA per pdf-eval (the
+                                default log-space kernel sums centred terms in float32x2 tiles of 64
+                                observations and folds the tiles into float64) */
   CGE_VARIANT_HYBRID = 4     /* hybrid, forced: packed f32x2 arithmetic; of the 16 exponentials a
                                 thread evaluates per observation, 12 use MUFU.EX2 and 4 an FMA-pipe
                                 degree-5 polynomial with Cody-Waite range reduction */

@@ -170,6 +170,28 @@ def test_many_observations_product_and_streamed_logspace(ctx):
         check_against(res, ref, what=f"log-space n={n}")
 
 
+@pytest.mark.parametrize("variant", [0, 6, api.VARIANT_LOG_F64, 2])
+def test_logspace_kernel_variants(ctx, variant):
+    """The tiled float32x2 log-space kernel (default; 6 = capped at 128 registers) and the
+    float64 one-DFMA-per-eval kernel (5; 2 = capped) against the float64 oracle: a few hundred
+    and 10^4 observations on the README ranges, a grid that does not contain the sample mean (the
+    centre clamps to an edge row, so the centred terms are large), a narrow sigma range at small
+    sigma (large |a_j|), and n not a multiple of the 64-observation tile."""
+    cases = [
+        (257, 1000, (18, 22), (1, 3)),
+        (1024, 10000, (18, 22), (1, 3)),
+        (130, 777, (21, 23), (1, 3)),       # sample mean ~20 is below the grid
+        (130, 5000, (19.8, 20.2), (0.5, 0.7)),
+        (64, 63, (18, 22), (1, 3)),
+        (64, 65, (18, 22), (1, 3)),
+    ]
+    for N, n, mu_r, sg_r in cases:
+        obs = oracle.readme_observations(n=n, seed=5)
+        res = ctx.grid_posterior(obs, N, mu_r, sg_r, mode=cge.MODE_LOGSPACE, variant=variant)
+        ref = oracle.grid_posterior(obs, N, *mu_r, *sg_r, oracle.NUM_LOG)
+        check_against(res, ref, what=f"log-space variant {variant} N={N} n={n} mu={mu_r} sigma={sg_r}")
+
+
 def test_error_behaviour(ctx, readme_obs):
     with pytest.raises(cge.CgeError) as ei:
         ctx.grid_posterior(readme_obs, 0, (18, 22), (1, 3))
@@ -224,11 +246,11 @@ def test_phase_api_with_row_shards(ctx, readme_obs, N):
             ex, mm, ms, z = c.read_results(p, stream)
             # cells are bit-identical to the unsharded run (tiles are anchored to global rows);
             # the sums differ only in the order of the float64 adds and in the float32 4-row
-            # patch sums that a shard edge cuts in two (relative 1e-9 at most)
-            assert np.abs(ex - full.expectations).max() < 2e-9
-            assert np.abs(ms - full.marg_sigma).max() < 1e-9 * full.marg_sigma.max()
+            # patch sums that a shard edge cuts in two (one float32 rounding, 6e-8 of a 4-row sum)
+            assert np.abs(ex - full.expectations).max() < 1e-8
+            assert np.abs(ms - full.marg_sigma).max() < 1e-8 * full.marg_sigma.max()
             assert np.abs(mm[p.row_begin:p.row_end] - full.marg_mu[p.row_begin:p.row_end]).max() \
-                < 1e-9 * full.marg_mu.max()
+                < 1e-8 * full.marg_mu.max()
             assert mm[:p.row_begin].sum() == 0 and mm[p.row_end:].sum() == 0
             rows.append(post.cpu().numpy())
         got = np.concatenate(rows, axis=0)
