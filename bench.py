@@ -45,6 +45,11 @@ WORKLOADS = {
     "16384x10k-log": (16384, 10000, 1),
 }
 DEFAULT_WORKLOAD = "16384x50"
+# dram__bytes_read.sum + dram__bytes_write.sum of the likelihood kernel, per launch, from the
+# committed ncu --set full captures (profiles/r01_ncu_full_*.csv); keyed by (workload, n_gpus)
+NCU_TRAFFIC = {
+    ("16384x50", 1): 1.0768e9,        # profiles/r01_ncu_full_paired_16384x50.csv
+}
 
 
 def log(*a):
@@ -313,7 +318,27 @@ def run_ours(args):
                                    want_timing=False)
         e2e_s = time.perf_counter() - t0
         e2e_check = r.expectations.tolist()
+        # the same call with the posterior ALSO copied to (pinned) host memory every step
+        e2e_full = None
+        if cells_local * 4 <= 4.5e9:
+            pinned = torch.empty((N, N), dtype=torch.float32).pin_memory()
+            host_np = pinned.numpy()
+            full_steps = max(2, min(e2e_steps, 10))
+            ctx.grid_posterior(obs_np, N, MU_RANGE, SIGMA_RANGE, mode=mode, posterior=host_np,
+                               want_timing=False)
+            t0 = time.perf_counter()
+            for _ in range(full_steps):
+                ctx.grid_posterior(obs_np, N, MU_RANGE, SIGMA_RANGE, mode=mode, posterior=host_np,
+                                   want_timing=False)
+            fs = time.perf_counter() - t0
+            e2e_full = {"value": total_evals * full_steps / fs / 1e9, "unit": UNIT,
+                        "ms_per_step": fs / full_steps * 1e3, "steps": full_steps,
+                        "d2h_bytes_per_step": d2h + N * N * 4,
+                        "note": "posterior (float32 N*N) copied to pinned host memory inside the "
+                                "timed region as well; PCIe-bound"}
+            del pinned, host_np
     else:
+        e2e_full = None
         def e2e_once():
             obs_dev.copy_(obs_host, non_blocking=True)
             sh.step(obs_dev, post)
@@ -343,19 +368,40 @@ def run_ours(args):
         like_s = phase["likelihood_ms"] * 1e-3
         evals_per_launch = float(sh.rows_local) * N * n
         ach = evals_per_launch / like_s
+        sinfo = ctx.scale_info()
+        traffic = NCU_TRAFFIC.get((args.workload, world))
         if mode == 0:
+            # executed op counts per pdf-eval of the path that ran (SASS of the inner loop):
+            #   paired rows: 8 MUFU.EX2 + 27 packed (2 lane-ops each) per 16 evals
+            #   hybrid     : 12 MUFU.EX2 + 8 + 8 packed (exponent, product) + 2 x 8 packed
+            #                (polynomial) + 8 scalar per 16 evals
+            paired = sinfo["product_path"] == "paired"
+            mufu_pe, fma_pe = (0.5, 54 / 16) if paired else (0.75, (2 * 32 + 8) / 16)
             roof = {"bound": "mufu", "achieved": ach / 1e9, "peak": ex2_peak / 1e9, "unit": "Gop/s",
-                    "frac": ach / ex2_peak, "traffic": None,
-                    "kernel": "grid_likelihood_kernel<ProductF32>",
-                    "algorithmic": "1 MUFU.EX2 per pdf-eval; evals per launch = rows*N*n",
+                    "frac": ach / ex2_peak, "traffic": traffic,
+                    "kernel": "grid_likelihood_dual_kernel<ProductPaired, ProductHybrid> -> "
+                              + sinfo["product_path"],
+                    "algorithmic": "1 ex2 per pdf-eval (SURVEY 8(d)); evals per launch = rows*N*n",
+                    "note": "frac > 1 is by design: the kernel takes " + str(mufu_pe) + " of its "
+                            "exponentials per eval from MUFU.EX2 and forms the rest on the FMA pipe "
+                            "(paired rows: e*2^u with a degree-2 polynomial; hybrid: degree-5 "
+                            "polynomial), so neither pipe alone bounds it; `executed` gives the "
+                            "utilisation of each pipe by the instructions actually issued, and "
+                            "variant 1 (MUFU-only) is the plain MUFU-roofline kernel",
+                    "executed": {"mufu_per_eval": mufu_pe, "fma_lane_ops_per_eval": fma_pe,
+                                 "mufu_util": mufu_pe * ach / ex2_peak,
+                                 "fma_util": fma_pe * ach / ffma_peak},
+                    "umax": sinfo["umax"], "paired_umax": sinfo["paired_umax"],
                     "peak_source": "ex2.approx.ftz micro-benchmark in this run (cge_microbench 0)",
                     "peak_nominal": 16 * info["sm_count"] * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9}
         else:
-            roof = {"bound": "fp64", "achieved": ach / 1e9, "peak": dfma_peak / 1e9, "unit": "Gop/s",
-                    "frac": ach / dfma_peak, "traffic": None,
-                    "kernel": "grid_likelihood_kernel<LogSpaceF64>",
-                    "algorithmic": "1 DFMA per pdf-eval; evals per launch = rows*N*n",
-                    "peak_source": "DFMA micro-benchmark in this run (cge_microbench 2)"}
+            roof = {"bound": "fp32", "achieved": ach / 1e9, "peak": ffma_peak / 1e9, "unit": "Gop/s",
+                    "frac": ach / ffma_peak, "traffic": traffic,
+                    "kernel": "grid_likelihood_kernel<LogSpaceTiled<256>>",
+                    "algorithmic": "1 FMA per pdf-eval; evals per launch = rows*N*n",
+                    "executed": {"fma_lane_ops_per_eval": 1.125,
+                                 "fma_util": 1.125 * ach / ffma_peak},
+                    "peak_source": "FFMA micro-benchmark in this run (cge_microbench 1)"}
         scale_s = phase["scale_ms"] * 1e-3
         hbm = {"bound": "hbm", "kernel": "scale_posterior_kernel",
                "achieved": 8.0 * cells_local / scale_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
@@ -363,7 +409,8 @@ def run_ours(args):
                "algorithmic": "4 B read + 4 B written per cell", "peak_source": hbm_src}
         fp32 = {"bound": "fp32", "achieved": 4 * ach / 1e9, "peak": ffma_peak / 1e9,
                 "unit": "G lane-instr/s", "frac": 4 * ach / ffma_peak,
-                "algorithmic": "4 FP32 instr per pdf-eval (SURVEY 8(d)); the kernel issues 3.5"}
+                "algorithmic": "4 FP32 instr per pdf-eval (SURVEY 8(d)'s count for the product "
+                               "path; see roofline.executed for what the kernel issues)"}
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
             "warmup": warmup, "ms_per_step": elapsed_ms / steps, "higher_is_better": True,
@@ -379,6 +426,7 @@ def run_ours(args):
                     "api": "cge_grid_posterior (host obs in; E, marginals to host; posterior stays "
                            "on the device like the reference's device_vector)" if world == 1 else
                            "pinned obs -> device, ShardedGridPosterior.step, cge_read_results"},
+            "e2e_posterior_to_host": e2e_full,
             "gpu_launches": launches_per_step * steps,
             "launches_per_step": launches_per_step,
             "roofline": roof, "roofline_hbm": hbm, "roofline_fp32": fp32,

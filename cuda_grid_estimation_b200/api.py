@@ -38,7 +38,7 @@ ABI_SYMBOLS = (
     "cge_profile_begin", "cge_profile_end", "cge_launch_count", "cge_linspace", "cge_meshgrid3", "cge_densities", "cge_densities_grid",
     "cge_row_products_rows", "cge_marginalize_rows", "cge_row_products",
     "cge_normalize", "cge_marginalize", "cge_expectation", "cge_microbench",
-    "cge_generate_normal", "cge_quantiles", "cge_set_prior",
+    "cge_generate_normal", "cge_quantiles", "cge_set_prior", "cge_scale_info",
 )
 
 
@@ -113,6 +113,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "cge_generate_normal": [vp, vp, i32, f32, f32, C.c_ulonglong, i32],
         "cge_quantiles": [vp, vp, i32, vp, i32, vp, vp],
         "cge_set_prior": [vp, vp, vp, i32, vp],
+        "cge_scale_info": [vp, vp, i32, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -344,6 +345,17 @@ def _set_prior(self, prior_mu=None, prior_sigma=None, grid_size=0, prior_full=No
                                    _ptr(prior_full)))
 
 
+def _scale_info(self, stream=None) -> dict:
+    """Scale statistics of the last likelihood call (see cge_scale_info)."""
+    out = np.empty(10, np.float64)
+    _check(self._lib.cge_scale_info(self._h, out.ctypes.data, 10, stream))
+    keys = ("log2s", "shift", "m2", "xbar", "ss", "smin", "mu_c", "s_c", "umax", "paired_umax")
+    d = dict(zip(keys, out.tolist()))
+    d["product_path"] = "paired" if d["umax"] <= d["paired_umax"] else "hybrid"
+    return d
+
+
+Context.scale_info = _scale_info
 Context.set_prior = _set_prior
 Context.generate_normal = _generate_normal
 Context.quantiles = _quantiles

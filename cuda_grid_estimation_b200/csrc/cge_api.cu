@@ -139,9 +139,9 @@ int check_params(const cge_params *p, int *rb, int *re) {
     return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
   switch (p->variant) {
     case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 2: case CGE_VARIANT_PAIRED:
-    case CGE_VARIANT_LOG_F64: case 6:
+    case CGE_VARIANT_LOG_F64: case 6: case 8: case 9:
     case CGE_VARIANT_HYBRID: case 100: case 122: case 133: case 222: case 522: case 523: case 633:
-    case 822: case 1322: case 31: case 33: case 34: case 35: case 381: case 382: case 384: break;
+    case 822: case 1322: case 31: case 32: case 33: case 34: case 35: case 37: case 381: case 382: case 384: break;
     default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
   }
   int b = p->row_begin, e = p->row_end;
@@ -167,7 +167,7 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->rows_local = re - rb;
   // columns per warp strip: 32 lanes x Policy::kCols (log-space keeps 8 columns per thread)
   const bool wide_patch = p->mode == CGE_MODE_PRODUCT_F32 && p->variant >= 381 && p->variant <= 384;
-  const int strip = 32 * (p->mode == CGE_MODE_LOGSPACE ? cge::LogSpaceF64::kCols : wide_patch ? 8 : 4);
+  const int strip = 32 * (p->mode == CGE_MODE_LOGSPACE ? cge::LogSpaceTiled<>::kCols : wide_patch ? 8 : 4);
   pl->ncw = (pl->N + strip - 1) / strip;
   if (pl->ncw >= 8) { pl->wm = 1; pl->wn = 8; }
   else if (pl->ncw >= 4) { pl->wm = 2; pl->wn = 4; }
@@ -228,15 +228,15 @@ int launch_like(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   return launch_like_shape<Policy, 8, 1, MINB>(pl, args, st);
 }
 
-template <class Fine, class Coarse, int WM, int WN>
+template <class Fine, class Coarse, int WM, int WN, int MINB = 1>
 int launch_dual_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
   if (pl.vec4) {
-    auto k = cge::grid_likelihood_dual_kernel<Fine, Coarse, WM, WN, true>;
+    auto k = cge::grid_likelihood_dual_kernel<Fine, Coarse, WM, WN, true, MINB>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     k<<<grid, block, pl.smem, st>>>(args);
   } else {
-    auto k = cge::grid_likelihood_dual_kernel<Fine, Coarse, WM, WN, false>;
+    auto k = cge::grid_likelihood_dual_kernel<Fine, Coarse, WM, WN, false, MINB>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
     k<<<grid, block, pl.smem, st>>>(args);
   }
@@ -244,12 +244,12 @@ int launch_dual_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st
   return CGE_OK;
 }
 
-template <class Fine, class Coarse>
+template <class Fine, class Coarse, int MINB>
 int launch_dual(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
-  if (pl.wm == 1) return launch_dual_shape<Fine, Coarse, 1, 8>(pl, args, st);
-  if (pl.wm == 2) return launch_dual_shape<Fine, Coarse, 2, 4>(pl, args, st);
-  if (pl.wm == 4) return launch_dual_shape<Fine, Coarse, 4, 2>(pl, args, st);
-  return launch_dual_shape<Fine, Coarse, 8, 1>(pl, args, st);
+  if (pl.wm == 1) return launch_dual_shape<Fine, Coarse, 1, 8, MINB>(pl, args, st);
+  if (pl.wm == 2) return launch_dual_shape<Fine, Coarse, 2, 4, MINB>(pl, args, st);
+  if (pl.wm == 4) return launch_dual_shape<Fine, Coarse, 4, 2, MINB>(pl, args, st);
+  return launch_dual_shape<Fine, Coarse, 8, 1, MINB>(pl, args, st);
 }
 
 // product path.  Default: grid_likelihood_dual_kernel -- ProductPaired (half the exponentials
@@ -259,13 +259,14 @@ int launch_dual(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
 // polynomial).  CGE_VARIANT_PAIRED / _HYBRID force one of the two, CGE_VARIANT_MUFU_ONLY is the
 // roofline case; the numbered variants document the tuning sweeps
 // (profiles/r01_variant_sweep_*.jsonl) and are only built for the wide tile shape.
-using DefaultFine = cge::ProductPaired<4, 2>;
+using DefaultFine = cge::ProductPaired<4, 4, true>;
+constexpr int kDefaultMinB = 2;  // <= 128 registers: two 256-thread CTAs per SM
 using DefaultCoarse = cge::ProductHybrid<2, 2, false, 1>;
 
 int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   switch (pl.variant) {
     case CGE_VARIANT_MUFU_ONLY: return launch_like<cge::ProductF32>(pl, args, st);
-    case CGE_VARIANT_PAIRED: return launch_like<DefaultFine>(pl, args, st);
+    case CGE_VARIANT_PAIRED: return launch_like<DefaultFine, kDefaultMinB>(pl, args, st);
     case CGE_VARIANT_HYBRID: return launch_like<DefaultCoarse>(pl, args, st);
     default: break;
   }
@@ -281,13 +282,16 @@ int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
       case 822: return launch_like_shape<cge::ProductHybrid<2, 2, false, 1>, 1, 8, 3>(pl, args, st);
       // 1322: exponent FMA as two scalar FFMAs, 1 observation per iteration
       case 1322: return launch_like_shape<cge::ProductHybrid<2, 2, false, 1, true>, 1, 8>(pl, args, st);
-      // paired rows (CGE_VARIANT_PAIRED = 4 columns per thread, 2 observations per iteration):
-      // 31 / 34 = 1 / 4 observations per iteration; 33 = capped at 80 registers (3 CTAs per SM);
-      // 35 = 4 observations, capped at 128 registers; 38x = 8 columns per thread
+      // paired rows (CGE_VARIANT_PAIRED = 4 columns per thread, 4 observations per iteration, the
+      // row pairs' scalars packed, capped at 128 registers): 31 / 32 / 34 = 1 / 2 / 4 observations
+      // per iteration, scalars unpacked, uncapped; 33 = 32 capped at 80 registers (3 CTAs per
+      // SM); 35 = 34 capped at 128; 37 = 32 with packed scalars; 38x = 8 columns per thread
       case 31: return launch_like_shape<cge::ProductPaired<4, 1>, 1, 8>(pl, args, st);
+      case 32: return launch_like_shape<cge::ProductPaired<4, 2>, 1, 8>(pl, args, st);
       case 33: return launch_like_shape<cge::ProductPaired<4, 2>, 1, 8, 3>(pl, args, st);
-      case 35: return launch_like_shape<cge::ProductPaired<4, 4>, 1, 8, 2>(pl, args, st);
       case 34: return launch_like_shape<cge::ProductPaired<4, 4>, 1, 8>(pl, args, st);
+      case 35: return launch_like_shape<cge::ProductPaired<4, 4>, 1, 8, 2>(pl, args, st);
+      case 37: return launch_like_shape<cge::ProductPaired<4, 2, true>, 1, 8>(pl, args, st);
       case 381: return launch_like_shape<cge::ProductPaired<8, 1>, 1, 8>(pl, args, st);
       case 382: return launch_like_shape<cge::ProductPaired<8, 2>, 1, 8>(pl, args, st);
       case 384: return launch_like_shape<cge::ProductPaired<8, 4>, 1, 8>(pl, args, st);
@@ -296,7 +300,7 @@ int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   }
   if (pl.variant >= 381 && pl.variant <= 384)
     return set_error(CGE_ERR_BAD_ARG, "variant %d needs grid_size >= 2048", pl.variant);
-  return launch_dual<DefaultFine, DefaultCoarse>(pl, args, st);
+  return launch_dual<DefaultFine, DefaultCoarse, kDefaultMinB>(pl, args, st);
 }
 
 int peer_release(cge_context *ctx);
@@ -504,17 +508,21 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   args.row_end = re;
   args.tile_rows = pl.tile_rows;
   args.ncw = pl.ncw;
-  if (p->mode == CGE_MODE_PRODUCT_F32)
+  if (p->mode == CGE_MODE_PRODUCT_F32) {
     CKRC(launch_product(pl, args, st));
-  else
-  {
-    // default: float32x2 tile sums of centred terms folded into float64 (LogSpaceTiled);
+  } else {
+    // default: float32x2 sums of centred terms in tiles of 256 observations folded into float64
+    // (LogSpaceTiled), capped at 128 registers; 6 / 8: tiles of 64 / 1024; 9: uncapped;
     // CGE_VARIANT_LOG_F64: one DFMA per pdf-eval (the first log-space kernel, kept as the
-    // FP64-pipe roofline case); 2: the same capped at 128 registers; 6: tiled capped at 128
-    if (p->variant == CGE_VARIANT_LOG_F64) CKRC((launch_like<cge::LogSpaceF64, 1>(pl, args, st)));
-    else if (p->variant == 2) CKRC((launch_like<cge::LogSpaceF64, 2>(pl, args, st)));
-    else if (p->variant == 6) CKRC((launch_like<cge::LogSpaceTiled, 2>(pl, args, st)));
-    else CKRC((launch_like<cge::LogSpaceTiled, 1>(pl, args, st)));
+    // FP64-pipe case); 2: the same capped at 128 registers
+    switch (p->variant) {
+      case CGE_VARIANT_LOG_F64: CKRC((launch_like<cge::LogSpaceF64, 1>(pl, args, st))); break;
+      case 2: CKRC((launch_like<cge::LogSpaceF64, 2>(pl, args, st))); break;
+      case 6: CKRC((launch_like<cge::LogSpaceTiled<64>, 2>(pl, args, st))); break;
+      case 8: CKRC((launch_like<cge::LogSpaceTiled<1024>, 2>(pl, args, st))); break;
+      case 9: CKRC((launch_like<cge::LogSpaceTiled<256>, 1>(pl, args, st))); break;
+      default: CKRC((launch_like<cge::LogSpaceTiled<256>, 2>(pl, args, st))); break;
+    }
   }
   ctx->launches += 1;
   CKRC(mark(ctx, 2, st));
@@ -834,6 +842,22 @@ CGE_EXPORT int cge_posterior_dev(cge_context *ctx, float **posterior_dev, size_t
   if (!ctx) return set_error(CGE_ERR_BAD_ARG, "context is NULL");
   if (posterior_dev) *posterior_dev = ctx->posterior.ptr;
   if (count) *count = ctx->plan.valid ? (size_t)ctx->plan.rows_local * ctx->plan.N : 0;
+  return CGE_OK;
+}
+
+// scale statistics of the last likelihood call (waits for `stream`)
+CGE_EXPORT int cge_scale_info(cge_context *ctx, double *out, int count, void *stream) {
+  CKRC(bind(ctx));
+  if (!out || count < 1) return set_error(CGE_ERR_BAD_ARG, "scale_info: bad argument");
+  if (!ctx->plan.valid || !ctx->scale.ptr)
+    return set_error(CGE_ERR_BAD_ARG, "no likelihood call has been made");
+  cge::ScaleInfo h;
+  cudaStream_t st = (cudaStream_t)stream;
+  CK(cudaMemcpyAsync(&h, ctx->scale.ptr, sizeof h, cudaMemcpyDeviceToHost, st));
+  CK(cudaStreamSynchronize(st));
+  const double v[10] = {h.log2s, h.shift, h.m2, h.xbar, h.ss, h.smin, h.mu_c, h.s_c, h.umax,
+                        cge::kPairedUmax};
+  for (int i = 0; i < count && i < 10; ++i) out[i] = v[i];
   return CGE_OK;
 }
 

@@ -334,22 +334,23 @@ struct LogSpaceF64 {
 // ---------------------------------------------------------------------------------------
 // log-space path, float32x2 tiles: the same sum of log2-pdf terms, one FMA per pdf-eval, but on
 // the FP32 pipe (packed FFMA2, twice the FP64 pipe's rate) with the float64 work reduced to one
-// add per cell and 64 observations.  What makes float32 accumulation accurate enough is
+// add per cell and tile of observations.  What makes float32 accumulation accurate enough is
 // centring: with mu_c the grid value nearest the sample mean, x' = x - mu_c, mu' = mu_i - mu_c,
 //   (x_k - mu_i)^2 = (x_k - mu_c)^2 + e_ik,    e_ik = mu'_i (mu'_i - 2 x'_k)      (exact identity)
 //   log2 L_ij = [a_j S_c + n c0_j] + sum_k a_j e_ik,        S_c = sum_k (x_k - mu_c)^2
 // The bracket is float64, once per cell (S_c from setup_kernel).  The per-eval terms a_j e_ik are
 // small wherever the posterior is not negligible (|mu'| <= ~sqrt(66 / (n |a|)) for cells within
-// 1e-20 of the peak), so 64-term float32 tile sums folded into float64 lose ~3e-6 relative on a
-// cell at n = 10^4 -- a plain float32 sum of a_j (x - mu)^2 would lose 1e-4.
+// 1e-20 of the peak), so float32 tile sums (TILE = 256 observations) folded into float64 lose
+// ~7e-6 relative on a cell at n = 10^4 -- a plain float32 sum of a_j (x - mu)^2 would lose 1e-4.
 // Per (row, observation): one scalar FFMA (e = x' * (-2 mu') + mu'^2) shared by the 8 columns,
 // then 4 FFMA2.
 // ---------------------------------------------------------------------------------------
+template <int TILE = 256>
 struct LogSpaceTiled {
   static constexpr int kRows = 4;
   static constexpr int kCols = 8;
   static constexpr int kObsStride = 1;
-  static constexpr int kTile = 64;  // observations per float32 tile sum
+  static constexpr int kTile = TILE;  // observations per float32 tile sum
   static constexpr int kPairs = kCols / 2;
   f32x2 a2[kPairs];
   double acc[kRows][kCols];
@@ -582,7 +583,7 @@ struct ProductHybrid {
 // ---------------------------------------------------------------------------------------
 constexpr double kPairedUmax = 0.011;
 
-template <int KC = 4, int OBS_PER_ITER = 1>
+template <int KC = 4, int OBS_PER_ITER = 1, bool PACKED_ROWS = false>
 struct ProductPaired {
   static constexpr int kRows = kRM;
   static constexpr int kCols = KC;
@@ -625,11 +626,23 @@ struct ProductPaired {
   // one observation: rows (0,1) and (2,3) of the patch are the pairs; gm/gb give g = x*gm + gb
   __device__ __forceinline__ void step(float x, const float (&mu)[kRM], const float (&gm)[kRM / 2],
                                        const float (&gb)[kRM / 2]) {
+    float ddv[kRM / 2], ggv[kRM / 2];
+    if (PACKED_ROWS) {  // the two row pairs' scalars as one packed FADD2 / FMUL2 / FFMA2 each
+      const f32x2 x2 = pack2(x, x);
+      const f32x2 d2 = sub2(x2, pack2(mu[0], mu[2]));
+      unpack2(mul2(d2, d2), ddv[0], ddv[1]);
+      unpack2(fma2(x2, pack2(gm[0], gm[1]), pack2(gb[0], gb[1])), ggv[0], ggv[1]);
+    } else {
+#pragma unroll
+      for (int rp = 0; rp < kRM / 2; ++rp) {
+        const float d = x - mu[2 * rp];  // same f32 rounding as the reference's (x - mu), kernels.h:111
+        ddv[rp] = d * d;
+        ggv[rp] = fmaf(x, gm[rp], gb[rp]);
+      }
+    }
 #pragma unroll
     for (int rp = 0; rp < kRM / 2; ++rp) {
-      const float d = x - mu[2 * rp];  // same f32 rounding as the reference's (x - mu), kernels.h:111
-      const float dd = d * d;
-      const float gg = fmaf(x, gm[rp], gb[rp]);
+      const float dd = ddv[rp], gg = ggv[rp];
       const f32x2 dd2 = pack2(dd, dd);
       const f32x2 g2 = pack2(gg, gg);
 #pragma unroll

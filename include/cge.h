@@ -85,7 +85,7 @@ enum {
                                 from it, e * 2^u with 2^u - 1 a degree-2 FMA-pipe polynomial (only
                                 accurate while the row spacing keeps |u| <= 0.011) */
   CGE_VARIANT_LOG_F64 = 5,   /* log-space mode only: float64 accumulation, one DFMA per pdf-eval (the
-                                default log-space kernel sums centred terms in float32x2 tiles of 64
+                                default log-space kernel sums centred terms in float32x2 tiles of 256
                                 observations and folds the tiles into float64) */
   CGE_VARIANT_HYBRID = 4     /* hybrid, forced: packed f32x2 arithmetic; of the 16 exponentials a
                                 thread evaluates per observation, 12 use MUFU.EX2 and 4 an FMA-pipe
@@ -94,9 +94,11 @@ enum {
      the full sweep incl. variants since removed is in profiles/r01_variant_sweep_*.jsonl):
      100 packed, MUFU only; 1ab / 5ab / 6ab hybrid with a / b polynomial column pairs (of 8) on
      even / odd observations and 4 / 2 / 1 observations per loop iteration; 222 scalar
-     polynomial; 822 = hybrid capped at 80 registers; 1322 = exponent FMAs scalar; 31 / 34 =
-     paired rows with 1 / 4 observations per loop iteration (CGE_VARIANT_PAIRED has 2); 33 / 35 =
-     paired rows capped at 80 / 128 registers; 38x = paired rows, 8 columns per thread.  In log-space mode variant 2 caps the kernel at 128 registers. */
+     polynomial; 822 = hybrid capped at 80 registers; 1322 = exponent FMAs scalar; 31 / 32 / 34 =
+     paired rows with 1 / 2 / 4 observations per loop iteration, uncapped registers; 33 / 35 =
+     32 / 34 capped at 80 / 128 registers; 37 = 32 with the row pairs' scalars packed; 38x = paired
+     rows, 8 columns per thread.  Log-space: 6 / 8 = tiles of 64 / 1024 observations (default
+     256), 9 = uncapped registers.  In log-space mode variant 2 caps the kernel at 128 registers. */
 };
 
 /* per-phase device timings of the last synchronous call, milliseconds (CUDA events) */
@@ -241,6 +243,13 @@ int cge_generate_normal(cge_context *ctx, float *out_dev, int n, float mu, float
  * (notebooks/quick-prototyping.ipynb cell 5).  cdf_dev (n float64) is optional. */
 int cge_quantiles(cge_context *ctx, const double *marginal_dev, int n, const double *probs_host,
                   int nprobs, int *indices_host, double *cdf_dev);
+
+/* Scale statistics the setup kernel derived for the last likelihood call (diagnostics; waits for
+ * `stream`): out[0..9] = log2 of the per-factor rescale, log-space shift, log2 of the largest
+ * likelihood on the grid, sample mean, sum of squared deviations, min_i sum_k (x_k - mu_i)^2,
+ * log-space centre mu_c, sum_k (x_k - mu_c)^2, umax (largest exponent step between vertically
+ * adjacent cells), and the bound on umax below which the paired-rows product kernel runs. */
+int cge_scale_info(cge_context *ctx, double *out, int count, void *stream);
 
 /* ---- roofline micro-benchmarks (bench.py): measured pipe peaks on this device ------------
  * kind: 0 = MUFU ex2.approx.ftz.f32, 1 = FFMA, 2 = DFMA, 3 = FFMA2 (fma.rn.f32x2);

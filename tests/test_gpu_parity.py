@@ -170,10 +170,10 @@ def test_many_observations_product_and_streamed_logspace(ctx):
         check_against(res, ref, what=f"log-space n={n}")
 
 
-@pytest.mark.parametrize("variant", [0, 6, api.VARIANT_LOG_F64, 2])
+@pytest.mark.parametrize("variant", [0, 6, 8, 9, api.VARIANT_LOG_F64, 2])
 def test_logspace_kernel_variants(ctx, variant):
-    """The tiled float32x2 log-space kernel (default; 6 = capped at 128 registers) and the
-    float64 one-DFMA-per-eval kernel (5; 2 = capped) against the float64 oracle: a few hundred
+    """The tiled float32x2 log-space kernel (default: tiles of 256 observations; 6 / 8: 64 /
+    1024; 9: uncapped registers) and the float64 one-DFMA-per-eval kernel (5; 2 = capped) against the float64 oracle: a few hundred
     and 10^4 observations on the README ranges, a grid that does not contain the sample mean (the
     centre clamps to an edge row, so the centred terms are large), a narrow sigma range at small
     sigma (large |a_j|), and n not a multiple of the 64-observation tile."""
@@ -184,6 +184,7 @@ def test_logspace_kernel_variants(ctx, variant):
         (130, 5000, (19.8, 20.2), (0.5, 0.7)),
         (64, 63, (18, 22), (1, 3)),
         (64, 65, (18, 22), (1, 3)),
+        (64, 257, (18, 22), (1, 3)),
     ]
     for N, n, mu_r, sg_r in cases:
         obs = oracle.readme_observations(n=n, seed=5)
@@ -302,7 +303,7 @@ def _ref_4096(readme_obs):
     return _REF_4096["f64"]
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4, 31, 33, 34, 35, 381, 382, 384])
+@pytest.mark.parametrize("variant", [0, 3, 4, 31, 32, 33, 34, 35, 37, 381, 382, 384])
 def test_paired_rows_variants_4096(ctx, readme_obs, variant):
     """README ranges at N=4096: |u| <= 0.0084, inside the paired kernel's bound (0.011).  Every
     paired variant (and the hybrid one it replaces here) against the float64 oracle."""
