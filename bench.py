@@ -56,6 +56,25 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly one JSON line: everything libraries print there (the NCCL version banner,
+# for one) is sent to stderr by pointing fd 1 at fd 2 for the duration of the run
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    data = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, data)
+
+
 def observations(n: int) -> np.ndarray:
     """Synthetic observations ~ N(20, 2): README.md:34-36 recipe for n=50 (legacy seed 42),
     default_rng(42) otherwise.  Stated here rather than imported
@@ -210,7 +229,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
 
 
@@ -454,7 +473,7 @@ def run_ours(args):
         dist.destroy_process_group()
     ctx.close()
     if out is not None:
-        print(json.dumps(out), flush=True)
+        emit(out)
     return 0
 
 
@@ -471,6 +490,7 @@ def main():
     ap.add_argument("--exchange", choices=["auto", "p2p", "nccl"], default="auto",
                     help="N>1: how the N+2 float64 partial vector is summed over ranks")
     args = ap.parse_args()
+    quiet_stdout()
     args.steps_defaulted = args.steps is None
     if args.steps is None:
         args.steps = 100

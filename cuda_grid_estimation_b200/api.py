@@ -26,6 +26,7 @@ VARIANT_MUFU_ONLY = 1
 VARIANT_PAIRED = 3
 VARIANT_HYBRID = 4
 VARIANT_LOG_F64 = 5
+VARIANT_UNFUSED = 7
 
 OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_DEGENERATE, ERR_NCCL, ERR_SIZE = range(7)
 

@@ -70,6 +70,31 @@ struct DevBuf {
   }
 };
 
+// grow-only pinned host buffer (staging for small host<->device copies: a copy from or to
+// pageable memory costs ~10 us of driver staging each, a pinned one is a plain DMA)
+template <class T>
+struct PinnedBuf {
+  T *ptr = nullptr;
+  size_t cap = 0;
+  int reserve(size_t count) {
+    if (count <= cap) return CGE_OK;
+    if (ptr) {
+      CK(cudaFreeHost(ptr));
+      ptr = nullptr;
+      cap = 0;
+    }
+    size_t want = count + count / 8 + 64;
+    CK(cudaMallocHost(&ptr, want * sizeof(T)));
+    cap = want;
+    return CGE_OK;
+  }
+  void release() {
+    if (ptr) cudaFreeHost(ptr);
+    ptr = nullptr;
+    cap = 0;
+  }
+};
+
 struct Plan {
   bool valid = false;
   int N = 0, n = 0, n_pad = 0, mode = 0, variant = 0;
@@ -98,6 +123,9 @@ struct cge_context {
   const float *prior_full = nullptr;     // caller-owned device table, shard layout
   DevBuf<cge::ScaleInfo> scale;
   DevBuf<float> sink;
+  PinnedBuf<float> host_obs;       // staging for host observations
+  PinnedBuf<double> host_results;  // staging for {E, Z, 1/Z}, both marginals
+  bool host_results_valid = false;  // the last step's kernel wrote host_results itself
   Plan plan;
   cge_timing timing = {};
   int launches = 0;
@@ -139,7 +167,7 @@ int check_params(const cge_params *p, int *rb, int *re) {
     return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
   switch (p->variant) {
     case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 2: case CGE_VARIANT_PAIRED:
-    case CGE_VARIANT_LOG_F64: case 6: case 8: case 9:
+    case CGE_VARIANT_LOG_F64: case 6: case 8: case 9: case CGE_VARIANT_UNFUSED:
     case CGE_VARIANT_HYBRID: case 100: case 122: case 133: case 222: case 522: case 523: case 633:
     case 822: case 1322: case 31: case 32: case 33: case 34: case 35: case 37: case 381: case 382: case 384: break;
     default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
@@ -152,6 +180,11 @@ int check_params(const cge_params *p, int *rb, int *re) {
   *rb = b;
   *re = e;
   return CGE_OK;
+}
+
+// log-space kernels other than the float64 ones read centred observations (x_k - mu_c)
+int centred_obs(const cge_params *p) {
+  return (p->mode == CGE_MODE_LOGSPACE && p->variant != CGE_VARIANT_LOG_F64 && p->variant != 2) ? 1 : 0;
 }
 
 // tile shape and grid for one shard
@@ -303,6 +336,131 @@ int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   return launch_dual<DefaultFine, DefaultCoarse, kDefaultMinB>(pl, args, st);
 }
 
+// ---------------------------------------------------------------------------------------
+// single-launch path for small grids (cge::small_grid_kernel): whole grid, no exchange
+// ---------------------------------------------------------------------------------------
+constexpr int kSmallGridMax = 256;
+constexpr int kZeroCopyObsMax = 1024;  // host observations read in place (mapped pinned) up to this n
+int mark(cge_context *ctx, int k, cudaStream_t st);
+
+template <class Fine, class Coarse, int WM, int WN>
+int launch_small_shape(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st) {
+  dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
+  if (pl.vec4) {
+    auto k = cge::small_grid_kernel<Fine, Coarse, WM, WN, true>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    k<<<grid, block, pl.smem, st>>>(a);
+  } else {
+    auto k = cge::small_grid_kernel<Fine, Coarse, WM, WN, false>;
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
+    k<<<grid, block, pl.smem, st>>>(a);
+  }
+  CK(cudaGetLastError());
+  return CGE_OK;
+}
+
+template <class Fine, class Coarse>
+int launch_small(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st) {
+  if (pl.wm == 1) return launch_small_shape<Fine, Coarse, 1, 8>(pl, a, st);
+  if (pl.wm == 2) return launch_small_shape<Fine, Coarse, 2, 4>(pl, a, st);
+  if (pl.wm == 4) return launch_small_shape<Fine, Coarse, 4, 2>(pl, a, st);
+  return launch_small_shape<Fine, Coarse, 8, 1>(pl, a, st);
+}
+
+bool small_grid_eligible(const cge_context *ctx, const cge_params *p, int rb, int re) {
+  return p->variant == CGE_VARIANT_DEFAULT && p->grid_size <= kSmallGridMax && rb == 0 &&
+         re == p->grid_size && !ctx->peer_on && ((p->n_obs + 3) & ~3) <= cge::kObsSingleMax;
+}
+
+int reserve_step_buffers(cge_context *ctx, const Plan &pl, cudaStream_t st) {
+  const int N = pl.N;
+  CKRC(ctx->mu.reserve((size_t)N + 4));
+  CKRC(ctx->sigma.reserve(N));
+  CKRC(ctx->ad.reserve(N));
+  CKRC(ctx->cd0.reserve(N));
+  CKRC(ctx->obs_pad.reserve(pl.n_pad));
+  CKRC(ctx->scale.reserve(1));
+  CKRC(ctx->espart.reserve((size_t)(N + 255) / 256));
+  if (!ctx->tickets.ptr) {
+    CKRC(ctx->tickets.reserve(3));
+    CK(cudaMemsetAsync(ctx->tickets.ptr, 0, 3 * sizeof(unsigned int), st));
+  }
+  CKRC(ctx->rowpart.reserve((size_t)pl.rows_local * pl.ncw));
+  CKRC(ctx->colpart.reserve((size_t)pl.ncolparts * N));
+  CKRC(ctx->partials.reserve((size_t)N + 2));
+  CKRC(ctx->rowsum.reserve(pl.rows_local));
+  CKRC(ctx->zpart.reserve(pl.nb_row));
+  CKRC(ctx->smupart.reserve(pl.nb_row));
+  CKRC(ctx->results.reserve(4 + 2 * (size_t)N));
+  return CGE_OK;
+}
+
+int fill_like_args(cge_context *ctx, const Plan &pl, float *posterior_dev, cge::LikeArgs *args) {
+  const int N = pl.N;
+  args->obs_pad = ctx->obs_pad.ptr;
+  args->mu = ctx->mu.ptr;
+  args->ad = ctx->ad.ptr;
+  args->cd0 = ctx->cd0.ptr;
+  args->scale = ctx->scale.ptr;
+  if ((ctx->has_prior_mu || ctx->has_prior_sigma) && ctx->prior_n != N)
+    return set_error(CGE_ERR_BAD_ARG, "prior was set for grid_size %d, call has %d", ctx->prior_n, N);
+  args->prior_mu = ctx->has_prior_mu ? ctx->prior_mu.ptr : nullptr;
+  args->prior_sigma = ctx->has_prior_sigma ? ctx->prior_sigma.ptr : nullptr;
+  args->prior_full = ctx->prior_full;
+  args->post = posterior_dev;
+  args->rowpart = ctx->rowpart.ptr;
+  args->colpart = ctx->colpart.ptr;
+  args->n = pl.n;
+  args->n_pad = pl.n_pad;
+  args->N = N;
+  args->row_begin = pl.row_begin;
+  args->row_end = pl.row_end;
+  args->tile_rows = pl.tile_rows;
+  args->ncw = pl.ncw;
+  return CGE_OK;
+}
+
+// the whole step in one launch; leaves the context as cge_likelihood_partials + cge_finalize would
+int small_grid_step(cge_context *ctx, const cge_params *p, const float *obs_dev,
+                    float *posterior_dev, cudaStream_t st, bool results_to_host) {
+  Plan &pl = ctx->plan;
+  pl.valid = false;
+  make_plan(ctx, p, 0, p->grid_size, posterior_dev, &pl);
+  CKRC(reserve_step_buffers(ctx, pl, st));
+  cge::SmallArgs a = {};
+  CKRC(fill_like_args(ctx, pl, posterior_dev, &a.like));
+  a.range = cge::RangeArgs{pl.N, p->mu_start, p->mu_end, p->sigma_start, p->sigma_end};
+  a.obs = obs_dev;
+  a.mu = ctx->mu.ptr;
+  a.sigma = ctx->sigma.ptr;
+  a.ad = ctx->ad.ptr;
+  a.cd0 = ctx->cd0.ptr;
+  a.scale = ctx->scale.ptr;
+  a.centred = centred_obs(p);
+  a.ncolparts = pl.ncolparts;
+  a.partials = ctx->partials.ptr;
+  a.rowsum = ctx->rowsum.ptr;
+  a.results = ctx->results.ptr;
+  a.results_host = nullptr;
+  if (results_to_host) {
+    CKRC(ctx->host_results.reserve(4 + 2 * (size_t)pl.N));
+    a.results_host = ctx->host_results.ptr;
+  }
+  ctx->host_results_valid = results_to_host;
+  a.ticket = ctx->tickets.ptr + 2;
+  ctx->launches = 0;
+  CKRC(mark(ctx, 0, st));
+  CKRC(mark(ctx, 1, st));
+  if (p->mode == CGE_MODE_PRODUCT_F32)
+    CKRC((launch_small<DefaultFine, DefaultCoarse>(pl, a, st)));
+  else
+    CKRC((launch_small<cge::LogSpaceTiled<256>, cge::LogSpaceTiled<256>>(pl, a, st)));
+  ctx->launches += 1;
+  for (int k = 2; k <= 6; ++k) CKRC(mark(ctx, k, st));
+  if (ctx->prof_on && ctx->prof_step < ctx->prof_cap) ctx->prof_step++;
+  return CGE_OK;
+}
+
 int peer_release(cge_context *ctx);
 constexpr size_t kPeerHeader = 256;
 double *peer_buf(const cge_context *ctx, int rank, unsigned long long step) {
@@ -425,6 +583,8 @@ CGE_EXPORT int cge_destroy(cge_context *ctx) {
   ctx->colpart.release(); ctx->partials.release(); ctx->rowsum.release(); ctx->zpart.release();
   ctx->smupart.release(); ctx->results.release(); ctx->tmp.release(); ctx->scale.release();
   ctx->sink.release();
+  ctx->host_obs.release();
+  ctx->host_results.release();
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : ctx->prof_events) cudaEventDestroy(ev);
@@ -454,60 +614,24 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   cudaStream_t st = (cudaStream_t)stream;
   Plan &pl = ctx->plan;
   pl.valid = false;
+  ctx->host_results_valid = false;
   make_plan(ctx, p, rb, re, posterior_dev, &pl);
   const int N = pl.N;
 
-  CKRC(ctx->mu.reserve((size_t)N + 4));
-  CKRC(ctx->sigma.reserve(N));
-  CKRC(ctx->ad.reserve(N));
-  CKRC(ctx->cd0.reserve(N));
-  CKRC(ctx->obs_pad.reserve(pl.n_pad));
-  CKRC(ctx->scale.reserve(1));
-  CKRC(ctx->espart.reserve((size_t)(N + 255) / 256));
-  if (!ctx->tickets.ptr) {
-    CKRC(ctx->tickets.reserve(2));
-    CK(cudaMemsetAsync(ctx->tickets.ptr, 0, 2 * sizeof(unsigned int), st));
-  }
-  CKRC(ctx->rowpart.reserve((size_t)pl.rows_local * pl.ncw));
-  CKRC(ctx->colpart.reserve((size_t)pl.ncolparts * N));
-  CKRC(ctx->partials.reserve((size_t)N + 2));
-  CKRC(ctx->rowsum.reserve(pl.rows_local));
-  CKRC(ctx->zpart.reserve(pl.nb_row));
-  CKRC(ctx->smupart.reserve(pl.nb_row));
-  CKRC(ctx->results.reserve(4 + 2 * (size_t)N));
+  CKRC(reserve_step_buffers(ctx, pl, st));
 
   ctx->launches = 0;
   CKRC(mark(ctx, 0, st));
+  const cge::RangeArgs range = {N, p->mu_start, p->mu_end, p->sigma_start, p->sigma_end};
   cge::setup_kernel<<<(N + 3 + 255) / 256, 256, 0, st>>>(
-      ctx->mu.ptr, ctx->sigma.ptr, ctx->ad.ptr, ctx->cd0.ptr, N, p->mu_start, p->mu_end,
-      p->sigma_start, p->sigma_end, obs_dev, ctx->obs_pad.ptr, pl.n, pl.n_pad,
-      (p->mode == CGE_MODE_LOGSPACE && p->variant != CGE_VARIANT_LOG_F64 && p->variant != 2) ? 1 : 0,
-      ctx->scale.ptr);
+      ctx->mu.ptr, ctx->sigma.ptr, ctx->ad.ptr, ctx->cd0.ptr, range, obs_dev, ctx->obs_pad.ptr, pl.n,
+      pl.n_pad, centred_obs(p), ctx->scale.ptr);
   CK(cudaGetLastError());
   ctx->launches += 1;
   CKRC(mark(ctx, 1, st));
 
   cge::LikeArgs args;
-  args.obs_pad = ctx->obs_pad.ptr;
-  args.mu = ctx->mu.ptr;
-  args.ad = ctx->ad.ptr;
-  args.cd0 = ctx->cd0.ptr;
-  args.scale = ctx->scale.ptr;
-  if ((ctx->has_prior_mu || ctx->has_prior_sigma) && ctx->prior_n != N)
-    return set_error(CGE_ERR_BAD_ARG, "prior was set for grid_size %d, call has %d", ctx->prior_n, N);
-  args.prior_mu = ctx->has_prior_mu ? ctx->prior_mu.ptr : nullptr;
-  args.prior_sigma = ctx->has_prior_sigma ? ctx->prior_sigma.ptr : nullptr;
-  args.prior_full = ctx->prior_full;
-  args.post = posterior_dev;
-  args.rowpart = ctx->rowpart.ptr;
-  args.colpart = ctx->colpart.ptr;
-  args.n = pl.n;
-  args.n_pad = pl.n_pad;
-  args.N = N;
-  args.row_begin = rb;
-  args.row_end = re;
-  args.tile_rows = pl.tile_rows;
-  args.ncw = pl.ncw;
+  CKRC(fill_like_args(ctx, pl, posterior_dev, &args));
   if (p->mode == CGE_MODE_PRODUCT_F32) {
     CKRC(launch_product(pl, args, st));
   } else {
@@ -726,18 +850,40 @@ CGE_EXPORT int cge_read_results(cge_context *ctx, const cge_params *p, double *e
   cudaStream_t st = (cudaStream_t)stream;
   const size_t N = (size_t)ctx->plan.N;
   double head[4];
-  CK(cudaMemcpyAsync(head, ctx->results.ptr, sizeof head, cudaMemcpyDeviceToHost, st));
-  if (marg_sigma)
-    CK(cudaMemcpyAsync(marg_sigma, ctx->results.ptr + 4, N * sizeof(double), cudaMemcpyDefault, st));
-  if (marg_mu)
-    CK(cudaMemcpyAsync(marg_mu, ctx->results.ptr + 4 + N, N * sizeof(double), cudaMemcpyDefault, st));
-  CK(cudaStreamSynchronize(st));
-  if (expectations) {
-    if (is_device_pointer(expectations))
-      CK(cudaMemcpy(expectations, head, 2 * sizeof(double), cudaMemcpyHostToDevice));
-    else {
+  const bool dev_out = (marg_sigma && is_device_pointer(marg_sigma)) ||
+                       (marg_mu && is_device_pointer(marg_mu)) ||
+                       (expectations && is_device_pointer(expectations));
+  if (!dev_out) {
+    // host destinations: one DMA of the whole results block into pinned staging, then host copies
+    const size_t count = 4 + ((marg_mu || marg_sigma) ? 2 * N : 0);
+    if (!ctx->host_results_valid) {  // (small_grid_kernel writes the staging block itself)
+      CKRC(ctx->host_results.reserve(count));
+      CK(cudaMemcpyAsync(ctx->host_results.ptr, ctx->results.ptr, count * sizeof(double),
+                         cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    const double *h = ctx->host_results.ptr;
+    std::memcpy(head, h, sizeof head);
+    if (marg_sigma) std::memcpy(marg_sigma, h + 4, N * sizeof(double));
+    if (marg_mu) std::memcpy(marg_mu, h + 4 + N, N * sizeof(double));
+    if (expectations) {
       expectations[0] = head[0];
       expectations[1] = head[1];
+    }
+  } else {
+    CK(cudaMemcpyAsync(head, ctx->results.ptr, sizeof head, cudaMemcpyDeviceToHost, st));
+    if (marg_sigma)
+      CK(cudaMemcpyAsync(marg_sigma, ctx->results.ptr + 4, N * sizeof(double), cudaMemcpyDefault, st));
+    if (marg_mu)
+      CK(cudaMemcpyAsync(marg_mu, ctx->results.ptr + 4 + N, N * sizeof(double), cudaMemcpyDefault, st));
+    CK(cudaStreamSynchronize(st));
+    if (expectations) {
+      if (is_device_pointer(expectations))
+        CK(cudaMemcpy(expectations, head, 2 * sizeof(double), cudaMemcpyHostToDevice));
+      else {
+        expectations[0] = head[0];
+        expectations[1] = head[1];
+      }
     }
   }
   if (z) *z = head[2];
@@ -795,12 +941,21 @@ CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const f
   }
 
   const float *obs_dev = obs;
+  const bool small = small_grid_eligible(ctx, p, rb, re);
   if (timing) CK(cudaEventRecord(ctx->ev[7], st));
   if (!is_device_pointer(obs)) {
-    CKRC(ctx->obs_in.reserve(p->n_obs));
-    CK(cudaMemcpyAsync(ctx->obs_in.ptr, obs, (size_t)p->n_obs * sizeof(float),
-                       cudaMemcpyHostToDevice, st));
-    obs_dev = ctx->obs_in.ptr;
+    // (the previous call's use of this staging buffer has completed: every call ends with a
+    // stream synchronisation in cge_read_results)
+    CKRC(ctx->host_obs.reserve(p->n_obs));
+    std::memcpy(ctx->host_obs.ptr, obs, (size_t)p->n_obs * sizeof(float));
+    if (small && p->n_obs <= kZeroCopyObsMax) {
+      obs_dev = ctx->host_obs.ptr;  // mapped pinned memory: the kernel reads it in place
+    } else {
+      CKRC(ctx->obs_in.reserve(p->n_obs));
+      CK(cudaMemcpyAsync(ctx->obs_in.ptr, ctx->host_obs.ptr, (size_t)p->n_obs * sizeof(float),
+                         cudaMemcpyHostToDevice, st));
+      obs_dev = ctx->obs_in.ptr;
+    }
   }
   if (timing) CK(cudaEventRecord(ctx->ev[0], st));
   float *post_dev = posterior;
@@ -809,8 +964,16 @@ CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const f
     CKRC(ctx->posterior.reserve(cells));
     post_dev = ctx->posterior.ptr;
   }
-  int rc = cge_likelihood_partials(ctx, p, obs_dev, post_dev, st);
-  if (rc == CGE_OK) rc = cge_finalize(ctx, p, post_dev, st);
+  int rc;
+  if (small) {
+    const bool host_out = !(marg_mu && is_device_pointer(marg_mu)) &&
+                          !(marg_sigma && is_device_pointer(marg_sigma)) &&
+                          !(expectations && is_device_pointer(expectations));
+    rc = small_grid_step(ctx, p, obs_dev, post_dev, st, host_out);
+  } else {
+    rc = cge_likelihood_partials(ctx, p, obs_dev, post_dev, st);
+    if (rc == CGE_OK) rc = cge_finalize(ctx, p, post_dev, st);
+  }
   if (rc != CGE_OK) {
     if (!was_on) ctx->prof_on = false;
     return rc;

@@ -109,29 +109,38 @@ __device__ __forceinline__ int first_column(int kcols) {
 __device__ __forceinline__ double coef_a(double sd) { return -0.5 * 1.4426950408889634074 / (sd * sd); }
 __device__ __forceinline__ double coef_c0(double sd) { return -log2(sd * 2.5066282746310005024); }
 
-__global__ void __launch_bounds__(256)
-    setup_kernel(float *__restrict__ mu, float *__restrict__ sigma, double *__restrict__ ad,
-                 double *__restrict__ cd0, int N, float mu0, float mu1, float sg0, float sg1,
-                 const float *__restrict__ obs, float *__restrict__ obs_pad, int n, int n_pad,
-                 int centred, ScaleInfo *__restrict__ out) {
-  const int tid = threadIdx.x;
-  const int idx = blockIdx.x * blockDim.x + tid;
-  if (idx >= N && idx < N + 3) mu[idx] = range_value(N - 1, N, mu0, mu1);  // float4 row loads
-  if (idx < N) {
-    mu[idx] = range_value(idx, N, mu0, mu1);
-    const float s = range_value(idx, N, sg0, sg1);
+struct RangeArgs {
+  int N;
+  float mu0, mu1, sg0, sg1;
+};
+
+// one grid point of the four tables; idx in [N, N+3) pads mu for the kernels' float4 row loads
+__device__ __forceinline__ void setup_point(int idx, const RangeArgs &r, float *__restrict__ mu,
+                                            float *__restrict__ sigma, double *__restrict__ ad,
+                                            double *__restrict__ cd0) {
+  if (idx >= r.N && idx < r.N + 3) mu[idx] = range_value(r.N - 1, r.N, r.mu0, r.mu1);
+  if (idx < r.N) {
+    mu[idx] = range_value(idx, r.N, r.mu0, r.mu1);
+    const float s = range_value(idx, r.N, r.sg0, r.sg1);
     sigma[idx] = s;
     ad[idx] = coef_a((double)s);
     cd0[idx] = coef_c0((double)s);
   }
-  if (blockIdx.x != 0) return;
+}
 
-  __shared__ double scratch[32];
-  const int nt = blockDim.x;
+// Block-wide (every thread of the block must call it, every thread gets the result): stage the
+// observations -- zero-padded to n_pad, raw or centred (x_k - mu_c) -- into `stage` (global or
+// shared) and derive the scale statistics.  `scratch` holds >= 32 doubles of shared memory.
+__device__ __forceinline__ ScaleInfo setup_scale(const RangeArgs &r, const float *__restrict__ obs,
+                                                 float *stage, int n, int n_pad, int centred,
+                                                 double *scratch) {
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
+  const int N = r.N;
+  const float mu0 = r.mu0, mu1 = r.mu1, sg0 = r.sg0, sg1 = r.sg1;
   double sum = 0.0, xlo = 1.0 / 0.0, xhi = -1.0 / 0.0;
   for (int k = tid; k < n_pad; k += nt) {
     const float x = k < n ? obs[k] : 0.0f;
-    obs_pad[k] = x;
+    stage[k] = x;
     sum += (double)x;
     if (k < n) {
       xlo = fmin(xlo, (double)x);
@@ -152,20 +161,19 @@ __global__ void __launch_bounds__(256)
     if (pos > (double)(N - 1)) pos = (double)(N - 1);
     mu_c = (double)range_value((int)(pos + 0.5), N, mu0, mu1);
   }
-  if (centred) {
-    __syncthreads();
-    for (int k = tid; k < n; k += nt) obs_pad[k] = (float)((double)obs[k] - mu_c);
-  }
+  // (from here on the observations are read back from `stage`, not from `obs`, which may be
+  // mapped host memory: each thread re-reads exactly the elements it staged itself)
   double q = 0.0;
   for (int k = tid; k < n; k += nt) {
-    const double d = (double)obs[k] - xbar;
+    const double d = (double)stage[k] - xbar;
     q += d * d;
   }
   const double ss = block_sum(q, scratch);
-  if (tid >= 32) return;
+  if (centred)
+    for (int k = tid; k < n; k += nt) stage[k] = (float)((double)stage[k] - mu_c);
 
   // candidate grid indices around a continuous optimum `pos`: both ends + 4 neighbours;
-  // lane t < 6 evaluates candidate t, the rest of warp 0 idles through the shuffles
+  // lane t < 6 of every warp evaluates candidate t, the other lanes idle through the shuffles
   auto candidate = [N](double pos, int t) {
     if (!(pos == pos) || pos < 0.0) pos = 0.0;          // NaN / below range
     if (pos > (double)(N - 1)) pos = (double)(N - 1);
@@ -177,8 +185,8 @@ __global__ void __launch_bounds__(256)
   const double mspan = (double)mu1 - (double)mu0;
   const double mpos = mspan != 0.0 ? (xbar - (double)mu0) / mspan * (double)(N - 1) : 0.0;
   double smin = 1.0 / 0.0;
-  if (tid < 6) {
-    const double d = xbar - (double)range_value(candidate(mpos, tid), N, mu0, mu1);
+  if (lane < 6) {
+    const double d = xbar - (double)range_value(candidate(mpos, lane), N, mu0, mu1);
     smin = ss + (double)n * d * d;
   }
   smin = warp_min(smin);
@@ -186,20 +194,20 @@ __global__ void __launch_bounds__(256)
   const double spos =
       sspan != 0.0 ? (sqrt(smin / (double)n) - (double)sg0) / sspan * (double)(N - 1) : 0.0;
   double m2 = -1.0 / 0.0;
-  if (tid < 6) {
-    const double sd = (double)range_value(candidate(spos, tid), N, sg0, sg1);
+  if (lane < 6) {
+    const double sd = (double)range_value(candidate(spos, lane), N, sg0, sg1);
     m2 = coef_a(sd) * smin + (double)n * coef_c0(sd);
   }
   m2 = warp_max(m2);
-  if (tid != 0) return;
-  out->log2s = (kPeakLog2 - m2) / (double)n;
-  out->shift = kPeakLog2 - m2;
-  out->m2 = m2;
-  out->xbar = xbar;
-  out->ss = ss;
-  out->smin = smin;
-  out->mu_c = mu_c;
-  out->s_c = ss + (double)n * (xbar - mu_c) * (xbar - mu_c);
+  ScaleInfo out;
+  out.log2s = (kPeakLog2 - m2) / (double)n;
+  out.shift = kPeakLog2 - m2;
+  out.m2 = m2;
+  out.xbar = xbar;
+  out.ss = ss;
+  out.smin = smin;
+  out.mu_c = mu_c;
+  out.s_c = ss + (double)n * (xbar - mu_c) * (xbar - mu_c);
   // Largest exponent step between vertically adjacent cells,
   //   |t_(i+1,j,k) - t_(i,j,k)| = |a_j| |mu_(i+1) - mu_i| |mu_i + mu_(i+1) - 2 x_k|,
   // bounded over the whole grid and every observation.  The row spacing gets 2 ulp of slack for
@@ -209,8 +217,21 @@ __global__ void __launch_bounds__(256)
     const double reach = fmax(fmax(fabs(xhi - mlo), fabs(xlo - mlo)), fmax(fabs(xhi - mhi), fabs(xlo - mhi)));
     const double dmu = N > 1 ? (mhi - mlo) / (double)(N - 1) + 2.4e-7 * fmax(fabs(mlo), fabs(mhi)) : 0.0;
     const double sdmin = fmin((double)sg0, (double)sg1);
-    out->umax = fabs(coef_a(sdmin)) * dmu * 2.0 * reach;
+    out.umax = fabs(coef_a(sdmin)) * dmu * 2.0 * reach;
   }
+  return out;
+}
+
+__global__ void __launch_bounds__(256)
+    setup_kernel(float *__restrict__ mu, float *__restrict__ sigma, double *__restrict__ ad,
+                 double *__restrict__ cd0, const RangeArgs r, const float *__restrict__ obs,
+                 float *__restrict__ obs_pad, int n, int n_pad, int centred,
+                 ScaleInfo *__restrict__ out) {
+  __shared__ double scratch[32];
+  setup_point(blockIdx.x * blockDim.x + threadIdx.x, r, mu, sigma, ad, cd0);
+  if (blockIdx.x != 0) return;
+  const ScaleInfo sc = setup_scale(r, obs, obs_pad, n, n_pad, centred, scratch);
+  if (threadIdx.x == 0) *out = sc;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -708,7 +729,9 @@ struct ProductPaired {
 //   Per row group the warp emits its partial row sums (fixed-order shuffle tree) and keeps
 //   float64 column sums in registers until the tile ends: no atomics anywhere.
 // ---------------------------------------------------------------------------------------
-template <class Policy, int WM, int WN, bool VEC4>
+// PRELOADED: the caller has already staged all n_pad observations at smem_raw + 128 and
+// synchronised the block (small_grid_kernel); no mbarrier / bulk copy is used then.
+template <class Policy, int WM, int WN, bool VEC4, bool PRELOADED = false>
 __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleInfo &sc,
                                                 const ColumnCoefs<Policy::kCols> &cf,
                                                 unsigned char *smem_raw) {
@@ -730,15 +753,17 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
   const int groups = g.tile_rows / (WM * kRows);    // row groups this warp walks
   constexpr int kStride = Policy::kObsStride;        // staged floats per observation
   constexpr int kChunkObs = kObsChunk / kStride;     // observations per streamed chunk
-  const bool streamed = g.n_pad > kObsSingleMax;      // n_pad counts staged floats
+  const bool streamed = !PRELOADED && g.n_pad > kObsSingleMax;  // n_pad counts staged floats
   const int nchunks = streamed ? (g.n_pad + kObsChunk - 1) / kObsChunk : 1;
 
-  if (tid == 0) {
-    mbar_init(&bars[0], 1);
-    mbar_init(&bars[1], 1);
-    mbar_init_fence();
+  if (!PRELOADED) {
+    if (tid == 0) {
+      mbar_init(&bars[0], 1);
+      mbar_init(&bars[1], 1);
+      mbar_init_fence();
+    }
+    __syncthreads();
   }
-  __syncthreads();
 
   auto issue = [&](int seq) {  // thread 0 only: start the bulk copy of load number `seq`
     const int ch = seq % nchunks, st = seq & 1;
@@ -748,7 +773,7 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
     bulk_copy_g2s(obs_s + (size_t)st * kObsChunk, g.obs_pad + (size_t)ch * kObsChunk, bytes,
                   &bars[st]);
   };
-  if (tid == 0) issue(0);
+  if (!PRELOADED && tid == 0) issue(0);
 
   Policy pol;
   pol.load_columns(g, j0, sc, cf);
@@ -853,7 +878,7 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
   };
 
   if (!streamed) {
-    mbar_wait(&bars[0], 0);
+    if (!PRELOADED) mbar_wait(&bars[0], 0);
     for (int grp = 0; grp < groups; ++grp) {
       begin_group(grp);
       if (rows_any && col_any) Policy::consume(pol, obs_s, g.n, mu);
@@ -912,6 +937,166 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
     likelihood_body<Fine, WM, WN, VEC4>(g, sc, cf, smem_raw);
   else
     likelihood_body<Coarse, WM, WN, VEC4>(g, sc, cf, smem_raw);
+}
+
+// ---------------------------------------------------------------------------------------
+// small_grid_kernel: the whole step in ONE launch for grids of a few hundred points per axis,
+// where five launches are all latency (the README workload, N = 101, is 510 050 pdf-evals:
+// ~2 us of arithmetic).  Every CTA
+//   1. fills the four range tables and derives the scale statistics itself (identical values
+//      from every CTA: a benign race) and stages the observations straight into its shared
+//      memory -- setup_kernel's work, redundantly, instead of a launch and a dependency;
+//   2. runs the same fused likelihood body on its tile (unnormalised cells + partial sums);
+//   3. takes a ticket; the last CTA to finish folds the partials in a fixed order, writes Z, the
+//      marginals and the expectations, and scales the whole posterior by 1/Z (it fits in L2).
+// Observations may be read from, and the results block also written to, mapped pinned host
+// memory, which removes both small DMA copies (~6 us and ~10 us) from the call's latency.
+// No grid-wide barrier, so no co-residency requirement.  Sums are in a fixed order (index
+// order within a thread, then the fixed block tree): bit-reproducible run to run.
+// ---------------------------------------------------------------------------------------
+constexpr int kSmallColChunk = 256;  // columns folded per pass of the last CTA (8 x 256 f64 of smem)
+
+struct SmallArgs {
+  LikeArgs like;  // tables written by this kernel; row_begin = 0, row_end = N
+  RangeArgs range;
+  const float *obs;  // raw observations (device)
+  float *mu, *sigma;
+  double *ad, *cd0;
+  ScaleInfo *scale;
+  int centred;
+  int ncolparts;
+  double *partials, *rowsum, *results;
+  double *results_host;  // optional mapped pinned copy of `results` (saves the D2H copy)
+  unsigned int *ticket;
+};
+
+template <class Fine, class Coarse, int WM, int WN, bool VEC4>
+__global__ void __launch_bounds__(WM *WN * 32)
+    small_grid_kernel(const SmallArgs a) {
+  static_assert(Fine::kCols == Coarse::kCols && Fine::kRows == Coarse::kRows, "same tiling");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ double scratch[32];
+  __shared__ double colred[WM * WN][kSmallColChunk];
+  __shared__ bool is_last;
+  const LikeArgs &g = a.like;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int N = g.N;
+  float *obs_s = reinterpret_cast<float *>(smem_raw + 128);
+
+  for (int idx = tid; idx < N + 3; idx += nt) setup_point(idx, a.range, a.mu, a.sigma, a.ad, a.cd0);
+  const ScaleInfo sc = setup_scale(a.range, a.obs, obs_s, g.n, g.n_pad, a.centred, scratch);
+  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *a.scale = sc;
+  __syncthreads();  // this CTA's own table writes and staged observations are visible to it
+
+  ColumnCoefs<Fine::kCols> cf;
+  cf.load(g, first_column<WN>(Fine::kCols));
+  if (sc.umax <= kPairedUmax)
+    likelihood_body<Fine, WM, WN, VEC4, true>(g, sc, cf, smem_raw);
+  else
+    likelihood_body<Coarse, WM, WN, VEC4, true>(g, sc, cf, smem_raw);
+
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1;
+  __syncthreads();
+  if (!is_last) return;
+  __threadfence();
+
+  // ---- last CTA: K6-K8 on the partial buffers of every CTA (read through L2).  Every loop
+  // keeps several independent loads in flight: one CTA is latency-bound, not bandwidth-bound.
+  double z = 0.0, smu = 0.0;
+  for (int i = tid; i < N; i += nt) {
+    double s = 0.0;
+    for (int w = 0; w < g.ncw; ++w) s += __ldcg(g.rowpart + (size_t)i * g.ncw + w);
+    a.rowsum[i] = s;
+    z += s;
+    smu += s * (double)a.mu[i];
+  }
+  {  // column sums: warp w takes slots w, w+NW, ... of a column (all its loads in flight at
+     // once), then the NW partial sums are added in warp order
+    constexpr int NW = WM * WN;
+    const int lane = tid & 31, warp = tid >> 5;
+    for (int j0c = 0; j0c < N; j0c += kSmallColChunk) {
+      for (int j = j0c + lane; j < min(N, j0c + kSmallColChunk); j += 32) {
+        const double *src = g.colpart + j;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        int t = warp;
+        for (; t + 3 * NW < a.ncolparts; t += 4 * NW) {
+          s0 += __ldcg(src + (size_t)t * N);
+          s1 += __ldcg(src + (size_t)(t + NW) * N);
+          s2 += __ldcg(src + (size_t)(t + 2 * NW) * N);
+          s3 += __ldcg(src + (size_t)(t + 3 * NW) * N);
+        }
+        for (; t < a.ncolparts; t += NW) s0 += __ldcg(src + (size_t)t * N);
+        colred[warp][j - j0c] = (s0 + s1) + (s2 + s3);
+      }
+      __syncthreads();
+      for (int j = j0c + tid; j < min(N, j0c + kSmallColChunk); j += nt) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) s += colred[w][j - j0c];
+        a.partials[2 + j] = s;
+      }
+      __syncthreads();
+    }
+  }
+  z = block_sum(z, scratch);
+  smu = block_sum(smu, scratch);
+  const double inv = 1 / z;  // reciprocal multiply, as inc/utils.h:82-84
+  double *marg_sigma = a.results + 4, *marg_mu = a.results + 4 + N;
+  double es = 0.0;
+  for (int j = tid; j < N; j += nt) {  // partials[2 + j]: written before the block-wide syncs above
+    const double m = a.partials[2 + j] * inv;
+    marg_sigma[j] = m;
+    if (a.results_host) a.results_host[4 + j] = m;
+    es += m * (double)a.sigma[j];
+  }
+  for (int i = tid; i < N; i += nt) {
+    const double m = a.rowsum[i] * inv;
+    marg_mu[i] = m;
+    if (a.results_host) a.results_host[4 + N + i] = m;
+  }
+  es = block_sum(es, scratch);
+  if (tid == 0) {
+    a.partials[0] = z;
+    a.partials[1] = smu;
+    const double head[4] = {smu * inv, es, z, inv};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      a.results[q] = head[q];
+      if (a.results_host) a.results_host[q] = head[q];
+    }
+    *a.ticket = 0u;
+  }
+  const float finv = (float)inv;
+  const size_t cells = (size_t)N * N;
+  constexpr int kDepth = 8;  // independent loads in flight per thread
+  if (VEC4) {
+    float4 *p4 = reinterpret_cast<float4 *>(g.post);
+    const size_t nvec = cells >> 2;  // VEC4 implies N % 4 == 0
+    for (size_t base = tid; base < nvec; base += (size_t)nt * kDepth) {
+      float4 v[kDepth];
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u)
+        if (base + (size_t)u * nt < nvec) v[u] = __ldcg(p4 + base + (size_t)u * nt);
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u)
+        if (base + (size_t)u * nt < nvec) {
+          v[u].x *= finv; v[u].y *= finv; v[u].z *= finv; v[u].w *= finv;
+          p4[base + (size_t)u * nt] = v[u];
+        }
+    }
+  } else {
+    for (size_t base = tid; base < cells; base += (size_t)nt * kDepth) {
+      float v[kDepth];
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u)
+        if (base + (size_t)u * nt < cells) v[u] = __ldcg(g.post + base + (size_t)u * nt);
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u)
+        if (base + (size_t)u * nt < cells) g.post[base + (size_t)u * nt] = v[u] * finv;
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------

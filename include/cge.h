@@ -87,6 +87,9 @@ enum {
   CGE_VARIANT_LOG_F64 = 5,   /* log-space mode only: float64 accumulation, one DFMA per pdf-eval (the
                                 default log-space kernel sums centred terms in float32x2 tiles of 256
                                 observations and folds the tiles into float64) */
+  CGE_VARIANT_UNFUSED = 7,   /* the default kernels, but cge_grid_posterior always takes the five-launch
+                                path (by default grids up to 512 points per axis run as ONE launch:
+                                tables, likelihood, fold, results and scale in a single kernel) */
   CGE_VARIANT_HYBRID = 4     /* hybrid, forced: packed f32x2 arithmetic; of the 16 exponentials a
                                 thread evaluates per observation, 12 use MUFU.EX2 and 4 an FMA-pipe
                                 degree-5 polynomial with Cody-Waite range reduction */

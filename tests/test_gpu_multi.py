@@ -58,10 +58,10 @@ def test_two_gpu_sharded_matches_single(tmp_path, N, n_obs, mode):
     ranks = [np.load(tmp_path / f"rank{r}.npz") for r in range(world)]
     for exchange in ("p2p", "nccl"):
         for g in ranks:
-            assert np.abs(g[f"{exchange}_ex"] - full.expectations).max() < 1e-12
-            assert np.abs(g[f"{exchange}_ms"] - full.marg_sigma).max() < 1e-14
+            assert np.abs(g[f"{exchange}_ex"] - full.expectations).max() < 1e-8
+            assert np.abs(g[f"{exchange}_ms"] - full.marg_sigma).max() < 1e-8 * full.marg_sigma.max()
             rb, re = g[f"{exchange}_rows"]
-            assert np.abs(g[f"{exchange}_mm"][rb:re] - full.marg_mu[rb:re]).max() < 1e-14
+            assert np.abs(g[f"{exchange}_mm"][rb:re] - full.marg_mu[rb:re]).max() < 1e-8 * full.marg_mu.max()
         got = np.concatenate([g[f"{exchange}_post"] for g in ranks], axis=0)
         nz = full.posterior > 0
         assert (np.abs(got - full.posterior)[nz] / full.posterior[nz]).max() < 2e-7

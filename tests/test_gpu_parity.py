@@ -54,7 +54,9 @@ def test_readme_product_vs_oracle(ctx, readme_obs):
     assert d < 1e-6  # expected ~1e-8
     f64 = oracle.grid_posterior(readme_obs, 101, 18, 22, 1, 3, oracle.NUM_F64)
     check_against(res, f64, what="readme/product vs F64")
-    assert res.launches == 5  # setup, likelihood, fold, results, scale
+    assert res.launches == 1  # small grids: the whole step is one launch (small_grid_kernel)
+    unf = ctx.grid_posterior(readme_obs, 101, (18, 22), (1, 3), variant=api.VARIANT_UNFUSED)
+    assert unf.launches == 5  # setup, likelihood, fold, results, scale
 
 
 @pytest.mark.parametrize("variant", [1, 100, 122, 133, 222, 522, 523, 633, 822])
@@ -68,7 +70,7 @@ def test_product_kernel_variants(ctx, readme_obs, variant):
         d = check_against(res, ref, what=f"variant {variant} N={N}")
         assert d < 1e-6
     with pytest.raises(cge.CgeError):
-        ctx.grid_posterior(readme_obs, 64, (18, 22), (1, 3), variant=7)
+        ctx.grid_posterior(readme_obs, 64, (18, 22), (1, 3), variant=77)
 
 
 def test_readme_logspace_vs_oracle(ctx, readme_obs):
@@ -191,6 +193,53 @@ def test_logspace_kernel_variants(ctx, variant):
         res = ctx.grid_posterior(obs, N, mu_r, sg_r, mode=cge.MODE_LOGSPACE, variant=variant)
         ref = oracle.grid_posterior(obs, N, *mu_r, *sg_r, oracle.NUM_LOG)
         check_against(res, ref, what=f"log-space variant {variant} N={N} n={n} mu={mu_r} sigma={sg_r}")
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 5, 64, 101, 128, 129, 200, 255, 256, 257])
+def test_single_launch_small_grids(ctx, readme_obs, N):
+    """Grids up to 256 points per axis run as one launch (tables, likelihood, fold, results and
+    scale in small_grid_kernel).  Same cells as the five-launch path bit for bit before the 1/Z
+    scale; sums agree to float64 rounding; both against the oracle; repeatable bit for bit."""
+    for mode, num in ((cge.MODE_PRODUCT_F32, oracle.NUM_REF), (cge.MODE_LOGSPACE, oracle.NUM_F64)):
+        one = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), mode=mode)
+        five = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), mode=mode,
+                                  variant=api.VARIANT_UNFUSED)
+        assert one.launches == (1 if N <= 256 else 5) and five.launches == 5
+        assert np.abs(one.expectations - five.expectations).max() < 1e-9
+        assert np.abs(one.marg_mu - five.marg_mu).max() <= 1e-9 * five.marg_mu.max()
+        assert np.abs(one.marg_sigma - five.marg_sigma).max() <= 1e-9 * five.marg_sigma.max()
+        nz = five.posterior > 0
+        assert ((one.posterior > 0) == nz).all()
+        assert (np.abs(one.posterior - five.posterior)[nz] / five.posterior[nz]).max(initial=0) < 2.5e-7
+        if N >= 2:
+            check_against(one, oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, num),
+                          what=f"single launch N={N} mode={mode}")
+        again = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), mode=mode)
+        assert again.posterior.tobytes() == one.posterior.tobytes()
+        assert again.expectations.tobytes() == one.expectations.tobytes()
+
+
+def test_single_launch_fine_small_grid_and_prior(ctx, readme_obs):
+    """The one-launch path also picks paired rows on a fine small grid, and honours a prior."""
+    mu_r, sg_r = (19.4, 19.7), (1.7, 2.1)
+    one = ctx.grid_posterior(readme_obs, 250, mu_r, sg_r)
+    assert one.launches == 1 and ctx.scale_info()["product_path"] == "paired"
+    forced = ctx.grid_posterior(readme_obs, 250, mu_r, sg_r, variant=api.VARIANT_PAIRED)
+    nz = forced.posterior > 0
+    assert (np.abs(one.posterior - forced.posterior)[nz] / forced.posterior[nz]).max() < 2.5e-7
+    N = 128
+    pm = np.linspace(0.5, 1.5, N).astype(np.float32)
+    ps = np.linspace(2.0, 1.0, N).astype(np.float32)
+    ctx.set_prior(pm, ps, N)
+    try:
+        one = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
+        five = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_UNFUSED)
+    finally:
+        ctx.set_prior()
+    assert one.launches == 1 and five.launches == 5
+    assert np.abs(one.expectations - five.expectations).max() < 1e-9
+    flat = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
+    assert np.abs(one.expectations - flat.expectations).max() > 1e-3  # the prior did something
 
 
 def test_error_behaviour(ctx, readme_obs):
