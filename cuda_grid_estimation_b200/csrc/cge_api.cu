@@ -169,7 +169,7 @@ int check_params(const cge_params *p, int *rb, int *re) {
     case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 2: case CGE_VARIANT_PAIRED:
     case CGE_VARIANT_LOG_F64: case 6: case 8: case 9: case CGE_VARIANT_UNFUSED:
     case CGE_VARIANT_HYBRID: case 100: case 122: case 133: case 222: case 522: case 523: case 633:
-    case 822: case 1322: case 31: case 32: case 33: case 34: case 35: case 37: case 381: case 382: case 384: break;
+    case 822: case 1322: case 31: case 32: case 33: case 34: case 35: case 37: case 39: case 41: case 42: case 45: case 381: case 382: case 384: break;
     default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
   }
   int b = p->row_begin, e = p->row_end;
@@ -240,14 +240,15 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
 template <class Policy, int WM, int WN, int MINB = 1>
 int launch_like_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
+  const size_t smem = pl.smem + 16 + (Policy::kColSmem ? (size_t)WM * WN * 32 * Policy::kCols * 8 : 0);
   if (pl.vec4) {
     auto k = cge::grid_likelihood_kernel<Policy, WM, WN, true, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k<<<grid, block, pl.smem, st>>>(args);
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, block, smem, st>>>(args);
   } else {
     auto k = cge::grid_likelihood_kernel<Policy, WM, WN, false, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k<<<grid, block, pl.smem, st>>>(args);
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, block, smem, st>>>(args);
   }
   CK(cudaGetLastError());
   return CGE_OK;
@@ -264,14 +265,16 @@ int launch_like(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
 template <class Fine, class Coarse, int WM, int WN, int MINB = 1>
 int launch_dual_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
   dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
+  const size_t smem = pl.smem + 16 +
+      ((Fine::kColSmem || Coarse::kColSmem) ? (size_t)WM * WN * 32 * Fine::kCols * 8 : 0);
   if (pl.vec4) {
     auto k = cge::grid_likelihood_dual_kernel<Fine, Coarse, WM, WN, true, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k<<<grid, block, pl.smem, st>>>(args);
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, block, smem, st>>>(args);
   } else {
     auto k = cge::grid_likelihood_dual_kernel<Fine, Coarse, WM, WN, false, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k<<<grid, block, pl.smem, st>>>(args);
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, block, smem, st>>>(args);
   }
   CK(cudaGetLastError());
   return CGE_OK;
@@ -292,8 +295,8 @@ int launch_dual(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
 // polynomial).  CGE_VARIANT_PAIRED / _HYBRID force one of the two, CGE_VARIANT_MUFU_ONLY is the
 // roofline case; the numbered variants document the tuning sweeps
 // (profiles/r01_variant_sweep_*.jsonl) and are only built for the wide tile shape.
-using DefaultFine = cge::ProductPaired<4, 4, true>;
-constexpr int kDefaultMinB = 2;  // <= 128 registers: two 256-thread CTAs per SM
+using DefaultFine = cge::ProductPaired<4, 4, true, true>;
+constexpr int kDefaultMinB = 3;  // <= 80 registers: three 256-thread CTAs (24 warps) per SM
 using DefaultCoarse = cge::ProductHybrid<2, 2, false, 1>;
 
 int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
@@ -316,15 +319,22 @@ int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
       // 1322: exponent FMA as two scalar FFMAs, 1 observation per iteration
       case 1322: return launch_like_shape<cge::ProductHybrid<2, 2, false, 1, true>, 1, 8>(pl, args, st);
       // paired rows (CGE_VARIANT_PAIRED = 4 columns per thread, 4 observations per iteration, the
-      // row pairs' scalars packed, capped at 128 registers): 31 / 32 / 34 = 1 / 2 / 4 observations
-      // per iteration, scalars unpacked, uncapped; 33 = 32 capped at 80 registers (3 CTAs per
-      // SM); 35 = 34 capped at 128; 37 = 32 with packed scalars; 38x = 8 columns per thread
+      // row pairs' scalars packed, column sums in shared memory, capped at 80 registers = 3 CTAs
+      // per SM): 31 / 32 / 34 = 1 / 2 / 4 observations per iteration, scalars unpacked, column
+      // sums in registers, uncapped; 33 = 32 capped at 80 registers; 35 = 34 capped at 128;
+      // 37 = 32 with packed scalars; 38x = 8 columns per thread
       case 31: return launch_like_shape<cge::ProductPaired<4, 1>, 1, 8>(pl, args, st);
       case 32: return launch_like_shape<cge::ProductPaired<4, 2>, 1, 8>(pl, args, st);
       case 33: return launch_like_shape<cge::ProductPaired<4, 2>, 1, 8, 3>(pl, args, st);
       case 34: return launch_like_shape<cge::ProductPaired<4, 4>, 1, 8>(pl, args, st);
       case 35: return launch_like_shape<cge::ProductPaired<4, 4>, 1, 8, 2>(pl, args, st);
       case 37: return launch_like_shape<cge::ProductPaired<4, 2, true>, 1, 8>(pl, args, st);
+      // column sums in shared memory: 41 / 42 = 1 / 2 observations per iteration at 80 registers;
+      // 45 = 4 observations at 128 registers (2 CTAs per SM); 39 = 45 with column sums in registers
+      case 39: return launch_like_shape<cge::ProductPaired<4, 4, true>, 1, 8, 2>(pl, args, st);
+      case 41: return launch_like_shape<cge::ProductPaired<4, 1, true, true>, 1, 8, 3>(pl, args, st);
+      case 42: return launch_like_shape<cge::ProductPaired<4, 2, true, true>, 1, 8, 3>(pl, args, st);
+      case 45: return launch_like_shape<cge::ProductPaired<4, 4, true, true>, 1, 8, 2>(pl, args, st);
       case 381: return launch_like_shape<cge::ProductPaired<8, 1>, 1, 8>(pl, args, st);
       case 382: return launch_like_shape<cge::ProductPaired<8, 2>, 1, 8>(pl, args, st);
       case 384: return launch_like_shape<cge::ProductPaired<8, 4>, 1, 8>(pl, args, st);
@@ -346,14 +356,16 @@ int mark(cge_context *ctx, int k, cudaStream_t st);
 template <class Fine, class Coarse, int WM, int WN>
 int launch_small_shape(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st) {
   dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
+  const size_t smem = pl.smem + 16 +
+      ((Fine::kColSmem || Coarse::kColSmem) ? (size_t)WM * WN * 32 * Fine::kCols * 8 : 0);
   if (pl.vec4) {
     auto k = cge::small_grid_kernel<Fine, Coarse, WM, WN, true>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k<<<grid, block, pl.smem, st>>>(a);
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, block, smem, st>>>(a);
   } else {
     auto k = cge::small_grid_kernel<Fine, Coarse, WM, WN, false>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl.smem));
-    k<<<grid, block, pl.smem, st>>>(a);
+    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k<<<grid, block, smem, st>>>(a);
   }
   CK(cudaGetLastError());
   return CGE_OK;
@@ -1184,11 +1196,12 @@ extern "C" int cge_internal_error(int code, const char *msg) { return set_error(
 // ---------------------------------------------------------------------------------------
 CGE_EXPORT int cge_microbench(cge_context *ctx, int kind, double *ops_per_second) {
   CKRC(bind(ctx));
-  if (!ops_per_second || kind < 0 || kind > 7)
+  if (!ops_per_second || kind < 0 || kind > 10)
     return set_error(CGE_ERR_BAD_ARG, "microbench: bad argument");
   CKRC(ctx->sink.reserve(4));
   const int iters = 4096, chains = 8;
-  const int blocks = ctx->sm_count * 8, threads = 256;
+  // kinds 8, 9, 10: the 6 FFMA2 + 2 MUFU mix at 2, 3 and 4 CTAs per SM (8, 12, 16 warps per SM)
+  const int blocks = ctx->sm_count * (kind == 8 ? 2 : kind == 9 ? 3 : kind == 10 ? 4 : 8), threads = 256;
   cudaStream_t st = ctx->stream;
   auto launch = [&]() {
     switch (kind) {
@@ -1199,7 +1212,8 @@ CGE_EXPORT int cge_microbench(cge_context *ctx, int kind, double *ops_per_second
       case 4: cge::microbench_kernel<4><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
       case 5: cge::microbench_kernel<5><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
       case 6: cge::microbench_kernel<6><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
-      default: cge::microbench_kernel<7><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+      case 7: cge::microbench_kernel<7><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+      default: cge::microbench_kernel<6><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
     }
   };
   for (int w = 0; w < 3; ++w) launch();
@@ -1217,7 +1231,8 @@ CGE_EXPORT int cge_microbench(cge_context *ctx, int kind, double *ops_per_second
   CK(cudaGetLastError());
   // kinds 0-3: one instruction class, 8 chains; kinds 4-7: FMA lane-ops of the mix per iteration
   // (packed count as 2; the MUFU chains' bounding FFMA counts as 1; MUFU ops are not counted)
-  static const double per_iter[8] = {8, 8, 8, 16, 4 * 2 + 4, 4 * 2 + 8, 6 * 2 + 2, 4 * 2 + 4 + 2};
+  static const double per_iter[11] = {8, 8, 8, 16, 4 * 2 + 4, 4 * 2 + 8, 6 * 2 + 2, 4 * 2 + 4 + 2,
+                                      6 * 2 + 2, 6 * 2 + 2, 6 * 2 + 2};
   (void)chains;
   double ops = (double)blocks * threads * (double)iters * per_iter[kind];
   *ops_per_second = ops / (best * 1e-3);

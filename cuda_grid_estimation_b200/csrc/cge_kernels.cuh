@@ -246,6 +246,7 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 // product); the subtract and square are shared by the kRN columns of a row.
 //   factor_k = 2^(a_j*(x_k-mu_i)^2 + c_j),  c_j = c0_j + log2 s   (constants FMA-folded)
 struct ProductF32 {
+  static constexpr bool kColSmem = false;
   static constexpr int kRows = kRM;
   static constexpr int kCols = 4;
   static constexpr int kObsStride = 1;  // floats of shared memory per observation
@@ -296,6 +297,7 @@ struct ProductF32 {
 // cell after 10^4 observations) and widened once per (row, observation); 8 columns per thread
 // amortise that widening over 8 evaluations.
 struct LogSpaceF64 {
+  static constexpr bool kColSmem = false;
   static constexpr int kRows = 4;   // 4 x 8 patch (a 2 x 8 patch measured 4 % slower: the bound is
                                     // the FP64 pipe's operand bandwidth, not occupancy)
   static constexpr int kCols = 8;
@@ -368,6 +370,7 @@ struct LogSpaceF64 {
 // ---------------------------------------------------------------------------------------
 template <int TILE = 256>
 struct LogSpaceTiled {
+  static constexpr bool kColSmem = false;
   static constexpr int kRows = 4;
   static constexpr int kCols = 8;
   static constexpr int kObsStride = 1;
@@ -490,6 +493,7 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 // ---------------------------------------------------------------------------------------
 template <int NPA, int NPB, bool SCALAR_POLY = false, int OBS_PER_ITER = 4, bool SCALAR_T = false>
 struct ProductHybrid {
+  static constexpr bool kColSmem = false;
   static constexpr int kRows = kRM;
   static constexpr int kCols = 4;
   static constexpr int kObsStride = 1;
@@ -604,8 +608,11 @@ struct ProductHybrid {
 // ---------------------------------------------------------------------------------------
 constexpr double kPairedUmax = 0.011;
 
-template <int KC = 4, int OBS_PER_ITER = 1, bool PACKED_ROWS = false>
+template <int KC = 4, int OBS_PER_ITER = 1, bool PACKED_ROWS = false, bool COL_SMEM = false>
 struct ProductPaired {
+  // COL_SMEM: the tile's float64 column sums live in shared memory instead of 2*KC registers
+  // (they are touched once per row group), which is what lets the kernel fit 80 registers
+  static constexpr bool kColSmem = COL_SMEM;
   static constexpr int kRows = kRM;
   static constexpr int kCols = KC;
   static constexpr int kObsStride = 1;
@@ -777,9 +784,17 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
 
   Policy pol;
   pol.load_columns(g, j0, sc, cf);
-  double colacc[kCols];
+  // float64 column sums of this thread's columns over the tile: registers, or (Policy::kColSmem)
+  // shared memory behind the observation stage, element cidx of thread tid at [cidx*nthreads + tid]
+  constexpr bool kColSmem = Policy::kColSmem;
+  double colreg[kColSmem ? 1 : kCols];
+  double *colsm = reinterpret_cast<double *>(
+      smem_raw + 128 + (((streamed ? 2 * kObsChunk : g.n_pad) * 4 + 15) & ~15));
 #pragma unroll
-  for (int cidx = 0; cidx < kCols; ++cidx) colacc[cidx] = 0.0;
+  for (int cidx = 0; cidx < kCols; ++cidx) {
+    if (kColSmem) colsm[cidx * (WM * WN * 32) + tid] = 0.0;
+    else colreg[cidx] = 0.0;
+  }
   const bool col_any = j0 < g.N;  // columns only grow with cidx
   const bool has_prior = g.prior_mu || g.prior_sigma || g.prior_full;
 
@@ -836,20 +851,31 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
       }
     }
     float *rowp = g.post + (ptrdiff_t)(row - g.row_begin) * (ptrdiff_t)g.N + j0;
+    if (VEC4 && __all_sync(0xffffffffu, interior)) {
+      // the whole warp is inside the shard and the grid (all but the edge tiles): straight-line
+      // stores, one 512-byte run per instruction
 #pragma unroll
-    for (int r = 0; r < kRows; ++r, rowp += g.N) {
-      if (!interior && !(row + r >= g.row_begin && row + r < g.row_end)) continue;
+      for (int r = 0; r < kRows; ++r, rowp += g.N)
 #pragma unroll
-      for (int grp4 = 0; grp4 < kGroups; ++grp4) {
-        const int jg = j0 + grp4 * kGroupCols;
-        if (!interior && jg >= g.N) continue;
-        if (VEC4) {
+        for (int grp4 = 0; grp4 < kGroups; ++grp4)
           st_stream_f4(rowp + grp4 * kGroupCols, v[r][4 * grp4], v[r][4 * grp4 + 1],
                        v[r][4 * grp4 + 2], v[r][4 * grp4 + 3]);
-        } else {
+    } else {
 #pragma unroll
-          for (int e = 0; e < kRN; ++e)
-            if (jg + e < g.N) st_stream_f1(rowp + grp4 * kGroupCols + e, v[r][4 * grp4 + e]);
+      for (int r = 0; r < kRows; ++r, rowp += g.N) {
+        const bool rv = interior || (row + r >= g.row_begin && row + r < g.row_end);
+#pragma unroll
+        for (int grp4 = 0; grp4 < kGroups; ++grp4) {
+          const int jg = j0 + grp4 * kGroupCols;
+          if (VEC4) {
+            if (rv && jg < g.N)
+              st_stream_f4(rowp + grp4 * kGroupCols, v[r][4 * grp4], v[r][4 * grp4 + 1],
+                           v[r][4 * grp4 + 2], v[r][4 * grp4 + 3]);
+          } else {
+#pragma unroll
+            for (int e = 0; e < kRN; ++e)
+              if (rv && jg + e < g.N) st_stream_f1(rowp + grp4 * kGroupCols + e, v[r][4 * grp4 + e]);
+          }
         }
       }
     }
@@ -857,7 +883,11 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
     static_assert(kRows == 4, "the patch reductions below are written for 4 rows");
 #pragma unroll
     for (int cidx = 0; cidx < kCols; ++cidx)
-      colacc[cidx] += (double)((v[0][cidx] + v[1][cidx]) + (v[2][cidx] + v[3][cidx]));
+    {
+      const double add = (double)((v[0][cidx] + v[1][cidx]) + (v[2][cidx] + v[3][cidx]));
+      if (kColSmem) colsm[cidx * (WM * WN * 32) + tid] += add;
+      else colreg[cidx] += add;
+    }
     double rs[kRows];
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
@@ -905,7 +935,7 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
 #pragma unroll
     for (int cidx = 0; cidx < kCols; ++cidx) {
       const int j = patch_col(j0, cidx);
-      if (j < g.N) dst[j] = colacc[cidx];
+      if (j < g.N) dst[j] = kColSmem ? colsm[cidx * (WM * WN * 32) + tid] : colreg[cidx];
     }
   }
 }

@@ -99,8 +99,10 @@ enum {
      even / odd observations and 4 / 2 / 1 observations per loop iteration; 222 scalar
      polynomial; 822 = hybrid capped at 80 registers; 1322 = exponent FMAs scalar; 31 / 32 / 34 =
      paired rows with 1 / 2 / 4 observations per loop iteration, uncapped registers; 33 / 35 =
-     32 / 34 capped at 80 / 128 registers; 37 = 32 with the row pairs' scalars packed; 38x = paired
-     rows, 8 columns per thread.  Log-space: 6 / 8 = tiles of 64 / 1024 observations (default
+     32 / 34 capped at 80 / 128 registers; 37 = 32 with the row pairs' scalars packed; 39 / 45 = the
+     default paired kernel at 128 registers with the column sums in registers / shared memory;
+     41 / 42 = the default with 1 / 2 observations per iteration; 38x = paired rows, 8 columns per
+     thread.  Log-space: 6 / 8 = tiles of 64 / 1024 observations (default
      256), 9 = uncapped registers.  In log-space mode variant 2 caps the kernel at 128 registers. */
 };
 
@@ -257,7 +259,8 @@ int cge_scale_info(cge_context *ctx, double *out, int count, void *stream);
 /* ---- roofline micro-benchmarks (bench.py): measured pipe peaks on this device ------------
  * kind: 0 = MUFU ex2.approx.ftz.f32, 1 = FFMA, 2 = DFMA, 3 = FFMA2 (fma.rn.f32x2);
  * 4-7 = instruction mixes per loop iteration: 4 FFMA2 + 4 FFMA, 4 FFMA2 + 8 FFMA,
- * 6 FFMA2 + 2 MUFU, 4 FFMA2 + 4 FFMA + 2 MUFU (how packed, scalar and MUFU work overlap).
+ * 6 FFMA2 + 2 MUFU, 4 FFMA2 + 4 FFMA + 2 MUFU (how packed, scalar and MUFU work overlap);
+ * 8-10 = the 6 FFMA2 + 2 MUFU mix at 8 / 12 / 16 resident warps per SM instead of 64.
  * Returns operations per second (FMA lane-ops; a packed FFMA2 counts as two; for the mixes the
  * MUFU ops are not counted). */
 int cge_microbench(cge_context *ctx, int kind, double *ops_per_second);

@@ -352,7 +352,7 @@ def _ref_4096(readme_obs):
     return _REF_4096["f64"]
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4, 31, 32, 33, 34, 35, 37, 381, 382, 384])
+@pytest.mark.parametrize("variant", [0, 3, 4, 31, 32, 33, 34, 35, 37, 39, 41, 42, 45, 381, 382, 384])
 def test_paired_rows_variants_4096(ctx, readme_obs, variant):
     """README ranges at N=4096: |u| <= 0.0084, inside the paired kernel's bound (0.011).  Every
     paired variant (and the hybrid one it replaces here) against the float64 oracle."""

@@ -7,9 +7,10 @@ sys.path.insert(0, ".")
 import cuda_grid_estimation_b200 as cge  # noqa: E402
 
 NAMES = ["mufu_ex2", "ffma", "dfma", "ffma2", "4ffma2+4ffma", "4ffma2+8ffma", "6ffma2+2mufu",
-         "4ffma2+4ffma+2mufu"]
-FMA_PER_ITER = [0, 8, 8, 16, 12, 16, 14, 14]
-MUFU_PER_ITER = [8, 0, 0, 0, 0, 0, 2, 2]
+         "4ffma2+4ffma+2mufu", "6ffma2+2mufu@8warps/SM", "6ffma2+2mufu@12warps/SM",
+         "6ffma2+2mufu@16warps/SM"]
+FMA_PER_ITER = [0, 8, 8, 16, 12, 16, 14, 14, 14, 14, 14]
+MUFU_PER_ITER = [8, 0, 0, 0, 0, 0, 2, 2, 2, 2, 2]
 with cge.Context(0) as ctx:
     sm = ctx.device_info()["sm_count"]
     out = {}
