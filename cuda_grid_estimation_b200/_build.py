@@ -8,13 +8,18 @@ import subprocess
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcge.so")
-SOURCES = ["cge_api.cu", "cge_extras.cu"]
-HEADERS = ["cge_kernels.cuh", "cge_device.cuh", os.path.join("..", "..", "include", "cge.h")]
+# one object per translation unit, compiled concurrently: the likelihood-kernel instantiations
+# (cge_launch_*.cu) dominate the build time
+SOURCES = ["cge_api.cu", "cge_extras.cu", "cge_launch_product.cu", "cge_launch_logspace.cu",
+           "cge_launch_small.cu"]
+HEADERS = ["cge_kernels.cuh", "cge_kernels_misc.cuh", "cge_device.cuh", "cge_host.cuh",
+           os.path.join("..", "..", "include", "cge.h")]
+OBJ_DIR = os.path.join(PKG_DIR, "_obj")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC,-fvisibility=hidden",
+    "-Xcompiler", "-fPIC,-fvisibility=hidden",
 ]
 
 
@@ -37,14 +42,30 @@ def build(force: bool = False, verbose: bool = False) -> str:
     """Compile csrc/*.cu into cuda_grid_estimation_b200/libcge.so; returns its path."""
     if not force and not stale():
         return LIB_PATH
-    cmd = [_nvcc(), *NVCC_FLAGS, "-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+    from concurrent.futures import ThreadPoolExecutor
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    nvcc = _nvcc()
+
+    def compile_one(src):
+        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", obj, os.path.join(CSRC, src)]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {src}:\n" + res.stdout + res.stderr)
+        return obj, res.stderr
+
+    with ThreadPoolExecutor(max_workers=len(SOURCES)) as pool:
+        done = list(pool.map(compile_one, SOURCES))
     if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    res = subprocess.run(cmd, capture_output=True, text=True)
+        for _, log in done:
+            print(log)
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + \
+           [obj for obj, _ in done]
+    res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    if verbose:
-        print(res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB_PATH
 
 

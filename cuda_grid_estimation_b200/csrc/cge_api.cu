@@ -13,12 +13,12 @@
 #include <string>
 #include <vector>
 
-#include "../../include/cge.h"
-#include "cge_kernels.cuh"
+#include "cge_host.cuh"
+#include "cge_kernels_misc.cuh"
 
 #define CGE_EXPORT extern "C" __attribute__((visibility("default")))
 
-namespace {
+namespace cge_host {
 
 thread_local std::string g_last_error;
 
@@ -32,19 +32,12 @@ int set_error(int code, const char *fmt, ...) {
   return code;
 }
 
-#define CK(call)                                                                        \
-  do {                                                                                  \
-    cudaError_t e_ = (call);                                                            \
-    if (e_ != cudaSuccess)                                                              \
-      return set_error(CGE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
-                       __FILE__, __LINE__);                                             \
-  } while (0)
+}  // namespace cge_host
 
-#define CKRC(expr)            \
-  do {                        \
-    int rc_ = (expr);         \
-    if (rc_ != CGE_OK) return rc_; \
-  } while (0)
+using cge_host::Plan;
+using cge_host::set_error;
+
+namespace {
 
 // grow-only device buffer
 template <class T>
@@ -93,18 +86,6 @@ struct PinnedBuf {
     ptr = nullptr;
     cap = 0;
   }
-};
-
-struct Plan {
-  bool valid = false;
-  int N = 0, n = 0, n_pad = 0, mode = 0, variant = 0;
-  int row_begin = 0, row_end = 0, rows_local = 0;
-  int wm = 1, wn = 8;
-  int bands = 0, row_tiles = 0, tile_rows = 0;
-  int ncw = 0, ncolparts = 0;
-  int nb_col = 0, nb_row = 0;
-  bool vec4 = false;
-  size_t smem = 0;
 };
 
 }  // namespace
@@ -166,10 +147,9 @@ int check_params(const cge_params *p, int *rb, int *re) {
   if (p->mode != CGE_MODE_PRODUCT_F32 && p->mode != CGE_MODE_LOGSPACE)
     return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
   switch (p->variant) {
-    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case 2: case CGE_VARIANT_PAIRED:
-    case CGE_VARIANT_LOG_F64: case 6: case 8: case 9: case CGE_VARIANT_UNFUSED:
-    case CGE_VARIANT_HYBRID: case 100: case 122: case 133: case 222: case 522: case 523: case 633:
-    case 822: case 1322: case 31: case 32: case 33: case 34: case 35: case 37: case 39: case 41: case 42: case 45: case 381: case 382: case 384: break;
+    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case CGE_VARIANT_PAIRED:
+    case CGE_VARIANT_HYBRID: case CGE_VARIANT_LOG_F64: case CGE_VARIANT_UNFUSED:
+    case 6: case 31: case 39: case 45: case 381: break;
     default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
   }
   int b = p->row_begin, e = p->row_end;
@@ -184,7 +164,7 @@ int check_params(const cge_params *p, int *rb, int *re) {
 
 // log-space kernels other than the float64 ones read centred observations (x_k - mu_c)
 int centred_obs(const cge_params *p) {
-  return (p->mode == CGE_MODE_LOGSPACE && p->variant != CGE_VARIANT_LOG_F64 && p->variant != 2) ? 1 : 0;
+  return (p->mode == CGE_MODE_LOGSPACE && p->variant != CGE_VARIANT_LOG_F64) ? 1 : 0;
 }
 
 // tile shape and grid for one shard
@@ -199,7 +179,7 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->row_end = re;
   pl->rows_local = re - rb;
   // columns per warp strip: 32 lanes x Policy::kCols (log-space keeps 8 columns per thread)
-  const bool wide_patch = p->mode == CGE_MODE_PRODUCT_F32 && p->variant >= 381 && p->variant <= 384;
+  const bool wide_patch = p->mode == CGE_MODE_PRODUCT_F32 && p->variant == 381;
   const int strip = 32 * (p->mode == CGE_MODE_LOGSPACE ? cge::LogSpaceTiled<>::kCols : wide_patch ? 8 : 4);
   pl->ncw = (pl->N + strip - 1) / strip;
   if (pl->ncw >= 8) { pl->wm = 1; pl->wn = 8; }
@@ -237,147 +217,12 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->valid = true;
 }
 
-template <class Policy, int WM, int WN, int MINB = 1>
-int launch_like_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
-  dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
-  const size_t smem = pl.smem + 16 + (Policy::kColSmem ? (size_t)WM * WN * 32 * Policy::kCols * 8 : 0);
-  if (pl.vec4) {
-    auto k = cge::grid_likelihood_kernel<Policy, WM, WN, true, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, block, smem, st>>>(args);
-  } else {
-    auto k = cge::grid_likelihood_kernel<Policy, WM, WN, false, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, block, smem, st>>>(args);
-  }
-  CK(cudaGetLastError());
-  return CGE_OK;
-}
-
-template <class Policy, int MINB = 1>
-int launch_like(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
-  if (pl.wm == 1) return launch_like_shape<Policy, 1, 8, MINB>(pl, args, st);
-  if (pl.wm == 2) return launch_like_shape<Policy, 2, 4, MINB>(pl, args, st);
-  if (pl.wm == 4) return launch_like_shape<Policy, 4, 2, MINB>(pl, args, st);
-  return launch_like_shape<Policy, 8, 1, MINB>(pl, args, st);
-}
-
-template <class Fine, class Coarse, int WM, int WN, int MINB = 1>
-int launch_dual_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
-  dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
-  const size_t smem = pl.smem + 16 +
-      ((Fine::kColSmem || Coarse::kColSmem) ? (size_t)WM * WN * 32 * Fine::kCols * 8 : 0);
-  if (pl.vec4) {
-    auto k = cge::grid_likelihood_dual_kernel<Fine, Coarse, WM, WN, true, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, block, smem, st>>>(args);
-  } else {
-    auto k = cge::grid_likelihood_dual_kernel<Fine, Coarse, WM, WN, false, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, block, smem, st>>>(args);
-  }
-  CK(cudaGetLastError());
-  return CGE_OK;
-}
-
-template <class Fine, class Coarse, int MINB>
-int launch_dual(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
-  if (pl.wm == 1) return launch_dual_shape<Fine, Coarse, 1, 8, MINB>(pl, args, st);
-  if (pl.wm == 2) return launch_dual_shape<Fine, Coarse, 2, 4, MINB>(pl, args, st);
-  if (pl.wm == 4) return launch_dual_shape<Fine, Coarse, 4, 2, MINB>(pl, args, st);
-  return launch_dual_shape<Fine, Coarse, 8, 1, MINB>(pl, args, st);
-}
-
-// product path.  Default: grid_likelihood_dual_kernel -- ProductPaired (half the exponentials
-// from MUFU.EX2, the other half derived from the row above by a degree-2 FMA-pipe polynomial)
-// when the grid is fine enough (ScaleInfo::umax <= kPairedUmax, decided on the device), else
-// ProductHybrid<2, 2, false, 1> (12 of 16 exponentials from MUFU.EX2, 4 from a degree-5
-// polynomial).  CGE_VARIANT_PAIRED / _HYBRID force one of the two, CGE_VARIANT_MUFU_ONLY is the
-// roofline case; the numbered variants document the tuning sweeps
-// (profiles/r01_variant_sweep_*.jsonl) and are only built for the wide tile shape.
-using DefaultFine = cge::ProductPaired<4, 4, true, true>;
-constexpr int kDefaultMinB = 3;  // <= 80 registers: three 256-thread CTAs (24 warps) per SM
-using DefaultCoarse = cge::ProductHybrid<2, 2, false, 1>;
-
-int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
-  switch (pl.variant) {
-    case CGE_VARIANT_MUFU_ONLY: return launch_like<cge::ProductF32>(pl, args, st);
-    case CGE_VARIANT_PAIRED: return launch_like<DefaultFine, kDefaultMinB>(pl, args, st);
-    case CGE_VARIANT_HYBRID: return launch_like<DefaultCoarse>(pl, args, st);
-    default: break;
-  }
-  if (pl.wm == 1) {
-    switch (pl.variant) {
-      case 100: return launch_like_shape<cge::ProductHybrid<0, 0>, 1, 8>(pl, args, st);
-      case 122: return launch_like_shape<cge::ProductHybrid<2, 2>, 1, 8>(pl, args, st);
-      case 133: return launch_like_shape<cge::ProductHybrid<3, 3>, 1, 8>(pl, args, st);
-      case 222: return launch_like_shape<cge::ProductHybrid<2, 2, true>, 1, 8>(pl, args, st);
-      case 522: return launch_like_shape<cge::ProductHybrid<2, 2, false, 2>, 1, 8>(pl, args, st);
-      case 523: return launch_like_shape<cge::ProductHybrid<2, 3, false, 2>, 1, 8>(pl, args, st);
-      case 633: return launch_like_shape<cge::ProductHybrid<3, 3, false, 1>, 1, 8>(pl, args, st);
-      case 822: return launch_like_shape<cge::ProductHybrid<2, 2, false, 1>, 1, 8, 3>(pl, args, st);
-      // 1322: exponent FMA as two scalar FFMAs, 1 observation per iteration
-      case 1322: return launch_like_shape<cge::ProductHybrid<2, 2, false, 1, true>, 1, 8>(pl, args, st);
-      // paired rows (CGE_VARIANT_PAIRED = 4 columns per thread, 4 observations per iteration, the
-      // row pairs' scalars packed, column sums in shared memory, capped at 80 registers = 3 CTAs
-      // per SM): 31 / 32 / 34 = 1 / 2 / 4 observations per iteration, scalars unpacked, column
-      // sums in registers, uncapped; 33 = 32 capped at 80 registers; 35 = 34 capped at 128;
-      // 37 = 32 with packed scalars; 38x = 8 columns per thread
-      case 31: return launch_like_shape<cge::ProductPaired<4, 1>, 1, 8>(pl, args, st);
-      case 32: return launch_like_shape<cge::ProductPaired<4, 2>, 1, 8>(pl, args, st);
-      case 33: return launch_like_shape<cge::ProductPaired<4, 2>, 1, 8, 3>(pl, args, st);
-      case 34: return launch_like_shape<cge::ProductPaired<4, 4>, 1, 8>(pl, args, st);
-      case 35: return launch_like_shape<cge::ProductPaired<4, 4>, 1, 8, 2>(pl, args, st);
-      case 37: return launch_like_shape<cge::ProductPaired<4, 2, true>, 1, 8>(pl, args, st);
-      // column sums in shared memory: 41 / 42 = 1 / 2 observations per iteration at 80 registers;
-      // 45 = 4 observations at 128 registers (2 CTAs per SM); 39 = 45 with column sums in registers
-      case 39: return launch_like_shape<cge::ProductPaired<4, 4, true>, 1, 8, 2>(pl, args, st);
-      case 41: return launch_like_shape<cge::ProductPaired<4, 1, true, true>, 1, 8, 3>(pl, args, st);
-      case 42: return launch_like_shape<cge::ProductPaired<4, 2, true, true>, 1, 8, 3>(pl, args, st);
-      case 45: return launch_like_shape<cge::ProductPaired<4, 4, true, true>, 1, 8, 2>(pl, args, st);
-      case 381: return launch_like_shape<cge::ProductPaired<8, 1>, 1, 8>(pl, args, st);
-      case 382: return launch_like_shape<cge::ProductPaired<8, 2>, 1, 8>(pl, args, st);
-      case 384: return launch_like_shape<cge::ProductPaired<8, 4>, 1, 8>(pl, args, st);
-      default: break;
-    }
-  }
-  if (pl.variant >= 381 && pl.variant <= 384)
-    return set_error(CGE_ERR_BAD_ARG, "variant %d needs grid_size >= 2048", pl.variant);
-  return launch_dual<DefaultFine, DefaultCoarse, kDefaultMinB>(pl, args, st);
-}
-
 // ---------------------------------------------------------------------------------------
 // single-launch path for small grids (cge::small_grid_kernel): whole grid, no exchange
 // ---------------------------------------------------------------------------------------
 constexpr int kSmallGridMax = 256;
 constexpr int kZeroCopyObsMax = 1024;  // host observations read in place (mapped pinned) up to this n
 int mark(cge_context *ctx, int k, cudaStream_t st);
-
-template <class Fine, class Coarse, int WM, int WN>
-int launch_small_shape(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st) {
-  dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
-  const size_t smem = pl.smem + 16 +
-      ((Fine::kColSmem || Coarse::kColSmem) ? (size_t)WM * WN * 32 * Fine::kCols * 8 : 0);
-  if (pl.vec4) {
-    auto k = cge::small_grid_kernel<Fine, Coarse, WM, WN, true>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, block, smem, st>>>(a);
-  } else {
-    auto k = cge::small_grid_kernel<Fine, Coarse, WM, WN, false>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, block, smem, st>>>(a);
-  }
-  CK(cudaGetLastError());
-  return CGE_OK;
-}
-
-template <class Fine, class Coarse>
-int launch_small(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st) {
-  if (pl.wm == 1) return launch_small_shape<Fine, Coarse, 1, 8>(pl, a, st);
-  if (pl.wm == 2) return launch_small_shape<Fine, Coarse, 2, 4>(pl, a, st);
-  if (pl.wm == 4) return launch_small_shape<Fine, Coarse, 4, 2>(pl, a, st);
-  return launch_small_shape<Fine, Coarse, 8, 1>(pl, a, st);
-}
 
 bool small_grid_eligible(const cge_context *ctx, const cge_params *p, int rb, int re) {
   return p->variant == CGE_VARIANT_DEFAULT && p->grid_size <= kSmallGridMax && rb == 0 &&
@@ -464,9 +309,9 @@ int small_grid_step(cge_context *ctx, const cge_params *p, const float *obs_dev,
   CKRC(mark(ctx, 0, st));
   CKRC(mark(ctx, 1, st));
   if (p->mode == CGE_MODE_PRODUCT_F32)
-    CKRC((launch_small<DefaultFine, DefaultCoarse>(pl, a, st)));
+    CKRC(cge_host::launch_small_product(pl, a, st));
   else
-    CKRC((launch_small<cge::LogSpaceTiled<256>, cge::LogSpaceTiled<256>>(pl, a, st)));
+    CKRC(cge_host::launch_small_logspace(pl, a, st));
   ctx->launches += 1;
   for (int k = 2; k <= 6; ++k) CKRC(mark(ctx, k, st));
   if (ctx->prof_on && ctx->prof_step < ctx->prof_cap) ctx->prof_step++;
@@ -540,7 +385,7 @@ bool is_device_pointer(const void *p) {
 // ---------------------------------------------------------------------------------------
 CGE_EXPORT int cge_version(void) { return CGE_VERSION; }
 
-CGE_EXPORT const char *cge_last_error(void) { return g_last_error.c_str(); }
+CGE_EXPORT const char *cge_last_error(void) { return cge_host::g_last_error.c_str(); }
 
 CGE_EXPORT int cge_create(int device, cge_context **out) {
   if (!out) return set_error(CGE_ERR_BAD_ARG, "out is NULL");
@@ -645,20 +490,9 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   cge::LikeArgs args;
   CKRC(fill_like_args(ctx, pl, posterior_dev, &args));
   if (p->mode == CGE_MODE_PRODUCT_F32) {
-    CKRC(launch_product(pl, args, st));
+    CKRC(cge_host::launch_product(pl, args, st));
   } else {
-    // default: float32x2 sums of centred terms in tiles of 256 observations folded into float64
-    // (LogSpaceTiled), capped at 128 registers; 6 / 8: tiles of 64 / 1024; 9: uncapped;
-    // CGE_VARIANT_LOG_F64: one DFMA per pdf-eval (the first log-space kernel, kept as the
-    // FP64-pipe case); 2: the same capped at 128 registers
-    switch (p->variant) {
-      case CGE_VARIANT_LOG_F64: CKRC((launch_like<cge::LogSpaceF64, 1>(pl, args, st))); break;
-      case 2: CKRC((launch_like<cge::LogSpaceF64, 2>(pl, args, st))); break;
-      case 6: CKRC((launch_like<cge::LogSpaceTiled<64>, 2>(pl, args, st))); break;
-      case 8: CKRC((launch_like<cge::LogSpaceTiled<1024>, 2>(pl, args, st))); break;
-      case 9: CKRC((launch_like<cge::LogSpaceTiled<256>, 1>(pl, args, st))); break;
-      default: CKRC((launch_like<cge::LogSpaceTiled<256>, 2>(pl, args, st))); break;
-    }
+    CKRC(cge_host::launch_logspace(pl, args, st));
   }
   ctx->launches += 1;
   CKRC(mark(ctx, 2, st));

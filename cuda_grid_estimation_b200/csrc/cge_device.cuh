@@ -102,26 +102,6 @@ __device__ __forceinline__ f32x2 ex2_poly2(f32x2 t) {
   return pack2(el, eh);
 }
 
-// scalar form of ex2_poly2 (plain FADD/FFMA can issue to either FMA half-pipe; the packed
-// forms only to the heavy one)
-__device__ __forceinline__ float ex2_poly1(float t) {
-  t = fmaxf(t, -125.0f);
-  const float r = __fadd_rn(t, 12582912.0f);
-  const float n = __fsub_rn(r, 12582912.0f);
-  const float f = __fsub_rn(t, n);
-  float q = fmaf(f, 0.0013276472454890609f, 0.009675540961325169f);
-  q = fmaf(q, f, 0.05550713092088699f);
-  q = fmaf(q, f, 0.24022120237350464f);
-  q = fmaf(q, f, 0.6931469440460205f);
-  q = fmaf(q, f, 1.0000001192092896f);
-  return __int_as_float(__float_as_int(q) + (__float_as_int(r) << 23));
-}
-__device__ __forceinline__ f32x2 ex2_poly2_scalar(f32x2 t) {
-  float lo, hi;
-  unpack2(t, lo, hi);
-  return pack2(ex2_poly1(lo), ex2_poly1(hi));
-}
-
 // ---------------------------------------------------------------------------------------
 // shared-memory addressing, mbarrier and TMA 1-D bulk copy (cp.async.bulk -> SASS UBLKCP)
 // ---------------------------------------------------------------------------------------

@@ -93,17 +93,12 @@ enum {
   CGE_VARIANT_HYBRID = 4     /* hybrid, forced: packed f32x2 arithmetic; of the 16 exponentials a
                                 thread evaluates per observation, 12 use MUFU.EX2 and 4 an FMA-pipe
                                 degree-5 polynomial with Cody-Waite range reduction */
-  /* tuning variants kept for the record (wide tile shape only, see cge_api.cu launch_product;
-     the full sweep incl. variants since removed is in profiles/r01_variant_sweep_*.jsonl):
-     100 packed, MUFU only; 1ab / 5ab / 6ab hybrid with a / b polynomial column pairs (of 8) on
-     even / odd observations and 4 / 2 / 1 observations per loop iteration; 222 scalar
-     polynomial; 822 = hybrid capped at 80 registers; 1322 = exponent FMAs scalar; 31 / 32 / 34 =
-     paired rows with 1 / 2 / 4 observations per loop iteration, uncapped registers; 33 / 35 =
-     32 / 34 capped at 80 / 128 registers; 37 = 32 with the row pairs' scalars packed; 39 / 45 = the
-     default paired kernel at 128 registers with the column sums in registers / shared memory;
-     41 / 42 = the default with 1 / 2 observations per iteration; 38x = paired rows, 8 columns per
-     thread.  Log-space: 6 / 8 = tiles of 64 / 1024 observations (default
-     256), 9 = uncapped registers.  In log-space mode variant 2 caps the kernel at 128 registers. */
+  /* tuning variants still built (wide tile shape only; see cge_api.cu launch_product): 31 = the
+     first paired kernel (1 observation per iteration, unpacked scalars, uncapped registers);
+     39 / 45 = the default paired kernel at 128 registers with the column sums in registers /
+     shared memory; 381 = paired rows, 8 columns per thread.  Log-space: 6 = tiles of 64
+     observations (default 256).  profiles/r01_variant_sweep_*.jsonl record ~25 more variants
+     (hybrid splits, loop shapes, register caps) that were removed after the sweeps. */
 };
 
 /* per-phase device timings of the last synchronous call, milliseconds (CUDA events) */
