@@ -394,6 +394,34 @@ def test_paired_rows_on_small_fine_grids(ctx, readme_obs, N):
     check_against(d, ref, what=f"narrow ranges N={N}")
 
 
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 5, 7, 49, 51, 64, 200])
+def test_paired_rows_observation_counts(ctx, n):
+    """Observation counts around the 4-per-iteration loop of the paired kernel (fine grid, wide
+    tile shape and the single-launch path)."""
+    obs = oracle.readme_observations(n=n, seed=7)
+    for N, mu_r in ((200, (19.9, 20.1)), (1100, (19.6, 20.4))):
+        sg_r = (1.6, 2.4)
+        res = ctx.grid_posterior(obs, N, mu_r, sg_r)
+        assert ctx.scale_info()["product_path"] == "paired"
+        ref = oracle.grid_posterior(obs, N, *mu_r, *sg_r, oracle.NUM_F64)
+        check_against(res, ref, what=f"paired n={n} N={N}")
+
+
+def test_descending_and_sign_crossing_ranges(ctx):
+    """Ranges given high-to-low and a mu range that crosses zero: the row-pair identity uses the
+    signed spacing, the eligibility bound its magnitude."""
+    rng = np.random.default_rng(3)
+    obs = rng.normal(0.1, 1.0, 40).astype(np.float32)
+    for N in (150, 2048):
+        for mu_r, sg_r in (((0.6, -0.4), (0.7, 1.5)), ((-0.4, 0.6), (1.5, 0.7))):
+            for mode, num in ((cge.MODE_PRODUCT_F32, oracle.NUM_F64), (cge.MODE_LOGSPACE, oracle.NUM_LOG)):
+                res = ctx.grid_posterior(obs, N, mu_r, sg_r, mode=mode)
+                ref = oracle.grid_posterior(obs, N, *mu_r, *sg_r, num)
+                check_against(res, ref, what=f"N={N} mu={mu_r} sigma={sg_r} mode={mode}")
+    res = ctx.grid_posterior(obs, 2048, (0.6, -0.4), (0.7, 1.5))
+    assert ctx.scale_info()["product_path"] == "paired"
+
+
 def test_paired_rows_at_the_eligibility_bound(ctx, readme_obs):
     """Forced paired rows on grids around the bound: the polynomial's error grows as |u|^3, so
     the result must still be well inside tolerance at the bound and degrade gracefully past it
