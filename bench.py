@@ -394,12 +394,14 @@ def run_ours(args):
             #   paired rows: 8 MUFU.EX2 + 27 packed (2 lane-ops each) per 16 evals
             #   hybrid     : 12 MUFU.EX2 + 8 + 8 packed (exponent, product) + 2 x 8 packed
             #                (polynomial) + 8 scalar per 16 evals
-            paired = sinfo["product_path"] == "paired"
-            mufu_pe, fma_pe = (0.5, 54 / 16) if paired else (0.75, (2 * 32 + 8) / 16)
+            #   paired, degree 3: 4 more packed per 16 evals
+            path = sinfo["product_path"]
+            mufu_pe, fma_pe = {"paired": (0.5, 54 / 16), "paired3": (0.5, 62 / 16)}.get(
+                path, (0.75, (2 * 32 + 8) / 16))
             roof = {"bound": "mufu", "achieved": ach / 1e9, "peak": ex2_peak / 1e9, "unit": "Gop/s",
                     "frac": ach / ex2_peak, "traffic": traffic,
-                    "kernel": "grid_likelihood_dual_kernel<ProductPaired, ProductHybrid> -> "
-                              + sinfo["product_path"],
+                    "kernel": "grid_likelihood_select_kernel<ProductPaired deg 2, ProductPaired deg 3, "
+                              "ProductHybrid> -> " + path,
                     "algorithmic": "1 ex2 per pdf-eval (SURVEY 8(d)); evals per launch = rows*N*n",
                     "note": "frac > 1 is by design: the kernel takes " + str(mufu_pe) + " of its "
                             "exponentials per eval from MUFU.EX2 and forms the rest on the FMA pipe "
@@ -411,6 +413,7 @@ def run_ours(args):
                                  "mufu_util": mufu_pe * ach / ex2_peak,
                                  "fma_util": fma_pe * ach / ffma_peak},
                     "umax": sinfo["umax"], "paired_umax": sinfo["paired_umax"],
+                    "paired3_umax": sinfo["paired3_umax"],
                     "peak_source": "ex2.approx.ftz micro-benchmark in this run (cge_microbench 0)",
                     "peak_nominal": 16 * info["sm_count"] * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9}
         else:

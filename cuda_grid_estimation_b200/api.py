@@ -26,6 +26,7 @@ VARIANT_MUFU_ONLY = 1
 VARIANT_PAIRED = 3
 VARIANT_HYBRID = 4
 VARIANT_LOG_F64 = 5
+VARIANT_PAIRED3 = 8
 VARIANT_UNFUSED = 7
 
 OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_DEGENERATE, ERR_NCCL, ERR_SIZE = range(7)
@@ -348,11 +349,13 @@ def _set_prior(self, prior_mu=None, prior_sigma=None, grid_size=0, prior_full=No
 
 def _scale_info(self, stream=None) -> dict:
     """Scale statistics of the last likelihood call (see cge_scale_info)."""
-    out = np.empty(10, np.float64)
-    _check(self._lib.cge_scale_info(self._h, out.ctypes.data, 10, stream))
-    keys = ("log2s", "shift", "m2", "xbar", "ss", "smin", "mu_c", "s_c", "umax", "paired_umax")
+    out = np.empty(11, np.float64)
+    _check(self._lib.cge_scale_info(self._h, out.ctypes.data, 11, stream))
+    keys = ("log2s", "shift", "m2", "xbar", "ss", "smin", "mu_c", "s_c", "umax", "paired_umax",
+            "paired3_umax")
     d = dict(zip(keys, out.tolist()))
-    d["product_path"] = "paired" if d["umax"] <= d["paired_umax"] else "hybrid"
+    d["product_path"] = ("paired" if d["umax"] <= d["paired_umax"] else
+                         "paired3" if d["umax"] <= d["paired3_umax"] else "hybrid")
     return d
 
 

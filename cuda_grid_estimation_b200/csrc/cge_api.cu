@@ -147,7 +147,7 @@ int check_params(const cge_params *p, int *rb, int *re) {
   if (p->mode != CGE_MODE_PRODUCT_F32 && p->mode != CGE_MODE_LOGSPACE)
     return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
   switch (p->variant) {
-    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case CGE_VARIANT_PAIRED:
+    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case CGE_VARIANT_PAIRED: case CGE_VARIANT_PAIRED3:
     case CGE_VARIANT_HYBRID: case CGE_VARIANT_LOG_F64: case CGE_VARIANT_UNFUSED:
     case 6: case 31: case 39: case 45: case 381: break;
     default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
@@ -864,9 +864,9 @@ CGE_EXPORT int cge_scale_info(cge_context *ctx, double *out, int count, void *st
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemcpyAsync(&h, ctx->scale.ptr, sizeof h, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const double v[10] = {h.log2s, h.shift, h.m2, h.xbar, h.ss, h.smin, h.mu_c, h.s_c, h.umax,
-                        cge::kPairedUmax};
-  for (int i = 0; i < count && i < 10; ++i) out[i] = v[i];
+  const double v[11] = {h.log2s, h.shift, h.m2, h.xbar, h.ss, h.smin, h.mu_c, h.s_c, h.umax,
+                        cge::kPairedUmax, cge::kPairedUmax3};
+  for (int i = 0; i < count && i < 11; ++i) out[i] = v[i];
   return CGE_OK;
 }
 

@@ -40,7 +40,8 @@ struct Plan {
 };
 
 // the default product policies (cge_launch_product.cu, cge_launch_small.cu)
-using DefaultFine = cge::ProductPaired<4, 4, true, true>;
+using DefaultFine = cge::ProductPaired<4, 4, true, true>;     // degree-2 polynomial, umax <= 0.011
+using DefaultMid = cge::ProductPaired<4, 4, true, true, 3>;   // degree-3 polynomial, umax <= 0.05
 using DefaultCoarse = cge::ProductHybrid<2, 2, false, 1>;
 constexpr int kDefaultMinB = 3;  // <= 80 registers: three 256-thread CTAs (24 warps) per SM
 

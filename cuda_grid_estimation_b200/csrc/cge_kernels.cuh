@@ -358,6 +358,7 @@ struct LogSpaceF64 {
 // ---------------------------------------------------------------------------------------
 template <int TILE = 256>
 struct LogSpaceTiled {
+  static constexpr double kUmax = 1.0 / 0.0;
   static constexpr bool kColSmem = false;
   static constexpr int kRows = 4;
   static constexpr int kCols = 8;
@@ -481,6 +482,7 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 // ---------------------------------------------------------------------------------------
 template <int NPA, int NPB, bool /*unused*/ = false, int OBS_PER_ITER = 4>
 struct ProductHybrid {
+  static constexpr double kUmax = 1.0 / 0.0;  // any grid
   static constexpr bool kColSmem = false;
   static constexpr int kRows = kRM;
   static constexpr int kCols = 4;
@@ -582,13 +584,21 @@ struct ProductHybrid {
 // k1 = ln 2 + (ln(2)^3/6)(3/4) U^2 (Chebyshev economisation on [-U, U], U = ScaleInfo::umax):
 // error <= 0.0139 U^3 = 1.8e-8 at the eligibility bound kPairedUmax, below the float32 rounding
 // of the factor itself.  The derived factor is e*(1+v) evaluated as fma(e, v, e): one rounding.
-// Grids too coarse for that bound run ProductHybrid instead (chosen on the device, see
-// grid_likelihood_dual_kernel); which rows are MUFU rows depends on the global row index only.
+// DEG = 3 adds the cubic term, 2^u - 1 = u (k1 + u (k2 + u k3)), k3 = ln(2)^3/6 and the quartic
+// folded into k2 = ln(2)^2/2 + (ln(2)^4/24) U^2: error <= 0.0024 U^4 = 1.5e-8 at its bound
+// kPairedUmax3 = 0.05, which takes grids 4.5x coarser (README ranges: N >= 690) for one more
+// FFMA2 per derived pair.  Grids too coarse for that run ProductHybrid instead (chosen on the
+// device, see grid_likelihood_select_kernel); which rows are MUFU rows depends on the global row
+// index only.
 // ---------------------------------------------------------------------------------------
 constexpr double kPairedUmax = 0.011;
+constexpr double kPairedUmax3 = 0.05;
 
-template <int KC = 4, int OBS_PER_ITER = 1, bool PACKED_ROWS = false, bool COL_SMEM = false>
+template <int KC = 4, int OBS_PER_ITER = 1, bool PACKED_ROWS = false, bool COL_SMEM = false,
+          int DEG = 2>
 struct ProductPaired {
+  static_assert(DEG == 2 || DEG == 3, "polynomial degree of 2^u - 1");
+  static constexpr double kUmax = DEG == 2 ? kPairedUmax : kPairedUmax3;  // eligibility bound
   // COL_SMEM: the tile's float64 column sums live in shared memory instead of 2*KC registers
   // (they are touched once per row group), which is what lets the kernel fit 80 registers
   static constexpr bool kColSmem = COL_SMEM;
@@ -598,16 +608,18 @@ struct ProductPaired {
   static constexpr int kPairs = KC / 2;
   f32x2 a2[kPairs], c2[kPairs];    // exponent coefficients of the MUFU rows
   f32x2 k1a[kPairs], k2a[kPairs];  // a_j k1, a_j^2 k2 of the derived rows
+  f32x2 k3a[DEG == 3 ? kPairs : 1];  // a_j^3 k3
   f32x2 p2[kRM][kPairs];
 
   __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
                                                const ColumnCoefs<kCols> &cf) {
     const double U = sc.umax;
-    const double k1 = 0.69314718055994530942 + 0.0555041086648215799 * 0.75 * U * U;
-    const double k2 = 0.24022650695910071233;
+    const double k1 = 0.69314718055994530942 + (DEG == 2 ? 0.0555041086648215799 * 0.75 * U * U : 0.0);
+    const double k2 = 0.24022650695910071233 + (DEG == 3 ? 0.00961812910762847716 * U * U : 0.0);
+    const double k3 = 0.0555041086648215799;
 #pragma unroll
     for (int h = 0; h < kPairs; ++h) {
-      float av[2], cv[2], k1v[2], k2v[2];
+      float av[2], cv[2], k1v[2], k2v[2], k3v[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         const int j = patch_col(j0, 2 * h + e);
@@ -616,11 +628,13 @@ struct ProductPaired {
         cv[e] = j < g.N ? (float)(cf.c0[2 * h + e] + sc.log2s) : 0.0f;
         k1v[e] = (float)(a * k1);
         k2v[e] = (float)(a * a * k2);
+        k3v[e] = (float)(a * a * a * k3);
       }
       a2[h] = pack2(av[0], av[1]);
       c2[h] = pack2(cv[0], cv[1]);
       k1a[h] = pack2(k1v[0], k1v[1]);
       k2a[h] = pack2(k2v[0], k2v[1]);
+      if (DEG == 3) k3a[h] = pack2(k3v[0], k3v[1]);
     }
   }
   __device__ __forceinline__ void begin_rows() {
@@ -656,7 +670,8 @@ struct ProductPaired {
       for (int h = 0; h < kPairs; ++h) {
         const f32x2 e2 = ex2_mufu2(fma2(dd2, a2[h], c2[h]));
         p2[2 * rp][h] = mul2(p2[2 * rp][h], e2);
-        const f32x2 v2 = mul2(g2, fma2(g2, k2a[h], k1a[h]));  // 2^u - 1
+        const f32x2 q2 = DEG == 3 ? fma2(g2, k3a[h], k2a[h]) : k2a[h];
+        const f32x2 v2 = mul2(g2, fma2(g2, q2, k1a[h]));  // 2^u - 1
         const f32x2 f2 = fma2(e2, v2, e2);                    // neighbour's factor
         p2[2 * rp + 1][h] = mul2(p2[2 * rp + 1][h], f2);
       }
@@ -929,21 +944,25 @@ __global__ void __launch_bounds__(WM *WN * 32, MINB)
   likelihood_body<Policy, WM, WN, VEC4>(g, sc, cf, smem_raw);
 }
 
-// The default product kernel: ProductPaired where the grid is fine enough for its polynomial
-// (ScaleInfo::umax, computed by setup_kernel from the ranges and the observations that are
-// already on the device), ProductHybrid otherwise.  The choice is uniform over the launch and
-// depends on (ranges, N, observations) only -- never on the shard -- so every rank of a sharded
-// run takes the same path and results stay bit-reproducible.  Both policies share the tiling.
-template <class Fine, class Coarse, int WM, int WN, bool VEC4, int MINB = 1>
+// The default product kernel: ProductPaired with the degree-2 polynomial where the grid is fine
+// enough for it (ScaleInfo::umax, computed by setup_kernel from the ranges and the observations
+// that are already on the device), with the degree-3 polynomial on grids up to 4.5x coarser,
+// ProductHybrid otherwise.  The choice is uniform over the launch and depends on (ranges, N,
+// observations) only -- never on the shard -- so every rank of a sharded run takes the same path
+// and results stay bit-reproducible.  The policies share the tiling.
+template <class Fine, class Mid, class Coarse, int WM, int WN, bool VEC4, int MINB = 1>
 __global__ void __launch_bounds__(WM *WN * 32, MINB)
-    grid_likelihood_dual_kernel(const LikeArgs g) {
+    grid_likelihood_select_kernel(const LikeArgs g) {
   static_assert(Fine::kCols == Coarse::kCols && Fine::kRows == Coarse::kRows, "same tiling");
+  static_assert(Fine::kCols == Mid::kCols && Fine::kRows == Mid::kRows, "same tiling");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const ScaleInfo sc = *g.scale;
   ColumnCoefs<Fine::kCols> cf;  // in flight together with `sc`, before the path is known
   cf.load(g, first_column<WN>(Fine::kCols));
-  if (sc.umax <= kPairedUmax)
+  if (sc.umax <= Fine::kUmax)
     likelihood_body<Fine, WM, WN, VEC4>(g, sc, cf, smem_raw);
+  else if (sc.umax <= Mid::kUmax)
+    likelihood_body<Mid, WM, WN, VEC4>(g, sc, cf, smem_raw);
   else
     likelihood_body<Coarse, WM, WN, VEC4>(g, sc, cf, smem_raw);
 }
@@ -979,10 +998,11 @@ struct SmallArgs {
   unsigned int *ticket;
 };
 
-template <class Fine, class Coarse, int WM, int WN, bool VEC4>
+template <class Fine, class Mid, class Coarse, int WM, int WN, bool VEC4>
 __global__ void __launch_bounds__(WM *WN * 32)
     small_grid_kernel(const SmallArgs a) {
   static_assert(Fine::kCols == Coarse::kCols && Fine::kRows == Coarse::kRows, "same tiling");
+  static_assert(Fine::kCols == Mid::kCols && Fine::kRows == Mid::kRows, "same tiling");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double scratch[32];
   __shared__ double colred[WM * WN][kSmallColChunk];
@@ -999,8 +1019,10 @@ __global__ void __launch_bounds__(WM *WN * 32)
 
   ColumnCoefs<Fine::kCols> cf;
   cf.load(g, first_column<WN>(Fine::kCols));
-  if (sc.umax <= kPairedUmax)
+  if (sc.umax <= Fine::kUmax)
     likelihood_body<Fine, WM, WN, VEC4, true>(g, sc, cf, smem_raw);
+  else if (sc.umax <= Mid::kUmax)
+    likelihood_body<Mid, WM, WN, VEC4, true>(g, sc, cf, smem_raw);
   else
     likelihood_body<Coarse, WM, WN, VEC4, true>(g, sc, cf, smem_raw);
 

@@ -3,16 +3,16 @@
 
 namespace cge_host {
 
-template <class Fine, class Coarse, int WM, int WN>
+template <class Fine, class Mid, class Coarse, int WM, int WN>
 int launch_small_shape(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st) {
   dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
   const size_t smem = like_smem<Fine, WM, WN>(pl);
   if (pl.vec4) {
-    auto k = cge::small_grid_kernel<Fine, Coarse, WM, WN, true>;
+    auto k = cge::small_grid_kernel<Fine, Mid, Coarse, WM, WN, true>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, block, smem, st>>>(a);
   } else {
-    auto k = cge::small_grid_kernel<Fine, Coarse, WM, WN, false>;
+    auto k = cge::small_grid_kernel<Fine, Mid, Coarse, WM, WN, false>;
     CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, block, smem, st>>>(a);
   }
@@ -20,20 +20,20 @@ int launch_small_shape(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st)
   return CGE_OK;
 }
 
-template <class Fine, class Coarse>
+template <class Fine, class Mid, class Coarse>
 int launch_small(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st) {
-  if (pl.wm == 1) return launch_small_shape<Fine, Coarse, 1, 8>(pl, a, st);
-  if (pl.wm == 2) return launch_small_shape<Fine, Coarse, 2, 4>(pl, a, st);
-  if (pl.wm == 4) return launch_small_shape<Fine, Coarse, 4, 2>(pl, a, st);
-  return launch_small_shape<Fine, Coarse, 8, 1>(pl, a, st);
+  if (pl.wm == 1) return launch_small_shape<Fine, Mid, Coarse, 1, 8>(pl, a, st);
+  if (pl.wm == 2) return launch_small_shape<Fine, Mid, Coarse, 2, 4>(pl, a, st);
+  if (pl.wm == 4) return launch_small_shape<Fine, Mid, Coarse, 4, 2>(pl, a, st);
+  return launch_small_shape<Fine, Mid, Coarse, 8, 1>(pl, a, st);
 }
 
 int launch_small_product(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st) {
-  return launch_small<DefaultFine, DefaultCoarse>(pl, a, st);
+  return launch_small<DefaultFine, DefaultMid, DefaultCoarse>(pl, a, st);
 }
 
 int launch_small_logspace(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st) {
-  return launch_small<cge::LogSpaceTiled<256>, cge::LogSpaceTiled<256>>(pl, a, st);
+  return launch_small<cge::LogSpaceTiled<256>, cge::LogSpaceTiled<256>, cge::LogSpaceTiled<256>>(pl, a, st);
 }
 
 }  // namespace cge_host

@@ -352,7 +352,7 @@ def _ref_4096(readme_obs):
     return _REF_4096["f64"]
 
 
-@pytest.mark.parametrize("variant", [0, 3, 4, 31, 39, 45, 381])
+@pytest.mark.parametrize("variant", [0, 3, 8, 4, 31, 39, 45, 381])
 def test_paired_rows_variants_4096(ctx, readme_obs, variant):
     """README ranges at N=4096: |u| <= 0.0084, inside the paired kernel's bound (0.011).  Every
     paired variant (and the hybrid one it replaces here) against the float64 oracle."""
@@ -362,21 +362,23 @@ def test_paired_rows_variants_4096(ctx, readme_obs, variant):
 
 
 def test_default_picks_the_path_on_the_device(ctx, readme_obs):
-    """The default kernel chooses paired rows vs hybrid from ScaleInfo::umax (ranges, N and the
-    observations, all on the device): README ranges are too coarse at N=1024 (|u| <= 0.034 ->
-    bit-identical to the forced hybrid) and fine enough at N=4096 (bit-identical to forced
-    paired).  Far-out observations raise |u| and push N=4096 back to the hybrid."""
-    for N, same, other in ((1024, api.VARIANT_HYBRID, api.VARIANT_PAIRED),
-                           (4096, api.VARIANT_PAIRED, api.VARIANT_HYBRID)):
-        d = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
-        a = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=same)
-        b = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=other)
-        assert d.posterior.tobytes() == a.posterior.tobytes()
-        assert d.posterior.tobytes() != b.posterior.tobytes()
+    """The default kernel chooses its arithmetic from ScaleInfo::umax (ranges, N and the
+    observations, all on the device).  README ranges: N=512 is too coarse for paired rows
+    (|u| <= 0.067 -> hybrid), N=1024 takes the degree-3 polynomial (0.034), N=4096 the degree-2
+    one (0.0084); each is bit-identical to the corresponding forced variant and differs from the
+    others.  A far-out observation raises |u| and moves N=4096 to the degree-3 polynomial."""
+    forced = {"hybrid": api.VARIANT_HYBRID, "paired3": api.VARIANT_PAIRED3, "paired": api.VARIANT_PAIRED}
+    for N, want in ((512, "hybrid"), (1024, "paired3"), (4096, "paired")):
+        d = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_UNFUSED)
+        assert ctx.scale_info()["product_path"] == want
+        for name, variant in forced.items():
+            f = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=variant)
+            assert (d.posterior.tobytes() == f.posterior.tobytes()) == (name == want), (N, name)
     far = readme_obs.copy()
     far[0] = 30.0  # reach 12 instead of ~5: |u| <= 0.017 at N=4096
     d = ctx.grid_posterior(far, 4096, (18, 22), (1, 3))
-    a = ctx.grid_posterior(far, 4096, (18, 22), (1, 3), variant=api.VARIANT_HYBRID)
+    assert ctx.scale_info()["product_path"] == "paired3"
+    a = ctx.grid_posterior(far, 4096, (18, 22), (1, 3), variant=api.VARIANT_PAIRED3)
     assert d.posterior.tobytes() == a.posterior.tobytes()
     ref = oracle.grid_posterior(far, 4096, 18, 22, 1, 3, oracle.NUM_F64)
     check_against(d, ref, what="far observation, N=4096")
@@ -419,7 +421,7 @@ def test_descending_and_sign_crossing_ranges(ctx):
                 ref = oracle.grid_posterior(obs, N, *mu_r, *sg_r, num)
                 check_against(res, ref, what=f"N={N} mu={mu_r} sigma={sg_r} mode={mode}")
     res = ctx.grid_posterior(obs, 2048, (0.6, -0.4), (0.7, 1.5))
-    assert ctx.scale_info()["product_path"] == "paired"
+    assert ctx.scale_info()["product_path"] in ("paired", "paired3")
 
 
 def test_paired_rows_at_the_eligibility_bound(ctx, readme_obs):
@@ -430,6 +432,10 @@ def test_paired_rows_at_the_eligibility_bound(ctx, readme_obs):
         res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_PAIRED)
         ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_F64)
         check_against(res, ref, post_rel=rel_max, what=f"forced paired N={N}")
+    for N, rel_max in ((700, 3e-5), (560, 1e-4)):  # degree 3: |u| <= 0.0495, 0.062
+        res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_PAIRED3)
+        ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_F64)
+        check_against(res, ref, post_rel=rel_max, what=f"forced paired3 N={N}")
 
 
 # ---------------------------------------------------------------------------------------
