@@ -41,6 +41,7 @@ ABI_SYMBOLS = (
     "cge_row_products_rows", "cge_marginalize_rows", "cge_row_products",
     "cge_normalize", "cge_marginalize", "cge_expectation", "cge_microbench",
     "cge_generate_normal", "cge_quantiles", "cge_set_prior", "cge_scale_info",
+    "cge_grid_posterior_async",
 )
 
 
@@ -116,6 +117,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "cge_quantiles": [vp, vp, i32, vp, i32, vp, vp],
         "cge_set_prior": [vp, vp, vp, i32, vp],
         "cge_scale_info": [vp, vp, i32, vp],
+        "cge_grid_posterior_async": [vp, vp, vp, vp, vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -229,6 +231,11 @@ class Context:
                                             C.byref(tm) if want_timing else None))
         return GridResult(ex, mm, ms, post_arr, tm.as_dict() if want_timing else {},
                           self.launch_count())
+
+    def grid_posterior_async(self, params: Params, obs_dev, posterior_dev, stream=None):
+        """Enqueue the whole step on `stream` (device buffers, whole grid); read_results waits."""
+        _check(self._lib.cge_grid_posterior_async(self._h, C.byref(params), _ptr(obs_dev),
+                                                  _ptr(posterior_dev), stream))
 
     # ---- phase API (device pointers, asynchronous on `stream`) -------------------------
     def likelihood_partials(self, params: Params, obs_dev, posterior_dev, stream=None):

@@ -845,6 +845,23 @@ CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const f
   return rc;
 }
 
+// asynchronous fused entry: device buffers, whole grid, nothing waited for
+CGE_EXPORT int cge_grid_posterior_async(cge_context *ctx, const cge_params *p, const float *obs_dev,
+                                        float *posterior_dev, void *stream) {
+  CKRC(bind(ctx));
+  int rb, re;
+  CKRC(check_params(p, &rb, &re));
+  if (rb != 0 || re != p->grid_size)
+    return set_error(CGE_ERR_BAD_ARG, "cge_grid_posterior_async needs the whole grid; a shard [%d, %d) "
+                     "goes through cge_likelihood_partials / cge_finalize", rb, re);
+  if (!obs_dev || !posterior_dev || !is_device_pointer(obs_dev) || !is_device_pointer(posterior_dev))
+    return set_error(CGE_ERR_BAD_ARG, "cge_grid_posterior_async needs device pointers");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (small_grid_eligible(ctx, p, rb, re)) return small_grid_step(ctx, p, obs_dev, posterior_dev, st, false);
+  CKRC(cge_likelihood_partials(ctx, p, obs_dev, posterior_dev, st));
+  return cge_finalize(ctx, p, posterior_dev, st);
+}
+
 // posterior kept by the context when cge_grid_posterior was called with posterior == NULL or a
 // host pointer
 CGE_EXPORT int cge_posterior_dev(cge_context *ctx, float **posterior_dev, size_t *count) {

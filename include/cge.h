@@ -138,6 +138,14 @@ int cge_grid_posterior(cge_context *ctx, const cge_params *p, const float *obs,
                        float *posterior, double *marg_mu, double *marg_sigma,
                        double *expectations, cge_timing *timing);
 
+/* Asynchronous form of the fused call for device buffers: enqueues the whole step on `stream`
+ * (one launch for grids up to 256 points per axis, five otherwise) and returns without waiting.
+ * Results stay on the device (cge_results / cge_read_results, which waits for `stream`);
+ * posterior_dev receives the normalised posterior.  Whole grid only (row_begin/row_end must cover
+ * it): a shard needs the exchange between the two phases below. */
+int cge_grid_posterior_async(cge_context *ctx, const cge_params *p, const float *obs_dev,
+                             float *posterior_dev, void *stream);
+
 /* ---- phase API (multi-GPU: one process per GPU, the caller owns the collective) ----------
  * phase 1: tables + likelihood + local deterministic reduction.  Leaves the packed partial
  *          vector {Z, sum_i mu_i*rowsum_i, colsum[0..N)} (N+2 float64) in a context-owned

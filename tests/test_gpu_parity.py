@@ -311,6 +311,30 @@ def test_phase_api_with_row_shards(ctx, readme_obs, N):
             c.close()
 
 
+def test_async_fused_entry(ctx, readme_obs):
+    """cge_grid_posterior_async: device buffers on the caller's stream, nothing waited for until
+    read_results; same bits as the synchronous call (one launch at N=101, five at N=1000)."""
+    import torch
+    dev = torch.device("cuda", 0)
+    obs_t = torch.from_numpy(readme_obs).to(dev)
+    side = torch.cuda.Stream()
+    for N in (101, 1000):
+        ref = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
+        p = cge.make_params(50, N, (18, 22), (1, 3))
+        post = torch.empty((N, N), dtype=torch.float32, device=dev)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(side):
+            for _ in range(3):  # back to back, no host wait in between
+                ctx.grid_posterior_async(p, obs_t, post, side.cuda_stream)
+            ex, mm, ms, z = ctx.read_results(p, side.cuda_stream)
+        assert post.cpu().numpy().tobytes() == ref.posterior.tobytes()
+        assert ex.tobytes() == ref.expectations.tobytes()
+        assert ms.tobytes() == ref.marg_sigma.tobytes() and mm.tobytes() == ref.marg_mu.tobytes()
+    with pytest.raises(cge.CgeError):  # a shard needs the exchange between the phases
+        ctx.grid_posterior_async(cge.make_params(50, 101, (18, 22), (1, 3), rows=(0, 50)), obs_t,
+                                 post, None)
+
+
 def test_device_buffers_and_unaligned_posterior(ctx, readme_obs):
     import torch
     dev = torch.device("cuda", 0)
