@@ -905,7 +905,9 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
     if (!PRELOADED) mbar_wait(&bars[0], 0);
     for (int grp = 0; grp < groups; ++grp) {
       begin_group(grp);
-      if (rows_any && col_any) Policy::consume(pol, obs_s, g.n, mu);
+      // (no skip for groups or columns outside the grid: they are masked in the epilogue, and a
+      // single control path keeps the patch initialisation from being emitted per branch)
+      Policy::consume(pol, obs_s, g.n, mu);
       end_group();
     }
   } else {
