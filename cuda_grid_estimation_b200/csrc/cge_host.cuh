@@ -45,6 +45,10 @@ using DefaultMid = cge::ProductPaired<4, 4, true, true, 3>;   // degree-3 polyno
 using DefaultCoarse = cge::ProductHybrid<2, 2, false, 1>;
 constexpr int kDefaultMinB = 3;  // <= 80 registers: three 256-thread CTAs (24 warps) per SM
 
+// static + dynamic shared memory beyond 48 KB needs the opt-in attribute; the kernels have up to
+// ~17 KB static (small_grid_kernel), so opt in above 24 KB of dynamic and skip the call below it
+constexpr size_t kDefaultSmemLimit = 24 * 1024;
+
 // dynamic shared memory of a likelihood launch: mbarriers + observation stage (+ column sums)
 template <class Policy, int WM, int WN>
 inline size_t like_smem(const Plan &pl) {
@@ -57,11 +61,13 @@ int launch_like_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st
   const size_t smem = like_smem<Policy, WM, WN>(pl);
   if (pl.vec4) {
     auto k = cge::grid_likelihood_kernel<Policy, WM, WN, true, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > kDefaultSmemLimit)  // only stages of thousands of observations get there
+      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, block, smem, st>>>(args);
   } else {
     auto k = cge::grid_likelihood_kernel<Policy, WM, WN, false, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > kDefaultSmemLimit)  // only stages of thousands of observations get there
+      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, block, smem, st>>>(args);
   }
   CK(cudaGetLastError());

@@ -9,11 +9,13 @@ int launch_select_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t 
   const size_t smem = like_smem<Fine, WM, WN>(pl);
   if (pl.vec4) {
     auto k = cge::grid_likelihood_select_kernel<Fine, Mid, Coarse, WM, WN, true, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > kDefaultSmemLimit)  // only stages of thousands of observations get there
+      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, block, smem, st>>>(args);
   } else {
     auto k = cge::grid_likelihood_select_kernel<Fine, Mid, Coarse, WM, WN, false, MINB>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > kDefaultSmemLimit)  // only stages of thousands of observations get there
+      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, block, smem, st>>>(args);
   }
   CK(cudaGetLastError());

@@ -9,11 +9,13 @@ int launch_small_shape(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st)
   const size_t smem = like_smem<Fine, WM, WN>(pl);
   if (pl.vec4) {
     auto k = cge::small_grid_kernel<Fine, Mid, Coarse, WM, WN, true>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > kDefaultSmemLimit)  // only stages of thousands of observations get there
+      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, block, smem, st>>>(a);
   } else {
     auto k = cge::small_grid_kernel<Fine, Mid, Coarse, WM, WN, false>;
-    CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (smem > kDefaultSmemLimit)  // only stages of thousands of observations get there
+      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k<<<grid, block, smem, st>>>(a);
   }
   CK(cudaGetLastError());
