@@ -525,6 +525,61 @@ def test_16384_product_properties(ctx, readme_obs):
                           [0, 1, peak_row - 1500, peak_row, peak_row + 1, peak_row + 2000, N - 1])
 
 
+def test_65536_product_properties(ctx, readme_obs):
+    """BASELINE config 4 at full size on one GPU (17.2 GB posterior): sum = 1, marginals are the
+    row / column sums of what was written, expectations and sampled rows against an independent
+    float64 closed form (sufficient statistics) evaluated with torch on the device."""
+    import torch
+    N = 65536
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~20 GB of device memory for the posterior and its checks")
+    dev = torch.device("cuda", 0)
+    ranges = (18.0, 22.0, 1.0, 3.0)
+    res = ctx.grid_posterior(readme_obs, N, ranges[:2], ranges[2:], posterior="device")
+    assert ctx.scale_info()["product_path"] == "paired"
+    ptr, cnt = ctx.posterior_ptr()
+    post = cge.device_tensor(ptr, cnt, "float32", 0).view(N, N)
+    mu = torch.from_numpy(oracle.linspace(N, *ranges[:2]).astype(np.float64)).to(dev)
+    sg = torch.from_numpy(oracle.linspace(N, *ranges[2:]).astype(np.float64)).to(dev)
+    x = torch.from_numpy(readme_obs.astype(np.float64)).to(dev)
+    n, xbar = x.numel(), x.mean()
+    ss = ((x - xbar) ** 2).sum()
+
+    def loglik(rows):  # [len(rows), N] float64
+        s_i = ss + n * (xbar - mu[rows]) ** 2
+        return -n * torch.log(sg)[None, :] - 0.5 * n * np.log(2 * np.pi) \
+            - s_i[:, None] / (2 * sg ** 2)[None, :]
+
+    chunk = 2048
+    llmax = max(float(loglik(torch.arange(r0, r0 + chunk, device=dev)).max()) for r0 in range(0, N, chunk))
+    z = e_mu = e_sg = total = 0.0
+    rows_sum = torch.empty(N, dtype=torch.float64, device=dev)
+    cols_sum = torch.zeros(N, dtype=torch.float64, device=dev)
+    for r0 in range(0, N, chunk):
+        idx = torch.arange(r0, r0 + chunk, device=dev)
+        p = torch.exp(loglik(idx) - llmax)
+        z += float(p.sum())
+        e_mu += float((p.sum(dim=1) * mu[idx]).sum())
+        e_sg += float((p.sum(dim=0) * sg).sum())
+        blk = post[r0:r0 + chunk].to(torch.float64)
+        rows_sum[idx] = blk.sum(dim=1)
+        cols_sum += blk.sum(dim=0)
+        total += float(blk.sum())
+    assert abs(total - 1.0) <= 1e-6
+    assert abs(res.expectations[0] - e_mu / z) <= E_TOL and abs(res.expectations[1] - e_sg / z) <= E_TOL
+    assert np.abs(rows_sum.cpu().numpy() - res.marg_mu).max() <= 1e-7 * res.marg_mu.max()
+    assert np.abs(cols_sum.cpu().numpy() - res.marg_sigma).max() <= 1e-7 * res.marg_sigma.max()
+    peak_row = int(round((19.549 - 18) / 4 * (N - 1)))
+    for i in (0, 1, peak_row - 6000, peak_row, peak_row + 1, peak_row + 8000, N - 1):
+        want = torch.exp(loglik(torch.tensor([i], device=dev))[0] - llmax) / z
+        got = post[i].to(torch.float64)
+        big = want >= FLOOR / z
+        if bool(big.any()):
+            rel = ((got[big] - want[big]).abs() / want[big]).max().item()
+            assert rel <= POST_REL, f"row {i}: {rel:.3e}"
+
+
 def test_16384_logspace_10k_observations(ctx):
     N = 16384
     obs = oracle.readme_observations(n=10000)
