@@ -356,14 +356,39 @@ def _set_prior(self, prior_mu=None, prior_sigma=None, grid_size=0, prior_full=No
 
 def _scale_info(self, stream=None) -> dict:
     """Scale statistics of the last likelihood call (see cge_scale_info)."""
-    out = np.empty(11, np.float64)
-    _check(self._lib.cge_scale_info(self._h, out.ctypes.data, 11, stream))
+    out = np.empty(12, np.float64)
+    _check(self._lib.cge_scale_info(self._h, out.ctypes.data, 12, stream))
     keys = ("log2s", "shift", "m2", "xbar", "ss", "smin", "mu_c", "s_c", "umax", "paired_umax",
-            "paired3_umax")
+            "paired3_umax", "ustep")
     d = dict(zip(keys, out.tolist()))
+    # product_path: the arithmetic of the most demanding column band (the one at the smallest
+    # sigma); bands at larger sigma may run a cheaper policy (see band_paths)
     d["product_path"] = ("paired" if d["umax"] <= d["paired_umax"] else
                          "paired3" if d["umax"] <= d["paired3_umax"] else "hybrid")
     return d
+
+
+def band_columns(grid_size: int) -> int:
+    """Sigma columns per CTA column band (mirrors make_plan in cge_api.cu: 128 columns per warp
+    strip, 8 / 4 / 2 / 1 strips per CTA depending on the grid width)."""
+    ncw = (grid_size + 127) // 128
+    wn = 8 if ncw >= 8 else 4 if ncw >= 4 else 2 if ncw >= 2 else 1
+    return wn * 128
+
+
+def band_paths(info: dict, sigma: np.ndarray) -> list:
+    """Which product policy each column band takes, from scale_info() and the sigma table:
+    mirrors cge::band_scale (|a_j| = 0.5*log2(e)/sigma_j^2 at the band's two ends)."""
+    out = []
+    band_cols = band_columns(len(sigma))
+    for j0 in range(0, len(sigma), band_cols):
+        j1 = min(j0 + band_cols, len(sigma)) - 1
+        a = max(0.5 * 1.4426950408889634 / float(sigma[j0]) ** 2,
+                0.5 * 1.4426950408889634 / float(sigma[j1]) ** 2)
+        u = a * info["ustep"]
+        out.append("paired" if u <= info["paired_umax"] else
+                   "paired3" if u <= info["paired3_umax"] else "hybrid")
+    return out
 
 
 Context.scale_info = _scale_info

@@ -881,9 +881,9 @@ CGE_EXPORT int cge_scale_info(cge_context *ctx, double *out, int count, void *st
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemcpyAsync(&h, ctx->scale.ptr, sizeof h, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const double v[11] = {h.log2s, h.shift, h.m2, h.xbar, h.ss, h.smin, h.mu_c, h.s_c, h.umax,
-                        cge::kPairedUmax, cge::kPairedUmax3};
-  for (int i = 0; i < count && i < 11; ++i) out[i] = v[i];
+  const double v[12] = {h.log2s, h.shift, h.m2, h.xbar, h.ss, h.smin, h.mu_c, h.s_c, h.umax,
+                        cge::kPairedUmax, cge::kPairedUmax3, h.ustep};
+  for (int i = 0; i < count && i < 12; ++i) out[i] = v[i];
   return CGE_OK;
 }
 

@@ -53,7 +53,8 @@ struct ScaleInfo {
   double smin;
   double mu_c;   // log-space: grid value nearest the sample mean; obs_pad holds x_k - mu_c
   double s_c;    // log-space: sum_k (x_k - mu_c)^2
-  double umax;   // bound on |t_(i+1,j,k) - t_(i,j,k)| over adjacent mu rows (ProductPaired eligibility)
+  double umax;   // bound on |t_(i+1,j,k) - t_(i,j,k)| over adjacent mu rows, whole grid
+  double ustep;  // the same bound per unit |a_j|: umax of a column band = max |a_j| in it * ustep
 };
 
 struct LikeArgs {
@@ -217,7 +218,8 @@ __device__ __forceinline__ ScaleInfo setup_scale(const RangeArgs &r, const float
     const double reach = fmax(fmax(fabs(xhi - mlo), fabs(xlo - mlo)), fmax(fabs(xhi - mhi), fabs(xlo - mhi)));
     const double dmu = N > 1 ? (mhi - mlo) / (double)(N - 1) + 2.4e-7 * fmax(fabs(mlo), fabs(mhi)) : 0.0;
     const double sdmin = fmin((double)sg0, (double)sg1);
-    out.umax = fabs(coef_a(sdmin)) * dmu * 2.0 * reach;
+    out.ustep = dmu * 2.0 * reach;
+    out.umax = fabs(coef_a(sdmin)) * out.ustep;
   }
   return out;
 }
@@ -936,31 +938,46 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
   }
 }
 
+// ScaleInfo as this CTA's column band sees it: `umax` becomes the bound over the band's own
+// columns (|a_j| is monotone along the sigma axis, so its maximum sits at one end of the band).
+// The exponent step scales with |a_j| = 0.72/sigma_j^2, so on a grid with a wide sigma range only
+// the bands at small sigma need the costlier arithmetic.  A function of the band (columns) and of
+// the global statistics only: the same for every row tile, shard and rank.
+template <int WN>
+__device__ __forceinline__ ScaleInfo band_scale(const LikeArgs &g, int kcols) {
+  ScaleInfo sc = *g.scale;
+  const int jfirst = blockIdx.x * WN * 32 * kcols;
+  const int jlast = min(jfirst + WN * 32 * kcols, g.N) - 1;
+  sc.umax = fmax(fabs(g.ad[jfirst]), fabs(g.ad[jlast])) * sc.ustep;
+  return sc;
+}
+
 template <class Policy, int WM, int WN, bool VEC4, int MINB = 1>
 __global__ void __launch_bounds__(WM *WN * 32, MINB)
     grid_likelihood_kernel(const LikeArgs g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const ScaleInfo sc = *g.scale;
   ColumnCoefs<Policy::kCols> cf;
   cf.load(g, first_column<WN>(Policy::kCols));
+  const ScaleInfo sc = band_scale<WN>(g, Policy::kCols);
   likelihood_body<Policy, WM, WN, VEC4>(g, sc, cf, smem_raw);
 }
 
 // The default product kernel: ProductPaired with the degree-2 polynomial where the grid is fine
-// enough for it (ScaleInfo::umax, computed by setup_kernel from the ranges and the observations
-// that are already on the device), with the degree-3 polynomial on grids up to 4.5x coarser,
-// ProductHybrid otherwise.  The choice is uniform over the launch and depends on (ranges, N,
-// observations) only -- never on the shard -- so every rank of a sharded run takes the same path
-// and results stay bit-reproducible.  The policies share the tiling.
+// enough for it (the band's umax, from the statistics setup_kernel derives on the device out of
+// the ranges and the observations), with the degree-3 polynomial up to 4.5x coarser,
+// ProductHybrid otherwise.  The choice is made per column band and depends on (ranges, N,
+// observations, band) only -- never on the row tile or the shard -- so every rank of a sharded
+// run takes the same path for the same cells and results stay bit-reproducible.  The policies
+// share the tiling.
 template <class Fine, class Mid, class Coarse, int WM, int WN, bool VEC4, int MINB = 1>
 __global__ void __launch_bounds__(WM *WN * 32, MINB)
     grid_likelihood_select_kernel(const LikeArgs g) {
   static_assert(Fine::kCols == Coarse::kCols && Fine::kRows == Coarse::kRows, "same tiling");
   static_assert(Fine::kCols == Mid::kCols && Fine::kRows == Mid::kRows, "same tiling");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const ScaleInfo sc = *g.scale;
-  ColumnCoefs<Fine::kCols> cf;  // in flight together with `sc`, before the path is known
+  ColumnCoefs<Fine::kCols> cf;  // in flight together with the statistics, before the path is known
   cf.load(g, first_column<WN>(Fine::kCols));
+  const ScaleInfo sc = band_scale<WN>(g, Fine::kCols);
   if (sc.umax <= Fine::kUmax)
     likelihood_body<Fine, WM, WN, VEC4>(g, sc, cf, smem_raw);
   else if (sc.umax <= Mid::kUmax)
@@ -1015,12 +1032,17 @@ __global__ void __launch_bounds__(WM *WN * 32)
   float *obs_s = reinterpret_cast<float *>(smem_raw + 128);
 
   for (int idx = tid; idx < N + 3; idx += nt) setup_point(idx, a.range, a.mu, a.sigma, a.ad, a.cd0);
-  const ScaleInfo sc = setup_scale(a.range, a.obs, obs_s, g.n, g.n_pad, a.centred, scratch);
+  ScaleInfo sc = setup_scale(a.range, a.obs, obs_s, g.n, g.n_pad, a.centred, scratch);
   if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *a.scale = sc;
   __syncthreads();  // this CTA's own table writes and staged observations are visible to it
 
   ColumnCoefs<Fine::kCols> cf;
   cf.load(g, first_column<WN>(Fine::kCols));
+  {  // the band's own bound, as band_scale() computes it from the tables
+    const int jfirst = blockIdx.x * WN * 32 * Fine::kCols;
+    const int jlast = min(jfirst + WN * 32 * Fine::kCols, N) - 1;
+    sc.umax = fmax(fabs(a.ad[jfirst]), fabs(a.ad[jlast])) * sc.ustep;
+  }
   if (sc.umax <= Fine::kUmax)
     likelihood_body<Fine, WM, WN, VEC4, true>(g, sc, cf, smem_raw);
   else if (sc.umax <= Mid::kUmax)

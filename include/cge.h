@@ -78,8 +78,8 @@ typedef struct cge_params {
 /* likelihood-kernel variants for cge_params.variant (product mode; ignored in log-space) */
 enum {
   CGE_VARIANT_DEFAULT = 0,   /* paired rows on fine grids -- degree-2 polynomial, or degree-3 on grids
-                                up to 4.5x coarser (chosen on the device from the ranges and the
-                                observations) -- hybrid otherwise */
+                                up to 4.5x coarser (chosen on the device, per CTA column band of
+                                up to 1024 sigma columns, from the ranges and the observations) -- hybrid otherwise */
   CGE_VARIANT_MUFU_ONLY = 1, /* scalar arithmetic, every 2^t on MUFU.EX2 (the MUFU roofline case) */
   CGE_VARIANT_PAIRED = 3,    /* paired rows, forced: packed f32x2 arithmetic; of two vertically
                                 adjacent cells one factor is 2^t on MUFU.EX2, the other is derived
@@ -255,11 +255,12 @@ int cge_quantiles(cge_context *ctx, const double *marginal_dev, int n, const dou
                   int nprobs, int *indices_host, double *cdf_dev);
 
 /* Scale statistics the setup kernel derived for the last likelihood call (diagnostics; waits for
- * `stream`): out[0..10] = log2 of the per-factor rescale, log-space shift, log2 of the largest
+ * `stream`): out[0..11] = log2 of the per-factor rescale, log-space shift, log2 of the largest
  * likelihood on the grid, sample mean, sum of squared deviations, min_i sum_k (x_k - mu_i)^2,
  * log-space centre mu_c, sum_k (x_k - mu_c)^2, umax (largest exponent step between vertically
- * adjacent cells), and the bounds on umax below which the paired-rows product kernel runs with
- * its degree-2 and degree-3 polynomial. */
+ * adjacent cells, over the whole grid), the bounds on umax below which the paired-rows product
+ * kernel runs with its degree-2 and degree-3 polynomial, and ustep (umax per unit |a_j|: a column
+ * band's own bound is max |a_j| over the band times ustep -- the kernel chooses per band). */
 int cge_scale_info(cge_context *ctx, double *out, int count, void *stream);
 
 /* ---- roofline micro-benchmarks (bench.py): measured pipe peaks on this device ------------

@@ -398,14 +398,33 @@ def test_default_picks_the_path_on_the_device(ctx, readme_obs):
         for name, variant in forced.items():
             f = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=variant)
             assert (d.posterior.tobytes() == f.posterior.tobytes()) == (name == want), (N, name)
+    # The choice is per column band (|u| scales with 0.72 / sigma^2).  A far-out observation
+    # (reach 12 instead of ~5: |u| <= 0.017 at sigma = 1) moves only the band at the smallest
+    # sigma of the N=4096 grid to the degree-3 polynomial; the other three stay on degree 2.
     far = readme_obs.copy()
-    far[0] = 30.0  # reach 12 instead of ~5: |u| <= 0.017 at N=4096
+    far[0] = 30.0
     d = ctx.grid_posterior(far, 4096, (18, 22), (1, 3))
-    assert ctx.scale_info()["product_path"] == "paired3"
-    a = ctx.grid_posterior(far, 4096, (18, 22), (1, 3), variant=api.VARIANT_PAIRED3)
-    assert d.posterior.tobytes() == a.posterior.tobytes()
+    info = ctx.scale_info()
+    assert info["product_path"] == "paired3"
+    paths = api.band_paths(info, oracle.linspace(4096, 1, 3))
+    assert paths == ["paired3", "paired", "paired", "paired"]
+    bw = api.band_columns(4096)
+    for name in ("paired", "paired3"):
+        f = ctx.grid_posterior(far, 4096, (18, 22), (1, 3), variant=forced[name])
+        for b, want in enumerate(paths):
+            same = d.posterior[:, b * bw:(b + 1) * bw].tobytes() == f.posterior[:, b * bw:(b + 1) * bw].tobytes()
+            # (normalised cells: the two runs share Z only to rounding, so compare unnormalised ratios)
+            ratio = d.posterior[2000, b * bw:(b + 1) * bw].astype(np.float64) / \
+                f.posterior[2000, b * bw:(b + 1) * bw].astype(np.float64)
+            assert same == (want == name) or (want == name and np.ptp(ratio) < 3e-7), (b, name)
     ref = oracle.grid_posterior(far, 4096, 18, 22, 1, 3, oracle.NUM_F64)
     check_against(d, ref, what="far observation, N=4096")
+    # a wide sigma range: hybrid only where sigma is small, paired rows in the other bands
+    d = ctx.grid_posterior(readme_obs, 4096, (18, 22), (0.4, 3))
+    paths = api.band_paths(ctx.scale_info(), oracle.linspace(4096, 0.4, 3))
+    assert paths[0] != "paired" and paths[-1] == "paired", paths
+    check_against(d, oracle.grid_posterior(readme_obs, 4096, 18, 22, 0.4, 3, oracle.NUM_F64),
+                  what="wide sigma range, N=4096")
 
 
 @pytest.mark.parametrize("N", [2, 3, 64, 130, 301, 700, 1026])
