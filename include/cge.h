@@ -51,9 +51,10 @@ enum {
 
 /* arithmetic mode of the likelihood kernel */
 enum {
-  CGE_MODE_PRODUCT_F32 = 0, /* running float32 product of per-observation pdfs, MUFU ex2 per
-                               pdf-eval, one global per-factor rescale (posterior is
-                               scale-invariant) -- BASELINE.json "float32 product path" */
+  CGE_MODE_PRODUCT_F32 = 0, /* running float32 product of per-observation pdf factors (2^t from
+                               MUFU ex2, or derived from a neighbouring cell's on the FMA pipe),
+                               one global per-factor rescale (posterior is scale-invariant) --
+                               BASELINE.json "float32 product path" */
   CGE_MODE_LOGSPACE = 1     /* sum of log-pdf (float32x2 tile sums of centred terms folded into
                                float64), log-sum-exp normalisation -- for observation counts where
                                any product underflows */
@@ -75,11 +76,12 @@ typedef struct cge_params {
                            of the likelihood kernel (same results within tolerance) */
 } cge_params;
 
-/* likelihood-kernel variants for cge_params.variant (product mode; ignored in log-space) */
+/* likelihood-kernel variants for cge_params.variant */
 enum {
-  CGE_VARIANT_DEFAULT = 0,   /* paired rows on fine grids -- degree-2 polynomial, or degree-3 on grids
-                                up to 4.5x coarser (chosen on the device, per CTA column band of
-                                up to 1024 sigma columns, from the ranges and the observations) -- hybrid otherwise */
+  CGE_VARIANT_DEFAULT = 0,   /* paired rows on fine grids -- degree-2 polynomial, or degree-3 on
+                                grids up to 4.5x coarser -- hybrid otherwise; chosen on the device,
+                                per CTA column band of up to 1024 sigma columns, from the ranges
+                                and the observations */
   CGE_VARIANT_MUFU_ONLY = 1, /* scalar arithmetic, every 2^t on MUFU.EX2 (the MUFU roofline case) */
   CGE_VARIANT_PAIRED = 3,    /* paired rows, forced: packed f32x2 arithmetic; of two vertically
                                 adjacent cells one factor is 2^t on MUFU.EX2, the other is derived
@@ -89,9 +91,10 @@ enum {
   CGE_VARIANT_LOG_F64 = 5,   /* log-space mode only: float64 accumulation, one DFMA per pdf-eval (the
                                 default log-space kernel sums centred terms in float32x2 tiles of 256
                                 observations and folds the tiles into float64) */
-  CGE_VARIANT_UNFUSED = 7,   /* the default kernels, but cge_grid_posterior always takes the five-launch
-                                path (by default grids up to 512 points per axis run as ONE launch:
-                                tables, likelihood, fold, results and scale in a single kernel) */
+  CGE_VARIANT_UNFUSED = 7,   /* the default kernels, but cge_grid_posterior always takes the
+                                five-launch path (by default grids up to 256 points per axis run
+                                as ONE launch: tables, likelihood, fold, results and scale in a
+                                single kernel) */
   CGE_VARIANT_HYBRID = 4     /* hybrid, forced: packed f32x2 arithmetic; of the 16 exponentials a
                                 thread evaluates per observation, 12 use MUFU.EX2 and 4 an FMA-pipe
                                 degree-5 polynomial with Cody-Waite range reduction */
