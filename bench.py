@@ -186,6 +186,29 @@ def cpu_rate_sample(N, n, mode, target_seconds, max_rows=None):
     return ev / dt, dt, rows, cores
 
 
+def reference_cuda_binary():
+    """Context for the reference line, not part of its value: the reference's own CUDA program
+    (src/grid.cu compiled unmodified into oracle/_ref/grid by oracle/Makefile) run once on this
+    box's GPU.  It has one workload -- README, 101 x 101 x 50 with cuRAND observations -- and is
+    not valid beyond 256, so it cannot serve any of the benchmark configurations."""
+    import subprocess
+    exe = os.path.join(ROOT, "oracle", "_ref", "grid")
+    if not os.path.exists(exe):
+        return {"available": False, "why": "oracle/_ref/grid not built"}
+    try:
+        subprocess.run([exe], capture_output=True, text=True, timeout=120)  # context warm-up
+        t0 = time.perf_counter()
+        res = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        wall = time.perf_counter() - t0
+    except Exception as e:
+        return {"available": False, "why": repr(e)}
+    if res.returncode != 0:
+        return {"available": False, "why": f"exit {res.returncode} (no GPU?)"}
+    return {"available": True, "workload": "README: 101 x 101 grid x 50 cuRAND observations",
+            "process_wall_ms": wall * 1e3, "pdf_evals": 101 * 101 * 50,
+            "stdout": res.stdout.strip().splitlines()[-2:]}
+
+
 def run_reference(args):
     """--impl reference: the reference algorithm's CPU implementation.  The reference's only CPU
     code is Python (numpy_estimator) and cannot travel to the GPU box, and its C++ is CUDA-only,
@@ -218,6 +241,7 @@ def run_reference(args):
     value = evals / dt / 1e9
     sample = (f"{rows} of {N} mu rows x {N} sigma x {n} obs per step "
               f"({rows * N * n:.3g} pdf-evals), rows centred on the posterior peak")
+    ref_cuda = reference_cuda_binary()
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3,
@@ -228,6 +252,7 @@ def run_reference(args):
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "reference_cuda_binary": ref_cuda,
     }
     emit(line)
     return 0
