@@ -74,6 +74,30 @@ def test_non_flat_prior(readme_obs, N, mode):
 
 
 # ---- 8(f) row 2: the reference's observation generator ----------------------------------------
+@pytest.mark.parametrize("N", [200, 1500])
+def test_sequential_update_equals_batch(readme_obs, N):
+    """The prior row used the way Bayes updating uses it: the posterior of the first 20
+    observations, left on the device, becomes the full prior table for the other 30; the result
+    must be the posterior of all 50 (flat prior).  N=200 goes through the single-launch kernel,
+    N=1500 through the five-launch path."""
+    import torch
+    dev = torch.device("cuda", 0)
+    with cge.Context(0) as ctx:
+        batch = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
+        first = torch.empty((N, N), dtype=torch.float32, device=dev)
+        ctx.grid_posterior(readme_obs[:20], N, (18, 22), (1, 3), posterior=first)
+        ctx.set_prior(None, None, N, first)
+        try:
+            seq = ctx.grid_posterior(readme_obs[20:], N, (18, 22), (1, 3))
+        finally:
+            ctx.set_prior()
+    assert np.abs(seq.expectations - batch.expectations).max() <= 1e-6
+    P, Q = seq.posterior.astype(np.float64), batch.posterior.astype(np.float64)
+    big = Q >= 1e-20 * Q.max()
+    assert (np.abs(P[big] - Q[big]) / Q[big]).max() <= 1e-4
+    assert abs(P.sum() - 1) <= 1e-6
+
+
 def test_generate_normal_known_answers(ctx):
     import torch
     out = torch.empty(50, dtype=torch.float32, device="cuda")
