@@ -137,6 +137,10 @@ class ShardedGridPosterior:
         """Enqueue one pass of the hot path; returns nothing (results stay on the device)."""
         from .api import device_tensor
         stream = self.torch.cuda.current_stream().cuda_stream
+        if self.world == 1:
+            # no exchange: the fused asynchronous entry (one launch for small grids, five otherwise)
+            self.ctx.grid_posterior_async(self.params, obs_dev, posterior_dev, stream)
+            return
         self.ctx.likelihood_partials(self.params, obs_dev, posterior_dev, stream)
         if self.exchange == "nccl":
             ptr, cnt = self.ctx.partials_ptr()
