@@ -186,6 +186,10 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   else if (pl->ncw >= 4) { pl->wm = 2; pl->wn = 4; }
   else if (pl->ncw >= 2) { pl->wm = 4; pl->wn = 2; }
   else { pl->wm = 8; pl->wn = 1; }
+  if (const char *ov = std::getenv("CGE_WARP_ROWS")) {  // tuning knob, not part of the ABI
+    const int v = std::atoi(ov);
+    if (v == 1 || v == 2 || v == 4 || v == 8) { pl->wm = v; pl->wn = 8 / v; }
+  }
   pl->bands = (pl->ncw + pl->wn - 1) / pl->wn;
   // tile heights are multiples of the patch rows of every warp row and of the global alignment
   const int patch_rows = p->mode == CGE_MODE_LOGSPACE ? cge::LogSpaceF64::kRows : cge::kRM;
