@@ -77,3 +77,15 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
                 assert "liboracle" not in src, f
+    # the timing tools neither (the ones that check accuracy against the oracle live in tests/tools/)
+    tools = os.path.join(ROOT, "tools")
+    for f in os.listdir(tools):
+        if f.endswith(".py"):
+            src = open(os.path.join(tools, f)).read()
+            assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), f
+    # bench.py: only the CPU legs (cpu_rate_sample, run_reference) may import it, and only lazily
+    bench = open(os.path.join(ROOT, "bench.py")).read()
+    assert not re.search(r"^(import|from)\s+oracle\b", bench, flags=re.M)
+    for m in re.finditer(r"^def (\w+)\(.*?(?=^def |\Z)", bench, flags=re.M | re.S):
+        if re.search(r"^\s+import oracle\b", m.group(0), flags=re.M):
+            assert m.group(1) in ("cpu_rate_sample", "run_reference"), m.group(1)

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """GPU: time the likelihood kernel of every product-path variant (CUDA events inside libcge's
 per-step capture) and report accuracy against the oracle on the README workload.
-usage: python tools/sweep_variants.py [N] [n_obs] [steps]"""
+usage: python tests/tools/sweep_variants.py [N] [n_obs] [steps]
+(lives under tests/ because it checks accuracy against the oracle, which is test infrastructure)"""
 import json
 import os
 import sys

@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """GPU experiment: how far is the normaliser of the float32 product kernel (the sum of the cells it
 actually wrote) from the closed-form normaliser (float64, sufficient statistics)?  Decides whether
-normalising on write with the closed-form value could replace the scale pass."""
+normalising on write with the closed-form value could replace the scale pass.
+(lives under tests/: it uses the oracle, which is test infrastructure)"""
 import json
 import sys
 

@@ -7,11 +7,11 @@ import torch
 
 sys.path.insert(0, ".")
 import cuda_grid_estimation_b200 as cge  # noqa: E402
-import oracle  # noqa: E402
+from tools._obs import observations  # noqa: E402
 
 N, n, variant, steps = (int(a) for a in sys.argv[1:5])
 mode = int(sys.argv[5]) if len(sys.argv) > 5 else 0
-obs = oracle.readme_observations(n=n)
+obs = observations(n)
 dev = torch.device("cuda", 0)
 with cge.Context(0) as ctx:
     obs_t = torch.from_numpy(obs).to(dev)

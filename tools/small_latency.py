@@ -8,10 +8,10 @@ import time
 
 sys.path.insert(0, ".")
 import cuda_grid_estimation_b200 as cge  # noqa: E402
-import oracle  # noqa: E402
+from tools._obs import observations  # noqa: E402
 from cuda_grid_estimation_b200 import api  # noqa: E402
 
-obs = oracle.readme_observations()
+obs = observations()
 with cge.Context(0) as ctx:
     for N in (101, 256, 512, 1024):
         for mode in (0, 1):

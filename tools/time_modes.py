@@ -7,14 +7,14 @@ import torch
 
 sys.path.insert(0, ".")
 import cuda_grid_estimation_b200 as cge  # noqa: E402
-import oracle  # noqa: E402
+from tools._obs import observations  # noqa: E402
 
 dev = torch.device("cuda", 0)
 with cge.Context(0) as ctx:
     for spec in sys.argv[1:]:
         N, n, mode, variant = (int(v) for v in spec.split(":"))
         steps = 5 if n > 1000 else 20
-        obs_t = torch.from_numpy(oracle.readme_observations(n=n)).to(dev)
+        obs_t = torch.from_numpy(observations(n)).to(dev)
         post = torch.empty((N, N), dtype=torch.float32, device=dev)
         p = cge.make_params(n, N, (18, 22), (1, 3), mode, None, variant)
         for _ in range(2):

@@ -9,12 +9,12 @@ import torch
 
 sys.path.insert(0, ".")
 import cuda_grid_estimation_b200 as cge  # noqa: E402
-import oracle  # noqa: E402
+from tools._obs import observations  # noqa: E402
 
 N, n, rows, steps = (int(a) for a in sys.argv[1:5])
 dev = torch.device("cuda", 0)
 with cge.Context(0) as ctx:
-    obs_t = torch.from_numpy(oracle.readme_observations(n=n)).to(dev)
+    obs_t = torch.from_numpy(observations(n)).to(dev)
     post = torch.empty((rows, N), dtype=torch.float32, device=dev)
     rb = (N - rows) // 2 // 4 * 4
     p = cge.make_params(n, N, (18, 22), (1, 3), 0, (rb, rb + rows), 0)
