@@ -218,6 +218,7 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->vec4 = (pl->N % 4 == 0) && ((reinterpret_cast<uintptr_t>(post) & 15u) == 0);
   const bool streamed = pl->n_pad > cge::kObsSingleMax;
   pl->smem = 128 + (streamed ? 2 * (size_t)cge::kObsChunk * 4 : (size_t)pl->n_pad * 4);
+  pl->cluster = false;
   pl->valid = true;
 }
 
@@ -287,6 +288,17 @@ int small_grid_step(cge_context *ctx, const cge_params *p, const float *obs_dev,
   Plan &pl = ctx->plan;
   pl.valid = false;
   make_plan(ctx, p, 0, p->grid_size, posterior_dev, &pl);
+  // One column band (always the case up to 256 columns) and at most 8 row tiles (the portable
+  // cluster size) -> the grid runs as one thread-block cluster: taller tiles if need be.
+  if (pl.bands == 1 && !std::getenv("CGE_NO_CLUSTER")) {
+    const int unit = pl.wm * cge::kRM;
+    if (pl.row_tiles > 8) {
+      pl.tile_rows = (((pl.N + 7) / 8 + unit - 1) / unit) * unit;
+      pl.row_tiles = (pl.N + pl.tile_rows - 1) / pl.tile_rows;
+      pl.ncolparts = pl.row_tiles * pl.wm;
+    }
+    pl.cluster = pl.row_tiles <= 8;
+  }
   CKRC(reserve_step_buffers(ctx, pl, st));
   cge::SmallArgs a = {};
   CKRC(fill_like_args(ctx, pl, posterior_dev, &a.like));

@@ -36,6 +36,7 @@ struct Plan {
   int ncw = 0, ncolparts = 0;
   int nb_col = 0, nb_row = 0;
   bool vec4 = false;
+  bool cluster = false;  // small-grid path: launch the grid as one thread-block cluster
   size_t smem = 0;
 };
 

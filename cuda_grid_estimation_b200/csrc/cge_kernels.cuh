@@ -1017,7 +1017,55 @@ struct SmallArgs {
   unsigned int *ticket;
 };
 
-template <class Fine, class Mid, class Coarse, int WM, int WN, bool VEC4>
+// in place: post[0..count) *= finv, reading through L2 (other CTAs wrote some of it), several
+// independent loads in flight per thread; `post` is 16-byte aligned when VEC4
+template <bool VEC4>
+__device__ __forceinline__ void scale_cells_cta(float *post, size_t count, float finv) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  constexpr int kDepth = 8;
+  if (VEC4) {
+    float4 *p4 = reinterpret_cast<float4 *>(post);
+    const size_t nvec = count >> 2;  // VEC4 implies N % 4 == 0, so count % 4 == 0
+    for (size_t base = tid; base < nvec; base += (size_t)nt * kDepth) {
+      float4 v[kDepth];
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u)
+        if (base + (size_t)u * nt < nvec) v[u] = __ldcg(p4 + base + (size_t)u * nt);
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u)
+        if (base + (size_t)u * nt < nvec) {
+          v[u].x *= finv; v[u].y *= finv; v[u].z *= finv; v[u].w *= finv;
+          p4[base + (size_t)u * nt] = v[u];
+        }
+    }
+  } else {
+    for (size_t base = tid; base < count; base += (size_t)nt * kDepth) {
+      float v[kDepth];
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u)
+        if (base + (size_t)u * nt < count) v[u] = __ldcg(post + base + (size_t)u * nt);
+#pragma unroll
+      for (int u = 0; u < kDepth; ++u)
+        if (base + (size_t)u * nt < count) post[base + (size_t)u * nt] = v[u] * finv;
+    }
+  }
+}
+
+// hardware barrier over the thread-block cluster; release/acquire at cluster scope orders the
+// global-memory writes made before it against the reads made after it in the other CTAs
+__device__ __forceinline__ void cluster_barrier() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::
+                   : "memory");
+}
+
+// CLUSTER = false: any grid; the last CTA to take the ticket does K6-K8 and scales the whole
+//   posterior.
+// CLUSTER = true: the grid is ONE thread-block cluster (one column band, <= 8 row tiles: every
+//   grid up to 256 x 256), so its CTAs are co-scheduled and a hardware cluster barrier replaces
+//   the ticket: after it every CTA folds the row partials itself (same order everywhere, so the
+//   same Z bit for bit) and scales ITS OWN tile in parallel; CTA 0 also writes the marginals and
+//   expectations.  No single CTA walks the whole posterior.
+template <class Fine, class Mid, class Coarse, int WM, int WN, bool VEC4, bool CLUSTER = false>
 __global__ void __launch_bounds__(WM *WN * 32)
     small_grid_kernel(const SmallArgs a) {
   static_assert(Fine::kCols == Coarse::kCols && Fine::kRows == Coarse::kRows, "same tiling");
@@ -1050,25 +1098,32 @@ __global__ void __launch_bounds__(WM *WN * 32)
   else
     likelihood_body<Coarse, WM, WN, VEC4, true>(g, sc, cf, smem_raw);
 
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
+  bool writer;  // the CTA that writes partials / results: the last one, or cluster rank 0
+  if (CLUSTER) {
+    cluster_barrier();
+    writer = blockIdx.y == 0;
+  } else {
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    writer = true;
+  }
 
-  // ---- last CTA: K6-K8 on the partial buffers of every CTA (read through L2).  Every loop
-  // keeps several independent loads in flight: one CTA is latency-bound, not bandwidth-bound.
+  // ---- K6-K8 on the partial buffers of every CTA (read through L2).  Every loop keeps several
+  // independent loads in flight: one CTA is latency-bound, not bandwidth-bound.
   double z = 0.0, smu = 0.0;
   for (int i = tid; i < N; i += nt) {
     double s = 0.0;
     for (int w = 0; w < g.ncw; ++w) s += __ldcg(g.rowpart + (size_t)i * g.ncw + w);
-    a.rowsum[i] = s;
+    if (writer) a.rowsum[i] = s;
     z += s;
     smu += s * (double)a.mu[i];
   }
-  {  // column sums: warp w takes slots w, w+NW, ... of a column (all its loads in flight at
-     // once), then the NW partial sums are added in warp order
+  if (writer) {  // column sums: warp w takes slots w, w+NW, ... of a column (all its loads in
+                 // flight at once), then the NW partial sums are added in warp order
     constexpr int NW = WM * WN;
     const int lane = tid & 31, warp = tid >> 5;
     for (int j0c = 0; j0c < N; j0c += kSmallColChunk) {
@@ -1098,59 +1153,40 @@ __global__ void __launch_bounds__(WM *WN * 32)
   z = block_sum(z, scratch);
   smu = block_sum(smu, scratch);
   const double inv = 1 / z;  // reciprocal multiply, as inc/utils.h:82-84
-  double *marg_sigma = a.results + 4, *marg_mu = a.results + 4 + N;
-  double es = 0.0;
-  for (int j = tid; j < N; j += nt) {  // partials[2 + j]: written before the block-wide syncs above
-    const double m = a.partials[2 + j] * inv;
-    marg_sigma[j] = m;
-    if (a.results_host) a.results_host[4 + j] = m;
-    es += m * (double)a.sigma[j];
-  }
-  for (int i = tid; i < N; i += nt) {
-    const double m = a.rowsum[i] * inv;
-    marg_mu[i] = m;
-    if (a.results_host) a.results_host[4 + N + i] = m;
-  }
-  es = block_sum(es, scratch);
-  if (tid == 0) {
-    a.partials[0] = z;
-    a.partials[1] = smu;
-    const double head[4] = {smu * inv, es, z, inv};
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      a.results[q] = head[q];
-      if (a.results_host) a.results_host[q] = head[q];
+  if (writer) {
+    double *marg_sigma = a.results + 4, *marg_mu = a.results + 4 + N;
+    double es = 0.0;
+    for (int j = tid; j < N; j += nt) {  // partials[2 + j]: written before the block-wide syncs above
+      const double m = a.partials[2 + j] * inv;
+      marg_sigma[j] = m;
+      if (a.results_host) a.results_host[4 + j] = m;
+      es += m * (double)a.sigma[j];
     }
-    *a.ticket = 0u;
+    for (int i = tid; i < N; i += nt) {
+      const double m = a.rowsum[i] * inv;
+      marg_mu[i] = m;
+      if (a.results_host) a.results_host[4 + N + i] = m;
+    }
+    es = block_sum(es, scratch);
+    if (tid == 0) {
+      a.partials[0] = z;
+      a.partials[1] = smu;
+      const double head[4] = {smu * inv, es, z, inv};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        a.results[q] = head[q];
+        if (a.results_host) a.results_host[q] = head[q];
+      }
+      if (!CLUSTER) *a.ticket = 0u;
+    }
   }
   const float finv = (float)inv;
-  const size_t cells = (size_t)N * N;
-  constexpr int kDepth = 8;  // independent loads in flight per thread
-  if (VEC4) {
-    float4 *p4 = reinterpret_cast<float4 *>(g.post);
-    const size_t nvec = cells >> 2;  // VEC4 implies N % 4 == 0
-    for (size_t base = tid; base < nvec; base += (size_t)nt * kDepth) {
-      float4 v[kDepth];
-#pragma unroll
-      for (int u = 0; u < kDepth; ++u)
-        if (base + (size_t)u * nt < nvec) v[u] = __ldcg(p4 + base + (size_t)u * nt);
-#pragma unroll
-      for (int u = 0; u < kDepth; ++u)
-        if (base + (size_t)u * nt < nvec) {
-          v[u].x *= finv; v[u].y *= finv; v[u].z *= finv; v[u].w *= finv;
-          p4[base + (size_t)u * nt] = v[u];
-        }
-    }
+  if (CLUSTER) {  // this CTA's own rows
+    const int r0 = blockIdx.y * g.tile_rows;
+    const int r1 = min(N, r0 + g.tile_rows);
+    if (r0 < N) scale_cells_cta<VEC4>(g.post + (size_t)r0 * N, (size_t)(r1 - r0) * N, finv);
   } else {
-    for (size_t base = tid; base < cells; base += (size_t)nt * kDepth) {
-      float v[kDepth];
-#pragma unroll
-      for (int u = 0; u < kDepth; ++u)
-        if (base + (size_t)u * nt < cells) v[u] = __ldcg(g.post + base + (size_t)u * nt);
-#pragma unroll
-      for (int u = 0; u < kDepth; ++u)
-        if (base + (size_t)u * nt < cells) g.post[base + (size_t)u * nt] = v[u] * finv;
-    }
+    scale_cells_cta<VEC4>(g.post, (size_t)N * N, finv);
   }
 }
 

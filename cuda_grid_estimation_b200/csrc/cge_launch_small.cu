@@ -3,10 +3,39 @@
 
 namespace cge_host {
 
+// the whole grid as ONE thread-block cluster (1 x row_tiles x 1 CTAs, row_tiles <= 8)
+template <class K>
+int launch_as_cluster(K kernel, const Plan &pl, int threads, size_t smem, const cge::SmallArgs &a,
+                      cudaStream_t st) {
+  if (smem > kDefaultSmemLimit)
+    CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(1, pl.row_tiles, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = pl.row_tiles;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  CK(cudaLaunchKernelEx(&cfg, kernel, a));
+  return CGE_OK;
+}
+
 template <class Fine, class Mid, class Coarse, int WM, int WN>
 int launch_small_shape(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st) {
   dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
   const size_t smem = like_smem<Fine, WM, WN>(pl);
+  if (pl.cluster) {  // one band, <= 8 row tiles: hardware cluster barrier instead of the ticket
+    if (pl.vec4)
+      return launch_as_cluster(cge::small_grid_kernel<Fine, Mid, Coarse, WM, WN, true, true>, pl,
+                               WM * WN * 32, smem, a, st);
+    return launch_as_cluster(cge::small_grid_kernel<Fine, Mid, Coarse, WM, WN, false, true>, pl,
+                             WM * WN * 32, smem, a, st);
+  }
   if (pl.vec4) {
     auto k = cge::small_grid_kernel<Fine, Mid, Coarse, WM, WN, true>;
     if (smem > kDefaultSmemLimit)  // only stages of thousands of observations get there
