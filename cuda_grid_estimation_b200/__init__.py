@@ -5,12 +5,14 @@ nablabits/cuda-grid-estimation (cpp/grid-algorithm/src/grid.cu:79-127), behind a
 the benchmark: ctypes marshalling, row sharding, and the torch.distributed plumbing around the
 one collective of the path.  All arithmetic runs in the CUDA library; there is no CPU fallback.
 """
-from .api import (MODE_LOGSPACE, MODE_PRODUCT_F32, CgeError, Context, GridResult, Params, Timing,
-                  device_tensor, load_library, make_params)
+from .api import (MODE_LOGSPACE, MODE_PRODUCT_F32, POSTERIOR_F32, POSTERIOR_F64, CgeError, Context,
+                  GridResult, MultiContext, Params, Timing, device_tensor, load_library,
+                  make_params)
 from .sharding import ShardedGridPosterior, finalize_from_partials, pack_partials, shard_rows
 
 __all__ = [
-    "MODE_LOGSPACE", "MODE_PRODUCT_F32", "CgeError", "Context", "GridResult", "Params", "Timing",
+    "MODE_LOGSPACE", "MODE_PRODUCT_F32", "POSTERIOR_F32", "POSTERIOR_F64", "CgeError", "Context",
+    "GridResult", "MultiContext", "Params", "Timing",
     "device_tensor", "load_library", "make_params", "ShardedGridPosterior",
     "finalize_from_partials", "pack_partials", "shard_rows",
 ]

@@ -10,8 +10,8 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libcge.so")
 # one object per translation unit, compiled concurrently: the likelihood-kernel instantiations
 # (cge_launch_*.cu) dominate the build time
-SOURCES = ["cge_api.cu", "cge_extras.cu", "cge_launch_product.cu", "cge_launch_logspace.cu",
-           "cge_launch_small.cu"]
+SOURCES = ["cge_api.cu", "cge_extras.cu", "cge_multi.cu", "cge_launch_product.cu",
+           "cge_launch_logspace.cu", "cge_launch_small.cu"]
 HEADERS = ["cge_kernels.cuh", "cge_kernels_misc.cuh", "cge_device.cuh", "cge_host.cuh",
            os.path.join("..", "..", "include", "cge.h")]
 OBJ_DIR = os.path.join(PKG_DIR, "_obj")
@@ -20,7 +20,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
-]
+] + os.environ.get("CGE_BUILD_DEFINES", "").split()   # e.g. -DCGE_DEBUG_TIMES (diagnostic builds)
 
 
 def _nvcc() -> str:
@@ -38,17 +38,19 @@ def stale() -> bool:
     return any(os.path.exists(d) and os.path.getmtime(d) > built for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu into cuda_grid_estimation_b200/libcge.so; returns its path."""
-    if not force and not stale():
+def build(force: bool = False, verbose: bool = False, out: str = None, defines=()) -> str:
+    """Compile csrc/*.cu into cuda_grid_estimation_b200/libcge.so; returns its path.
+    `out` / `defines`: a differently configured copy for A/B tuning runs (CGE_LIBRARY selects it)."""
+    if out is None and not force and not stale():
         return LIB_PATH
     from concurrent.futures import ThreadPoolExecutor
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    obj_dir = OBJ_DIR if out is None else OBJ_DIR + "_" + os.path.basename(out)
+    os.makedirs(obj_dir, exist_ok=True)
     nvcc = _nvcc()
 
     def compile_one(src):
-        obj = os.path.join(OBJ_DIR, os.path.splitext(src)[0] + ".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", "-o", obj, os.path.join(CSRC, src)]
+        obj = os.path.join(obj_dir, os.path.splitext(src)[0] + ".o")
+        cmd = [nvcc, *NVCC_FLAGS, *defines, "-c", "-o", obj, os.path.join(CSRC, src)]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         res = subprocess.run(cmd, capture_output=True, text=True)
@@ -61,12 +63,13 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if verbose:
         for _, log in done:
             print(log)
-    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB_PATH] + \
+    target = LIB_PATH if out is None else out
+    link = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target] + \
            [obj for obj, _ in done]
     res = subprocess.run(link, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
-    return LIB_PATH
+    return target
 
 
 # ---- host-side programs on top of the C ABI (C++/CUDA, like the reference's own binaries) ----

@@ -29,7 +29,9 @@ VARIANT_LOG_F64 = 5
 VARIANT_PAIRED3 = 8
 VARIANT_UNFUSED = 7
 
-OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_DEGENERATE, ERR_NCCL, ERR_SIZE = range(7)
+OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_DEGENERATE, ERR_PEER, ERR_SIZE = range(7)
+POSTERIOR_F32 = 0
+POSTERIOR_F64 = 1
 
 # every symbol include/cge.h declares (tests check the library exports each one)
 ABI_SYMBOLS = (
@@ -42,6 +44,8 @@ ABI_SYMBOLS = (
     "cge_normalize", "cge_marginalize", "cge_expectation", "cge_microbench",
     "cge_generate_normal", "cge_quantiles", "cge_set_prior", "cge_scale_info",
     "cge_grid_posterior_async",
+    "cge_create_multi", "cge_destroy_multi", "cge_multi_size", "cge_grid_posterior_multi",
+    "cge_multi_shard", "cge_multi_step_async", "cge_multi_synchronize",
 )
 
 
@@ -55,7 +59,7 @@ class Params(C.Structure):
     _fields_ = [("n_obs", C.c_int32), ("grid_size", C.c_int32), ("mu_start", C.c_float),
                 ("mu_end", C.c_float), ("sigma_start", C.c_float), ("sigma_end", C.c_float),
                 ("mode", C.c_int32), ("row_begin", C.c_int32), ("row_end", C.c_int32),
-                ("variant", C.c_int32)]
+                ("variant", C.c_int32), ("posterior_dtype", C.c_int32)]
 
 
 class Timing(C.Structure):
@@ -75,7 +79,7 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("CGE_LIBRARY") or _build.LIB_PATH   # (A/B builds for tuning runs)
     if not os.path.exists(path):
         if not build_if_missing:
             raise FileNotFoundError(f"{path} is missing; run __graft_entry__.build()")
@@ -118,6 +122,13 @@ def load_library(build_if_missing: bool = True) -> C.CDLL:
         "cge_set_prior": [vp, vp, vp, i32, vp],
         "cge_scale_info": [vp, vp, i32, vp],
         "cge_grid_posterior_async": [vp, vp, vp, vp, vp],
+        "cge_create_multi": [i32, C.POINTER(i32), C.POINTER(vp)],
+        "cge_destroy_multi": [vp],
+        "cge_multi_size": [vp, C.POINTER(i32)],
+        "cge_grid_posterior_multi": [vp, PP, vp, vp, vp, vp, vp, C.POINTER(Timing)],
+        "cge_multi_shard": [vp, i32, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.POINTER(vp)],
+        "cge_multi_step_async": [vp, PP, C.POINTER(vp)],
+        "cge_multi_synchronize": [vp],
     }
     for name, argtypes in sig.items():
         fn = getattr(L, name)
@@ -135,10 +146,11 @@ def _check(rc: int):
 
 
 def make_params(n_obs, grid_size, mu_range, sigma_range, mode=MODE_PRODUCT_F32, rows=None,
-                variant=0) -> Params:
+                variant=0, posterior_dtype=POSTERIOR_F32) -> Params:
     rb, re = (0, 0) if rows is None else (int(rows[0]), int(rows[1]))
     return Params(int(n_obs), int(grid_size), float(mu_range[0]), float(mu_range[1]),
-                  float(sigma_range[0]), float(sigma_range[1]), int(mode), rb, re, int(variant))
+                  float(sigma_range[0]), float(sigma_range[1]), int(mode), rb, re, int(variant),
+                  int(posterior_dtype))
 
 
 @dataclass
@@ -158,6 +170,11 @@ def _ptr(a) -> Optional[int]:
     if isinstance(a, np.ndarray):
         return a.ctypes.data
     return int(a.data_ptr())
+
+
+def _is_cuda_tensor(t) -> bool:
+    return (t is not None and not isinstance(t, (str, np.ndarray)) and
+            bool(getattr(t, "is_cuda", False)))
 
 
 class Context:
@@ -201,27 +218,37 @@ class Context:
 
     # ---- fused path, synchronous, host or device buffers ---------------------------------
     def grid_posterior(self, obs, grid_size, mu_range, sigma_range, mode=MODE_PRODUCT_F32,
-                       rows=None, posterior="host", want_timing=True, variant=0) -> GridResult:
+                       rows=None, posterior="host", want_timing=True, variant=0,
+                       posterior_dtype=POSTERIOR_F32) -> GridResult:
         """The whole hot path in one call (replaces src/grid.cu:79-127).
 
         obs        numpy float32 array (host) or CUDA torch tensor (device)
         posterior  "host": return it as numpy; "device"/None: leave it in the context's device
                    buffer; or a CUDA torch tensor / numpy array to write into.
+        posterior_dtype  POSTERIOR_F32 (default) or POSTERIOR_F64 (the reference's type)
+
+        The call runs on the context's own stream.  CUDA tensors passed in are first ordered
+        against torch's current stream (the work that produced them is waited for), and the call
+        returns only after its own work is complete, so torch may use the outputs at once.
         """
         if isinstance(obs, np.ndarray):
             obs = np.ascontiguousarray(obs, np.float32)
         n = int(obs.shape[0])
-        p = make_params(n, grid_size, mu_range, sigma_range, mode, rows, variant)
+        p = make_params(n, grid_size, mu_range, sigma_range, mode, rows, variant, posterior_dtype)
         nrows = grid_size if rows is None else rows[1] - rows[0]
+        np_dtype = np.float64 if posterior_dtype == POSTERIOR_F64 else np.float32
         post_arr = None
         if isinstance(posterior, str) and posterior == "host":
-            post_arr = np.empty((nrows, grid_size), np.float32)
+            post_arr = np.empty((nrows, grid_size), np_dtype)
             post_ptr = post_arr.ctypes.data
         elif posterior is None or (isinstance(posterior, str) and posterior == "device"):
             post_ptr = None
         else:
             post_ptr = _ptr(posterior)
             post_arr = posterior if isinstance(posterior, np.ndarray) else None
+        if any(_is_cuda_tensor(t) for t in (obs, posterior)):
+            import torch
+            torch.cuda.current_stream(self.device).synchronize()
         mm = np.empty(grid_size, np.float64)
         ms = np.empty(grid_size, np.float64)
         ex = np.empty(2, np.float64)
@@ -410,3 +437,71 @@ def device_tensor(ptr: int, count: int, dtype: str, device_index: int):
     import torch
     typestr = {"float64": "<f8", "float32": "<f4"}[dtype]
     return torch.as_tensor(_DeviceView(ptr, count, typestr), device=torch.device("cuda", device_index))
+
+
+class MultiContext:
+    """Several GPUs driven from this one process (cge_create_multi): the grid is row-sharded over
+    `devices` and every call is one C entry with host buffers."""
+
+    def __init__(self, devices):
+        self._lib = load_library()
+        devs = (C.c_int * len(devices))(*[int(d) for d in devices])
+        h = C.c_void_p()
+        _check(self._lib.cge_create_multi(len(devices), devs, C.byref(h)))
+        self._h = h
+        self.devices = [int(d) for d in devices]
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.cge_destroy_multi(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def grid_posterior(self, obs, grid_size, mu_range, sigma_range, mode=MODE_PRODUCT_F32,
+                       posterior="host", want_timing=False, variant=0,
+                       posterior_dtype=POSTERIOR_F32) -> GridResult:
+        """cge_grid_posterior_multi: host observations in; expectations, marginals (and, with
+        posterior="host" or a numpy array, the gathered posterior) out.  posterior=None leaves the
+        shards on their devices (see shard())."""
+        obs = np.ascontiguousarray(obs, np.float32)
+        p = make_params(obs.shape[0], grid_size, mu_range, sigma_range, mode, None, variant,
+                        posterior_dtype)
+        np_dtype = np.float64 if posterior_dtype == POSTERIOR_F64 else np.float32
+        post_arr = None
+        if isinstance(posterior, str) and posterior == "host":
+            post_arr = np.empty((grid_size, grid_size), np_dtype)
+        elif isinstance(posterior, np.ndarray):
+            post_arr = posterior
+        mm = np.empty(grid_size, np.float64)
+        ms = np.empty(grid_size, np.float64)
+        ex = np.empty(2, np.float64)
+        tm = Timing()
+        _check(self._lib.cge_grid_posterior_multi(
+            self._h, C.byref(p), obs.ctypes.data, None if post_arr is None else post_arr.ctypes.data,
+            mm.ctypes.data, ms.ctypes.data, ex.ctypes.data, C.byref(tm) if want_timing else None))
+        return GridResult(ex, mm, ms, post_arr, tm.as_dict() if want_timing else {}, 3 * len(self.devices))
+
+    def shard(self, index: int):
+        """(device, row_begin, row_end, device pointer) of shard `index` of the last call."""
+        dev, rb, re, ptr = C.c_int(), C.c_int(), C.c_int(), C.c_void_p()
+        _check(self._lib.cge_multi_shard(self._h, int(index), C.byref(dev), C.byref(rb), C.byref(re),
+                                         C.byref(ptr)))
+        return dev.value, rb.value, re.value, ptr.value
+
+    def step_async(self, params: Params, obs_dev_ptrs):
+        arr = (C.c_void_p * len(obs_dev_ptrs))(*[int(x) for x in obs_dev_ptrs])
+        _check(self._lib.cge_multi_step_async(self._h, C.byref(params), arr))
+
+    def synchronize(self):
+        _check(self._lib.cge_multi_synchronize(self._h))

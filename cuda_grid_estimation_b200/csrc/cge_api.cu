@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <new>
 #include <string>
 #include <vector>
@@ -93,28 +94,48 @@ struct PinnedBuf {
 struct cge_context {
   int device = 0;
   int sm_count = 0, cc_major = 0, cc_minor = 0;
+  size_t l2_bytes = 0;
   cudaStream_t stream = nullptr;
+  bool own_stream = true;
   cudaEvent_t ev[10] = {};
-  DevBuf<float> mu, sigma, obs_pad, obs_in, posterior;
-  DevBuf<double> ad, cd0, rowpart, colpart, partials, rowsum, zpart, smupart, espart, results, tmp;
-  DevBuf<unsigned int> tickets;  // [0] fold, [1] results; zero between launches
+  DevBuf<float> obs_pad, obs_in, posterior, like32;
+  DevBuf<double> posterior64;
+  DevBuf<double> rowpart, partials, rowsum, zpart, smupart, espart, results, tmp;
+  DevBuf<unsigned long long> colacc;  // fixed-point column sums; zero between steps
+  DevBuf<int> strip_next;             // claim counters; zero between steps
+  float prior_mu_max = 1.0f, prior_sigma_max = 1.0f, prior_full_max = 1.0f;  // largest |factor| of each piece
+  size_t prior_full_cells = 0;        // cells of the full table prior_full_max was measured over
+  DevBuf<unsigned int> tickets;  // [0] fold, [1] finish, [2] small-grid kernel; zero between steps
   DevBuf<float> prior_mu, prior_sigma;   // owned copies of the separable prior factors
   bool has_prior_mu = false, has_prior_sigma = false;
   int prior_n = 0;
   const float *prior_full = nullptr;     // caller-owned device table, shard layout
   DevBuf<cge::ScaleInfo> scale;
   DevBuf<float> sink;
+#ifdef CGE_DEBUG_TIMES
+  DevBuf<unsigned long long> debug_times;
+#endif
   PinnedBuf<float> host_obs;       // staging for host observations
   PinnedBuf<double> host_results;  // staging for {E, Z, 1/Z}, both marginals
   bool host_results_valid = false;  // the last step's kernel wrote host_results itself
   Plan plan;
+  cge_host::KernelChoice kernel;   // the likelihood kernel of the current plan
   cge_timing timing = {};
   int launches = 0;
-  // per-step event capture: 7 marks per step
-  //   0 before tables | 1 after setup | 2 after likelihood | 3 after fold |
-  //   4 before results | 5 after results | 6 after scale
-  // peer exchange (CUDA IPC): block = [flag word, padded to 256 B][buf 0: cap f64][buf 1: cap f64]
+  // tuning knobs, read from the environment ONCE at cge_create (not part of the ABI)
+  int knob_ctas_per_sm = 0;  // CGE_CTAS_PER_SM: cap the persistent grid
+  int knob_grid_mult = 1;    // CGE_GRID_MULT: CTAs per resident slot (1 = persistent)
+  int knob_chunk = 0;        // CGE_ITEM_STEPS: CTA steps per claimed item
+  bool knob_no_cluster = false;  // CGE_NO_CLUSTER: small grids without the cluster launch
+  bool knob_no_pdl = false;      // CGE_NO_PDL: ordinary stream-ordered launches
+  // resident CTAs per SM of each likelihood kernel at its shared-memory size (occupancy query)
+  std::map<std::pair<const void *, size_t>, int> occupancy;
+  // per-step event capture: 6 marks per step
+  //   0 start | 1 after the streamed set-up (== 0 otherwise) | 2 after likelihood |
+  //   3 after fold + publish | 4 before finish | 5 after finish
+  // peer exchange: block = [flag word, padded to 256 B][buf 0: cap f64][buf 1: cap f64]
   bool peer_on = false;
+  bool peer_ipc = false;               // peers mapped through CUDA IPC (else: same-process pointers)
   int peer_rank = 0, peer_world = 1;
   size_t peer_cap = 0;                 // doubles per buffer
   unsigned char *peer_block[cge::kMaxPeers] = {};  // [peer_rank] is this context's own allocation
@@ -146,12 +167,24 @@ int check_params(const cge_params *p, int *rb, int *re) {
     return set_error(CGE_ERR_BAD_ARG, "ranges must be finite");
   if (p->mode != CGE_MODE_PRODUCT_F32 && p->mode != CGE_MODE_LOGSPACE)
     return set_error(CGE_ERR_BAD_ARG, "unknown mode %d", p->mode);
+  if (p->posterior_dtype != CGE_POSTERIOR_F32 && p->posterior_dtype != CGE_POSTERIOR_F64)
+    return set_error(CGE_ERR_BAD_ARG, "unknown posterior_dtype %d", p->posterior_dtype);
   switch (p->variant) {
-    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_MUFU_ONLY: case CGE_VARIANT_PAIRED: case CGE_VARIANT_PAIRED3:
-    case CGE_VARIANT_HYBRID: case CGE_VARIANT_LOG_F64: case CGE_VARIANT_UNFUSED:
-    case 6: case 31: case 39: case 45: case 381: break;
+    case CGE_VARIANT_DEFAULT: case CGE_VARIANT_UNFUSED: break;
+    case CGE_VARIANT_MUFU_ONLY: case CGE_VARIANT_PAIRED: case CGE_VARIANT_PAIRED3: case CGE_VARIANT_HYBRID:
+      if (p->mode != CGE_MODE_PRODUCT_F32)
+        return set_error(CGE_ERR_BAD_ARG, "variant %d belongs to the product mode", p->variant);
+      break;
+    case CGE_VARIANT_LOG_F64:
+      if (p->mode != CGE_MODE_LOGSPACE)
+        return set_error(CGE_ERR_BAD_ARG, "variant %d belongs to the log-space mode", p->variant);
+      break;
     default: return set_error(CGE_ERR_BAD_ARG, "unknown kernel variant %d", p->variant);
   }
+  if (p->mode == CGE_MODE_PRODUCT_F32 && ((p->n_obs + 3) & ~3) > cge::kObsSingleMax)
+    return set_error(CGE_ERR_BAD_ARG,
+                     "the float32 product path takes at most %d observations (got %d): use "
+                     "CGE_MODE_LOGSPACE", cge::kObsSingleMax, p->n_obs);
   int b = p->row_begin, e = p->row_end;
   if (b == 0 && e == 0) e = p->grid_size;
   if (b < 0 || e > p->grid_size || b >= e)
@@ -162,12 +195,13 @@ int check_params(const cge_params *p, int *rb, int *re) {
   return CGE_OK;
 }
 
-// log-space kernels other than the float64 ones read centred observations (x_k - mu_c)
+// log-space kernels other than the float64 one read centred observations (x_k - mu_c)
 int centred_obs(const cge_params *p) {
   return (p->mode == CGE_MODE_LOGSPACE && p->variant != CGE_VARIANT_LOG_F64) ? 1 : 0;
 }
 
-// tile shape and grid for one shard
+// CTA shape and unit decomposition for one shard (everything but the persistent grid size, which
+// needs the kernel: size_grid below).  `post` is where the float32 cells go.
 void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, const float *post,
                Plan *pl) {
   pl->N = p->grid_size;
@@ -175,51 +209,80 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->n_pad = (p->n_obs + 3) & ~3;
   pl->mode = p->mode;
   pl->variant = p->variant;
+  pl->post_f64 = p->posterior_dtype == CGE_POSTERIOR_F64;
   pl->row_begin = rb;
   pl->row_end = re;
   pl->rows_local = re - rb;
   // columns per warp strip: 32 lanes x Policy::kCols (log-space keeps 8 columns per thread)
-  const bool wide_patch = p->mode == CGE_MODE_PRODUCT_F32 && p->variant == 381;
-  const int strip = 32 * (p->mode == CGE_MODE_LOGSPACE ? cge::LogSpaceTiled<>::kCols : wide_patch ? 8 : 4);
+  pl->kcols = p->mode == CGE_MODE_LOGSPACE ? 8 : 4;
+  const int strip = 32 * pl->kcols;
   pl->ncw = (pl->N + strip - 1) / strip;
-  if (pl->ncw >= 8) { pl->wm = 1; pl->wn = 8; }
-  else if (pl->ncw >= 4) { pl->wm = 2; pl->wn = 4; }
-  else if (pl->ncw >= 2) { pl->wm = 4; pl->wn = 2; }
-  else { pl->wm = 8; pl->wn = 1; }
-  if (const char *ov = std::getenv("CGE_WARP_ROWS")) {  // tuning knob, not part of the ABI
-    const int v = std::atoi(ov);
-    if (v == 1 || v == 2 || v == 4 || v == 8) { pl->wm = v; pl->wn = 8 / v; }
-  }
-  pl->bands = (pl->ncw + pl->wn - 1) / pl->wn;
-  // tile heights are multiples of the patch rows of every warp row and of the global alignment
-  const int patch_rows = p->mode == CGE_MODE_LOGSPACE ? cge::LogSpaceF64::kRows : cge::kRM;
-  int unit = pl->wm * patch_rows;
-  if (unit % cge::kRM) unit *= cge::kRM / patch_rows;
-  // Tile height: tall enough that the per-tile column partials stay small (the fold kernel reads
-  // row_tiles*WM*N doubles) and the per-CTA prologue is amortised, short enough that the grid is
-  // still >= ~8 CTAs per resident slot.  Measured sweep: profiles/r01_tile_rows_sweep.jsonl
-  // (16..48 rows is flat for the likelihood kernel; the fold time falls with the height).
-  const int span = re - (rb & ~(cge::kRM - 1));  // tiles start at a multiple of kRM (see kernel)
-  const long long want_ctas = (long long)ctx->sm_count * 2 * 8;
-  long long tr = ((long long)span * pl->bands) / want_ctas;
-  if (tr < 16) tr = 16;
-  if (tr > 48) tr = 48;
-  if (tr > span) tr = span;
-  tr = ((tr + unit - 1) / unit) * unit;
-  if (const char *ov = std::getenv("CGE_TILE_ROWS")) {  // tuning knob, not part of the ABI
-    long long v = std::atoll(ov);
-    if (v >= unit) tr = (v / unit) * unit;
-  }
-  pl->tile_rows = (int)tr;
-  pl->row_tiles = (span + pl->tile_rows - 1) / pl->tile_rows;
-  pl->ncolparts = pl->row_tiles * pl->wm;
-  pl->nb_col = (pl->N + 31) / 32;
+  // row groups start at a multiple of kRM rows (see run_strip)
+  const int span = re - (rb & ~(cge::kRM - 1));
+  const int groups = (span + cge::kRM - 1) / cge::kRM;
+  pl->groups = groups;
+  // fixed-point column sums: at most `groups` addends per column (col_fixed_shift)
+  int lc = 0;
+  while ((1ll << lc) < (long long)groups + 1) ++lc;
+  pl->fixed_bits = 58 - lc;
+  pl->nb_col = (pl->N + 255) / 256;
   pl->nb_row = (pl->rows_local + 7) / 8;
+  pl->nb_res = (pl->N + 255) / 256;
   pl->vec4 = (pl->N % 4 == 0) && ((reinterpret_cast<uintptr_t>(post) & 15u) == 0);
-  const bool streamed = pl->n_pad > cge::kObsSingleMax;
-  pl->smem = 128 + (streamed ? 2 * (size_t)cge::kObsChunk * 4 : (size_t)pl->n_pad * 4);
+  // a shard that fits in L2 with room to spare is stored with the default cache policy, so the
+  // scale pass reads it back from there; larger ones stream past L2 (st.global.cs)
+  pl->keep_l2 = (size_t)pl->rows_local * pl->N * sizeof(float) * 4 <= ctx->l2_bytes * 3;
+  pl->streamed = pl->n_pad > cge::kObsSingleMax;
+  pl->reorder = p->mode == CGE_MODE_PRODUCT_F32 && pl->n <= cge::kReorderMax;
   pl->cluster = false;
-  pl->valid = true;
+  pl->nctas = 0;
+}
+
+// dynamic shared memory of a likelihood / small-grid launch: header + observation stage + the
+// larger of the per-thread float64 slots and the sort scratch of the set-up
+size_t like_smem(const Plan &pl, const cge_host::KernelChoice &kc) {
+  size_t slots = (size_t)kc.smem_bytes * kc.threads;
+  size_t sort = pl.reorder ? (size_t)pl.n_pad * sizeof(float) : 0;
+  return cge::kSmemHeader + cge::stage_bytes(pl.n_pad) + (slots > sort ? slots : sort) + 16;
+}
+
+// fixes the persistent grid: one CTA per resident slot of the device (occupancy of this kernel at
+// this shared-memory size), never more than there are items for; and the item size
+int size_grid(cge_context *ctx, Plan *pl, const cge_host::KernelChoice &kc, int max_ctas) {
+  pl->smem = like_smem(*pl, kc);
+  const auto key = std::make_pair(kc.fn, pl->smem);
+  auto it = ctx->occupancy.find(key);
+  if (it == ctx->occupancy.end()) {
+    if (pl->smem > 40 * 1024)  // static + dynamic beyond 48 KB needs the opt-in
+      CK(cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+    int per_sm = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc.fn, kc.threads, pl->smem));
+    if (per_sm < 1)
+      return set_error(CGE_ERR_CUDA, "likelihood kernel does not fit an SM with %zu B of shared memory",
+                       pl->smem);
+    it = ctx->occupancy.emplace(key, per_sm).first;
+  }
+  int per_sm = it->second;
+  if (ctx->knob_ctas_per_sm > 0 && ctx->knob_ctas_per_sm < per_sm) per_sm = ctx->knob_ctas_per_sm;
+  long long P = (long long)ctx->sm_count * per_sm * ctx->knob_grid_mult;
+  if (max_ctas > 0 && P > max_ctas) P = max_ctas;
+  // item size: ~32 items per worker (a warp; a whole CTA when the observations are streamed) so
+  // that the last item of the slowest worker is a small tail, at most 8 row groups so that a claim
+  // (one atomic, hidden behind the item) stays far below 1 % of an item
+  const long long per_item = pl->streamed ? cge::kWarps : 1;  // groups one chunk step covers
+  const long long total = (long long)pl->ncw * pl->groups;
+  const long long workers = P * (pl->streamed ? 1 : cge::kWarps);
+  long long chunk = total / (workers * 32 * per_item);
+  if (chunk < 1) chunk = 1;
+  if (chunk > 8) chunk = 8;
+  if (ctx->knob_chunk > 0) chunk = ctx->knob_chunk < 8 ? ctx->knob_chunk : 8;  // (run_strip: one lane per row of an item)
+  pl->chunk = (int)chunk;
+  pl->items_per_strip = (int)((pl->groups + chunk * per_item - 1) / (chunk * per_item));
+  const long long items = (long long)pl->ncw * pl->items_per_strip;
+  const long long useful = pl->streamed ? items : (items + cge::kWarps - 1) / cge::kWarps;
+  if (P > useful) P = useful;
+  pl->nctas = (int)P;
+  return CGE_OK;
 }
 
 // ---------------------------------------------------------------------------------------
@@ -231,39 +294,48 @@ int mark(cge_context *ctx, int k, cudaStream_t st);
 
 bool small_grid_eligible(const cge_context *ctx, const cge_params *p, int rb, int re) {
   return p->variant == CGE_VARIANT_DEFAULT && p->grid_size <= kSmallGridMax && rb == 0 &&
-         re == p->grid_size && !ctx->peer_on && ((p->n_obs + 3) & ~3) <= cge::kObsSingleMax;
+         re == p->grid_size && !ctx->peer_on && p->posterior_dtype == CGE_POSTERIOR_F32 &&
+         ((p->n_obs + 3) & ~3) <= cge::kObsSingleMax;
 }
 
 int reserve_step_buffers(cge_context *ctx, const Plan &pl, cudaStream_t st) {
   const int N = pl.N;
-  CKRC(ctx->mu.reserve((size_t)N + 4));
-  CKRC(ctx->sigma.reserve(N));
-  CKRC(ctx->ad.reserve(N));
-  CKRC(ctx->cd0.reserve(N));
-  CKRC(ctx->obs_pad.reserve(pl.n_pad));
   CKRC(ctx->scale.reserve(1));
-  CKRC(ctx->espart.reserve((size_t)(N + 255) / 256));
+  CKRC(ctx->espart.reserve((size_t)pl.nb_res));
   if (!ctx->tickets.ptr) {
     CKRC(ctx->tickets.reserve(3));
     CK(cudaMemsetAsync(ctx->tickets.ptr, 0, 3 * sizeof(unsigned int), st));
   }
   CKRC(ctx->rowpart.reserve((size_t)pl.rows_local * pl.ncw));
-  CKRC(ctx->colpart.reserve((size_t)pl.ncolparts * N));
+  if ((size_t)N > ctx->colacc.cap) {   // (re)allocated zeroed; every step leaves it zeroed
+    CKRC(ctx->colacc.reserve(N));
+    CK(cudaMemsetAsync(ctx->colacc.ptr, 0, ctx->colacc.cap * sizeof(unsigned long long), st));
+  }
+  if ((size_t)pl.ncw > ctx->strip_next.cap) {
+    CKRC(ctx->strip_next.reserve(pl.ncw));
+    CK(cudaMemsetAsync(ctx->strip_next.ptr, 0, ctx->strip_next.cap * sizeof(int), st));
+  }
   CKRC(ctx->partials.reserve((size_t)N + 2));
   CKRC(ctx->rowsum.reserve(pl.rows_local));
   CKRC(ctx->zpart.reserve(pl.nb_row));
   CKRC(ctx->smupart.reserve(pl.nb_row));
   CKRC(ctx->results.reserve(4 + 2 * (size_t)N));
+  if (pl.streamed) CKRC(ctx->obs_pad.reserve(pl.n_pad));
   return CGE_OK;
 }
 
-int fill_like_args(cge_context *ctx, const Plan &pl, float *posterior_dev, cge::LikeArgs *args) {
+int device_absmax(cge_context *ctx, const float *v_dev, size_t count, float *out);
+
+int fill_like_args(cge_context *ctx, const cge_params *p, const Plan &pl, const float *obs_dev,
+                   float *posterior_dev, cge::LikeArgs *args) {
   const int N = pl.N;
-  args->obs_pad = ctx->obs_pad.ptr;
-  args->mu = ctx->mu.ptr;
-  args->ad = ctx->ad.ptr;
-  args->cd0 = ctx->cd0.ptr;
-  args->scale = ctx->scale.ptr;
+  *args = cge::LikeArgs{};
+  args->obs = pl.streamed ? ctx->obs_pad.ptr : obs_dev;
+  args->scale_in = pl.streamed ? ctx->scale.ptr : nullptr;
+  args->scale_out = ctx->scale.ptr;
+  args->range = cge::RangeArgs{N, p->mu_start, p->mu_end, p->sigma_start, p->sigma_end};
+  args->centred = centred_obs(p);
+  args->reorder = pl.reorder ? 1 : 0;
   if ((ctx->has_prior_mu || ctx->has_prior_sigma) && ctx->prior_n != N)
     return set_error(CGE_ERR_BAD_ARG, "prior was set for grid_size %d, call has %d", ctx->prior_n, N);
   args->prior_mu = ctx->has_prior_mu ? ctx->prior_mu.ptr : nullptr;
@@ -271,14 +343,71 @@ int fill_like_args(cge_context *ctx, const Plan &pl, float *posterior_dev, cge::
   args->prior_full = ctx->prior_full;
   args->post = posterior_dev;
   args->rowpart = ctx->rowpart.ptr;
-  args->colpart = ctx->colpart.ptr;
+  args->colacc = ctx->colacc.ptr;
+  args->strip_next = ctx->strip_next.ptr;
+  args->prior_log2max = 0.0f;
+  if (args->prior_mu || args->prior_sigma || args->prior_full) {
+    const size_t cells = (size_t)pl.rows_local * N;
+    if (args->prior_full && ctx->prior_full_cells != cells) {  // once per table and shard shape
+      CKRC(device_absmax(ctx, ctx->prior_full, cells, &ctx->prior_full_max));
+      ctx->prior_full_cells = cells;
+    }
+    const double bound = (args->prior_mu ? (double)ctx->prior_mu_max : 1.0) *
+                         (args->prior_sigma ? (double)ctx->prior_sigma_max : 1.0) *
+                         (args->prior_full ? (double)ctx->prior_full_max : 1.0);
+    args->prior_log2max = bound > 0.0 ? (float)std::ceil(std::log2(bound)) : -1000.0f;
+  }
   args->n = pl.n;
   args->n_pad = pl.n_pad;
   args->N = N;
   args->row_begin = pl.row_begin;
   args->row_end = pl.row_end;
-  args->tile_rows = pl.tile_rows;
+  args->groups = pl.groups;
+  args->chunk = pl.chunk;
+  args->items_per_strip = pl.items_per_strip;
+  args->fixed_bits = pl.fixed_bits;
   args->ncw = pl.ncw;
+  args->vec4 = pl.vec4 ? 1 : 0;
+  args->keep_l2 = pl.keep_l2 ? 1 : 0;
+#ifdef CGE_DEBUG_TIMES
+  CKRC(ctx->debug_times.reserve((size_t)4 * pl.nctas));
+  args->debug = ctx->debug_times.ptr;
+#endif
+  return CGE_OK;
+}
+
+// one launch through the extensible API: optional programmatic dependent launch (the kernel may
+// be set up while its predecessor in the stream drains; it orders itself with griddepcontrol.wait)
+// and optional cluster shape
+int launch_ex(const cge_context *ctx, const void *fn, unsigned grid, unsigned block, size_t smem,
+              cudaStream_t st, void *arg, bool pdl, unsigned cluster) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid, 1, 1);
+  cfg.blockDim = dim3(block, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned na = 0;
+  if (pdl && !ctx->knob_no_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  if (cluster > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = cluster;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  void *args[1] = {arg};
+  const cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+  if (e != cudaSuccess)
+    return set_error(CGE_ERR_CUDA, "kernel launch failed: %s (grid %u, block %u, %zu B dynamic smem, "
+                     "cluster %u, pdl %d)", cudaGetErrorString(e), grid, block, smem, cluster,
+                     (int)(pdl && !ctx->knob_no_pdl));
   return CGE_OK;
 }
 
@@ -288,29 +417,15 @@ int small_grid_step(cge_context *ctx, const cge_params *p, const float *obs_dev,
   Plan &pl = ctx->plan;
   pl.valid = false;
   make_plan(ctx, p, 0, p->grid_size, posterior_dev, &pl);
-  // One column band (always the case up to 256 columns) and at most 8 row tiles (the portable
-  // cluster size) -> the grid runs as one thread-block cluster: taller tiles if need be.
-  if (pl.bands == 1 && !std::getenv("CGE_NO_CLUSTER")) {
-    const int unit = pl.wm * cge::kRM;
-    if (pl.row_tiles > 8) {
-      pl.tile_rows = (((pl.N + 7) / 8 + unit - 1) / unit) * unit;
-      pl.row_tiles = (pl.N + pl.tile_rows - 1) / pl.tile_rows;
-      pl.ncolparts = pl.row_tiles * pl.wm;
-    }
-    pl.cluster = pl.row_tiles <= 8;
-  }
+  // at most 8 CTAs (the portable cluster size) -> the grid runs as one thread-block cluster
+  pl.cluster = !ctx->knob_no_cluster;
+  cge_host::KernelChoice kc;
+  if (p->mode == CGE_MODE_PRODUCT_F32) CKRC(cge_host::choose_small_product(pl, &kc));
+  else CKRC(cge_host::choose_small_logspace(pl, &kc));
+  CKRC(size_grid(ctx, &pl, kc, pl.cluster ? 8 : 0));
   CKRC(reserve_step_buffers(ctx, pl, st));
   cge::SmallArgs a = {};
-  CKRC(fill_like_args(ctx, pl, posterior_dev, &a.like));
-  a.range = cge::RangeArgs{pl.N, p->mu_start, p->mu_end, p->sigma_start, p->sigma_end};
-  a.obs = obs_dev;
-  a.mu = ctx->mu.ptr;
-  a.sigma = ctx->sigma.ptr;
-  a.ad = ctx->ad.ptr;
-  a.cd0 = ctx->cd0.ptr;
-  a.scale = ctx->scale.ptr;
-  a.centred = centred_obs(p);
-  a.ncolparts = pl.ncolparts;
+  CKRC(fill_like_args(ctx, p, pl, obs_dev, posterior_dev, &a.like));
   a.partials = ctx->partials.ptr;
   a.rowsum = ctx->rowsum.ptr;
   a.results = ctx->results.ptr;
@@ -324,13 +439,12 @@ int small_grid_step(cge_context *ctx, const cge_params *p, const float *obs_dev,
   ctx->launches = 0;
   CKRC(mark(ctx, 0, st));
   CKRC(mark(ctx, 1, st));
-  if (p->mode == CGE_MODE_PRODUCT_F32)
-    CKRC(cge_host::launch_small_product(pl, a, st));
-  else
-    CKRC(cge_host::launch_small_logspace(pl, a, st));
+  CKRC(launch_ex(ctx, kc.fn, pl.nctas, kc.threads, pl.smem, st, &a, false, pl.cluster ? pl.nctas : 0));
   ctx->launches += 1;
-  for (int k = 2; k <= 6; ++k) CKRC(mark(ctx, k, st));
+  for (int k = 2; k <= 5; ++k) CKRC(mark(ctx, k, st));
   if (ctx->prof_on && ctx->prof_step < ctx->prof_cap) ctx->prof_step++;
+  ctx->kernel = kc;
+  pl.valid = true;
   return CGE_OK;
 }
 
@@ -344,14 +458,15 @@ unsigned long long *peer_flag(const cge_context *ctx, int rank) {
 }
 
 // record profiling mark `k` of the current step (no-op unless capture is on and has room)
+constexpr int kMarks = 6;
 int mark(cge_context *ctx, int k, cudaStream_t st) {
   if (!ctx->prof_on || ctx->prof_step >= ctx->prof_cap) return CGE_OK;
-  CK(cudaEventRecord(ctx->prof_events[(size_t)ctx->prof_step * 7 + k], st));
+  CK(cudaEventRecord(ctx->prof_events[(size_t)ctx->prof_step * kMarks + k], st));
   return CGE_OK;
 }
 
 int prof_reserve(cge_context *ctx, int steps) {
-  while ((int)ctx->prof_events.size() < steps * 7) {
+  while ((int)ctx->prof_events.size() < steps * kMarks) {
     cudaEvent_t e;
     CK(cudaEventCreate(&e));
     ctx->prof_events.push_back(e);
@@ -365,17 +480,16 @@ int prof_reserve(cge_context *ctx, int steps) {
 int prof_collect(cge_context *ctx, cge_timing *out, int *steps) {
   cge_timing t = {};
   const int n = ctx->prof_step;
-  if (n > 0) CK(cudaEventSynchronize(ctx->prof_events[(size_t)(n - 1) * 7 + 6]));
+  if (n > 0) CK(cudaEventSynchronize(ctx->prof_events[(size_t)(n - 1) * kMarks + 5]));
   for (int s = 0; s < n; ++s) {
-    cudaEvent_t *e = &ctx->prof_events[(size_t)s * 7];
-    float a = 0, b = 0, c = 0, d = 0, f = 0, tot = 0;
+    cudaEvent_t *e = &ctx->prof_events[(size_t)s * kMarks];
+    float a = 0, b = 0, c = 0, f = 0, tot = 0;
     CK(cudaEventElapsedTime(&a, e[0], e[1]));
     CK(cudaEventElapsedTime(&b, e[1], e[2]));
     CK(cudaEventElapsedTime(&c, e[2], e[3]));
-    CK(cudaEventElapsedTime(&d, e[4], e[5]));
-    CK(cudaEventElapsedTime(&f, e[5], e[6]));
-    CK(cudaEventElapsedTime(&tot, e[0], e[6]));
-    t.setup_ms += a; t.likelihood_ms += b; t.reduce_ms += c + d; t.scale_ms += f; t.total_ms += tot;
+    CK(cudaEventElapsedTime(&f, e[4], e[5]));
+    CK(cudaEventElapsedTime(&tot, e[0], e[5]));
+    t.setup_ms += a; t.likelihood_ms += b; t.reduce_ms += c; t.scale_ms += f; t.total_ms += tot;
   }
   if (n > 0) {
     t.setup_ms /= n; t.likelihood_ms /= n; t.reduce_ms /= n; t.scale_ms /= n; t.total_ms /= n;
@@ -428,6 +542,13 @@ CGE_EXPORT int cge_create(int device, cge_context **out) {
   ctx->sm_count = prop.multiProcessorCount;
   ctx->cc_major = prop.major;
   ctx->cc_minor = prop.minor;
+  ctx->l2_bytes = (size_t)prop.l2CacheSize;
+  // tuning knobs: read once here, never on the step path
+  if (const char *v = std::getenv("CGE_CTAS_PER_SM")) ctx->knob_ctas_per_sm = std::atoi(v);
+  if (const char *v = std::getenv("CGE_GRID_MULT")) ctx->knob_grid_mult = std::atoi(v) > 0 ? std::atoi(v) : 1;
+  if (const char *v = std::getenv("CGE_ITEM_STEPS")) ctx->knob_chunk = std::atoi(v);
+  ctx->knob_no_cluster = std::getenv("CGE_NO_CLUSTER") != nullptr;
+  ctx->knob_no_pdl = std::getenv("CGE_NO_PDL") != nullptr;
   cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
   if (se != cudaSuccess) {
     delete ctx;
@@ -450,10 +571,10 @@ CGE_EXPORT int cge_destroy(cge_context *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaDeviceSynchronize();
   peer_release(ctx);
-  ctx->mu.release(); ctx->sigma.release(); ctx->obs_pad.release();
-  ctx->obs_in.release(); ctx->espart.release(); ctx->tickets.release(); ctx->prior_mu.release(); ctx->prior_sigma.release();
-  ctx->posterior.release(); ctx->ad.release(); ctx->cd0.release(); ctx->rowpart.release();
-  ctx->colpart.release(); ctx->partials.release(); ctx->rowsum.release(); ctx->zpart.release();
+  ctx->obs_pad.release(); ctx->obs_in.release(); ctx->espart.release(); ctx->tickets.release();
+  ctx->prior_mu.release(); ctx->prior_sigma.release(); ctx->posterior.release();
+  ctx->like32.release(); ctx->posterior64.release(); ctx->rowpart.release();
+  ctx->colacc.release(); ctx->strip_next.release(); ctx->partials.release(); ctx->rowsum.release(); ctx->zpart.release();
   ctx->smupart.release(); ctx->results.release(); ctx->tmp.release(); ctx->scale.release();
   ctx->sink.release();
   ctx->host_obs.release();
@@ -461,7 +582,7 @@ CGE_EXPORT int cge_destroy(cge_context *ctx) {
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : ctx->prof_events) cudaEventDestroy(ev);
-  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CGE_OK;
 }
@@ -475,10 +596,25 @@ CGE_EXPORT int cge_device_sm_count(cge_context *ctx, int *sm_count, int *cc_majo
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 1: tables + scale + fused likelihood + local fold
+// phase 1: fused likelihood (set-up included) + local fold + publish
 // ---------------------------------------------------------------------------------------
+namespace {
+// float64 output: the kernels write float32 likelihoods to context scratch, the finish kernel
+// widens and normalises them into the caller's float64 buffer
+int like_target(cge_context *ctx, const cge_params *p, int rb, int re, void *posterior_dev,
+                float **target) {
+  if (p->posterior_dtype == CGE_POSTERIOR_F64) {
+    CKRC(ctx->like32.reserve((size_t)(re - rb) * p->grid_size));
+    *target = ctx->like32.ptr;
+  } else {
+    *target = static_cast<float *>(posterior_dev);
+  }
+  return CGE_OK;
+}
+}  // namespace
+
 CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, const float *obs_dev,
-                                       float *posterior_dev, void *stream) {
+                                       void *posterior_dev, void *stream) {
   CKRC(bind(ctx));
   int rb, re;
   CKRC(check_params(p, &rb, &re));
@@ -488,73 +624,118 @@ CGE_EXPORT int cge_likelihood_partials(cge_context *ctx, const cge_params *p, co
   Plan &pl = ctx->plan;
   pl.valid = false;
   ctx->host_results_valid = false;
-  make_plan(ctx, p, rb, re, posterior_dev, &pl);
-  const int N = pl.N;
-
+  const int N = p->grid_size;
+  // everything that can fail is checked before anything is launched: a rank that returned an
+  // error after publishing nothing would leave its peers polling
+  if (ctx->peer_on && (size_t)N + 2 > ctx->peer_cap)
+    return set_error(CGE_ERR_BAD_ARG, "grid_size %d exceeds the peer exchange capacity %zu", N,
+                     ctx->peer_cap - 2);
+  float *like = nullptr;
+  CKRC(like_target(ctx, p, rb, re, posterior_dev, &like));
+  make_plan(ctx, p, rb, re, like, &pl);
+  cge_host::KernelChoice kc;
+  if (p->mode == CGE_MODE_PRODUCT_F32) CKRC(cge_host::choose_product(pl, &kc));
+  else CKRC(cge_host::choose_logspace(pl, &kc));
+  CKRC(size_grid(ctx, &pl, kc, 0));
   CKRC(reserve_step_buffers(ctx, pl, st));
+  cge::LikeArgs args;
+  CKRC(fill_like_args(ctx, p, pl, obs_dev, like, &args));
 
   ctx->launches = 0;
   CKRC(mark(ctx, 0, st));
-  const cge::RangeArgs range = {N, p->mu_start, p->mu_end, p->sigma_start, p->sigma_end};
-  cge::setup_kernel<<<(N + 3 + 255) / 256, 256, 0, st>>>(
-      ctx->mu.ptr, ctx->sigma.ptr, ctx->ad.ptr, ctx->cd0.ptr, range, obs_dev, ctx->obs_pad.ptr, pl.n,
-      pl.n_pad, centred_obs(p), ctx->scale.ptr);
-  CK(cudaGetLastError());
-  ctx->launches += 1;
-  CKRC(mark(ctx, 1, st));
-
-  cge::LikeArgs args;
-  CKRC(fill_like_args(ctx, pl, posterior_dev, &args));
-  if (p->mode == CGE_MODE_PRODUCT_F32) {
-    CKRC(cge_host::launch_product(pl, args, st));
-  } else {
-    CKRC(cge_host::launch_logspace(pl, args, st));
+  if (pl.streamed) {  // > 16384 observations: stage them (padded, centred) once in global memory
+    cge::setup_kernel<<<1, 256, 0, st>>>(args.range, obs_dev, ctx->obs_pad.ptr, pl.n, pl.n_pad,
+                                         args.centred, ctx->scale.ptr);
+    CK(cudaGetLastError());
+    ctx->launches += 1;
   }
+  CKRC(mark(ctx, 1, st));
+  CKRC(launch_ex(ctx, kc.fn, pl.nctas, kc.threads, pl.smem, st, &args, true, 0));
   ctx->launches += 1;
   CKRC(mark(ctx, 2, st));
 
-  double *fold_out = ctx->partials.ptr;
-  unsigned long long *ready = nullptr;
+  cge::FoldArgs f = {};
+  f.colacc = ctx->colacc.ptr;
+  f.strip_next = ctx->strip_next.ptr;
+  f.scale = ctx->scale.ptr;
+  f.rowpart = ctx->rowpart.ptr;
+  f.out = ctx->partials.ptr;
+  f.ready_flag = nullptr;
   if (ctx->peer_on) {  // this step's vector goes where the peers can read it
-    if ((size_t)N + 2 > ctx->peer_cap)
-      return set_error(CGE_ERR_BAD_ARG, "grid_size %d exceeds the peer exchange capacity %zu", N,
-                       ctx->peer_cap - 2);
-    fold_out = peer_buf(ctx, ctx->peer_rank, ctx->peer_step);
-    ready = peer_flag(ctx, ctx->peer_rank);
+    f.out = peer_buf(ctx, ctx->peer_rank, ctx->peer_step);
+    f.ready_flag = peer_flag(ctx, ctx->peer_rank);
+    f.ready_value = ctx->peer_step + 1;
   }
-  cge::fold_partials_kernel<<<pl.nb_col + pl.nb_row, 256, 0, st>>>(
-      ctx->colpart.ptr, pl.ncolparts, ctx->rowpart.ptr, pl.ncw, pl.rows_local, rb, N, ctx->mu.ptr,
-      fold_out, ctx->rowsum.ptr, ctx->zpart.ptr, ctx->smupart.ptr, pl.nb_col, pl.nb_row,
-      ctx->tickets.ptr, ready, ctx->peer_step + 1);
-  CK(cudaGetLastError());
+  f.rowsum = ctx->rowsum.ptr;
+  f.zpart = ctx->zpart.ptr;
+  f.smupart = ctx->smupart.ptr;
+  f.ticket = ctx->tickets.ptr;
+  f.range = args.range;
+  f.prior_log2max = args.prior_log2max;
+  f.fixed_bits = pl.fixed_bits;
+  f.n = pl.n;
+  f.ncw = pl.ncw;
+  f.rows_local = pl.rows_local;
+  f.row_begin = rb;
+  f.N = N;
+  f.nb_col = pl.nb_col;
+  f.nb_row = pl.nb_row;
+  CKRC(launch_ex(ctx, (const void *)cge::fold_publish_kernel, pl.nb_col + pl.nb_row, 256, 0, st, &f,
+                 true, 0));
   ctx->launches += 1;
   CKRC(mark(ctx, 3, st));
+  ctx->kernel = kc;
+  pl.valid = true;
   return CGE_OK;
 }
 
-// optional non-flat prior for the following calls (NULL, NULL, n, NULL restores the flat prior)
+// optional non-flat prior for the following calls (NULL, NULL, n, NULL restores the flat prior).
+// The largest |factor| of each piece is kept: the fixed-point column sums are scaled from a bound
+// on the largest cell (col_fixed_shift), and the prior multiplies the cells.
+namespace {
+int device_absmax(cge_context *ctx, const float *v_dev, size_t count, float *out) {
+  CKRC(ctx->tmp.reserve(2));
+  unsigned int *slot = reinterpret_cast<unsigned int *>(ctx->tmp.ptr);
+  CK(cudaMemsetAsync(slot, 0, sizeof(unsigned int), ctx->stream));
+  size_t blocks = (count + 1023) / 1024;
+  if (blocks > (size_t)ctx->sm_count * 8) blocks = (size_t)ctx->sm_count * 8;
+  cge::absmax_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(v_dev, count, slot);
+  CK(cudaGetLastError());
+  unsigned int bits = 0;
+  CK(cudaMemcpyAsync(&bits, slot, sizeof bits, cudaMemcpyDeviceToHost, ctx->stream));
+  CK(cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out, &bits, sizeof bits);
+  return CGE_OK;
+}
+}  // namespace
+
 CGE_EXPORT int cge_set_prior(cge_context *ctx, const float *prior_mu, const float *prior_sigma,
                              int grid_size, const float *prior_full_dev) {
   CKRC(bind(ctx));
   if ((prior_mu || prior_sigma) && grid_size < 1)
     return set_error(CGE_ERR_BAD_ARG, "set_prior: grid_size must be >= 1");
+  if (prior_full_dev && !is_device_pointer(prior_full_dev))
+    return set_error(CGE_ERR_BAD_ARG, "set_prior: the full prior table must be device memory");
   CK(cudaStreamSynchronize(ctx->stream));
   ctx->has_prior_mu = ctx->has_prior_sigma = false;
   ctx->prior_n = grid_size;
+  ctx->prior_mu_max = ctx->prior_sigma_max = 1.0f;
   if (prior_mu) {
     CKRC(ctx->prior_mu.reserve(grid_size));
     CK(cudaMemcpy(ctx->prior_mu.ptr, prior_mu, (size_t)grid_size * sizeof(float), cudaMemcpyDefault));
+    CKRC(device_absmax(ctx, ctx->prior_mu.ptr, grid_size, &ctx->prior_mu_max));
     ctx->has_prior_mu = true;
   }
   if (prior_sigma) {
     CKRC(ctx->prior_sigma.reserve(grid_size));
     CK(cudaMemcpy(ctx->prior_sigma.ptr, prior_sigma, (size_t)grid_size * sizeof(float),
                   cudaMemcpyDefault));
+    CKRC(device_absmax(ctx, ctx->prior_sigma.ptr, grid_size, &ctx->prior_sigma_max));
     ctx->has_prior_sigma = true;
   }
-  if (prior_full_dev && !is_device_pointer(prior_full_dev))
-    return set_error(CGE_ERR_BAD_ARG, "set_prior: the full prior table must be device memory");
   ctx->prior_full = prior_full_dev;
+  ctx->prior_full_cells = 0;  // its largest factor is measured at the first call that knows its shape
+  ctx->prior_full_max = 1.0f;
   return CGE_OK;
 }
 
@@ -567,82 +748,87 @@ CGE_EXPORT int cge_partials(cge_context *ctx, double **partials_dev, size_t *cou
 }
 
 // ---------------------------------------------------------------------------------------
-// phase 2: results + in-place scale
+// phase 2: (peer sum) + results + scale, one launch
 // ---------------------------------------------------------------------------------------
-CGE_EXPORT int cge_finalize(cge_context *ctx, const cge_params *p, float *posterior_dev,
+CGE_EXPORT int cge_finalize(cge_context *ctx, const cge_params *p, void *posterior_dev,
                             void *stream) {
   CKRC(bind(ctx));
   int rb, re;
   CKRC(check_params(p, &rb, &re));
   const Plan &pl = ctx->plan;
-  if (!pl.valid || pl.N != p->grid_size || pl.row_begin != rb || pl.row_end != re)
+  if (!pl.valid || pl.N != p->grid_size || pl.row_begin != rb || pl.row_end != re ||
+      pl.post_f64 != (p->posterior_dtype == CGE_POSTERIOR_F64))
     return set_error(CGE_ERR_BAD_ARG, "cge_finalize does not match the last cge_likelihood_partials");
   if (!posterior_dev) return set_error(CGE_ERR_BAD_ARG, "posterior_dev is NULL");
   cudaStream_t st = (cudaStream_t)stream;
   const int N = pl.N;
   CKRC(mark(ctx, 4, st));
+  cge::FinishArgs a = {};
+  a.peers.world = 0;
   if (ctx->peer_on) {
-    cge::PeerView pv = {};
-    pv.world = ctx->peer_world;
-    pv.want = ctx->peer_step + 1;
+    a.peers.world = ctx->peer_world;
+    a.peers.want = ctx->peer_step + 1;
     for (int r = 0; r < ctx->peer_world; ++r) {
-      pv.buf[r] = peer_buf(ctx, r, ctx->peer_step);
-      pv.flag[r] = peer_flag(ctx, r);
+      a.peers.buf[r] = peer_buf(ctx, r, ctx->peer_step);
+      a.peers.flag[r] = peer_flag(ctx, r);
     }
-    cge::results_peer_kernel<<<(N + 255) / 256, 256, 0, st>>>(
-        pv, ctx->partials.ptr, ctx->rowsum.ptr, ctx->sigma.ptr, N, rb, re, ctx->results.ptr,
-        ctx->espart.ptr, ctx->tickets.ptr + 1);
-    ctx->peer_step++;
-  } else {
-    cge::results_kernel<<<(N + 255) / 256, 256, 0, st>>>(ctx->partials.ptr, ctx->rowsum.ptr,
-                                                         ctx->sigma.ptr, N, rb, re,
-                                                         ctx->results.ptr, ctx->espart.ptr,
-                                                         ctx->tickets.ptr + 1);
   }
-  CK(cudaGetLastError());
+  a.partials = ctx->partials.ptr;
+  a.rowsum = ctx->rowsum.ptr;
+  a.results = ctx->results.ptr;
+  a.espart = ctx->espart.ptr;
+  a.ticket = ctx->tickets.ptr + 1;
+  a.cells = (size_t)pl.rows_local * N;
+  if (pl.post_f64) {
+    a.post = ctx->like32.ptr;
+    a.post64 = static_cast<double *>(posterior_dev);
+    a.aligned = ((reinterpret_cast<uintptr_t>(a.post) | reinterpret_cast<uintptr_t>(a.post64)) & 15u) == 0;
+  } else {
+    a.post = static_cast<float *>(posterior_dev);
+    a.post64 = nullptr;
+    a.aligned = (reinterpret_cast<uintptr_t>(a.post) & 15u) == 0;
+  }
+  a.range = cge::RangeArgs{N, p->mu_start, p->mu_end, p->sigma_start, p->sigma_end};
+  a.N = N;
+  a.row_begin = rb;
+  a.row_end = re;
+  a.nb_res = pl.nb_res;
+  // enough CTAs to keep every SM's memory pipeline full, capped so tiny grids stay tiny; never
+  // fewer than the blocks that write the marginals
+  size_t want = a.aligned ? (a.cells / 4 + 1023) / 1024 : (a.cells + 255) / 256;
+  const size_t cap = (size_t)ctx->sm_count * 16;
+  if (want > cap) want = cap;
+  if (want < (size_t)pl.nb_res) want = pl.nb_res;
+  CKRC(launch_ex(ctx, (const void *)cge::finish_kernel, (unsigned)want, 256, 0, st, &a, true, 0));
+  if (ctx->peer_on) ctx->peer_step++;
+  ctx->launches += 1;
   CKRC(mark(ctx, 5, st));
-  const size_t cells = (size_t)pl.rows_local * N;
-  const bool aligned = (reinterpret_cast<uintptr_t>(posterior_dev) & 15u) == 0;
-  // enough CTAs to keep every SM's memory pipeline full, capped so tiny grids stay tiny
-  size_t want = aligned ? (cells / 4 + 1023) / 1024 : (cells + 255) / 256;
-  size_t cap = (size_t)ctx->sm_count * 16;
-  int blocks = (int)(want < 1 ? 1 : (want > cap ? cap : want));
-  if (aligned)
-    cge::scale_posterior_kernel<<<blocks, 256, 0, st>>>(posterior_dev, cells, ctx->partials.ptr);
-  else
-    cge::scale_posterior_scalar_kernel<<<blocks, 256, 0, st>>>(posterior_dev, cells,
-                                                               ctx->partials.ptr);
-  CK(cudaGetLastError());
-  ctx->launches += 2;
-  CKRC(mark(ctx, 6, st));
   if (ctx->prof_on && ctx->prof_step < ctx->prof_cap) ctx->prof_step++;
   return CGE_OK;
 }
 
 // ---------------------------------------------------------------------------------------
-// peer exchange over CUDA IPC (one process per GPU, one node)
+// peer exchange: CUDA IPC (one process per GPU, one node) or plain peer pointers (one process)
 // ---------------------------------------------------------------------------------------
 namespace {
 int peer_release(cge_context *ctx) {
   for (int r = 0; r < cge::kMaxPeers; ++r) {
     if (!ctx->peer_block[r]) continue;
-    if (r == ctx->peer_rank) cudaFree(ctx->peer_block[r]);
-    else cudaIpcCloseMemHandle(ctx->peer_block[r]);
+    if (r == ctx->peer_rank || !ctx->peer_on) cudaFree(ctx->peer_block[r]);  // (parked at slot 0 before connect)
+    else if (ctx->peer_ipc) cudaIpcCloseMemHandle(ctx->peer_block[r]);
     ctx->peer_block[r] = nullptr;
   }
   ctx->peer_on = false;
+  ctx->peer_ipc = false;
   ctx->peer_world = 1;
   ctx->peer_rank = 0;
   ctx->peer_cap = 0;
   ctx->peer_step = 0;
   return CGE_OK;
 }
-}  // namespace
 
-CGE_EXPORT int cge_peer_local_handle(cge_context *ctx, void *handle, int max_grid_size) {
-  CKRC(bind(ctx));
-  static_assert(sizeof(cudaIpcMemHandle_t) == CGE_IPC_HANDLE_BYTES, "IPC handle size");
-  if (!handle || max_grid_size < 1) return set_error(CGE_ERR_BAD_ARG, "peer_local_handle: bad argument");
+// this context's exchange block, parked at slot 0 until the rank is known
+int peer_alloc(cge_context *ctx, int max_grid_size) {
   CK(cudaStreamSynchronize(ctx->stream));
   peer_release(ctx);
   ctx->peer_cap = (((size_t)max_grid_size + 2) + 31) & ~(size_t)31;
@@ -651,9 +837,18 @@ CGE_EXPORT int cge_peer_local_handle(cge_context *ctx, void *handle, int max_gri
   CK(cudaMalloc(&block, bytes));
   CK(cudaMemset(block, 0, bytes));
   CK(cudaDeviceSynchronize());
-  ctx->peer_block[0] = block;  // parked at slot 0 until cge_peer_connect tells us our rank
+  ctx->peer_block[0] = block;
+  return CGE_OK;
+}
+}  // namespace
+
+CGE_EXPORT int cge_peer_local_handle(cge_context *ctx, void *handle, int max_grid_size) {
+  CKRC(bind(ctx));
+  static_assert(sizeof(cudaIpcMemHandle_t) == CGE_IPC_HANDLE_BYTES, "IPC handle size");
+  if (!handle || max_grid_size < 1) return set_error(CGE_ERR_BAD_ARG, "peer_local_handle: bad argument");
+  CKRC(peer_alloc(ctx, max_grid_size));
   cudaIpcMemHandle_t h;
-  CK(cudaIpcGetMemHandle(&h, block));
+  CK(cudaIpcGetMemHandle(&h, ctx->peer_block[0]));
   std::memcpy(handle, &h, sizeof h);
   return CGE_OK;
 }
@@ -668,6 +863,8 @@ CGE_EXPORT int cge_peer_connect(cge_context *ctx, int rank, int world, const voi
   ctx->peer_block[0] = nullptr;
   ctx->peer_rank = rank;
   ctx->peer_block[rank] = mine;
+  ctx->peer_on = true;   // (from here peer_release frees only slot `rank` and closes the others)
+  ctx->peer_ipc = true;
   const unsigned char *hb = static_cast<const unsigned char *>(handles);
   for (int r = 0; r < world; ++r) {
     if (r == rank) continue;
@@ -677,16 +874,14 @@ CGE_EXPORT int cge_peer_connect(cge_context *ctx, int rank, int world, const voi
     cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
     if (e != cudaSuccess) {
       cudaGetLastError();
-      ctx->peer_world = world;
       peer_release(ctx);
-      return set_error(CGE_ERR_CUDA, "cudaIpcOpenMemHandle for rank %d failed: %s", r,
+      return set_error(CGE_ERR_PEER, "cudaIpcOpenMemHandle for rank %d failed: %s", r,
                        cudaGetErrorString(e));
     }
     ctx->peer_block[r] = static_cast<unsigned char *>(p);
   }
   ctx->peer_world = world;
   ctx->peer_step = 0;
-  ctx->peer_on = true;
   return CGE_OK;
 }
 
@@ -694,6 +889,52 @@ CGE_EXPORT int cge_peer_disconnect(cge_context *ctx) {
   CKRC(bind(ctx));
   CK(cudaDeviceSynchronize());
   return peer_release(ctx);
+}
+
+// ---- same-process peers (cge_multi.cu): the contexts of one cge_multi exchange plain pointers
+extern "C" int cge_internal_peer_alloc(cge_context *ctx, int max_grid_size, unsigned char **block) {
+  CKRC(bind(ctx));
+  CKRC(peer_alloc(ctx, max_grid_size));
+  *block = ctx->peer_block[0];
+  return CGE_OK;
+}
+
+extern "C" int cge_internal_peer_attach(cge_context *ctx, int rank, int world,
+                                        unsigned char *const *blocks) {
+  CKRC(bind(ctx));
+  if (world < 2 || world > cge::kMaxPeers || rank < 0 || rank >= world || !ctx->peer_block[0])
+    return set_error(CGE_ERR_BAD_ARG, "peer_attach: bad argument");
+  unsigned char *mine = ctx->peer_block[0];
+  ctx->peer_block[0] = nullptr;
+  for (int r = 0; r < world; ++r) ctx->peer_block[r] = blocks[r];
+  if (ctx->peer_block[rank] != mine) return set_error(CGE_ERR_BAD_ARG, "peer_attach: block mismatch");
+  ctx->peer_rank = rank;
+  ctx->peer_world = world;
+  ctx->peer_step = 0;
+  ctx->peer_ipc = false;
+  ctx->peer_on = true;
+  return CGE_OK;
+}
+
+// the context stops owning its peers' blocks (their owners free them) before it is destroyed
+extern "C" int cge_internal_peer_detach(cge_context *ctx) {
+  CKRC(bind(ctx));
+  CK(cudaDeviceSynchronize());
+  for (int r = 0; r < cge::kMaxPeers; ++r)
+    if (r != ctx->peer_rank) ctx->peer_block[r] = nullptr;
+  return peer_release(ctx);
+}
+
+// all contexts of a cge_multi whose devices repeat share one stream (see cge_multi.cu)
+extern "C" int cge_internal_share_stream(cge_context *ctx, void *stream) {
+  CKRC(bind(ctx));
+  if (ctx->stream && ctx->own_stream) {
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaStreamDestroy(ctx->stream));
+  }
+  ctx->stream = (cudaStream_t)stream;
+  ctx->own_stream = false;
+  return CGE_OK;
 }
 
 CGE_EXPORT int cge_results(cge_context *ctx, double **results_dev, size_t *count) {
@@ -787,7 +1028,7 @@ CGE_EXPORT int cge_launch_count(cge_context *ctx, int *launches) {
 // fused synchronous entry: host or device buffers
 // ---------------------------------------------------------------------------------------
 CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const float *obs,
-                                  float *posterior, double *marg_mu, double *marg_sigma,
+                                  void *posterior, double *marg_mu, double *marg_sigma,
                                   double *expectations, cge_timing *timing) {
   CKRC(bind(ctx));
   int rb, re;
@@ -795,6 +1036,8 @@ CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const f
   if (!obs) return set_error(CGE_ERR_BAD_ARG, "obs is NULL");
   cudaStream_t st = ctx->stream;
   const size_t cells = (size_t)(re - rb) * p->grid_size;
+  const bool f64 = p->posterior_dtype == CGE_POSTERIOR_F64;
+  const size_t cell_bytes = f64 ? sizeof(double) : sizeof(float);
   ctx->timing = cge_timing{};
   const bool was_on = ctx->prof_on;
   if (timing && !was_on) {
@@ -810,8 +1053,8 @@ CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const f
     // stream synchronisation in cge_read_results)
     CKRC(ctx->host_obs.reserve(p->n_obs));
     std::memcpy(ctx->host_obs.ptr, obs, (size_t)p->n_obs * sizeof(float));
-    if (small && p->n_obs <= kZeroCopyObsMax) {
-      obs_dev = ctx->host_obs.ptr;  // mapped pinned memory: the kernel reads it in place
+    if (p->n_obs <= kZeroCopyObsMax && !(((p->n_obs + 3) & ~3) > cge::kObsSingleMax)) {
+      obs_dev = ctx->host_obs.ptr;  // mapped pinned memory: the kernels read it in place
     } else {
       CKRC(ctx->obs_in.reserve(p->n_obs));
       CK(cudaMemcpyAsync(ctx->obs_in.ptr, ctx->host_obs.ptr, (size_t)p->n_obs * sizeof(float),
@@ -820,18 +1063,23 @@ CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const f
     }
   }
   if (timing) CK(cudaEventRecord(ctx->ev[0], st));
-  float *post_dev = posterior;
+  void *post_dev = posterior;
   const bool post_to_host = posterior && !is_device_pointer(posterior);
   if (!posterior || post_to_host) {
-    CKRC(ctx->posterior.reserve(cells));
-    post_dev = ctx->posterior.ptr;
+    if (f64) {
+      CKRC(ctx->posterior64.reserve(cells));
+      post_dev = ctx->posterior64.ptr;
+    } else {
+      CKRC(ctx->posterior.reserve(cells));
+      post_dev = ctx->posterior.ptr;
+    }
   }
   int rc;
   if (small) {
     const bool host_out = !(marg_mu && is_device_pointer(marg_mu)) &&
                           !(marg_sigma && is_device_pointer(marg_sigma)) &&
                           !(expectations && is_device_pointer(expectations));
-    rc = small_grid_step(ctx, p, obs_dev, post_dev, st, host_out);
+    rc = small_grid_step(ctx, p, obs_dev, static_cast<float *>(post_dev), st, host_out);
   } else {
     rc = cge_likelihood_partials(ctx, p, obs_dev, post_dev, st);
     if (rc == CGE_OK) rc = cge_finalize(ctx, p, post_dev, st);
@@ -842,7 +1090,7 @@ CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const f
   }
   if (timing) CK(cudaEventRecord(ctx->ev[1], st));
   if (post_to_host)
-    CK(cudaMemcpyAsync(posterior, post_dev, cells * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(posterior, post_dev, cells * cell_bytes, cudaMemcpyDeviceToHost, st));
   rc = cge_read_results(ctx, p, expectations, marg_mu, marg_sigma, nullptr, st);
   if (timing) {
     cudaEventRecord(ctx->ev[2], st);
@@ -863,7 +1111,7 @@ CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const f
 
 // asynchronous fused entry: device buffers, whole grid, nothing waited for
 CGE_EXPORT int cge_grid_posterior_async(cge_context *ctx, const cge_params *p, const float *obs_dev,
-                                        float *posterior_dev, void *stream) {
+                                        void *posterior_dev, void *stream) {
   CKRC(bind(ctx));
   int rb, re;
   CKRC(check_params(p, &rb, &re));
@@ -873,16 +1121,18 @@ CGE_EXPORT int cge_grid_posterior_async(cge_context *ctx, const cge_params *p, c
   if (!obs_dev || !posterior_dev || !is_device_pointer(obs_dev) || !is_device_pointer(posterior_dev))
     return set_error(CGE_ERR_BAD_ARG, "cge_grid_posterior_async needs device pointers");
   cudaStream_t st = (cudaStream_t)stream;
-  if (small_grid_eligible(ctx, p, rb, re)) return small_grid_step(ctx, p, obs_dev, posterior_dev, st, false);
+  if (small_grid_eligible(ctx, p, rb, re))
+    return small_grid_step(ctx, p, obs_dev, static_cast<float *>(posterior_dev), st, false);
   CKRC(cge_likelihood_partials(ctx, p, obs_dev, posterior_dev, st));
   return cge_finalize(ctx, p, posterior_dev, st);
 }
 
 // posterior kept by the context when cge_grid_posterior was called with posterior == NULL or a
-// host pointer
-CGE_EXPORT int cge_posterior_dev(cge_context *ctx, float **posterior_dev, size_t *count) {
+// host pointer (float32 or float64 according to that call's posterior_dtype)
+CGE_EXPORT int cge_posterior_dev(cge_context *ctx, void **posterior_dev, size_t *count) {
   if (!ctx) return set_error(CGE_ERR_BAD_ARG, "context is NULL");
-  if (posterior_dev) *posterior_dev = ctx->posterior.ptr;
+  if (posterior_dev)
+    *posterior_dev = ctx->plan.post_f64 ? (void *)ctx->posterior64.ptr : (void *)ctx->posterior.ptr;
   if (count) *count = ctx->plan.valid ? (size_t)ctx->plan.rows_local * ctx->plan.N : 0;
   return CGE_OK;
 }
@@ -1057,6 +1307,17 @@ extern "C" int cge_internal_stream(cge_context *ctx, void **stream, int *sm_coun
   return CGE_OK;
 }
 extern "C" int cge_internal_error(int code, const char *msg) { return set_error(code, "%s", msg); }
+#ifdef CGE_DEBUG_TIMES
+// diagnostic build only: per-CTA {start ns, end ns, smid, units} of the last likelihood launch
+CGE_EXPORT int cge_debug_times(cge_context *ctx, unsigned long long *out, int max_ctas, int *nctas) {
+  CKRC(bind(ctx));
+  CK(cudaDeviceSynchronize());
+  const int n = ctx->plan.nctas < max_ctas ? ctx->plan.nctas : max_ctas;
+  CK(cudaMemcpy(out, ctx->debug_times.ptr, (size_t)4 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  *nctas = n;
+  return CGE_OK;
+}
+#endif
 
 // ---------------------------------------------------------------------------------------
 // pipe-peak micro-benchmarks

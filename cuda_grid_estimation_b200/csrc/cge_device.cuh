@@ -151,6 +151,20 @@ __device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_s
 }
 
 // ---------------------------------------------------------------------------------------
+// programmatic dependent launch (griddepcontrol): the kernels of a step are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so kernel k+1 is set up and made resident
+// while kernel k drains.  pdl_wait() returns once the preceding kernel of the stream has
+// completed and its writes are visible (a no-op for an ordinary launch); it comes before the
+// first read of anything an earlier kernel wrote -- and before the first write of anything an
+// earlier kernel still reads.  pdl_trigger() lets the next kernel's blocks start arriving as
+// soon as every block of this one has been scheduled.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------------------
 // global stores / loads for streamed data
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void st_stream_f4(float *p, float a, float b, float c, float d) {
@@ -161,6 +175,17 @@ __device__ __forceinline__ void st_stream_f4(float *p, float a, float b, float c
 
 __device__ __forceinline__ void st_stream_f1(float *p, float a) {
   asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
+}
+
+// the same stores with the default cache policy: a posterior shard that fits in L2 is read back
+// by the scale pass straight from there
+__device__ __forceinline__ void st_keep_f4(float *p, float a, float b, float c, float d) {
+  asm volatile("st.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d)
+               : "memory");
+}
+
+__device__ __forceinline__ void st_keep_f1(float *p, float a) {
+  asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
 // ---------------------------------------------------------------------------------------

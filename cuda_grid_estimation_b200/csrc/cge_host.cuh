@@ -1,6 +1,6 @@
 // cge_host.cuh -- host-side pieces shared by the translation units of libcge.so: error
-// reporting, the launch plan, and the launchers of the templated kernels.  The likelihood kernel
-// instantiations live in their own .cu files (cge_launch_*.cu) so nvcc compiles them in parallel.
+// reporting, the launch plan, and the kernel choosers.  The likelihood kernel instantiations live
+// in their own .cu files (cge_launch_*.cu) so nvcc compiles them in parallel.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -26,67 +26,51 @@ int set_error(int code, const char *fmt, ...);
     if (rc_ != CGE_OK) return rc_; \
   } while (0)
 
-// tile shape and grid of one likelihood launch (made by make_plan in cge_api.cu)
+// shape of one likelihood launch (made by make_plan in cge_api.cu)
 struct Plan {
   bool valid = false;
-  int N = 0, n = 0, n_pad = 0, mode = 0, variant = 0;
+  int N = 0, n = 0, n_pad = 0, mode = 0, variant = 0, post_f64 = 0;
   int row_begin = 0, row_end = 0, rows_local = 0;
-  int wm = 1, wn = 8;
-  int bands = 0, row_tiles = 0, tile_rows = 0;
-  int ncw = 0, ncolparts = 0;
-  int nb_col = 0, nb_row = 0;
-  bool vec4 = false;
-  bool cluster = false;  // small-grid path: launch the grid as one thread-block cluster
-  size_t smem = 0;
+  int kcols = 4;           // columns per thread: a warp's strip is 32 * kcols columns
+  int ncw = 0;             // strips per row
+  int groups = 0;          // row groups (kRM rows) that cover the shard's rows
+  int chunk = 1;           // row groups per claimed item
+  int items_per_strip = 0;
+  int fixed_bits = 0;      // 58 - ceil(log2(addends per column))
+  int nctas = 0;           // P: persistent CTAs (resident slots of the device)
+  int nb_col = 0, nb_row = 0, nb_res = 0;
+  bool vec4 = false, keep_l2 = false, streamed = false, reorder = false;
+  bool cluster = false;    // small-grid path: launch the grid as one thread-block cluster
+  size_t smem = 0;         // dynamic shared memory of the likelihood kernel
 };
 
-// the default product policies (cge_launch_product.cu, cge_launch_small.cu)
-using DefaultFine = cge::ProductPaired<4, 4, true, true>;     // degree-2 polynomial, umax <= 0.011
-using DefaultMid = cge::ProductPaired<4, 4, true, true, 3>;   // degree-3 polynomial, umax <= 0.05
-using DefaultCoarse = cge::ProductHybrid<2, 2, false, 1>;
+// one instantiation of the likelihood (or small-grid) kernel: every one takes a single by-value
+// argument struct, so they all launch through cudaLaunchKernelExC
+struct KernelChoice {
+  const void *fn = nullptr;
+  int threads = 256;
+  int smem_bytes = 0;    // per-thread bytes behind the observation stage
+  int kcols = 4;
+};
+
+// the default product policies
+using DefaultFine = cge::ProductPaired<2>;    // degree-2 polynomial, band umax <= 0.011
+using DefaultMid = cge::ProductPaired<3>;     // degree-3 polynomial, band umax <= 0.05
+using DefaultCoarse = cge::ProductHybrid;
 constexpr int kDefaultMinB = 3;  // <= 80 registers: three 256-thread CTAs (24 warps) per SM
 
-// static + dynamic shared memory beyond 48 KB needs the opt-in attribute; the kernels have up to
-// ~17 KB static (small_grid_kernel), so opt in above 24 KB of dynamic and skip the call below it
-constexpr size_t kDefaultSmemLimit = 24 * 1024;
-
-// dynamic shared memory of a likelihood launch: mbarriers + observation stage (+ column sums)
-template <class Policy, int WM, int WN>
-inline size_t like_smem(const Plan &pl) {
-  return pl.smem + 16 + (Policy::kColSmem ? (size_t)WM * WN * 32 * Policy::kCols * 8 : 0);
+template <class A, class B, class C>
+constexpr int smem_bytes3() {
+  constexpr int a = cge::policy_smem_bytes<A>(), b = cge::policy_smem_bytes<B>(),
+                c = cge::policy_smem_bytes<C>();
+  return a > b ? (a > c ? a : c) : (b > c ? b : c);
 }
 
-template <class Policy, int WM, int WN, int MINB = 1>
-int launch_like_shape(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
-  dim3 grid(pl.bands, pl.row_tiles), block(WM * WN * 32);
-  const size_t smem = like_smem<Policy, WM, WN>(pl);
-  if (pl.vec4) {
-    auto k = cge::grid_likelihood_kernel<Policy, WM, WN, true, MINB>;
-    if (smem > kDefaultSmemLimit)  // only stages of thousands of observations get there
-      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, block, smem, st>>>(args);
-  } else {
-    auto k = cge::grid_likelihood_kernel<Policy, WM, WN, false, MINB>;
-    if (smem > kDefaultSmemLimit)  // only stages of thousands of observations get there
-      CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k<<<grid, block, smem, st>>>(args);
-  }
-  CK(cudaGetLastError());
-  return CGE_OK;
-}
-
-template <class Policy, int MINB = 1>
-int launch_like(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
-  if (pl.wm == 1) return launch_like_shape<Policy, 1, 8, MINB>(pl, args, st);
-  if (pl.wm == 2) return launch_like_shape<Policy, 2, 4, MINB>(pl, args, st);
-  if (pl.wm == 4) return launch_like_shape<Policy, 4, 2, MINB>(pl, args, st);
-  return launch_like_shape<Policy, 8, 1, MINB>(pl, args, st);
-}
-
-// launchers defined in cge_launch_product.cu / cge_launch_logspace.cu / cge_launch_small.cu
-int launch_product(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st);
-int launch_logspace(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st);
-int launch_small_product(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st);
-int launch_small_logspace(const Plan &pl, const cge::SmallArgs &a, cudaStream_t st);
+// choosers defined in cge_launch_product.cu / cge_launch_logspace.cu / cge_launch_small.cu;
+// they read pl.variant, pl.streamed (and pl.cluster for the small-grid kernels)
+int choose_product(const Plan &pl, KernelChoice *out);
+int choose_logspace(const Plan &pl, KernelChoice *out);
+int choose_small_product(const Plan &pl, KernelChoice *out);
+int choose_small_logspace(const Plan &pl, KernelChoice *out);
 
 }  // namespace cge_host

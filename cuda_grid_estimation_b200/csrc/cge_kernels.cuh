@@ -6,20 +6,27 @@
 //   K6 thrust reduce+transform (inc/cuda_functions.h:155-158), K7 marginalizeKernel
 //   (inc/kernels.h:208-259), K8 computeExpectationsCuda (inc/cuda_functions.h:185-221).
 //
-// Here K1-K5 are ONE fused kernel (grid_likelihood_kernel) that never materialises the
-// N*N*n tensors, and K6-K8 are a fixed-order partial reduction (two small kernels) plus one
-// HBM-bound in-place scale pass.  A step is 5 launches: setup, likelihood, fold, results, scale.
+// A step is THREE launches chained by programmatic dependent launch (one for grids up to 256^2):
+//   1. grid_likelihood_kernel  K1-K5 fused, persistent: one CTA per resident slot claims
+//                              (column band, row chunk) items from per-band counters until the
+//                              grid is done.  Each CTA derives the scale statistics and its own
+//                              range values and column coefficients itself (no set-up launch, no
+//                              tables in HBM), writes the unnormalised cells, fixed-order partial
+//                              row sums, and column sums accumulated in exact fixed point.
+//   2. fold_publish_kernel     K6/K7 fold of the partial sums -> {Z, sum mu*rowsum, colsum[N]};
+//                              publishes the vector to the peer GPUs (release flag).
+//   3. finish_kernel           waits for the peers' vectors and adds them in rank order (when
+//                              sharded), K7/K8 marginals and expectations, and the in-place
+//                              posterior *= 1/Z (HBM-bound).
 //
 // Data layout in HBM
 //   posterior  float32 [rows_local][N], sigma fastest (the reference layout, kernels.h:92)
-//   mu, sigma  float32 [N]      range tables, bit-identical to the reference's linspaceKernel
-//   ad         float64 [N]      a_j  = -0.5*log2(e)/sigma_j^2
-//   cd0        float64 [N]      c0_j = -log2(sigma_j*sqrt(2*pi))
-//   obs_pad    float32 [n_pad]  observations, zero-padded to a multiple of 4, 16 B aligned
-//   rowpart    float64 [rows_local][ncw]   per (row, warp column strip) partial row sums
-//   colpart    float64 [ncolparts][N]      per (row tile x warp row) partial column sums
-//   partials   float64 [N+2]    {Z, sum_i mu_i*rowsum_i, colsum[0..N)}  <- the all-reduce payload
+//   rowpart    float64 [rows_local][ncw]    per (row, warp column strip) partial row sums
+//   colacc     int64   [N]      column sums in per-column fixed point (exact, order-independent)
+//   partials   float64 [N+2]    {Z, sum_i mu_i*rowsum_i, colsum[0..N)}  <- the exchange payload
 //   results    float64 [4+2N]   {E[mu], E[sigma], Z, 1/Z}, marg_sigma[N], marg_mu[N]
+// Nothing of size N*N*n exists, and no mu / sigma / coefficient table either: every value is a
+// function of (index, range) evaluated where it is used with the reference's float32 formula.
 #pragma once
 #include "cge_device.cuh"
 
@@ -30,9 +37,9 @@ namespace cge {
 // 166 bits (1e-50 relative to the peak) below it before a cell flushes to zero.
 constexpr double kPeakLog2 = 40.0;
 
-constexpr int kRM = 4;            // register patch rows (mu) per thread for the product policies;
-                                  // also the row alignment of every tile (Policy::kRows divides it)
-constexpr int kRN = 4;            // columns (sigma) per thread and float4 store; a policy owns
+constexpr int kRM = 4;            // register patch rows (mu) per thread; also the row alignment of
+                                  // every unit of work
+constexpr int kRN = 4;            // columns (sigma) per float4 store; a policy owns
                                   // Policy::kCols = 4 or 8 columns = 1 or 2 such groups
 constexpr int kGroupCols = 32 * kRN;  // 128 columns: one float4 per lane across a warp
 
@@ -43,6 +50,8 @@ __device__ __forceinline__ int patch_col(int jbase, int cidx) {
 }
 constexpr int kObsChunk = 8192;   // floats per streamed observation chunk (32 KB)
 constexpr int kObsSingleMax = 16384;  // up to this many (padded) observations live in smem at once
+constexpr int kReorderMax = 1024;     // product mode: observations are re-ordered up to this count
+constexpr int kMaxPeers = 16;         // GPUs whose partial vectors one finish kernel can sum
 
 struct ScaleInfo {
   double log2s;  // product mode: log2 of the per-factor rescale s
@@ -51,90 +60,133 @@ struct ScaleInfo {
   double xbar;
   double ss;
   double smin;
-  double mu_c;   // log-space: grid value nearest the sample mean; obs_pad holds x_k - mu_c
+  double mu_c;   // log-space: grid value nearest the sample mean; the stage holds x_k - mu_c
   double s_c;    // log-space: sum_k (x_k - mu_c)^2
   double umax;   // bound on |t_(i+1,j,k) - t_(i,j,k)| over adjacent mu rows, whole grid
   double ustep;  // the same bound per unit |a_j|: umax of a column band = max |a_j| in it * ustep
 };
-
-struct LikeArgs {
-  const float *obs_pad;
-  const float *mu;
-  const double *ad;
-  const double *cd0;
-  const ScaleInfo *scale;
-  // optional prior (NULL = flat, the reference's case): separable factors indexed by the global
-  // mu row / sigma column, and/or a full table laid out like this shard of the posterior
-  const float *prior_mu;
-  const float *prior_sigma;
-  const float *prior_full;
-  float *post;      // shard base (row `row_begin` at offset 0)
-  double *rowpart;  // [rows_local][ncw]
-  double *colpart;  // [ncolparts][N]
-  int n, n_pad, N;  // n observations; n_pad staged floats (multiple of 4)
-  int row_begin, row_end;
-  int tile_rows;    // rows per CTA tile, multiple of WM*Policy::kRows and of kRM
-  int ncw;          // column strips per row: ceil(N / (32 * Policy::kCols))
-};
-
-// per-thread column coefficients, fetched before the policy is known (dual kernel)
-template <int KC>
-struct ColumnCoefs {
-  double a[KC], c0[KC];
-  __device__ __forceinline__ void load(const LikeArgs &g, int j0) {
-#pragma unroll
-    for (int cidx = 0; cidx < KC; ++cidx) {
-      const int j = patch_col(j0, cidx);
-      a[cidx] = j < g.N ? g.ad[j] : 0.0;
-      c0[cidx] = j < g.N ? g.cd0[j] : 0.0;
-    }
-  }
-};
-
-template <int WN>
-__device__ __forceinline__ int first_column(int kcols) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  return (blockIdx.x * WN + warp % WN) * (32 * kcols) + lane * kRN;
-}
-
-// ---------------------------------------------------------------------------------------
-// setup_kernel: K1 twice + the per-sigma coefficients (every block), and in block 0 the
-// observation staging and the global rescale.
-//
-// The rescale only positions the float32 dynamic range; it cancels in the posterior.  It needs
-// max_ij log2 L_ij = max_j (a_j * S_min + n*c0_j) with S_min = min_i [SS + n (xbar - mu_i)^2].
-// S(mu) is a parabola and f(sigma) = a(sigma) S + n c0(sigma) is unimodal (peak at
-// sigma^2 = S/n), so the grid maxima sit next to the continuous ones: a handful of candidate
-// grid points (the neighbours of the continuous optimum plus both ends) is exact, O(1).
-// ---------------------------------------------------------------------------------------
-__device__ __forceinline__ double coef_a(double sd) { return -0.5 * 1.4426950408889634074 / (sd * sd); }
-__device__ __forceinline__ double coef_c0(double sd) { return -log2(sd * 2.5066282746310005024); }
 
 struct RangeArgs {
   int N;
   float mu0, mu1, sg0, sg1;
 };
 
-// one grid point of the four tables; idx in [N, N+3) pads mu for the kernels' float4 row loads
-__device__ __forceinline__ void setup_point(int idx, const RangeArgs &r, float *__restrict__ mu,
-                                            float *__restrict__ sigma, double *__restrict__ ad,
-                                            double *__restrict__ cd0) {
-  if (idx >= r.N && idx < r.N + 3) mu[idx] = range_value(r.N - 1, r.N, r.mu0, r.mu1);
-  if (idx < r.N) {
-    mu[idx] = range_value(idx, r.N, r.mu0, r.mu1);
-    const float s = range_value(idx, r.N, r.sg0, r.sg1);
-    sigma[idx] = s;
-    ad[idx] = coef_a((double)s);
-    cd0[idx] = coef_c0((double)s);
-  }
+// Work decomposition of the likelihood kernel.  A GROUP is kRM rows of one warp-wide column STRIP
+// (32 * kCols columns); an ITEM is `chunk` consecutive groups of one strip.  Items are not
+// assigned, they are CLAIMED, and the worker is the WARP, not the CTA: every strip has a counter,
+// a warp starts on its home strip (the warps of the grid are spread evenly over the strips), takes
+// items from that strip's counter until it runs out and then moves on to the next strip.  After
+// the set-up the warps of a CTA never synchronise again.  Two measured reasons (B200, 16384^2 x 50):
+//   * the warp scheduler does not share an SM fairly between resident CTAs -- with equal static
+//     shares some CTAs finished in 0.95 ms and others in 1.82 ms, the tail running at a third of
+//     the occupancy -- so the balance has to be dynamic;
+//   * warps that move in lock step all reach the epilogue (stores, shuffles, float64) together and
+//     all return to the MUFU-bound loop together; independent warps drift apart and the epilogue
+//     of one hides behind the exponentials of the others.
+//
+// Results must not depend on who computed what.  Cells and partial row sums go to fixed places.
+// Column sums cross items, so they are accumulated EXACTLY: every thread's 4-row float32 sum is
+// scaled by a power of two chosen per column -- from the closed-form largest cell of that column,
+// colmax_j = 2^(a_j S_min + n c0_j + shift), so that the shard's total stays below 2^62 -- rounded
+// to an integer and added in int64: per CTA in shared memory, then once per band with integer
+// atomics into colacc[N].  Integer addition is associative: the sums are bit-identical whatever the
+// order, with a resolution of colmax_j * 2^-(58 - log2(rows/4)), i.e. ~2^-46 relative to the
+// column's own largest cell at 16384 rows (finer than the float64 partial sums it replaces for the
+// columns that matter, and scaled per column, so the far tails keep their relative precision).
+struct LikeArgs {
+  // Observations: fused set-up (scale_in == NULL): the caller's n floats, any alignment, device
+  // or mapped host memory; every CTA stages them and derives the statistics itself.  Streamed
+  // (n_pad > kObsSingleMax): the padded (centred) copy setup_kernel made, with its statistics.
+  const float *obs;
+  const ScaleInfo *scale_in;
+  ScaleInfo *scale_out;  // fused set-up: CTA 0 leaves the statistics here (fold kernel, cge_scale_info)
+  RangeArgs range;
+  int centred;   // stage x_k - mu_c (log-space tiled kernels)
+  int reorder;   // product mode: stage the observations in a range-balanced order (setup_scale)
+  // optional prior (NULL = flat, the reference's case): separable factors indexed by the global
+  // mu row / sigma column, and/or a full table laid out like this shard of the posterior
+  const float *prior_mu;
+  const float *prior_sigma;
+  const float *prior_full;
+  float prior_log2max;  // log2 of the largest |prior factor product| (0 for the flat prior)
+  float *post;      // shard base (row `row_begin` at offset 0)
+  double *rowpart;  // [rows_local][ncw]
+  unsigned long long *colacc;  // [N] fixed-point column sums (zero at launch; the fold kernel clears them)
+  int *strip_next;  // [ncw] next unclaimed item of each strip (zero at launch; the fold kernel clears them)
+  int n, n_pad, N;  // n observations; n_pad staged floats (multiple of 4)
+  int row_begin, row_end;
+  int groups;          // row groups that cover the shard's rows
+  int chunk;           // row groups per item
+  int items_per_strip; // ceil(groups / chunk) (streamed: ceil(groups / (8 * chunk)), claimed per CTA)
+  int fixed_bits;      // 58 - ceil(log2(addends per column)): see col_fixed_shift
+  int ncw;             // column strips per row: ceil(N / (32 * Policy::kCols))
+  int vec4;            // N % 4 == 0 and the shard base is 16-byte aligned: float4 stores
+  int keep_l2;         // the shard fits in L2: store with the default policy instead of .cs
+#ifdef CGE_DEBUG_TIMES
+  unsigned long long *debug;  // per CTA: {start ns, end ns, smid, items}
+#endif
+};
+
+__device__ __forceinline__ double coef_a(double sd) { return -0.5 * 1.4426950408889634074 / (sd * sd); }
+__device__ __forceinline__ double coef_c0(double sd) { return -log2(sd * 2.5066282746310005024); }
+
+// Fixed-point exponent of column j: its 4-row sums are accumulated as rint(x * 2^s).  The cells of
+// the column are at most 2^e, e = ceil(log2 colmax_j + log2 prior_max) + 1 (one binade of slack
+// for the float32 rounding of the product); a 4-row sum is below 2^(e+2), and with at most
+// 2^(58 - fixed_bits) addends the int64 total stays below 2^62 for s = fixed_bits - e - 2.  The
+// clamp keeps 2^s a float32 normal: columns whose largest cell is below ~2^-70 keep an absolute
+// resolution of 2^-120 (their cells flush to zero at 2^-126 anyway).  Evaluated with identical
+// arithmetic by the likelihood kernel (to scale) and the fold kernel (to scale back).
+__device__ __forceinline__ int col_fixed_shift(double a, double c0, const ScaleInfo &sc, int n,
+                                               float prior_log2max, int fixed_bits) {
+  // (explicit roundings: the two kernels must get the same bits whatever the compiler contracts)
+  const double t = __dadd_rn(__dadd_rn(__fma_rn(a, sc.smin, __dmul_rn((double)n, c0)), sc.shift),
+                             (double)prior_log2max);
+  const int e = t > -2000.0 ? (t < 2000.0 ? (int)ceil(t) + 1 : 2001) : -2000;  // (NaN -> -2000)
+  return max(-120, min(120, fixed_bits - e - 2));
 }
 
-// Block-wide (every thread of the block must call it, every thread gets the result): stage the
-// observations -- zero-padded to n_pad, raw or centred (x_k - mu_c) -- into `stage` (global or
-// shared) and derive the scale statistics.  `scratch` holds >= 32 doubles of shared memory.
+// per-thread column coefficients in float64: a_j = -0.5*log2(e)/sigma_j^2, c0_j = -log2(sigma_j*sqrt(2 pi)),
+// sigma_j from the reference's float32 range formula
+template <int KC>
+struct ColumnCoefs {
+  double a[KC], c0[KC];
+  __device__ __forceinline__ void compute(const RangeArgs &r, int j0) {
+#pragma unroll
+    for (int cidx = 0; cidx < KC; ++cidx) {
+      const int j = patch_col(j0, cidx);
+      const double sd = (double)range_value(min(j, r.N - 1), r.N, r.sg0, r.sg1);
+      a[cidx] = j < r.N ? coef_a(sd) : 0.0;
+      c0[cidx] = j < r.N ? coef_c0(sd) : 0.0;
+    }
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// setup_scale: block-wide (every thread of the block calls it, every thread gets the result).
+// Stages the observations into `stage` (shared, or global for the streamed path) -- zero-padded
+// to n_pad, raw or centred (x_k - mu_c), optionally re-ordered -- and derives the scale statistics.
+//
+// The rescale only positions the float32 dynamic range; it cancels in the posterior.  It needs
+// max_ij log2 L_ij = max_j (a_j * S_min + n*c0_j) with S_min = min_i [SS + n (xbar - mu_i)^2].
+// S(mu) is a parabola and f(sigma) = a(sigma) S + n c0(sigma) is unimodal (peak at
+// sigma^2 = S/n), so the grid maxima sit next to the continuous ones: a handful of candidate
+// grid points (the neighbours of the continuous optimum plus both ends) is exact, O(1).
+//
+// Re-ordering (product mode, n <= kReorderMax, `sorted` = n floats of shared scratch): the global
+// rescale pins the FINAL product of the peak cell at 2^40, but a float32 running product also has
+// to stay in range on the way there, and that depends on the order of the factors -- ascending
+// input at n = 250 overflows 2^127 on the README grid, input sorted by |x - mean| at n = 300
+// flushes live cells through 2^-126 (the reference multiplies in float64 and does not care).  The
+// stage therefore holds the observations sorted and then visited with a golden-ratio stride,
+// rank(p) = p*s mod n, s ~ 0.618 n coprime to n: every prefix is spread evenly over the sample's
+// quantiles, so for every cell the running product follows its own geometric mean to within a few
+// binades whatever order the caller supplied (a product does not depend on the order of its
+// factors, so this changes rounding only).  `scratch` holds >= 32 doubles of shared memory.
+// ---------------------------------------------------------------------------------------
 __device__ __forceinline__ ScaleInfo setup_scale(const RangeArgs &r, const float *__restrict__ obs,
                                                  float *stage, int n, int n_pad, int centred,
-                                                 double *scratch) {
+                                                 float *sorted, double *scratch) {
   const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31;
   const int N = r.N;
   const float mu0 = r.mu0, mu1 = r.mu1, sg0 = r.sg0, sg1 = r.sg1;
@@ -169,9 +221,30 @@ __device__ __forceinline__ ScaleInfo setup_scale(const RangeArgs &r, const float
     const double d = (double)stage[k] - xbar;
     q += d * d;
   }
-  const double ss = block_sum(q, scratch);
+  const double ss = block_sum(q, scratch);  // (its barriers also make the whole stage visible)
   if (centred)
     for (int k = tid; k < n; k += nt) stage[k] = (float)((double)stage[k] - mu_c);
+  if (sorted != nullptr && n >= 3) {
+    __syncthreads();  // (the centred values, if any, are visible to every thread)
+    // rank by counting (ties broken by index): O(n^2 / threads), no barrier inside
+    for (int k = tid; k < n; k += nt) {
+      const float x = stage[k];
+      int rank = 0;
+      for (int m = 0; m < n; ++m) {
+        const float y = stage[m];
+        rank += (y < x || (y == x && m < k)) ? 1 : 0;
+      }
+      sorted[min(rank, n - 1)] = x;  // (NaN input collides here; Z is NaN then anyway)
+    }
+    int stride = (int)(0.6180339887498949 * (double)n + 0.5);
+    for (;; --stride) {  // largest stride <= 0.618 n coprime to n (1 always is)
+      int a = n, b = stride;
+      while (b) { const int t = a % b; a = b; b = t; }
+      if (a == 1) break;
+    }
+    __syncthreads();
+    for (int p = tid; p < n; p += nt) stage[p] = sorted[(int)(((long long)p * stride) % n)];
+  }
 
   // candidate grid indices around a continuous optimum `pos`: both ends + 4 neighbours;
   // lane t < 6 of every warp evaluates candidate t, the other lanes idle through the shuffles
@@ -221,25 +294,30 @@ __device__ __forceinline__ ScaleInfo setup_scale(const RangeArgs &r, const float
     out.ustep = dmu * 2.0 * reach;
     out.umax = fabs(coef_a(sdmin)) * out.ustep;
   }
+  __syncthreads();  // the stage is complete for every thread of the block
   return out;
 }
 
 // ---------------------------------------------------------------------------------------
 // Arithmetic policies of the fused likelihood kernel.  Each owns the per-thread state for a
-// kRM x kRN patch of cells and consumes one observation at a time.
+// kRM x kCols patch of cells and consumes the observations of one row group.
+//   kSmemDoubles  float64 values per thread the policy keeps in shared memory (element k of
+//                 thread t at own[k * NT]; `own` is already offset by the thread index)
 // ---------------------------------------------------------------------------------------
 template <class Policy>
 __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs, int count,
                                                    const float (&mu)[Policy::kRows]);
 
-// float32 product path: per pdf-eval one FFMA (exponent), one MUFU.EX2, one FMUL (running
-// product); the subtract and square are shared by the kRN columns of a row.
+// float32 product path, every exponential on MUFU.EX2 (the MUFU-roofline case): per pdf-eval one
+// FFMA (exponent), one MUFU.EX2, one FMUL (running product); the subtract and square are shared
+// by the kRN columns of a row.
 //   factor_k = 2^(a_j*(x_k-mu_i)^2 + c_j),  c_j = c0_j + log2 s   (constants FMA-folded)
 struct ProductF32 {
+  static constexpr double kUmax = 1e300;
   static constexpr bool kColSmem = false;
   static constexpr int kRows = kRM;
   static constexpr int kCols = 4;
-  static constexpr int kObsStride = 1;  // floats of shared memory per observation
+  static constexpr int kSmemDoubles = 0;
   static __device__ __forceinline__ void consume(ProductF32 &pol, const float *xs, int count,
                                                  const float (&mu)[kRM]) {
     consume_scalar_obs(pol, xs, count, mu);
@@ -247,8 +325,9 @@ struct ProductF32 {
   float a[kRN], c[kRN];
   float p[kRM][kRN];
 
+  template <int NT>
   __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
-                                               const ColumnCoefs<kCols> &cf) {
+                                               const ColumnCoefs<kCols> &cf, double *) {
 #pragma unroll
     for (int cidx = 0; cidx < kRN; ++cidx) {
       const bool ok = j0 + cidx < g.N;
@@ -275,7 +354,8 @@ struct ProductF32 {
       for (int cidx = 0; cidx < kRN; ++cidx)
         p[r][cidx] *= ex2_approx(fmaf(dd[r], a[cidx], c[cidx]));
   }
-  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx) const {
+  template <int NT>
+  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx, const double *) const {
     return p[r][cidx];
   }
 };
@@ -287,11 +367,11 @@ struct ProductF32 {
 // cell after 10^4 observations) and widened once per (row, observation); 8 columns per thread
 // amortise that widening over 8 evaluations.
 struct LogSpaceF64 {
+  static constexpr double kUmax = 1e300;
   static constexpr bool kColSmem = false;
-  static constexpr int kRows = 4;   // 4 x 8 patch (a 2 x 8 patch measured 4 % slower: the bound is
-                                    // the FP64 pipe's operand bandwidth, not occupancy)
+  static constexpr int kRows = 4;
   static constexpr int kCols = 8;
-  static constexpr int kObsStride = 1;
+  static constexpr int kSmemDoubles = kCols;  // n*c0_j + shift of the thread's columns
   static __device__ __forceinline__ void consume(LogSpaceF64 &pol, const float *xs, int count,
                                                  const float (&mu)[kRows]) {
     const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
@@ -308,15 +388,15 @@ struct LogSpaceF64 {
   }
   double a[kCols];
   double acc[kRows][kCols];
-  double shift_;
-  int jbase_;
 
-  __device__ __forceinline__ void load_columns(const LikeArgs &, int jbase, const ScaleInfo &sc,
-                                               const ColumnCoefs<kCols> &cf) {
-    jbase_ = jbase;
-    shift_ = sc.shift;
+  template <int NT>
+  __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
+                                               const ColumnCoefs<kCols> &cf, double *own) {
 #pragma unroll
-    for (int cidx = 0; cidx < kCols; ++cidx) a[cidx] = cf.a[cidx];
+    for (int cidx = 0; cidx < kCols; ++cidx) {
+      a[cidx] = cf.a[cidx];
+      own[cidx * NT] = patch_col(j0, cidx) < g.N ? (double)g.n * cf.c0[cidx] + sc.shift : 0.0;
+    }
   }
   __device__ __forceinline__ void begin_rows() {
 #pragma unroll
@@ -336,11 +416,9 @@ struct LogSpaceF64 {
 #pragma unroll
       for (int cidx = 0; cidx < kCols; ++cidx) acc[r][cidx] = fma(dd[r], a[cidx], acc[r][cidx]);
   }
-  // n*c0_j + shift is only needed here, once per cell: read c0_j back instead of holding it
-  __device__ __forceinline__ float value(const LikeArgs &g, int r, int cidx) const {
-    const int j = patch_col(jbase_, cidx);
-    const double c = j < g.N ? (double)g.n * g.cd0[j] + shift_ : 0.0;
-    return ex2_approx((float)(acc[r][cidx] + c));
+  template <int NT>
+  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx, const double *own) const {
+    return ex2_approx((float)(acc[r][cidx] + own[cidx * NT]));
   }
 };
 
@@ -351,7 +429,7 @@ struct LogSpaceF64 {
 // centring: with mu_c the grid value nearest the sample mean, x' = x - mu_c, mu' = mu_i - mu_c,
 //   (x_k - mu_i)^2 = (x_k - mu_c)^2 + e_ik,    e_ik = mu'_i (mu'_i - 2 x'_k)      (exact identity)
 //   log2 L_ij = [a_j S_c + n c0_j] + sum_k a_j e_ik,        S_c = sum_k (x_k - mu_c)^2
-// The bracket is float64, once per cell (S_c from setup_kernel).  The per-eval terms a_j e_ik are
+// The bracket is float64, once per column (S_c from the set-up).  The per-eval terms a_j e_ik are
 // small wherever the posterior is not negligible (|mu'| <= ~sqrt(66 / (n |a|)) for cells within
 // 1e-20 of the peak), so float32 tile sums (TILE = 256 observations) folded into float64 lose
 // ~7e-6 relative on a cell at n = 10^4 -- a plain float32 sum of a_j (x - mu)^2 would lose 1e-4.
@@ -360,26 +438,28 @@ struct LogSpaceF64 {
 // ---------------------------------------------------------------------------------------
 template <int TILE = 256>
 struct LogSpaceTiled {
-  static constexpr double kUmax = 1.0 / 0.0;
+  static constexpr double kUmax = 1e300;
   static constexpr bool kColSmem = false;
   static constexpr int kRows = 4;
   static constexpr int kCols = 8;
-  static constexpr int kObsStride = 1;
+  static constexpr int kSmemDoubles = kCols;  // a_j S_c + n c0_j + shift of the thread's columns
   static constexpr int kTile = TILE;  // observations per float32 tile sum
   static constexpr int kPairs = kCols / 2;
   f32x2 a2[kPairs];
   double acc[kRows][kCols];
-  double s_c_, shift_, mu_c_;
-  int jbase_;
+  double mu_c_;
 
-  __device__ __forceinline__ void load_columns(const LikeArgs &, int jbase, const ScaleInfo &sc,
-                                               const ColumnCoefs<kCols> &cf) {
-    jbase_ = jbase;
-    s_c_ = sc.s_c;
-    shift_ = sc.shift;
+  template <int NT>
+  __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
+                                               const ColumnCoefs<kCols> &cf, double *own) {
     mu_c_ = sc.mu_c;
 #pragma unroll
     for (int h = 0; h < kPairs; ++h) a2[h] = pack2((float)cf.a[2 * h], (float)cf.a[2 * h + 1]);
+#pragma unroll
+    for (int cidx = 0; cidx < kCols; ++cidx)
+      own[cidx * NT] = patch_col(j0, cidx) < g.N
+                           ? cf.a[cidx] * sc.s_c + (double)g.n * cf.c0[cidx] + sc.shift
+                           : -1.0 / 0.0;
   }
   __device__ __forceinline__ void begin_rows() {
 #pragma unroll
@@ -445,11 +525,9 @@ struct LogSpaceTiled {
       pol.fold(t2);
     }
   }
-  __device__ __forceinline__ float value(const LikeArgs &g, int r, int cidx) const {
-    const int j = patch_col(jbase_, cidx);
-    if (j >= g.N) return 0.0f;
-    const double base = g.ad[j] * s_c_ + (double)g.n * g.cd0[j] + shift_;
-    return ex2_approx((float)(acc[r][cidx] + base));
+  template <int NT>
+  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx, const double *own) const {
+    return ex2_approx((float)(acc[r][cidx] + own[cidx * NT]));  // 2^-inf = 0 outside the grid
   }
 };
 
@@ -471,29 +549,30 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 }
 
 // ---------------------------------------------------------------------------------------
-// float32 product path, hybrid exponential: the same per-pdf-eval work as ProductF32
-// (exponent FMA, 2^t, running product) but
+// float32 product path, hybrid exponential (coarse grids): the same per-pdf-eval work as
+// ProductF32 (exponent FMA, 2^t, running product) but
 //   * the per-cell arithmetic runs as packed f32x2 (FFMA2/FMUL2): a thread's 4 columns are two
 //     register pairs; the per-row (x - mu)^2 stays scalar and enters FFMA2 as a broadcast operand;
-//   * of the 8 column pairs a thread updates per observation, NPA (even observations) or NPB
-//     (odd observations) pairs take 2^t from the degree-5 FMA-pipe polynomial (ex2_poly2)
-//     instead of MUFU.EX2.  With MUFU-only code the XU pipe is 96 % busy while the FMA pipe
-//     idles at 30 % and half the issue slots are free (profiles/r01_ncu_full_16384x50.csv);
-//     moving ~5/16 of the exponentials over balances the two pipes.
+//   * of the 8 column pairs a thread updates per observation, 2 take 2^t from the degree-5
+//     FMA-pipe polynomial (ex2_poly2) instead of MUFU.EX2.  With MUFU-only code the XU pipe is
+//     96 % busy while the FMA pipe idles at 30 % and half the issue slots are free
+//     (profiles/r01_ncu_full_mufu_only_16384x50.csv); moving 4 of 16 exponentials over balances
+//     the two pipes.
 // Which cells use which pipe is fixed at compile time, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------
-template <int NPA, int NPB, bool /*unused*/ = false, int OBS_PER_ITER = 4>
 struct ProductHybrid {
-  static constexpr double kUmax = 1.0 / 0.0;  // any grid
+  static constexpr double kUmax = 1e300;  // any grid
   static constexpr bool kColSmem = false;
   static constexpr int kRows = kRM;
   static constexpr int kCols = 4;
-  static constexpr int kObsStride = 1;
+  static constexpr int kSmemDoubles = 0;
+  static constexpr int kPoly = 2;  // (row, pair) slots per observation on the polynomial
   f32x2 a2[kRN / 2], c2[kRN / 2];
   f32x2 p2[kRM][kRN / 2];
 
+  template <int NT>
   __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
-                                               const ColumnCoefs<kCols> &cf) {
+                                               const ColumnCoefs<kCols> &cf, double *) {
 #pragma unroll
     for (int h = 0; h < kRN / 2; ++h) {
       float av[2], cv[2];
@@ -514,9 +593,7 @@ struct ProductHybrid {
 #pragma unroll
       for (int h = 0; h < kRN / 2; ++h) p2[r][h] = one;
   }
-  // one observation; the first NP (row, pair) slots take 2^t from the polynomial
-  template <int NP>
-  __device__ __forceinline__ void step_np(float x, const float (&mu)[kRM]) {
+  __device__ __forceinline__ void step(float x, const float (&mu)[kRM]) {
 #pragma unroll
     for (int r = 0; r < kRM; ++r) {
       const float d = x - mu[r];  // same f32 rounding as the reference's (x - mu), kernels.h:111
@@ -527,46 +604,21 @@ struct ProductHybrid {
         const f32x2 t2 = fma2(dd2, a2[h], c2[h]);
         // spread the polynomial slots over the rows: (r, h) = (0,0),(1,1),(2,0),(3,1), then the rest
         const int slot = ((h + r) & 1) * kRM + r;
-        const f32x2 e2 = slot < NP ? ex2_poly2(t2) : ex2_mufu2(t2);
+        const f32x2 e2 = slot < kPoly ? ex2_poly2(t2) : ex2_mufu2(t2);
         p2[r][h] = mul2(p2[r][h], e2);
       }
     }
   }
-  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx) const {
+  template <int NT>
+  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx, const double *) const {
     float lo, hi;
     unpack2(p2[r][cidx >> 1], lo, hi);
     return (cidx & 1) ? hi : lo;
   }
   static __device__ __forceinline__ void consume(ProductHybrid &pol, const float *xs, int count,
                                                  const float (&mu)[kRM]) {
-    if (OBS_PER_ITER == 4) {
-      const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
-      const int n4 = count >> 2;
-      for (int q = 0; q < n4; ++q) {
-        const float4 x = xs4[q];
-        pol.template step_np<NPA>(x.x, mu);
-        pol.template step_np<NPB>(x.y, mu);
-        pol.template step_np<NPA>(x.z, mu);
-        pol.template step_np<NPB>(x.w, mu);
-      }
-      for (int k = n4 << 2; k < count; ++k) {
-        if (k & 1) pol.template step_np<NPB>(xs[k], mu);
-        else pol.template step_np<NPA>(xs[k], mu);
-      }
-    } else if (OBS_PER_ITER == 2) {
-      const float2 *xs2 = reinterpret_cast<const float2 *>(xs);
-      const int n2 = count >> 1;
 #pragma unroll 1
-      for (int q = 0; q < n2; ++q) {
-        const float2 x = xs2[q];
-        pol.template step_np<NPA>(x.x, mu);
-        pol.template step_np<NPB>(x.y, mu);
-      }
-      if (count & 1) pol.template step_np<NPA>(xs[count - 1], mu);
-    } else {
-#pragma unroll 1
-      for (int k = 0; k < count; ++k) pol.template step_np<NPA>(xs[k], mu);
-    }
+    for (int k = 0; k < count; ++k) pol.step(xs[k], mu);
   }
 };
 
@@ -583,38 +635,41 @@ struct ProductHybrid {
 // i.e. half the MUFU work of ProductF32 for ~3 packed FMA-pipe instructions more per 4 evals;
 // ncu showed the MUFU-only kernel with the XU pipe 97 % busy and the FMA pipe at 30 %.
 // Polynomial: 2^u = 1 + u (k1 + k2 u) with k2 = ln(2)^2/2 and the cubic term folded into
-// k1 = ln 2 + (ln(2)^3/6)(3/4) U^2 (Chebyshev economisation on [-U, U], U = ScaleInfo::umax):
+// k1 = ln 2 + (ln(2)^3/6)(3/4) U^2 (Chebyshev economisation on [-U, U], U = the band's umax):
 // error <= 0.0139 U^3 = 1.8e-8 at the eligibility bound kPairedUmax, below the float32 rounding
 // of the factor itself.  The derived factor is e*(1+v) evaluated as fma(e, v, e): one rounding.
 // DEG = 3 adds the cubic term, 2^u - 1 = u (k1 + u (k2 + u k3)), k3 = ln(2)^3/6 and the quartic
 // folded into k2 = ln(2)^2/2 + (ln(2)^4/24) U^2: error <= 0.0024 U^4 = 1.5e-8 at its bound
 // kPairedUmax3 = 0.05, which takes grids 4.5x coarser (README ranges: N >= 690) for one more
 // FFMA2 per derived pair.  Grids too coarse for that run ProductHybrid instead (chosen on the
-// device, see grid_likelihood_select_kernel); which rows are MUFU rows depends on the global row
-// index only.
+// device per column band); which rows are MUFU rows depends on the global row index only.
+// Four observations per loop iteration (one LDS.128), the two row pairs' scalars packed; the
+// tile's float64 column sums live in shared memory, which is what lets the kernel fit 80 registers.
 // ---------------------------------------------------------------------------------------
+#ifndef CGE_Q_UNROLL
+#define CGE_Q_UNROLL 1
+#endif
+constexpr int kObsLoopUnroll = CGE_Q_UNROLL;  // iterations (of 4 observations) per unrolled loop body
 constexpr double kPairedUmax = 0.011;
 constexpr double kPairedUmax3 = 0.05;
 
-template <int KC = 4, int OBS_PER_ITER = 1, bool PACKED_ROWS = false, bool COL_SMEM = false,
-          int DEG = 2>
+template <int DEG = 2>
 struct ProductPaired {
   static_assert(DEG == 2 || DEG == 3, "polynomial degree of 2^u - 1");
   static constexpr double kUmax = DEG == 2 ? kPairedUmax : kPairedUmax3;  // eligibility bound
-  // COL_SMEM: the tile's float64 column sums live in shared memory instead of 2*KC registers
-  // (they are touched once per row group), which is what lets the kernel fit 80 registers
-  static constexpr bool kColSmem = COL_SMEM;
+  static constexpr bool kColSmem = true;
   static constexpr int kRows = kRM;
-  static constexpr int kCols = KC;
-  static constexpr int kObsStride = 1;
-  static constexpr int kPairs = KC / 2;
+  static constexpr int kCols = 4;
+  static constexpr int kSmemDoubles = 0;
+  static constexpr int kPairs = kCols / 2;
   f32x2 a2[kPairs], c2[kPairs];    // exponent coefficients of the MUFU rows
   f32x2 k1a[kPairs], k2a[kPairs];  // a_j k1, a_j^2 k2 of the derived rows
   f32x2 k3a[DEG == 3 ? kPairs : 1];  // a_j^3 k3
   f32x2 p2[kRM][kPairs];
 
+  template <int NT>
   __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
-                                               const ColumnCoefs<kCols> &cf) {
+                                               const ColumnCoefs<kCols> &cf, double *) {
     const double U = sc.umax;
     const double k1 = 0.69314718055994530942 + (DEG == 2 ? 0.0555041086648215799 * 0.75 * U * U : 0.0);
     const double k2 = 0.24022650695910071233 + (DEG == 3 ? 0.00961812910762847716 * U * U : 0.0);
@@ -650,18 +705,11 @@ struct ProductPaired {
   __device__ __forceinline__ void step(float x, const float (&mu)[kRM], const float (&gm)[kRM / 2],
                                        const float (&gb)[kRM / 2]) {
     float ddv[kRM / 2], ggv[kRM / 2];
-    if (PACKED_ROWS) {  // the two row pairs' scalars as one packed FADD2 / FMUL2 / FFMA2 each
+    {  // the two row pairs' scalars as one packed FADD2 / FMUL2 / FFMA2 each
       const f32x2 x2 = pack2(x, x);
-      const f32x2 d2 = sub2(x2, pack2(mu[0], mu[2]));
+      const f32x2 d2 = sub2(x2, pack2(mu[0], mu[2]));  // same f32 rounding as the reference's (x - mu)
       unpack2(mul2(d2, d2), ddv[0], ddv[1]);
       unpack2(fma2(x2, pack2(gm[0], gm[1]), pack2(gb[0], gb[1])), ggv[0], ggv[1]);
-    } else {
-#pragma unroll
-      for (int rp = 0; rp < kRM / 2; ++rp) {
-        const float d = x - mu[2 * rp];  // same f32 rounding as the reference's (x - mu), kernels.h:111
-        ddv[rp] = d * d;
-        ggv[rp] = fmaf(x, gm[rp], gb[rp]);
-      }
     }
 #pragma unroll
     for (int rp = 0; rp < kRM / 2; ++rp) {
@@ -679,7 +727,8 @@ struct ProductPaired {
       }
     }
   }
-  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx) const {
+  template <int NT>
+  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx, const double *) const {
     float lo, hi;
     unpack2(p2[r][cidx >> 1], lo, hi);
     return (cidx & 1) ? hi : lo;
@@ -693,103 +742,109 @@ struct ProductPaired {
       gm[rp] = -2.0f * delta;
       gb[rp] = __fmul_rn(delta, __fadd_rn(mu[2 * rp], mu[2 * rp + 1]));
     }
-    if (OBS_PER_ITER == 4) {
-      const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
-      const int n4 = count >> 2;
-#pragma unroll 1
-      for (int q = 0; q < n4; ++q) {
-        const float4 x = xs4[q];
-        pol.step(x.x, mu, gm, gb);
-        pol.step(x.y, mu, gm, gb);
-        pol.step(x.z, mu, gm, gb);
-        pol.step(x.w, mu, gm, gb);
-      }
-      for (int k = n4 << 2; k < count; ++k) pol.step(xs[k], mu, gm, gb);
-    } else if (OBS_PER_ITER == 2) {
-      const float2 *xs2 = reinterpret_cast<const float2 *>(xs);
-      const int n2 = count >> 1;
-#pragma unroll 1
-      for (int q = 0; q < n2; ++q) {
-        const float2 x = xs2[q];
-        pol.step(x.x, mu, gm, gb);
-        pol.step(x.y, mu, gm, gb);
-      }
-      if (count & 1) pol.step(xs[count - 1], mu, gm, gb);
-    } else {
-#pragma unroll 1
-      for (int k = 0; k < count; ++k) pol.step(xs[k], mu, gm, gb);
+    const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
+    const int n4 = count >> 2;
+#pragma unroll kObsLoopUnroll
+    for (int q = 0; q < n4; ++q) {
+      const float4 x = xs4[q];
+      pol.step(x.x, mu, gm, gb);
+      pol.step(x.y, mu, gm, gb);
+      pol.step(x.z, mu, gm, gb);
+      pol.step(x.w, mu, gm, gb);
     }
+    if (count & 2) {  // the tail as one LDS.64 and at most one scalar load
+      const float2 x = *reinterpret_cast<const float2 *>(xs + (n4 << 2));
+      pol.step(x.x, mu, gm, gb);
+      pol.step(x.y, mu, gm, gb);
+    }
+    if (count & 1) pol.step(xs[count - 1], mu, gm, gb);
   }
 };
 
 // ---------------------------------------------------------------------------------------
-// grid_likelihood_kernel: K1-K5 fused.
-//   CTA = WM x WN warps.  A warp owns a strip of 32*kCols sigma columns (lane -> kCols/4 groups
-//   of 4 adjacent columns, one 16-byte store per group and row) and walks down its rows kRM at
-//   a time.  blockIdx.x = column band (WN strips), blockIdx.y = row tile (tile_rows rows).
-//   Observations reach shared memory by TMA bulk copy (cp.async.bulk + mbarrier): once per CTA
-//   when they fit, else streamed in double-buffered 32 KB chunks.
-//   Per row group the warp emits its partial row sums (fixed-order shuffle tree) and keeps
-//   float64 column sums in registers until the tile ends: no atomics anywhere.
+// Shared-memory layout of the likelihood kernels (dynamic):
+//   [0, 16)    two mbarriers (streamed observations only)
+//   [16, 96)   ScaleInfo of this step (written once per CTA by the set-up)
+//   [96, 128)  two claim slots (the item a CTA takes next)
+//   [128, ...) observation stage: n_pad floats, or two chunks of kObsChunk when streamed
+//   then       per-thread slots [k][NT]: kCols int64 column accumulators (as 16-byte pairs), kCols
+//              float32 column scales 2^s_j (as 8-byte pairs), the policy's own float64 values, and
+//              4 floats per thread of row-sum transposition buffer (512 bytes per warp); during the
+//              set-up the same bytes serve as the sort scratch
 // ---------------------------------------------------------------------------------------
-// PRELOADED: the caller has already staged all n_pad observations at smem_raw + 128 and
-// synchronised the block (small_grid_kernel); no mbarrier / bulk copy is used then.
-template <class Policy, int WM, int WN, bool VEC4, bool PRELOADED = false>
-__device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleInfo &sc,
-                                                const ColumnCoefs<Policy::kCols> &cf,
-                                                unsigned char *smem_raw) {
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);         // 2 mbarriers
-  float *obs_s = reinterpret_cast<float *>(smem_raw + 128);         // stage 0 (and 1 if streamed)
+constexpr int kSmemHeader = 128;
+__host__ __device__ __forceinline__ size_t stage_bytes(int n_pad) {
+  return (((size_t)(n_pad > kObsSingleMax ? 2 * kObsChunk : n_pad) * 4) + 15) & ~(size_t)15;
+}
+// bytes per thread behind the observation stage
+template <class Policy>
+constexpr int policy_smem_bytes() {
+  return Policy::kCols * 8 + Policy::kCols * 4 + Policy::kSmemDoubles * 8 + 16;
+}
 
+// thread 0 only: start the bulk copy of chunk `ch` of the streamed observations into stage `st`
+__device__ __forceinline__ void issue_chunk(const LikeArgs &g, uint64_t *bars, float *obs_s, int ch,
+                                            int st) {
+  const int floats = min(kObsChunk, g.n_pad - ch * kObsChunk);
+  const uint32_t bytes = (uint32_t)floats * 4u;
+  mbar_arrive_expect_tx(&bars[st], bytes);
+  bulk_copy_g2s(obs_s + (size_t)st * kObsChunk, g.obs + (size_t)ch * kObsChunk, bytes, &bars[st]);
+}
+
+constexpr int kWarps = 8;             // warps per CTA of every likelihood kernel
+constexpr int kThreads = kWarps * 32;
+
+// ---------------------------------------------------------------------------------------
+// run_strip: everything this warp does in column strip `cw`, starting with item `item` (already
+// claimed) and claiming further items of the strip until none are left -- K1-K5 fused.
+//   The warp owns the strip's 32*kCols sigma columns (lane -> kCols/4 groups of 4 adjacent
+//   columns, one 16-byte store per group and row) and walks its items' row groups kRM rows at a
+//   time.  Per row group it emits its partial row sums (fixed-order shuffle tree) and adds its
+//   4-row column sums into its fixed-point accumulators (shared memory); when the strip is left
+//   they go to colacc[] with one integer atomic per column.  No floating-point atomics.
+//   STREAMED (more than 16384 observations): the CTA moves as one -- thread 0 claims for all 8
+//   warps, which take interleaved groups of the same strip and consume each 32 KB chunk of
+//   observations together (the chunks arrive by TMA bulk copy into two shared-memory stages).
+// ---------------------------------------------------------------------------------------
+template <class Policy, bool STREAMED>
+__device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc, int cw, int item,
+                                          uint64_t *bars, float *obs_s, unsigned char *tsm_raw,
+                                          volatile int *claim, int &claim_par, int &streams) {
+  constexpr int NT = kThreads;
+  constexpr int kRows = Policy::kRows;
+  constexpr int kCols = Policy::kCols;
+  constexpr int kGroups = kCols / kRN;
+  static_assert(kRows == kRM, "row groups are kRM rows");
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int wn = warp % WN, wm = warp / WN;
-  constexpr int kRows = Policy::kRows;            // rows per thread: 4 or 2
-  constexpr int kCols = Policy::kCols;            // columns per thread: 4 or 8
-  constexpr int kGroups = kCols / kRN;            // float4 groups per thread
-  const int cw = blockIdx.x * WN + wn;            // global column-strip index (32*kCols columns)
   const int j0 = cw * (32 * kCols) + lane * kRN;  // first column; group g starts 128*g further
-  // tiles start at a multiple of kRM below row_begin, so a cell's position inside the register
+  // row groups start at a multiple of kRM below row_begin, so a cell's position inside the register
   // patch (hence which exponential path it takes) depends on its GLOBAL row only: a row shard
   // computes bit-identical unnormalised cells to the single-GPU run
-  const int tile_row0 = (g.row_begin & ~(kRM - 1)) + blockIdx.y * g.tile_rows;
-  const int groups = g.tile_rows / (WM * kRows);    // row groups this warp walks
-  constexpr int kStride = Policy::kObsStride;        // staged floats per observation
-  constexpr int kChunkObs = kObsChunk / kStride;     // observations per streamed chunk
-  const bool streamed = !PRELOADED && g.n_pad > kObsSingleMax;  // n_pad counts staged floats
-  const int nchunks = streamed ? (g.n_pad + kObsChunk - 1) / kObsChunk : 1;
+  const int row_base = g.row_begin & ~(kRM - 1);
 
-  if (!PRELOADED) {
-    if (tid == 0) {
-      mbar_init(&bars[0], 1);
-      mbar_init(&bars[1], 1);
-      mbar_init_fence();
-    }
-    __syncthreads();
-  }
-
-  auto issue = [&](int seq) {  // thread 0 only: start the bulk copy of load number `seq`
-    const int ch = seq % nchunks, st = seq & 1;
-    const int floats = streamed ? min(kObsChunk, g.n_pad - ch * kObsChunk) : g.n_pad;
-    const uint32_t bytes = (uint32_t)floats * 4u;
-    mbar_arrive_expect_tx(&bars[st], bytes);
-    bulk_copy_g2s(obs_s + (size_t)st * kObsChunk, g.obs_pad + (size_t)ch * kObsChunk, bytes,
-                  &bars[st]);
-  };
-  if (!PRELOADED && tid == 0) issue(0);
+  // per-thread shared-memory slots, element k of thread t at [k * NT + t]
+  // (the column accumulators and scales are kept as pairs: one 16-byte / 8-byte access per pair)
+  constexpr int kPairs = kCols / 2;
+  longlong2 *colacc_s = reinterpret_cast<longlong2 *>(tsm_raw) + tid;
+  float2 *colscale_s = reinterpret_cast<float2 *>(tsm_raw + (size_t)kCols * 8 * NT) + tid;
+  double *own = reinterpret_cast<double *>(tsm_raw + (size_t)kCols * 12 * NT) + tid;
+  float *rowbuf = reinterpret_cast<float *>(tsm_raw + (size_t)(kCols * 12 + Policy::kSmemDoubles * 8) * NT) +
+                  warp * (kRows * 32);  // this warp's [kRows][32] transposition buffer
 
   Policy pol;
-  pol.load_columns(g, j0, sc, cf);
-  // float64 column sums of this thread's columns over the tile: registers, or (Policy::kColSmem)
-  // shared memory behind the observation stage, element cidx of thread tid at [cidx*nthreads + tid]
-  constexpr bool kColSmem = Policy::kColSmem;
-  double colreg[kColSmem ? 1 : kCols];
-  double *colsm = reinterpret_cast<double *>(
-      smem_raw + 128 + (((streamed ? 2 * kObsChunk : g.n_pad) * 4 + 15) & ~15));
+  {
+    ColumnCoefs<kCols> cf;
+    cf.compute(g.range, j0);
+    pol.template load_columns<NT>(g, j0, sc, cf, own);
 #pragma unroll
-  for (int cidx = 0; cidx < kCols; ++cidx) {
-    if (kColSmem) colsm[cidx * (WM * WN * 32) + tid] = 0.0;
-    else colreg[cidx] = 0.0;
+    for (int h = 0; h < kPairs; ++h) {
+      const int s0 = col_fixed_shift(cf.a[2 * h], cf.c0[2 * h], sc, g.n, g.prior_log2max, g.fixed_bits);
+      const int s1 = col_fixed_shift(cf.a[2 * h + 1], cf.c0[2 * h + 1], sc, g.n, g.prior_log2max, g.fixed_bits);
+      // 2^s, s in [-120, 120]
+      colscale_s[h * NT] = make_float2(__int_as_float((s0 + 127) << 23), __int_as_float((s1 + 127) << 23));
+      colacc_s[h * NT] = make_longlong2(0, 0);
+    }
   }
   const bool col_any = j0 < g.N;  // columns only grow with cidx
   const bool has_prior = g.prior_mu || g.prior_sigma || g.prior_full;
@@ -798,28 +853,37 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
   int row = 0;
   bool rows_any = false;
 
+  // The range values of an item's rows (at most 8 groups x 4 rows = one per lane) are evaluated
+  // once per item, lane l taking row first_row + l (rows past the end repeat the last value; they
+  // are masked in the epilogue); a group then takes its four by shuffle: the reference's float32
+  // divide is paid once per item, not once per group.
+  float mu_item = 0.0f;
+  int item_row0 = 0;
+  auto begin_item = [&](int grp0) {
+    item_row0 = row_base + grp0 * kRows;
+    mu_item = range_value(min(item_row0 + lane, g.N - 1), g.N, g.range.mu0, g.range.mu1);
+  };
   auto begin_group = [&](int grp) {
-    row = tile_row0 + (grp * WM + wm) * kRows;
+    row = row_base + grp * kRows;
     rows_any = row < g.row_end && row + kRows > g.row_begin;
-    // `row` is a multiple of 4 and setup_kernel pads the table with 3 copies of its last value,
-    // so the 4 rows of the patch are one aligned 16-byte load
-    const float4 m4 = *reinterpret_cast<const float4 *>(g.mu + min(row, (g.N - 1) & ~3));
-    mu[0] = m4.x; mu[1] = m4.y; mu[2] = m4.z; mu[3] = m4.w;
+    const int src = row - item_row0;
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) mu[r] = __shfl_sync(0xffffffffu, mu_item, src + r);
     pol.begin_rows();
   };
 
   // Epilogue of one row group: store the kRows x kCols patch, add it into the row / column sums.
-  // Within the patch the sums are float32 in a fixed pairwise order (4 or 8 terms); everything
-  // across threads, groups and tiles is float64 in a fixed order.  The kRows row sums of a warp
-  // are reduced together by a transposing butterfly (12 shuffles instead of 40): lane 8*q ends up
-  // with the total of row q.
+  // Within the patch the sums are float32 in a fixed pairwise order (4 or 8 terms).  The kRows row
+  // sums of a warp are reduced together in float64 by a transposing butterfly (12 shuffles instead
+  // of 40): lane 8*q ends up with the total of row q.  The column sums go to the fixed-point
+  // accumulators.
   auto end_group = [&]() {
     if (!rows_any) return;  // warp-uniform
     float v[kRows][kCols];
 #pragma unroll
     for (int r = 0; r < kRows; ++r)
 #pragma unroll
-      for (int cidx = 0; cidx < kCols; ++cidx) v[r][cidx] = pol.value(g, r, cidx);
+      for (int cidx = 0; cidx < kCols; ++cidx) v[r][cidx] = pol.template value<NT>(g, r, cidx, own);
     const bool interior =
         row >= g.row_begin && row + kRows <= g.row_end && patch_col(j0, kCols - 1) < g.N;
     if (!interior) {  // shard / grid edges: cells outside contribute exactly zero
@@ -832,30 +896,53 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
       }
     }
     if (has_prior) {  // likelihood x prior before normalisation (cuda_functions.h:145-148)
+      float pm[kRows], ps[kCols];
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         const bool rv = row + r >= g.row_begin && row + r < g.row_end;
+        pm[r] = (g.prior_mu && rv) ? g.prior_mu[row + r] : 1.0f;
+      }
 #pragma unroll
-        for (int cidx = 0; cidx < kCols; ++cidx) {
-          const int j = patch_col(j0, cidx);
-          if (!(rv && j < g.N)) continue;
-          if (g.prior_mu) v[r][cidx] *= g.prior_mu[row + r];
-          if (g.prior_sigma) v[r][cidx] *= g.prior_sigma[j];
-          if (g.prior_full)
-            v[r][cidx] *= g.prior_full[(size_t)(row + r - g.row_begin) * (size_t)g.N + j];
+      for (int cidx = 0; cidx < kCols; ++cidx) {
+        const int j = patch_col(j0, cidx);
+        ps[cidx] = (g.prior_sigma && j < g.N) ? g.prior_sigma[j] : 1.0f;
+      }
+#pragma unroll
+      for (int r = 0; r < kRows; ++r)
+#pragma unroll
+        for (int cidx = 0; cidx < kCols; ++cidx) v[r][cidx] *= pm[r] * ps[cidx];
+      if (g.prior_full) {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r) {
+          if (!(row + r >= g.row_begin && row + r < g.row_end)) continue;
+          const float *pf = g.prior_full + (size_t)(row + r - g.row_begin) * (size_t)g.N;
+#pragma unroll
+          for (int cidx = 0; cidx < kCols; ++cidx) {
+            const int j = patch_col(j0, cidx);
+            if (j < g.N) v[r][cidx] *= pf[j];
+          }
         }
       }
     }
     float *rowp = g.post + (ptrdiff_t)(row - g.row_begin) * (ptrdiff_t)g.N + j0;
-    if (VEC4 && __all_sync(0xffffffffu, interior)) {
-      // the whole warp is inside the shard and the grid (all but the edge tiles): straight-line
+    if (g.vec4 && __all_sync(0xffffffffu, interior)) {
+      // the whole warp is inside the shard and the grid (all but the edge groups): straight-line
       // stores, one 512-byte run per instruction
+      if (g.keep_l2) {
 #pragma unroll
-      for (int r = 0; r < kRows; ++r, rowp += g.N)
+        for (int r = 0; r < kRows; ++r, rowp += g.N)
 #pragma unroll
-        for (int grp4 = 0; grp4 < kGroups; ++grp4)
-          st_stream_f4(rowp + grp4 * kGroupCols, v[r][4 * grp4], v[r][4 * grp4 + 1],
+          for (int grp4 = 0; grp4 < kGroups; ++grp4)
+            st_keep_f4(rowp + grp4 * kGroupCols, v[r][4 * grp4], v[r][4 * grp4 + 1],
                        v[r][4 * grp4 + 2], v[r][4 * grp4 + 3]);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kRows; ++r, rowp += g.N)
+#pragma unroll
+          for (int grp4 = 0; grp4 < kGroups; ++grp4)
+            st_stream_f4(rowp + grp4 * kGroupCols, v[r][4 * grp4], v[r][4 * grp4 + 1],
+                         v[r][4 * grp4 + 2], v[r][4 * grp4 + 3]);
+      }
     } else {
 #pragma unroll
       for (int r = 0; r < kRows; ++r, rowp += g.N) {
@@ -863,169 +950,276 @@ __device__ __forceinline__ void likelihood_body(const LikeArgs &g, const ScaleIn
 #pragma unroll
         for (int grp4 = 0; grp4 < kGroups; ++grp4) {
           const int jg = j0 + grp4 * kGroupCols;
-          if (VEC4) {
+          if (g.vec4) {
             if (rv && jg < g.N)
-              st_stream_f4(rowp + grp4 * kGroupCols, v[r][4 * grp4], v[r][4 * grp4 + 1],
-                           v[r][4 * grp4 + 2], v[r][4 * grp4 + 3]);
+              st_keep_f4(rowp + grp4 * kGroupCols, v[r][4 * grp4], v[r][4 * grp4 + 1],
+                         v[r][4 * grp4 + 2], v[r][4 * grp4 + 3]);
           } else {
 #pragma unroll
             for (int e = 0; e < kRN; ++e)
-              if (rv && jg + e < g.N) st_stream_f1(rowp + grp4 * kGroupCols + e, v[r][4 * grp4 + e]);
+              if (rv && jg + e < g.N) st_keep_f1(rowp + grp4 * kGroupCols + e, v[r][4 * grp4 + e]);
           }
         }
       }
     }
-    // column sums over the patch rows, row sums over the patch columns (float32, pairwise)
-    static_assert(kRows == 4, "the patch reductions below are written for 4 rows");
+    // column sums over the patch rows (float32, pairwise), scaled by 2^s_j and added as integers
 #pragma unroll
-    for (int cidx = 0; cidx < kCols; ++cidx)
-    {
-      const double add = (double)((v[0][cidx] + v[1][cidx]) + (v[2][cidx] + v[3][cidx]));
-      if (kColSmem) colsm[cidx * (WM * WN * 32) + tid] += add;
-      else colreg[cidx] += add;
+    for (int h = 0; h < kPairs; ++h) {
+      const float c0 = (v[0][2 * h] + v[1][2 * h]) + (v[2][2 * h] + v[3][2 * h]);
+      const float c1 = (v[0][2 * h + 1] + v[1][2 * h + 1]) + (v[2][2 * h + 1] + v[3][2 * h + 1]);
+      const float2 sc2 = colscale_s[h * NT];
+      longlong2 acc = colacc_s[h * NT];
+      acc.x += __float2ll_rn(c0 * sc2.x);
+      acc.y += __float2ll_rn(c1 * sc2.y);
+      colacc_s[h * NT] = acc;
     }
-    double rs[kRows];
+    // row sums over the patch columns (float32, pairwise), then across the warp in float64 in a
+    // fixed order: every lane parks its kRows sums in the warp's shared [row][lane] buffer, lane l
+    // takes back 4 adjacent lanes' sums of row l / 8 (one LDS.128), adds them, and three shuffles
+    // finish the row inside its group of 8 lanes -- 6 SHFL instead of the 12 (+ selects) of a
+    // transposing butterfly on float64 values
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
       float t = (v[r][0] + v[r][1]) + (v[r][2] + v[r][3]);
       if (kCols == 8) t += (v[r][4] + v[r][5]) + (v[r][6] + v[r][7]);
-      rs[r] = (double)t;
+      rowbuf[r * 32 + lane] = t;
     }
-    const bool up16 = lane & 16, up8 = lane & 8;
-    const double k0 = (up16 ? rs[2] : rs[0]) + __shfl_xor_sync(0xffffffffu, up16 ? rs[0] : rs[2], 16);
-    const double k1 = (up16 ? rs[3] : rs[1]) + __shfl_xor_sync(0xffffffffu, up16 ? rs[1] : rs[3], 16);
-    double tot = (up8 ? k1 : k0) + __shfl_xor_sync(0xffffffffu, up8 ? k0 : k1, 8);
+    __syncwarp();
+    const float4 q = *reinterpret_cast<const float4 *>(rowbuf + lane * 4);  // row lane/8, lanes 4*(lane%8)..+3
+    __syncwarp();
+    double tot = ((double)q.x + (double)q.y) + ((double)q.z + (double)q.w);
     tot += __shfl_xor_sync(0xffffffffu, tot, 4);
     tot += __shfl_xor_sync(0xffffffffu, tot, 2);
     tot += __shfl_xor_sync(0xffffffffu, tot, 1);
     const int rq = row + (lane >> 3);  // lanes 0, 8, 16, 24 publish rows 0..3 of the patch
-    if ((lane & 7) == 0 && rq >= g.row_begin && rq < g.row_end && cw < g.ncw)
+    if ((lane & 7) == 0 && rq >= g.row_begin && rq < g.row_end)
       g.rowpart[(size_t)(rq - g.row_begin) * (size_t)g.ncw + cw] = tot;
   };
 
-  if (!streamed) {
-    if (!PRELOADED) mbar_wait(&bars[0], 0);
-    for (int grp = 0; grp < groups; ++grp) {
-      begin_group(grp);
-      // (no skip for groups or columns outside the grid: they are masked in the epilogue, and a
-      // single control path keeps the patch initialisation from being emitted per branch)
-      Policy::consume(pol, obs_s, g.n, mu);
-      end_group();
+  if (!STREAMED) {
+    while (item < g.items_per_strip) {
+      const int g0 = item * g.chunk, g1 = min(g.groups, g0 + g.chunk);
+      // the next item of this strip is claimed now and looked at after this one is done: the
+      // atomic's round trip hides behind the arithmetic
+      int next_item = 0;
+      if (lane == 0) next_item = atomicAdd(g.strip_next + cw, 1);
+      begin_item(g0);
+      for (int grp = g0; grp < g1; ++grp) {
+        begin_group(grp);
+        // (no skip for groups or columns outside the grid: they are masked in the epilogue, and a
+        // single control path keeps the patch initialisation from being emitted per branch)
+        Policy::consume(pol, obs_s, g.n, mu);
+        end_group();
+      }
+      item = __shfl_sync(0xffffffffu, next_item, 0);
     }
   } else {
-    const int total = groups * nchunks;
-    for (int seq = 0; seq < total; ++seq) {
-      if (tid == 0 && seq + 1 < total) issue(seq + 1);
-      mbar_wait(&bars[seq & 1], (seq >> 1) & 1);
-      const int ch = seq % nchunks;
-      if (ch == 0) begin_group(seq / nchunks);
-      const int count = min(kChunkObs, g.n - ch * kChunkObs);
-      if (rows_any && col_any)
-        Policy::consume(pol, obs_s + (size_t)(seq & 1) * kObsChunk, count, mu);
-      if (ch == nchunks - 1) end_group();
-      __syncthreads();  // every warp is done with this stage before it is refilled
+    const int nchunks = (g.n_pad + kObsChunk - 1) / kObsChunk;
+    while (item < g.items_per_strip) {
+      const int g0 = item * g.chunk * kWarps, g1 = min(g.groups, g0 + g.chunk * kWarps);
+      claim_par ^= 1;
+      int next_item = 0;
+      if (tid == 0) next_item = atomicAdd(g.strip_next + cw, 1);
+      for (int base = g0; base < g1; base += kWarps) {
+        // 32 KB chunks through two stages, the next chunk in flight while this one is consumed
+        // (stage = parity of the running load count)
+        if (tid == 0) issue_chunk(g, bars, obs_s, 0, streams & 1);
+        begin_item(base + warp);
+        begin_group(base + warp);
+        if (base + warp >= g1) rows_any = false;  // (belongs to the next item)
+        for (int ch = 0; ch < nchunks; ++ch, ++streams) {
+          if (tid == 0 && ch + 1 < nchunks) issue_chunk(g, bars, obs_s, ch + 1, (streams + 1) & 1);
+          mbar_wait(&bars[streams & 1], (streams >> 1) & 1);
+          const int count = min(kObsChunk, g.n - ch * kObsChunk);
+          if (rows_any && col_any)
+            Policy::consume(pol, obs_s + (size_t)(streams & 1) * kObsChunk, count, mu);
+          __syncthreads();  // every warp is done with this stage before it is refilled
+        }
+        end_group();
+      }
+      if (tid == 0) claim[claim_par] = next_item;
+      __syncthreads();
+      item = claim[claim_par];
     }
   }
 
-  // partial column sums of this warp's rows: one slot per (row tile, warp row)
+  // leave the strip: the exact partial column sums join the shard's, one integer atomic each
   if (col_any) {
-    double *dst = g.colpart + (size_t)(blockIdx.y * WM + wm) * (size_t)g.N;
 #pragma unroll
-    for (int cidx = 0; cidx < kCols; ++cidx) {
-      const int j = patch_col(j0, cidx);
-      if (j < g.N) dst[j] = kColSmem ? colsm[cidx * (WM * WN * 32) + tid] : colreg[cidx];
+    for (int h = 0; h < kPairs; ++h) {
+      const longlong2 part = colacc_s[h * NT];
+      const int ja = patch_col(j0, 2 * h), jb = patch_col(j0, 2 * h + 1);
+      if (ja < g.N && part.x != 0) atomicAdd(g.colacc + ja, (unsigned long long)part.x);
+      if (jb < g.N && part.y != 0) atomicAdd(g.colacc + jb, (unsigned long long)part.y);
     }
   }
 }
 
-// ScaleInfo as this CTA's column band sees it: `umax` becomes the bound over the band's own
-// columns (|a_j| is monotone along the sigma axis, so its maximum sits at one end of the band).
-// The exponent step scales with |a_j| = 0.72/sigma_j^2, so on a grid with a wide sigma range only
-// the bands at small sigma need the costlier arithmetic.  A function of the band (columns) and of
-// the global statistics only: the same for every row tile, shard and rank.
-template <int WN>
-__device__ __forceinline__ ScaleInfo band_scale(const LikeArgs &g, int kcols) {
-  ScaleInfo sc = *g.scale;
-  const int jfirst = blockIdx.x * WN * 32 * kcols;
-  const int jlast = min(jfirst + WN * 32 * kcols, g.N) - 1;
-  sc.umax = fmax(fabs(g.ad[jfirst]), fabs(g.ad[jlast])) * sc.ustep;
-  return sc;
+// |a_j| is monotone along the sigma axis, so a strip's largest exponent step sits at one of its
+// ends.  The exponent step scales with |a_j| = 0.72/sigma_j^2, so on a grid with a wide sigma range
+// only the strips at small sigma need the costlier arithmetic.  A function of the strip (columns)
+// and of the global statistics only: the same for every row range, shard and rank.
+__device__ __forceinline__ double strip_umax(const RangeArgs &r, int cw, int strip_cols, double ustep) {
+  const int jfirst = cw * strip_cols;
+  const int jlast = min(jfirst + strip_cols, r.N) - 1;
+  const double s0 = (double)range_value(jfirst, r.N, r.sg0, r.sg1);
+  const double s1 = (double)range_value(jlast, r.N, r.sg0, r.sg1);
+  return fmax(fabs(coef_a(s0)), fabs(coef_a(s1))) * ustep;
 }
 
-template <class Policy, int WM, int WN, bool VEC4, int MINB = 1>
-__global__ void __launch_bounds__(WM *WN * 32, MINB)
+// ---------------------------------------------------------------------------------------
+// likelihood_cta: everything CTA `cta` of `nctas` does in the likelihood phase.
+//   SELECT: the policy is chosen per column strip on the device -- Fine (ProductPaired, degree 2)
+//   where the strip's umax allows it, Mid (degree 3) up to 4.5x coarser, Coarse (ProductHybrid)
+//   otherwise.  The choice depends on (ranges, N, observations, strip) only -- never on the rows,
+//   the shard or the warp -- so every rank of a sharded run takes the same path for the same cells
+//   and results stay bit-reproducible.  !SELECT: Fine everywhere.
+//   PRELOADED: the caller (small_grid_kernel) has staged the observations and written the
+//   ScaleInfo slot of shared memory, and synchronised the block.
+// ---------------------------------------------------------------------------------------
+template <class Fine, class Mid, class Coarse, bool SELECT, bool PRELOADED, bool STREAMED = false>
+__device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char *smem_raw,
+                                               double *scratch, unsigned cta, unsigned nctas) {
+  static_assert(Fine::kCols == Coarse::kCols && Fine::kCols == Mid::kCols, "same tiling");
+  static_assert(!(PRELOADED && STREAMED), "the small-grid kernel stages every observation at once");
+  constexpr int kCols = Fine::kCols;
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
+  ScaleInfo *sc_s = reinterpret_cast<ScaleInfo *>(smem_raw + 16);
+  volatile int *claim = reinterpret_cast<volatile int *>(smem_raw + 96);
+  float *obs_s = reinterpret_cast<float *>(smem_raw + kSmemHeader);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned char *after_stage = smem_raw + kSmemHeader + stage_bytes(g.n_pad);
+
+  if (!PRELOADED) {
+    if (!STREAMED) {
+      // fused set-up: this CTA's own copy of the observations and of the statistics
+      const ScaleInfo sc = setup_scale(g.range, g.obs, obs_s, g.n, g.n_pad, g.centred,
+                                       g.reorder ? reinterpret_cast<float *>(after_stage) : nullptr,
+                                       scratch);
+      if (tid == 0) {
+        *sc_s = sc;
+        if (cta == 0) *g.scale_out = sc;
+      }
+    } else {
+      if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_init_fence();
+        *sc_s = *g.scale_in;
+      }
+    }
+    __syncthreads();
+  }
+
+  const int strip_cols = 32 * kCols;
+  int claim_par = 0, streams = 0;
+  // home strip: the workers (warps; whole CTAs when streamed) are spread evenly over the strips; a
+  // worker takes its home strip's items with everyone else who lives there, then moves on to help
+  // the next strip
+  const long long worker = STREAMED ? (long long)cta : (long long)cta * kWarps + warp;
+  const long long workers = STREAMED ? (long long)nctas : (long long)nctas * kWarps;
+  int cw = (int)((worker * g.ncw) / workers);
+  for (int visited = 0; visited < g.ncw; ++visited) {
+    int item;
+    if (!STREAMED) {
+      item = 0;
+      if (lane == 0) item = atomicAdd(g.strip_next + cw, 1);
+      item = __shfl_sync(0xffffffffu, item, 0);
+    } else {
+      if (tid == 0) claim[2] = atomicAdd(g.strip_next + cw, 1);
+      __syncthreads();
+      item = claim[2];
+      __syncthreads();  // (the slot is rewritten at the next strip)
+    }
+    if (item < g.items_per_strip) {
+      ScaleInfo sc = *sc_s;
+      sc.umax = strip_umax(g.range, cw, strip_cols, sc.ustep);  // the strip's own bound
+      if (!SELECT || sc.umax <= Fine::kUmax)
+        run_strip<Fine, STREAMED>(g, sc, cw, item, bars, obs_s, after_stage, claim, claim_par, streams);
+      else if (sc.umax <= Mid::kUmax)
+        run_strip<Mid, STREAMED>(g, sc, cw, item, bars, obs_s, after_stage, claim, claim_par, streams);
+      else
+        run_strip<Coarse, STREAMED>(g, sc, cw, item, bars, obs_s, after_stage, claim, claim_par, streams);
+    }
+    if (STREAMED) {  // (a step is hundreds of microseconds there: walk the strips one by one)
+      cw = cw + 1 == g.ncw ? 0 : cw + 1;
+      continue;
+    }
+    // this strip is finished: the next one that still has unclaimed items, 32 counters per look
+    // (one L2 round trip instead of one per strip); none left -> this warp is done
+    int step = 0;
+    for (int base = 1; base < g.ncw && step == 0; base += 32) {
+      const int idx = base + lane;
+      int left = 0;
+      if (idx < g.ncw)
+        left = __ldcg(g.strip_next + (cw + idx) % g.ncw) < g.items_per_strip ? 1 : 0;
+      const unsigned has = __ballot_sync(0xffffffffu, left);
+      if (has) step = base + __ffs(has) - 1;
+    }
+    if (step == 0) break;
+    cw = (cw + step) % g.ncw;
+    visited = 0;  // (termination is by the look above finding nothing)
+  }
+}
+
+template <class Fine, class Mid, class Coarse, bool SELECT, int MINB = 1, bool STREAMED = false>
+__global__ void __launch_bounds__(kThreads, MINB)
     grid_likelihood_kernel(const LikeArgs g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  ColumnCoefs<Policy::kCols> cf;
-  cf.load(g, first_column<WN>(Policy::kCols));
-  const ScaleInfo sc = band_scale<WN>(g, Policy::kCols);
-  likelihood_body<Policy, WM, WN, VEC4>(g, sc, cf, smem_raw);
-}
-
-// The default product kernel: ProductPaired with the degree-2 polynomial where the grid is fine
-// enough for it (the band's umax, from the statistics setup_kernel derives on the device out of
-// the ranges and the observations), with the degree-3 polynomial up to 4.5x coarser,
-// ProductHybrid otherwise.  The choice is made per column band and depends on (ranges, N,
-// observations, band) only -- never on the row tile or the shard -- so every rank of a sharded
-// run takes the same path for the same cells and results stay bit-reproducible.  The policies
-// share the tiling.
-template <class Fine, class Mid, class Coarse, int WM, int WN, bool VEC4, int MINB = 1>
-__global__ void __launch_bounds__(WM *WN * 32, MINB)
-    grid_likelihood_select_kernel(const LikeArgs g) {
-  static_assert(Fine::kCols == Coarse::kCols && Fine::kRows == Coarse::kRows, "same tiling");
-  static_assert(Fine::kCols == Mid::kCols && Fine::kRows == Mid::kRows, "same tiling");
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  ColumnCoefs<Fine::kCols> cf;  // in flight together with the statistics, before the path is known
-  cf.load(g, first_column<WN>(Fine::kCols));
-  const ScaleInfo sc = band_scale<WN>(g, Fine::kCols);
-  if (sc.umax <= Fine::kUmax)
-    likelihood_body<Fine, WM, WN, VEC4>(g, sc, cf, smem_raw);
-  else if (sc.umax <= Mid::kUmax)
-    likelihood_body<Mid, WM, WN, VEC4>(g, sc, cf, smem_raw);
-  else
-    likelihood_body<Coarse, WM, WN, VEC4>(g, sc, cf, smem_raw);
+  __shared__ double scratch[32];
+  pdl_trigger();  // the fold kernel may be made resident as this grid's CTAs retire
+  pdl_wait();     // the previous step's finish kernel still reads the posterior this one overwrites,
+                  // and the caller's kernels may have produced the observations
+#ifdef CGE_DEBUG_TIMES
+  unsigned long long t0 = 0;
+  if (g.debug && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+#endif
+  likelihood_cta<Fine, Mid, Coarse, SELECT, false, STREAMED>(g, smem_raw, scratch, blockIdx.x, gridDim.x);
+#ifdef CGE_DEBUG_TIMES
+  if (g.debug && threadIdx.x == 0) {
+    unsigned long long t1;
+    unsigned smid;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g.debug[4 * blockIdx.x + 0] = t0;
+    g.debug[4 * blockIdx.x + 1] = t1;
+    g.debug[4 * blockIdx.x + 2] = smid;
+    g.debug[4 * blockIdx.x + 3] = 0;
+  }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------
 // small_grid_kernel: the whole step in ONE launch for grids of a few hundred points per axis,
-// where five launches are all latency (the README workload, N = 101, is 510 050 pdf-evals:
+// where three launches are all latency (the README workload, N = 101, is 510 050 pdf-evals:
 // ~2 us of arithmetic).  Every CTA
-//   1. fills the four range tables and derives the scale statistics itself (identical values
-//      from every CTA: a benign race) and stages the observations straight into its shared
-//      memory -- setup_kernel's work, redundantly, instead of a launch and a dependency;
-//   2. runs the same fused likelihood body on its tile (unnormalised cells + partial sums);
-//   3. takes a ticket; the last CTA to finish folds the partials in a fixed order, writes Z, the
-//      marginals and the expectations, and scales the whole posterior by 1/Z (it fits in L2).
+//   1. stages the observations and derives the scale statistics itself (identical in every CTA);
+//   2. runs the same fused likelihood body on its units (unnormalised cells + partial sums);
+//   3. CLUSTER: the grid is ONE thread-block cluster (one column band, <= 8 CTAs: every grid up
+//      to 256 x 256), so its CTAs are co-scheduled and a hardware cluster barrier follows; after
+//      it every CTA folds the row partials itself (same order everywhere, so the same Z bit for
+//      bit) and scales ITS OWN rows in parallel; CTA 0 also writes the marginals and expectations.
+//      !CLUSTER: the last CTA to take a ticket does K6-K8 and scales the whole (L2-resident)
+//      posterior: no co-residency requirement.
 // Observations may be read from, and the results block also written to, mapped pinned host
 // memory, which removes both small DMA copies (~6 us and ~10 us) from the call's latency.
-// No grid-wide barrier, so no co-residency requirement.  Sums are in a fixed order (index
-// order within a thread, then the fixed block tree): bit-reproducible run to run.
+// Sums are in a fixed order (index order within a thread, then the fixed block tree).
 // ---------------------------------------------------------------------------------------
-constexpr int kSmallColChunk = 256;  // columns folded per pass of the last CTA (8 x 256 f64 of smem)
-
 struct SmallArgs {
-  LikeArgs like;  // tables written by this kernel; row_begin = 0, row_end = N
-  RangeArgs range;
-  const float *obs;  // raw observations (device)
-  float *mu, *sigma;
-  double *ad, *cd0;
-  ScaleInfo *scale;
-  int centred;
-  int ncolparts;
+  LikeArgs like;  // row_begin = 0, row_end = N; one band
   double *partials, *rowsum, *results;
   double *results_host;  // optional mapped pinned copy of `results` (saves the D2H copy)
   unsigned int *ticket;
 };
 
 // in place: post[0..count) *= finv, reading through L2 (other CTAs wrote some of it), several
-// independent loads in flight per thread; `post` is 16-byte aligned when VEC4
-template <bool VEC4>
-__device__ __forceinline__ void scale_cells_cta(float *post, size_t count, float finv) {
+// independent loads in flight per thread; `post` is 16-byte aligned when vec4
+__device__ __forceinline__ void scale_cells_cta(float *post, size_t count, float finv, bool vec4) {
   const int tid = threadIdx.x, nt = blockDim.x;
   constexpr int kDepth = 8;
-  if (VEC4) {
+  if (vec4) {
     float4 *p4 = reinterpret_cast<float4 *>(post);
-    const size_t nvec = count >> 2;  // VEC4 implies N % 4 == 0, so count % 4 == 0
+    const size_t nvec = count >> 2;  // vec4 implies N % 4 == 0, so count % 4 == 0
     for (size_t base = tid; base < nvec; base += (size_t)nt * kDepth) {
       float4 v[kDepth];
 #pragma unroll
@@ -1058,54 +1252,39 @@ __device__ __forceinline__ void cluster_barrier() {
                    : "memory");
 }
 
-// CLUSTER = false: any grid; the last CTA to take the ticket does K6-K8 and scales the whole
-//   posterior.
-// CLUSTER = true: the grid is ONE thread-block cluster (one column band, <= 8 row tiles: every
-//   grid up to 256 x 256), so its CTAs are co-scheduled and a hardware cluster barrier replaces
-//   the ticket: after it every CTA folds the row partials itself (same order everywhere, so the
-//   same Z bit for bit) and scales ITS OWN tile in parallel; CTA 0 also writes the marginals and
-//   expectations.  No single CTA walks the whole posterior.
-template <class Fine, class Mid, class Coarse, int WM, int WN, bool VEC4, bool CLUSTER = false>
-__global__ void __launch_bounds__(WM *WN * 32)
+template <class Fine, class Mid, class Coarse, bool SELECT, bool CLUSTER>
+__global__ void __launch_bounds__(kThreads)
     small_grid_kernel(const SmallArgs a) {
-  static_assert(Fine::kCols == Coarse::kCols && Fine::kRows == Coarse::kRows, "same tiling");
-  static_assert(Fine::kCols == Mid::kCols && Fine::kRows == Mid::kRows, "same tiling");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double scratch[32];
-  __shared__ double colred[WM * WN][kSmallColChunk];
   __shared__ bool is_last;
   const LikeArgs &g = a.like;
   const int tid = threadIdx.x, nt = blockDim.x;
   const int N = g.N;
-  float *obs_s = reinterpret_cast<float *>(smem_raw + 128);
+  const unsigned cta = blockIdx.x, nctas = gridDim.x;
+  float *obs_s = reinterpret_cast<float *>(smem_raw + kSmemHeader);
+  float *sort_s = reinterpret_cast<float *>(smem_raw + kSmemHeader + stage_bytes(g.n_pad));
 
-  for (int idx = tid; idx < N + 3; idx += nt) setup_point(idx, a.range, a.mu, a.sigma, a.ad, a.cd0);
-  ScaleInfo sc = setup_scale(a.range, a.obs, obs_s, g.n, g.n_pad, a.centred, scratch);
-  if (blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) *a.scale = sc;
-  __syncthreads();  // this CTA's own table writes and staged observations are visible to it
-
-  ColumnCoefs<Fine::kCols> cf;
-  cf.load(g, first_column<WN>(Fine::kCols));
-  {  // the band's own bound, as band_scale() computes it from the tables
-    const int jfirst = blockIdx.x * WN * 32 * Fine::kCols;
-    const int jlast = min(jfirst + WN * 32 * Fine::kCols, N) - 1;
-    sc.umax = fmax(fabs(a.ad[jfirst]), fabs(a.ad[jlast])) * sc.ustep;
+  {
+    const ScaleInfo sc = setup_scale(g.range, g.obs, obs_s, g.n, g.n_pad, g.centred,
+                                     g.reorder ? sort_s : nullptr, scratch);
+    if (tid == 0) {
+      *reinterpret_cast<ScaleInfo *>(smem_raw + 16) = sc;
+      if (cta == 0) *g.scale_out = sc;
+    }
+    __syncthreads();
   }
-  if (sc.umax <= Fine::kUmax)
-    likelihood_body<Fine, WM, WN, VEC4, true>(g, sc, cf, smem_raw);
-  else if (sc.umax <= Mid::kUmax)
-    likelihood_body<Mid, WM, WN, VEC4, true>(g, sc, cf, smem_raw);
-  else
-    likelihood_body<Coarse, WM, WN, VEC4, true>(g, sc, cf, smem_raw);
+  likelihood_cta<Fine, Mid, Coarse, SELECT, true>(g, smem_raw, scratch, cta, nctas);
+  __syncthreads();  // the warps of this CTA worked independently: all of them are done
 
   bool writer;  // the CTA that writes partials / results: the last one, or cluster rank 0
   if (CLUSTER) {
     cluster_barrier();
-    writer = blockIdx.y == 0;
+    writer = cta == 0;
   } else {
     __threadfence();
     __syncthreads();
-    if (tid == 0) is_last = atomicAdd(a.ticket, 1u) == gridDim.x * gridDim.y - 1;
+    if (tid == 0) is_last = atomicAdd(a.ticket, 1u) == nctas - 1;
     __syncthreads();
     if (!is_last) return;
     __threadfence();
@@ -1120,35 +1299,19 @@ __global__ void __launch_bounds__(WM *WN * 32)
     for (int w = 0; w < g.ncw; ++w) s += __ldcg(g.rowpart + (size_t)i * g.ncw + w);
     if (writer) a.rowsum[i] = s;
     z += s;
-    smu += s * (double)a.mu[i];
+    smu += s * (double)range_value(i, N, g.range.mu0, g.range.mu1);
   }
-  if (writer) {  // column sums: warp w takes slots w, w+NW, ... of a column (all its loads in
-                 // flight at once), then the NW partial sums are added in warp order
-    constexpr int NW = WM * WN;
-    const int lane = tid & 31, warp = tid >> 5;
-    for (int j0c = 0; j0c < N; j0c += kSmallColChunk) {
-      for (int j = j0c + lane; j < min(N, j0c + kSmallColChunk); j += 32) {
-        const double *src = g.colpart + j;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        int t = warp;
-        for (; t + 3 * NW < a.ncolparts; t += 4 * NW) {
-          s0 += __ldcg(src + (size_t)t * N);
-          s1 += __ldcg(src + (size_t)(t + NW) * N);
-          s2 += __ldcg(src + (size_t)(t + 2 * NW) * N);
-          s3 += __ldcg(src + (size_t)(t + 3 * NW) * N);
-        }
-        for (; t < a.ncolparts; t += NW) s0 += __ldcg(src + (size_t)t * N);
-        colred[warp][j - j0c] = (s0 + s1) + (s2 + s3);
-      }
-      __syncthreads();
-      for (int j = j0c + tid; j < min(N, j0c + kSmallColChunk); j += nt) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < NW; ++w) s += colred[w][j - j0c];
-        a.partials[2 + j] = s;
-      }
-      __syncthreads();
+  if (writer) {  // column sums: the exact fixed-point totals scaled back (col_fixed_shift), and the
+                 // accumulators and claim counters left at zero for the next call
+    const ScaleInfo sc = *reinterpret_cast<const ScaleInfo *>(smem_raw + 16);
+    for (int j = tid; j < N; j += nt) {
+      const double sd = (double)range_value(j, N, g.range.sg0, g.range.sg1);
+      const int s = col_fixed_shift(coef_a(sd), coef_c0(sd), sc, g.n, g.prior_log2max, g.fixed_bits);
+      a.partials[2 + j] = scalbn((double)(long long)__ldcg(g.colacc + j), -s);
+      g.colacc[j] = 0ull;
     }
+    for (int b = tid; b < g.ncw; b += nt) g.strip_next[b] = 0;
+    __syncthreads();
   }
   z = block_sum(z, scratch);
   smu = block_sum(smu, scratch);
@@ -1160,7 +1323,7 @@ __global__ void __launch_bounds__(WM *WN * 32)
       const double m = a.partials[2 + j] * inv;
       marg_sigma[j] = m;
       if (a.results_host) a.results_host[4 + j] = m;
-      es += m * (double)a.sigma[j];
+      es += m * (double)range_value(j, N, g.range.sg0, g.range.sg1);
     }
     for (int i = tid; i < N; i += nt) {
       const double m = a.rowsum[i] * inv;
@@ -1181,12 +1344,11 @@ __global__ void __launch_bounds__(WM *WN * 32)
     }
   }
   const float finv = (float)inv;
-  if (CLUSTER) {  // this CTA's own rows
-    const int r0 = blockIdx.y * g.tile_rows;
-    const int r1 = min(N, r0 + g.tile_rows);
-    if (r0 < N) scale_cells_cta<VEC4>(g.post + (size_t)r0 * N, (size_t)(r1 - r0) * N, finv);
+  if (CLUSTER) {  // an even share of the rows per CTA (whole rows, so float4 alignment holds)
+    const int r0 = (int)((long long)N * cta / nctas), r1 = (int)((long long)N * (cta + 1) / nctas);
+    if (r0 < r1) scale_cells_cta(g.post + (size_t)r0 * N, (size_t)(r1 - r0) * N, finv, g.vec4 != 0);
   } else {
-    scale_cells_cta<VEC4>(g.post, (size_t)N * N, finv);
+    scale_cells_cta(g.post, (size_t)N * N, finv, g.vec4 != 0);
   }
 }
 

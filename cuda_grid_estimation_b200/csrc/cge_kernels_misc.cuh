@@ -1,80 +1,88 @@
-// cge_kernels_misc.cuh -- the non-template kernels of the step (setup, fold, results, scale),
-// the stage-API kernels and the pipe micro-benchmarks.  Included by cge_api.cu only (they are
-// ordinary __global__ definitions: one translation unit must own them).
+// cge_kernels_misc.cuh -- the non-template kernels of the step (streamed set-up, fold + publish,
+// finish), the stage-API kernels and the pipe micro-benchmarks.  Included by cge_api.cu only (they
+// are ordinary __global__ definitions: one translation unit must own them).
 #pragma once
 #include "cge_kernels.cuh"
 
 namespace cge {
 
+// Streamed observations only (n_pad > kObsSingleMax, i.e. more than 16384): the likelihood
+// kernel re-reads the observations chunk by chunk for every row group, so they are staged once
+// in global memory (padded, centred) together with the statistics.  One block.
 __global__ void __launch_bounds__(256)
-    setup_kernel(float *__restrict__ mu, float *__restrict__ sigma, double *__restrict__ ad,
-                 double *__restrict__ cd0, const RangeArgs r, const float *__restrict__ obs,
-                 float *__restrict__ obs_pad, int n, int n_pad, int centred,
-                 ScaleInfo *__restrict__ out) {
+    setup_kernel(const RangeArgs r, const float *__restrict__ obs, float *__restrict__ obs_pad,
+                 int n, int n_pad, int centred, ScaleInfo *__restrict__ out) {
   __shared__ double scratch[32];
-  setup_point(blockIdx.x * blockDim.x + threadIdx.x, r, mu, sigma, ad, cd0);
-  if (blockIdx.x != 0) return;
-  const ScaleInfo sc = setup_scale(r, obs, obs_pad, n, n_pad, centred, scratch);
+  const ScaleInfo sc = setup_scale(r, obs, obs_pad, n, n_pad, centred, nullptr, scratch);
   if (threadIdx.x == 0) *out = sc;
 }
 
 // ---------------------------------------------------------------------------------------
-// K6-K8 replacement, stage 1: fold the partial buffers in a fixed order.
-//   blocks [0, nb_col): 32 columns each; 8 slot groups stride the ncolparts slots (4 loads in
-//                       flight per thread), then the groups are summed 0..7       -> colsum
+// K6-K8 replacement, stage 1: fold the partial sums and publish the result.
+//   blocks [0, nb_col): 256 columns each: colsum_j = colacc_j * 2^-s_j, the exact fixed-point total
+//                       the likelihood kernel accumulated, scaled back with the same per-column
+//                       exponent (col_fixed_shift); the accumulators and the claim counters are
+//                       cleared for the next step
 //   blocks [nb_col, ..): warp per row, lanes stride the ncw strips, shuffle tree  -> rowsum;
 //                        per-block partials of Z and sum mu_i*rowsum_i
 //   the last block to finish (threadfence + ticket) adds the block partials in index order:
-//                        partials[0] = Z, partials[1] = sum_i mu_i*rowsum_i
+//                        out[0] = Z, out[1] = sum_i mu_i*rowsum_i
+//   and, when sharded with the peer exchange, raises this rank's "vector of step s is complete"
+//   flag (st.release.sys) for the other GPUs to poll.
 // The ticket only decides WHO does the final sum, never its order: bit-reproducible.
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    fold_partials_kernel(const double *__restrict__ colpart, int ncolparts,
-                         const double *__restrict__ rowpart, int ncw, int rows_local,
-                         int row_begin, int N, const float *__restrict__ mu,
-                         double *__restrict__ partials, double *__restrict__ rowsum,
-                         double *__restrict__ zpart, double *__restrict__ smupart, int nb_col,
-                         int nb_row, unsigned int *__restrict__ ticket,
-                         unsigned long long *ready_flag, unsigned long long ready_value) {
+struct FoldArgs {
+  unsigned long long *colacc;  // [N] fixed-point column sums (read, then cleared)
+  int *strip_next;             // [ncw] claim counters (cleared)
+  const ScaleInfo *scale;      // statistics of this step (written by the likelihood kernel)
+  const double *rowpart;
+  double *out;      // N+2: the context's partial vector, or this rank's exchange buffer
+  double *rowsum;   // rows_local
+  double *zpart, *smupart;  // nb_row each
+  unsigned int *ticket;
+  unsigned long long *ready_flag;  // NULL unless the peer exchange is on
+  unsigned long long ready_value;
+  RangeArgs range;
+  float prior_log2max;
+  int fixed_bits, n;
+  int ncw, rows_local, row_begin, N;
+  int nb_col, nb_row;
+};
+
+__global__ void __launch_bounds__(256) fold_publish_kernel(const FoldArgs f) {
   __shared__ double sh[8][33];
   __shared__ bool is_last;
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  if ((int)blockIdx.x < nb_col) {
-    const int j = blockIdx.x * 32 + lane;
-    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  const int N = f.N;
+  pdl_trigger();
+  pdl_wait();  // the likelihood kernel's partial sums are complete and visible
+  if ((int)blockIdx.x < f.nb_col) {
+    const int j = blockIdx.x * 256 + tid;
     if (j < N) {
-      const double *src = colpart + j;
-      int t = warp;
-      for (; t + 24 < ncolparts; t += 32) {
-        s0 += src[(size_t)t * N];
-        s1 += src[(size_t)(t + 8) * N];
-        s2 += src[(size_t)(t + 16) * N];
-        s3 += src[(size_t)(t + 24) * N];
-      }
-      for (; t < ncolparts; t += 8) s0 += src[(size_t)t * N];
+      const ScaleInfo sc = *f.scale;
+      const double sd = (double)range_value(j, N, f.range.sg0, f.range.sg1);
+      const int s = col_fixed_shift(coef_a(sd), coef_c0(sd), sc, f.n, f.prior_log2max, f.fixed_bits);
+      f.out[2 + j] = scalbn((double)(long long)f.colacc[j], -s);
+      f.colacc[j] = 0ull;
     }
-    sh[warp][lane] = (s0 + s1) + (s2 + s3);
-    __syncthreads();
-    if (warp == 0 && j < N) {
-      double s = 0.0;
-#pragma unroll
-      for (int w = 0; w < 8; ++w) s += sh[w][lane];
-      partials[2 + j] = s;
-    }
+    if (blockIdx.x == 0)
+      for (int b = tid; b < f.ncw; b += 256) f.strip_next[b] = 0;
   } else {
-    const int rb = blockIdx.x - nb_col;
+    const int rb = blockIdx.x - f.nb_col;
     const int il = rb * 8 + warp;
     double s = 0.0;
-    if (il < rows_local) {
-      const double *src = rowpart + (size_t)il * ncw;
-      for (int w = lane; w < ncw; w += 32) s += src[w];
+    if (il < f.rows_local) {
+      const double *src = f.rowpart + (size_t)il * f.ncw;
+      for (int w = lane; w < f.ncw; w += 32) s += src[w];
     }
     s = warp_sum(s);
     if (lane == 0) {
-      if (il < rows_local) rowsum[il] = s;
+      if (il < f.rows_local) f.rowsum[il] = s;
       sh[0][warp] = s;
-      sh[1][warp] = il < rows_local ? s * (double)mu[row_begin + il] : 0.0;
+      sh[1][warp] = il < f.rows_local
+                        ? s * (double)range_value(f.row_begin + il, N, f.range.mu0, f.range.mu1)
+                        : 0.0;
     }
     __syncthreads();
     if (tid == 0) {
@@ -84,21 +92,21 @@ __global__ void __launch_bounds__(256)
         z += sh[0][w];
         m += sh[1][w];
       }
-      zpart[rb] = z;
-      smupart[rb] = m;
+      f.zpart[rb] = z;
+      f.smupart[rb] = m;
     }
   }
   // ---- last block: Z and sum mu*rowsum over the row-block partials, in index order
   __threadfence();
   __syncthreads();
-  if (tid == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  if (tid == 0) is_last = atomicAdd(f.ticket, 1u) == gridDim.x - 1;
   __syncthreads();
   if (!is_last) return;
   __threadfence();
   double z = 0.0, m = 0.0;
-  for (int b = tid; b < nb_row; b += 256) {
-    z += __ldcg(zpart + b);
-    m += __ldcg(smupart + b);
+  for (int b = tid; b < f.nb_row; b += 256) {
+    z += __ldcg(f.zpart + b);
+    m += __ldcg(f.smupart + b);
   }
   z = warp_sum(z);
   m = warp_sum(m);
@@ -115,80 +123,59 @@ __global__ void __launch_bounds__(256)
       zt += sh[2][w];
       mt += sh[3][w];
     }
-    partials[0] = zt;
-    partials[1] = mt;
-    *ticket = 0u;  // ready for the next launch on this stream
-    if (ready_flag) {
+    f.out[0] = zt;
+    f.out[1] = mt;
+    *f.ticket = 0u;  // ready for the next step of this context
+    if (f.ready_flag) {
       // peer exchange: every block's column sums are ordered before this point by the ticket
       // (fence + atomic); publish "the partial vector of step `ready_value - 1` is complete"
       // to the other GPUs, which poll this word over NVLink
       __threadfence_system();
-      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(ready_flag), "l"(ready_value)
+      asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f.ready_flag), "l"(f.ready_value)
                    : "memory");
     }
   }
 }
 
-// stage 2, after the cross-rank sum of `partials`: marginals and expectations.
-//   marg_sigma_j = colsum_j * (1/Z)   E[sigma] = sum_j marg_sigma_j * sigma_j   (cuda_functions.h:201-218)
-//   marg_mu_i    = rowsum_i * (1/Z)   E[mu]    = (sum_i mu_i*rowsum_i) * (1/Z)
-// 256 grid points per block; the last block adds the per-block E[sigma] partials in index order.
-__global__ void __launch_bounds__(256)
-    results_kernel(const double *__restrict__ partials, const double *__restrict__ rowsum,
-                   const float *__restrict__ sigma, int N, int row_begin, int row_end,
-                   double *__restrict__ results, double *__restrict__ espart,
-                   unsigned int *__restrict__ ticket) {
-  __shared__ double scratch[32];
-  __shared__ bool is_last;
-  const int tid = threadIdx.x;
-  const double z = partials[0];
-  const double inv = 1 / z;  // reciprocal multiply, as inc/utils.h:82-84
-  double *marg_sigma = results + 4, *marg_mu = results + 4 + N;
-  const int idx = blockIdx.x * 256 + tid;
-  double es = 0.0;
-  if (idx < N) {
-    const double m = partials[2 + idx] * inv;
-    marg_sigma[idx] = m;
-    es = m * (double)sigma[idx];
-    marg_mu[idx] = (idx >= row_begin && idx < row_end) ? rowsum[idx - row_begin] * inv : 0.0;
-  }
-  es = block_sum(es, scratch);
-  if (tid == 0) espart[blockIdx.x] = es;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  double e = 0.0;
-  for (int b = tid; b < (int)gridDim.x; b += 256) e += __ldcg(espart + b);
-  e = block_sum(e, scratch);
-  if (tid == 0) {
-    results[0] = partials[1] * inv;
-    results[1] = e;
-    results[2] = z;
-    results[3] = inv;
-    *ticket = 0u;
-  }
-}
-
 // ---------------------------------------------------------------------------------------
-// stage 2 with the exchange fused in (one process per GPU, one node): instead of a library
-// all-reduce between the fold and this kernel, every rank reads the peers' partial vectors
-// straight out of their HBM over NVLink (CUDA IPC mappings) and adds them in RANK ORDER -- the
-// sum is bit-identical on every rank and independent of any collective algorithm.
-//   peers.buf[r]   rank r's partial vector for this step (N+2 f64; this rank's own included)
-//   peers.flag[r]  rank r's "step s complete" word; polled with ld.acquire.sys until >= want
+// stage 2, finish_kernel: everything after the exchange, in one launch.
+//   every block   (sharded, peer exchange) waits for the peers' "step s complete" flags
+//                 (ld.acquire.sys, one lane per peer) and adds {Z_r, Smu_r} in RANK ORDER -- the
+//                 totals are bit-identical on every rank and independent of any collective
+//                 algorithm; without peers it reads the (locally folded or all-reduced) vector.
+//   blocks [0, nb_res): 256 grid points each --
+//                 marg_sigma_j = colsum_j * (1/Z), colsum_j the rank-ordered sum of the peers'
+//                 vectors read straight out of their HBM over NVLink; E[sigma] partials
+//                 (inc/cuda_functions.h:201-218); marg_mu_i = rowsum_i * (1/Z) for this shard's
+//                 rows; the last of them (ticket) adds the E[sigma] partials in index order and
+//                 writes {E[mu], E[sigma], Z, 1/Z}
+//   every block   its share of the in-place posterior *= 1/Z (reciprocal multiply, as
+//                 inc/utils.h:82-84): pure HBM streaming, 4 B read + 4 B written per cell, 4
+//                 independent 16-byte loads in flight per thread; or, for a float64 posterior,
+//                 reads the float32 likelihoods and writes float64 (4 + 8 B per cell).
 // A rank may overwrite its vector of step s at step s+2: by then it has itself waited for every
-// peer's step-(s+1) flag, which each peer raises only after its own step-s results kernel.
+// peer's step-(s+1) flag, which each peer raises only after its own step-s finish kernel.
 // The poll gives up after ~4e9 cycles and poisons the result (Z = NaN -> CGE_ERR_DEGENERATE).
 // ---------------------------------------------------------------------------------------
-constexpr int kMaxPeers = 16;
 struct PeerView {
   const double *buf[kMaxPeers];
   const unsigned long long *flag[kMaxPeers];
-  int world;
+  int world;  // 0: no peer exchange
   unsigned long long want;
+};
+
+struct FinishArgs {
+  PeerView peers;
+  double *partials;        // N+2: local / all-reduced vector in; summed vector out
+  const double *rowsum;    // rows_local
+  double *results;         // 4 + 2N
+  double *espart;          // nb_res
+  unsigned int *ticket;
+  float *post;             // float32 shard: scaled in place, or the source of post64
+  double *post64;          // float64 output shard (NULL: float32 in place)
+  size_t cells;
+  RangeArgs range;
+  int N, row_begin, row_end, nb_res, aligned;
 };
 
 __device__ __forceinline__ double ld_peer(const double *p) {
@@ -197,107 +184,147 @@ __device__ __forceinline__ double ld_peer(const double *p) {
   return v;
 }
 
-__global__ void __launch_bounds__(256)
-    results_peer_kernel(const PeerView peers, double *__restrict__ partials,
-                        const double *__restrict__ rowsum, const float *__restrict__ sigma, int N,
-                        int row_begin, int row_end, double *__restrict__ results,
-                        double *__restrict__ espart, unsigned int *__restrict__ ticket) {
+__global__ void __launch_bounds__(256) finish_kernel(const FinishArgs a) {
   __shared__ double scratch[32];
   __shared__ bool is_last;
   __shared__ int timed_out;
   const int tid = threadIdx.x;
-  if (tid == 0) timed_out = 0;
-  __syncthreads();
-  if (tid < peers.world) {  // one lane per peer polls that peer's flag
-    const long long t0 = clock64();
-    unsigned long long v;
-    do {
-      asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(peers.flag[tid]) : "memory");
-      if (v >= peers.want) break;
-      if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }
-      __nanosleep(100);
-    } while (true);
+  const int N = a.N;
+  pdl_trigger();
+  pdl_wait();  // the fold kernel (and whatever summed the vector over ranks) is complete
+  double z, smu;
+  if (a.peers.world > 0) {
+    if (tid == 0) timed_out = 0;
+    __syncthreads();
+    if (tid < a.peers.world) {  // one lane per peer polls that peer's flag
+      const long long t0 = clock64();
+      unsigned long long v;
+      do {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(a.peers.flag[tid]) : "memory");
+        if (v >= a.peers.want) break;
+        if (clock64() - t0 > 4000000000LL) { timed_out = 1; break; }
+        __nanosleep(100);
+      } while (true);
+    }
+    __syncthreads();
+    __threadfence_system();
+    z = 0.0;
+    smu = 0.0;
+    for (int r = 0; r < a.peers.world; ++r) {  // rank order: same bits on every rank
+      z += ld_peer(a.peers.buf[r]);
+      smu += ld_peer(a.peers.buf[r] + 1);
+    }
+    if (timed_out) z = __longlong_as_double(0x7ff8000000000000LL);
+  } else {
+    z = a.partials[0];
+    smu = a.partials[1];
   }
-  __syncthreads();
-  __threadfence_system();
-  double z = 0.0, smu = 0.0;
-  for (int r = 0; r < peers.world; ++r) {  // rank order: same bits on every rank
-    z += ld_peer(peers.buf[r]);
-    smu += ld_peer(peers.buf[r] + 1);
-  }
-  if (timed_out) z = __longlong_as_double(0x7ff8000000000000LL);
-  const double inv = 1 / z;
-  double *marg_sigma = results + 4, *marg_mu = results + 4 + N;
-  const int idx = blockIdx.x * 256 + tid;
-  double es = 0.0;
-  if (idx < N) {
-    double c = 0.0;
-    for (int r = 0; r < peers.world; ++r) c += ld_peer(peers.buf[r] + 2 + idx);
-    partials[2 + idx] = c;  // the summed vector, for callers that read cge_partials afterwards
-    const double m = c * inv;
-    marg_sigma[idx] = m;
-    es = m * (double)sigma[idx];
-    marg_mu[idx] = (idx >= row_begin && idx < row_end) ? rowsum[idx - row_begin] * inv : 0.0;
-  }
-  if (blockIdx.x == 0 && tid == 0) {
-    partials[0] = z;  // the scale pass reads Z from here
-    partials[1] = smu;
-  }
-  es = block_sum(es, scratch);
-  if (tid == 0) espart[blockIdx.x] = es;
-  __threadfence();
-  __syncthreads();
-  if (tid == 0) is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
-  __syncthreads();
-  if (!is_last) return;
-  __threadfence();
-  double e = 0.0;
-  for (int b = tid; b < (int)gridDim.x; b += 256) e += __ldcg(espart + b);
-  e = block_sum(e, scratch);
-  if (tid == 0) {
-    results[0] = smu * inv;
-    results[1] = e;
-    results[2] = z;
-    results[3] = inv;
-    *ticket = 0u;
-  }
-}
+  const double inv = 1 / z;  // reciprocal multiply, as inc/utils.h:82-84
 
-// ---------------------------------------------------------------------------------------
-// scale pass: posterior *= 1/Z in place.  Pure HBM streaming: 4 B read + 4 B written per cell.
-// ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-    scale_posterior_kernel(float *__restrict__ post, size_t count, const double *__restrict__ partials) {
-  const float inv = (float)(1 / partials[0]);
-  const size_t nvec = count >> 2;
-  float4 *p4 = reinterpret_cast<float4 *>(post);
+  if ((int)blockIdx.x < a.nb_res) {
+    double *marg_sigma = a.results + 4, *marg_mu = a.results + 4 + N;
+    const int idx = blockIdx.x * 256 + tid;
+    double es = 0.0;
+    if (idx < N) {
+      double c;
+      if (a.peers.world > 0) {
+        c = 0.0;
+        for (int r = 0; r < a.peers.world; ++r) c += ld_peer(a.peers.buf[r] + 2 + idx);
+        a.partials[2 + idx] = c;  // the summed vector, for callers that read cge_partials afterwards
+      } else {
+        c = a.partials[2 + idx];
+      }
+      const double m = c * inv;
+      marg_sigma[idx] = m;
+      es = m * (double)range_value(idx, N, a.range.sg0, a.range.sg1);
+      marg_mu[idx] = (idx >= a.row_begin && idx < a.row_end) ? a.rowsum[idx - a.row_begin] * inv : 0.0;
+    }
+    es = block_sum(es, scratch);
+    if (tid == 0) a.espart[blockIdx.x] = es;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) is_last = atomicAdd(a.ticket, 1u) == (unsigned)a.nb_res - 1;
+    __syncthreads();
+    if (is_last) {
+      __threadfence();
+      double e = 0.0;
+      for (int b = tid; b < a.nb_res; b += 256) e += __ldcg(a.espart + b);
+      e = block_sum(e, scratch);
+      if (tid == 0) {
+        if (a.peers.world > 0) {
+          a.partials[0] = z;
+          a.partials[1] = smu;
+        }
+        a.results[0] = smu * inv;
+        a.results[1] = e;
+        a.results[2] = z;
+        a.results[3] = inv;
+        *a.ticket = 0u;
+      }
+    }
+  }
+
+  // ---- the scale pass
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  // 4 independent 16-byte loads in flight per thread
-  for (; i + 3 * stride < nvec; i += 4 * stride) {
-    float4 a = p4[i], b = p4[i + stride], c = p4[i + 2 * stride], d = p4[i + 3 * stride];
-    a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
-    b.x *= inv; b.y *= inv; b.z *= inv; b.w *= inv;
-    c.x *= inv; c.y *= inv; c.z *= inv; c.w *= inv;
-    d.x *= inv; d.y *= inv; d.z *= inv; d.w *= inv;
-    p4[i] = a; p4[i + stride] = b; p4[i + 2 * stride] = c; p4[i + 3 * stride] = d;
+  size_t i = (size_t)blockIdx.x * blockDim.x + tid;
+  if (a.post64 != nullptr) {  // float32 likelihoods in, float64 posterior out (normalised in float64)
+    if (a.aligned) {
+      const size_t nvec = a.cells >> 2;
+      const float4 *s4 = reinterpret_cast<const float4 *>(a.post);
+      double2 *d2 = reinterpret_cast<double2 *>(a.post64);
+      for (; i + stride < nvec; i += 2 * stride) {
+        const float4 p = s4[i], q = s4[i + stride];
+        d2[2 * i] = make_double2((double)p.x * inv, (double)p.y * inv);
+        d2[2 * i + 1] = make_double2((double)p.z * inv, (double)p.w * inv);
+        d2[2 * (i + stride)] = make_double2((double)q.x * inv, (double)q.y * inv);
+        d2[2 * (i + stride) + 1] = make_double2((double)q.z * inv, (double)q.w * inv);
+      }
+      for (; i < nvec; i += stride) {
+        const float4 p = s4[i];
+        d2[2 * i] = make_double2((double)p.x * inv, (double)p.y * inv);
+        d2[2 * i + 1] = make_double2((double)p.z * inv, (double)p.w * inv);
+      }
+      if (blockIdx.x == 0 && tid < (int)(a.cells & 3))
+        a.post64[(nvec << 2) + tid] = (double)a.post[(nvec << 2) + tid] * inv;
+    } else {
+      for (; i < a.cells; i += stride) a.post64[i] = (double)a.post[i] * inv;
+    }
+    return;
   }
-  for (; i < nvec; i += stride) {
-    float4 a = p4[i];
-    a.x *= inv; a.y *= inv; a.z *= inv; a.w *= inv;
-    p4[i] = a;
+  const float finv = (float)inv;
+  if (a.aligned) {
+    const size_t nvec = a.cells >> 2;
+    float4 *p4 = reinterpret_cast<float4 *>(a.post);
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+      float4 p = p4[i], q = p4[i + stride], r = p4[i + 2 * stride], s = p4[i + 3 * stride];
+      p.x *= finv; p.y *= finv; p.z *= finv; p.w *= finv;
+      q.x *= finv; q.y *= finv; q.z *= finv; q.w *= finv;
+      r.x *= finv; r.y *= finv; r.z *= finv; r.w *= finv;
+      s.x *= finv; s.y *= finv; s.z *= finv; s.w *= finv;
+      p4[i] = p; p4[i + stride] = q; p4[i + 2 * stride] = r; p4[i + 3 * stride] = s;
+    }
+    for (; i < nvec; i += stride) {
+      float4 p = p4[i];
+      p.x *= finv; p.y *= finv; p.z *= finv; p.w *= finv;
+      p4[i] = p;
+    }
+    if (blockIdx.x == 0 && tid < (int)(a.cells & 3)) a.post[(nvec << 2) + tid] *= finv;
+  } else {  // a posterior pointer that is not 16-byte aligned (caller-owned sub-buffers)
+    for (; i < a.cells; i += stride) a.post[i] *= finv;
   }
-  if (blockIdx.x == 0 && threadIdx.x < (count & 3)) post[(nvec << 2) + threadIdx.x] *= inv;
 }
 
-// same pass for a posterior pointer that is not 16-byte aligned (caller-owned sub-buffers)
+// largest |v| of a float array as the bit pattern of a non-negative float (which orders like the
+// unsigned integer); NaN compares as a huge value, i.e. it is kept
 __global__ void __launch_bounds__(256)
-    scale_posterior_scalar_kernel(float *__restrict__ post, size_t count,
-                                  const double *__restrict__ partials) {
-  const float inv = (float)(1 / partials[0]);
+    absmax_kernel(const float *__restrict__ v, size_t count, unsigned int *__restrict__ out) {
+  unsigned int m = 0;
   for (size_t f = (size_t)blockIdx.x * blockDim.x + threadIdx.x; f < count;
        f += (size_t)gridDim.x * blockDim.x)
-    post[f] *= inv;
+    m = max(m, __float_as_uint(fabsf(v[f])));
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, off));
+  if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
 // ---------------------------------------------------------------------------------------

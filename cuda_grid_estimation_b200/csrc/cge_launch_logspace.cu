@@ -1,17 +1,27 @@
-// cge_launch_logspace.cu -- instantiations and launcher of the log-space likelihood kernels
+// cge_launch_logspace.cu -- instantiations of the log-space likelihood kernels
 #include "cge_host.cuh"
 
 namespace cge_host {
 
+template <class P, int MINB, bool STREAMED>
+static KernelChoice pick() {
+  KernelChoice kc;
+  kc.smem_bytes = cge::policy_smem_bytes<P>();
+  kc.kcols = P::kCols;
+  kc.fn = (const void *)cge::grid_likelihood_kernel<P, P, P, false, MINB, STREAMED>;
+  return kc;
+}
+
 // default: float32x2 sums of centred terms in tiles of 256 observations folded into float64
-// (LogSpaceTiled), capped at 128 registers; 6: tiles of 64; CGE_VARIANT_LOG_F64: one DFMA per
-// pdf-eval (the first log-space kernel, kept as the FP64-pipe case)
-int launch_logspace(const Plan &pl, const cge::LikeArgs &args, cudaStream_t st) {
-  switch (pl.variant) {
-    case CGE_VARIANT_LOG_F64: return launch_like<cge::LogSpaceF64, 1>(pl, args, st);
-    case 6: return launch_like<cge::LogSpaceTiled<64>, 2>(pl, args, st);
-    default: return launch_like<cge::LogSpaceTiled<256>, 2>(pl, args, st);
-  }
+// (LogSpaceTiled), capped at 128 registers; CGE_VARIANT_LOG_F64: one DFMA per pdf-eval (the
+// first log-space kernel, kept as the FP64-pipe case).  pl.streamed (more than 16384
+// observations): the instantiation that streams them through two 32 KB shared-memory stages.
+int choose_logspace(const Plan &pl, KernelChoice *out) {
+  if (pl.variant == CGE_VARIANT_LOG_F64)
+    *out = pl.streamed ? pick<cge::LogSpaceF64, 1, true>() : pick<cge::LogSpaceF64, 1, false>();
+  else
+    *out = pl.streamed ? pick<cge::LogSpaceTiled<256>, 2, true>() : pick<cge::LogSpaceTiled<256>, 2, false>();
+  return CGE_OK;
 }
 
 }  // namespace cge_host

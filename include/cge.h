@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CGE_VERSION 1
+#define CGE_VERSION 2
 
 /* status codes (the reference returns void and prints; src/grid.cu:15-17 is its only check) */
 enum {
@@ -45,7 +45,8 @@ enum {
   CGE_ERR_NO_DEVICE = 2,  /* no CUDA device / not sm_100 */
   CGE_ERR_CUDA = 3,       /* a CUDA runtime call failed; see cge_last_error() */
   CGE_ERR_DEGENERATE = 4, /* normaliser Z is zero or not finite (all cells underflowed) */
-  CGE_ERR_NCCL = 5,       /* collective failed */
+  CGE_ERR_PEER = 5,       /* the exchange between GPUs cannot be set up (no peer access between two
+                             devices of a cge_multi, or a CUDA IPC handle that cannot be opened) */
   CGE_ERR_SIZE = 6        /* stage API: densitiesSize != rows*cols (inc/wrappers.h:110-113) */
 };
 
@@ -60,7 +61,19 @@ enum {
                                any product underflows */
 };
 
-typedef struct cge_context cge_context; /* opaque: device, stream, scratch, tables */
+/* element type of the posterior the caller receives (cge_params.posterior_dtype) */
+enum {
+  CGE_POSTERIOR_F32 = 0,  /* float32 -- BASELINE.json "float32 product path"; normalised in place:
+                             12 bytes of HBM traffic per cell */
+  CGE_POSTERIOR_F64 = 1   /* float64, the reference's type (thrust::device_vector<double>,
+                             inc/cuda_functions.h:139-159, src/grid.cu:111-112): the likelihoods are
+                             the same float32 values (kept in context scratch), widened and normalised
+                             in float64 on the way out -- 16 bytes per cell instead of the 24 a
+                             float64 unnormalised buffer would cost */
+};
+
+typedef struct cge_context cge_context; /* opaque: device, stream, scratch */
+typedef struct cge_multi cge_multi;     /* opaque: one context per GPU of a single-process group */
 
 typedef struct cge_params {
   int32_t n_obs;        /* observations (reference: rvsSize, src/grid.cu:34) */
@@ -72,8 +85,9 @@ typedef struct cge_params {
   int32_t mode;         /* CGE_MODE_* */
   int32_t row_begin;    /* shard: this call owns mu rows [row_begin, row_end) of the global */
   int32_t row_end;      /* grid; 0,0 means the whole grid (0, grid_size) */
-  int32_t variant;      /* CGE_VARIANT_*: 0 = library default; other values pick a tuning variant
-                           of the likelihood kernel (same results within tolerance) */
+  int32_t variant;      /* CGE_VARIANT_*: 0 = library default; other values force one arithmetic
+                           policy of the likelihood kernel (same results within tolerance) */
+  int32_t posterior_dtype; /* CGE_POSTERIOR_*: what `posterior` points to */
 } cge_params;
 
 /* likelihood-kernel variants for cge_params.variant */
@@ -92,26 +106,21 @@ enum {
                                 default log-space kernel sums centred terms in float32x2 tiles of 256
                                 observations and folds the tiles into float64) */
   CGE_VARIANT_UNFUSED = 7,   /* the default kernels, but cge_grid_posterior always takes the
-                                five-launch path (by default grids up to 256 points per axis run
-                                as ONE launch: tables, likelihood, fold, results and scale in a
+                                three-launch path (by default grids up to 256 points per axis run
+                                as ONE launch: set-up, likelihood, fold, results and scale in a
                                 single kernel) */
   CGE_VARIANT_HYBRID = 4     /* hybrid, forced: packed f32x2 arithmetic; of the 16 exponentials a
                                 thread evaluates per observation, 12 use MUFU.EX2 and 4 an FMA-pipe
                                 degree-5 polynomial with Cody-Waite range reduction */
-  /* tuning variants still built (wide tile shape only; see cge_api.cu launch_product): 31 = the
-     first paired kernel (1 observation per iteration, unpacked scalars, uncapped registers);
-     39 / 45 = the default paired kernel at 128 registers with the column sums in registers /
-     shared memory; 381 = paired rows, 8 columns per thread.  Log-space: 6 = tiles of 64
-     observations (default 256).  profiles/r01_variant_sweep_*.jsonl record ~25 more variants
-     (hybrid splits, loop shapes, register caps) that were removed after the sweeps. */
 };
 
 /* per-phase device timings of the last synchronous call, milliseconds (CUDA events) */
 typedef struct cge_timing {
-  float setup_ms;       /* range/coefficient tables + scale statistics */
-  float likelihood_ms;  /* fused likelihood kernel */
-  float reduce_ms;      /* deterministic partial reduction (Z, marginals, expectations) */
-  float scale_ms;       /* posterior *= 1/Z */
+  float setup_ms;       /* staging of > 16384 observations (0 otherwise: the set-up is part of the
+                           likelihood kernel) */
+  float likelihood_ms;  /* fused likelihood kernel (set-up, K1-K5) */
+  float reduce_ms;      /* fold of the partial sums + publish */
+  float scale_ms;       /* finish kernel: (peer sum,) marginals, expectations, posterior *= 1/Z */
   float total_ms;
   float h2d_ms;         /* host-buffer entry points only */
   float d2h_ms;
@@ -127,45 +136,59 @@ int cge_device_sm_count(cge_context *ctx, int *sm_count, int *cc_major, int *cc_
 /* ---- the fused hot path: replaces src/grid.cu:79-127 in one call ------------------------
  * cge_grid_posterior: host or device buffers (detected with cudaPointerGetAttributes), runs
  * synchronously, returns when every requested output is written.
- *   obs            n_obs float32                                  (reference: observations)
- *   posterior      (row_end-row_begin) * grid_size float32, or NULL to keep it on device only
+ *   obs            n_obs float32, any order                       (reference: observations)
+ *   posterior      (row_end-row_begin) * grid_size elements of p->posterior_dtype, or NULL to keep
+ *                  it on device only (cge_posterior_dev)
  *   marg_mu        grid_size float64 (row sums; only [row_begin,row_end) are this shard's, the
  *                  rest are written as 0), or NULL               (inc/wrappers.h:169)
  *   marg_sigma     grid_size float64 (column sums of this shard), or NULL (inc/wrappers.h:170)
  *   expectations   2 float64 {E[mu], E[sigma]}, or NULL          (inc/wrappers.h:173-176)
  *   timing         optional
  * With a shard (row_begin/row_end not covering the grid) the normaliser is the SHARD's unless
- * the caller uses the phase API below and all-reduces the partials.
+ * the caller uses the phase API below and sums the partials over ranks, or cge_grid_posterior_multi.
+ * Product mode takes up to 16384 observations (the running float32 product stays in range for any
+ * input order: the kernel consumes the observations in a range-balanced order of its own); more
+ * need CGE_MODE_LOGSPACE.
  */
 int cge_grid_posterior(cge_context *ctx, const cge_params *p, const float *obs,
-                       float *posterior, double *marg_mu, double *marg_sigma,
+                       void *posterior, double *marg_mu, double *marg_sigma,
                        double *expectations, cge_timing *timing);
 
 /* Asynchronous form of the fused call for device buffers: enqueues the whole step on `stream`
- * (one launch for grids up to 256 points per axis, five otherwise) and returns without waiting.
+ * (one launch for grids up to 256 points per axis, three otherwise) and returns without waiting.
  * Results stay on the device (cge_results / cge_read_results, which waits for `stream`);
  * posterior_dev receives the normalised posterior.  Whole grid only (row_begin/row_end must cover
  * it): a shard needs the exchange between the two phases below. */
 int cge_grid_posterior_async(cge_context *ctx, const cge_params *p, const float *obs_dev,
-                             float *posterior_dev, void *stream);
+                             void *posterior_dev, void *stream);
 
 /* ---- phase API (multi-GPU: one process per GPU, the caller owns the collective) ----------
- * phase 1: tables + likelihood + local deterministic reduction.  Leaves the packed partial
- *          vector {Z, sum_i mu_i*rowsum_i, colsum[0..N)} (N+2 float64) in a context-owned
- *          device buffer (cge_partials) and the UNNORMALISED likelihoods in posterior_dev.
+ * phase 1: likelihood (scale statistics and range values derived inside the kernel) + local
+ *          deterministic reduction.  Leaves the packed partial vector
+ *          {Z, sum_i mu_i*rowsum_i, colsum[0..N)} (N+2 float64) in a context-owned device buffer
+ *          (cge_partials) and the UNNORMALISED float32 likelihoods in posterior_dev (float32
+ *          posterior) or in context scratch (float64 posterior).
  * ...      the caller sums the partial vector over ranks in place (ncclAllReduce / torch
  *          all_reduce, float64 sum) -- nothing else crosses NVLink.
- * phase 2: marginals, expectations and the in-place scale posterior_dev *= 1/Z.
+ * phase 2: marginals, expectations and the scale by 1/Z into posterior_dev, one launch.
  *          Results stay on the device in the context's result block (cge_results).
+ * A context runs ONE step at a time: both phases of a step, and consecutive steps, must be
+ * enqueued on the same stream (or be ordered by the caller); the scratch and the "last block"
+ * tickets are per context, not per stream.
+ * Pointers returned by cge_partials / cge_results / cge_posterior_dev stay valid until the next
+ * call on the context with a LARGER grid or shard (scratch is grow-only and reallocates then), a
+ * cge_set_prior, or cge_destroy.
  */
 /* Peer exchange (optional; one process per GPU on ONE node): replaces "the caller sums the partial
  * vector" by peer loads over NVLink fused into phase 2.  Each rank allocates an exchange block and
  * exports its CUDA IPC handle (cge_peer_local_handle), the caller gathers the handles of all ranks
  * (any transport) and hands the concatenation, in rank order, to cge_peer_connect.  From then on
  * cge_likelihood_partials publishes this rank's vector to the peers and cge_finalize waits for
- * theirs and adds all of them in rank order inside the results kernel -- no library collective,
+ * theirs and adds all of them in rank order inside the finish kernel -- no library collective,
  * bit-identical totals on every rank.  Every rank must make the same sequence of phase calls.
- * Ranks must not destroy/disconnect while a peer may still be reading (barrier first). */
+ * Ranks must not destroy/disconnect while a peer may still be reading (barrier first).
+ * (A single process driving several GPUs uses cge_create_multi instead: same kernels, plain peer
+ * pointers.) */
 #define CGE_IPC_HANDLE_BYTES 64
 int cge_peer_local_handle(cge_context *ctx, void *handle /* CGE_IPC_HANDLE_BYTES out */,
                           int max_grid_size);
@@ -174,9 +197,9 @@ int cge_peer_connect(cge_context *ctx, int rank, int world,
 int cge_peer_disconnect(cge_context *ctx);
 
 int cge_likelihood_partials(cge_context *ctx, const cge_params *p, const float *obs_dev,
-                            float *posterior_dev, void *stream);
+                            void *posterior_dev, void *stream);
 int cge_partials(cge_context *ctx, double **partials_dev, size_t *count);
-int cge_finalize(cge_context *ctx, const cge_params *p, float *posterior_dev, void *stream);
+int cge_finalize(cge_context *ctx, const cge_params *p, void *posterior_dev, void *stream);
 /* result block on device: {E[mu], E[sigma], Z, 1/Z} then marg_sigma[N] then marg_mu[N]
  * (marg_mu holds this shard's rows at their global index, 0 elsewhere) */
 int cge_results(cge_context *ctx, double **results_dev, size_t *count);
@@ -184,15 +207,46 @@ int cge_results(cge_context *ctx, double **results_dev, size_t *count);
 int cge_read_results(cge_context *ctx, const cge_params *p, double *expectations,
                      double *marg_mu, double *marg_sigma, double *z, void *stream);
 /* device posterior the context keeps when cge_grid_posterior got posterior == NULL or a host pointer */
-int cge_posterior_dev(cge_context *ctx, float **posterior_dev, size_t *count);
+int cge_posterior_dev(cge_context *ctx, void **posterior_dev, size_t *count);
 int cge_last_timing(cge_context *ctx, cge_timing *timing);
 /* per-step CUDA-event capture around every phase of the next `max_steps` phase-API steps (events
  * are recorded on the stream the kernels are launched on); cge_profile_end synchronises and
- * returns the mean per-phase device times.  h2d_ms/d2h_ms are not filled. */
+ * returns the mean per-phase device times.  h2d_ms/d2h_ms are not filled.  (An event between two
+ * kernels keeps the second from being set up while the first drains, so a profiled step is a few
+ * microseconds longer than an unprofiled one.) */
 int cge_profile_begin(cge_context *ctx, int max_steps);
 int cge_profile_end(cge_context *ctx, cge_timing *mean, int *steps_captured);
-/* number of kernels the last cge_likelihood_partials + cge_finalize pair launched */
+/* number of kernels the last step launched */
 int cge_launch_count(cge_context *ctx, int *launches);
+
+/* ---- several GPUs from ONE process (the reference's caller is a single-process main(),
+ * src/grid.cu:19-142) ------------------------------------------------------------------------
+ * cge_create_multi: one context per listed device (devices == NULL: 0 .. n_gpus-1), peer access
+ * enabled between every pair, exchange blocks cross-mapped.  The grid is row-sharded over the
+ * devices in list order (balanced, contiguous mu rows); each step issues, from the calling thread,
+ * likelihood + fold on every device and then the finish kernel on every device; the finish kernel
+ * of each GPU reads the other GPUs' partial vectors over NVLink (plain peer pointers) and adds them
+ * in device-list order.  A device may be listed more than once (the shards then share one stream
+ * and run back to back: the exchange kernels can be exercised on a single-GPU box).
+ *
+ * cge_grid_posterior_multi: the fused call.  obs is host (or managed) memory.
+ *   posterior_host   grid_size*grid_size elements of p->posterior_dtype gathered to host, or NULL
+ *   the normalised shards always stay on their devices: cge_multi_shard returns them
+ *   marg_mu, marg_sigma, expectations, timing: as cge_grid_posterior (whole grid)
+ * p->row_begin / row_end must be 0 (the whole grid). */
+int cge_create_multi(int n_gpus, const int *devices, cge_multi **out);
+int cge_destroy_multi(cge_multi *m);
+int cge_multi_size(cge_multi *m, int *n_gpus);
+int cge_grid_posterior_multi(cge_multi *m, const cge_params *p, const float *obs,
+                             void *posterior_host, double *marg_mu, double *marg_sigma,
+                             double *expectations, cge_timing *timing);
+/* shard `index` of the last cge_grid_posterior_multi: its device, row range and device pointer */
+int cge_multi_shard(cge_multi *m, int index, int *device, int *row_begin, int *row_end,
+                    void **posterior_dev);
+/* the same step without host synchronisation or result copies, for timing loops: observations
+ * already on every device (obs_dev[i] on device i) */
+int cge_multi_step_async(cge_multi *m, const cge_params *p, const float *const *obs_dev);
+int cge_multi_synchronize(cge_multi *m);
 
 /* ---- stage API: the reference's L1 functions, one C entry each (device/managed pointers) --
  * These exist so the reference's stage-by-stage callers and tests keep working; they
@@ -257,7 +311,7 @@ int cge_generate_normal(cge_context *ctx, float *out_dev, int n, float mu, float
 int cge_quantiles(cge_context *ctx, const double *marginal_dev, int n, const double *probs_host,
                   int nprobs, int *indices_host, double *cdf_dev);
 
-/* Scale statistics the setup kernel derived for the last likelihood call (diagnostics; waits for
+/* Scale statistics the likelihood kernel derived for the last call (diagnostics; waits for
  * `stream`): out[0..11] = log2 of the per-factor rescale, log-space shift, log2 of the largest
  * likelihood on the grid, sample mean, sum of squared deviations, min_i sum_k (x_k - mu_i)^2,
  * log-space centre mu_c, sum_k (x_k - mu_c)^2, umax (largest exponent step between vertically

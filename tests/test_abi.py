@@ -23,7 +23,7 @@ def test_library_builds_and_loads():
     path = _build.build()
     assert os.path.exists(path)
     lib = cge.load_library()
-    assert lib.cge_version() == 1
+    assert lib.cge_version() == 2
 
 
 def test_every_declared_symbol_is_exported():
@@ -49,7 +49,7 @@ def test_exports_are_plain_c_and_sm100a_only():
 
 
 def test_struct_layouts_match_header():
-    assert C.sizeof(api.Params) == 40
+    assert C.sizeof(api.Params) == 44
     assert C.sizeof(api.Timing) == 28
 
 

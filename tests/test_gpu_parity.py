@@ -56,7 +56,7 @@ def test_readme_product_vs_oracle(ctx, readme_obs):
     check_against(res, f64, what="readme/product vs F64")
     assert res.launches == 1  # small grids: the whole step is one launch (small_grid_kernel)
     unf = ctx.grid_posterior(readme_obs, 101, (18, 22), (1, 3), variant=api.VARIANT_UNFUSED)
-    assert unf.launches == 5  # setup, likelihood, fold, results, scale
+    assert unf.launches == 3  # likelihood (set-up fused), fold + publish, finish
 
 
 @pytest.mark.parametrize("variant", [api.VARIANT_MUFU_ONLY, api.VARIANT_HYBRID, api.VARIANT_UNFUSED])
@@ -172,9 +172,9 @@ def test_many_observations_product_and_streamed_logspace(ctx):
         check_against(res, ref, what=f"log-space n={n}")
 
 
-@pytest.mark.parametrize("variant", [0, 6, api.VARIANT_LOG_F64])
+@pytest.mark.parametrize("variant", [0, api.VARIANT_LOG_F64])
 def test_logspace_kernel_variants(ctx, variant):
-    """The tiled float32x2 log-space kernel (default: tiles of 256 observations; 6: tiles of 64)
+    """The tiled float32x2 log-space kernel (default: tiles of 256 observations)
     and the float64 one-DFMA-per-eval kernel (5) against the float64 oracle: a few hundred
     and 10^4 observations on the README ranges, a grid that does not contain the sample mean (the
     centre clamps to an edge row, so the centred terms are large), a narrow sigma range at small
@@ -204,7 +204,7 @@ def test_single_launch_small_grids(ctx, readme_obs, N):
         one = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), mode=mode)
         five = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), mode=mode,
                                   variant=api.VARIANT_UNFUSED)
-        assert one.launches == (1 if N <= 256 else 5) and five.launches == 5
+        assert one.launches == (1 if N <= 256 else 3) and five.launches == 3
         assert np.abs(one.expectations - five.expectations).max() < 1e-9
         assert np.abs(one.marg_mu - five.marg_mu).max() <= 1e-9 * five.marg_mu.max()
         assert np.abs(one.marg_sigma - five.marg_sigma).max() <= 1e-9 * five.marg_sigma.max()
@@ -236,7 +236,7 @@ def test_single_launch_fine_small_grid_and_prior(ctx, readme_obs):
         five = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_UNFUSED)
     finally:
         ctx.set_prior()
-    assert one.launches == 1 and five.launches == 5
+    assert one.launches == 1 and five.launches == 3
     assert np.abs(one.expectations - five.expectations).max() < 1e-9
     flat = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
     assert np.abs(one.expectations - flat.expectations).max() > 1e-3  # the prior did something
@@ -376,7 +376,7 @@ def _ref_4096(readme_obs):
     return _REF_4096["f64"]
 
 
-@pytest.mark.parametrize("variant", [0, 3, 8, 4, 31, 39, 45, 381])
+@pytest.mark.parametrize("variant", [0, 3, 8, 4, 1])
 def test_paired_rows_variants_4096(ctx, readme_obs, variant):
     """README ranges at N=4096: |u| <= 0.0084, inside the paired kernel's bound (0.011).  Every
     paired variant (and the hybrid one it replaces here) against the float64 oracle."""
