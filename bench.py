@@ -7,13 +7,16 @@ hot path (BASELINE.json: "G pdf-evals/s ... at 1/2/4/8 B200").
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
            --master-port P bench.py --gpus N --steps K --warmup W
 
-A "step" is one full pass of the hot path over one batch of synthetic observations:
-tables + rescale statistics, the fused likelihood kernel, the deterministic fold, (N>1: the sum of
-N+2 float64 over ranks, by peer loads inside the results kernel or NCCL), marginals/expectations
-and the in-place 1/Z scale.  The default
-workload is BASELINE.json configs[2] -- 16384 x 16384 grid x 50 observations, float32 product
-path -- the configuration the headline target (>= 60 % of MUFU peak on one GPU) is quoted on;
-with --gpus N the same grid is row-sharded (strong scaling, as configs[2] states).
+A "step" is one full pass of the hot path over one batch of synthetic observations, three kernel
+launches: the fused likelihood kernel (set-up, range values, pdf factors, running products,
+partial sums), the deterministic fold (+ publication of the N+2 float64 partial vector to the peer
+GPUs), and the finish kernel (N>1: rank-ordered sum of the peers' vectors read over NVLink;
+marginals, expectations, in-place 1/Z scale).  The default workload is BASELINE.json configs[2] --
+16384 x 16384 grid x 50 observations, float32 product path -- the configuration the headline
+target (>= 60 % of MUFU peak on one GPU) is quoted on; with --gpus N the same grid is row-sharded
+(strong scaling, as configs[2] states).  The same line also carries, as extra blocks, the
+65536 x 65536 grid at the same N (`scaling_65536`: the configuration the 8-GPU target is quoted
+on), a sustained run of >= 3 s (`sustained`), and at N=1 the log-space workload (`logspace`).
 One JSON line goes to stdout (rank 0); everything else goes to stderr.
 """
 from __future__ import annotations
@@ -45,10 +48,19 @@ WORKLOADS = {
     "16384x10k-log": (16384, 10000, 1),
 }
 DEFAULT_WORKLOAD = "16384x50"
-# dram__bytes_read.sum + dram__bytes_write.sum of the likelihood kernel, per launch, from the
-# committed ncu --set full captures (profiles/r01_ncu_full_*.csv); keyed by (workload, n_gpus)
-NCU_TRAFFIC = {
-    ("16384x50", 1): 1.0768e9,        # profiles/r01_ncu_full_paired_16384x50.csv
+# dram__bytes_read.sum + dram__bytes_write.sum of the likelihood kernel per launch, one entry per
+# (workload, n_gpus), each from a one-launch `ncu --metrics dram__bytes_read.sum,
+# dram__bytes_write.sum` capture of that shard shape under gpurun (tools/ncu_traffic.py writes the
+# file).  No entry -> `traffic` is null and `traffic_note` says so; never a guessed constant.
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
+
+# instructions the likelihood kernel issues per pdf-eval on the two pipes that bound it, by the
+# arithmetic policy that ran (cge_scale_info "product_path"); counted from the SASS of the inner
+# loop (profiles/r02_sass_inner_loop_*.txt): MUFU.EX2 per eval, FMA-pipe lane-ops per eval
+PIPE_OPS = {
+    "paired": (0.5, 54 / 16),    # per 16 evals: 8 MUFU.EX2 + 27 packed f32x2 (2 lane-ops each)
+    "paired3": (0.5, 62 / 16),   # + 4 packed for the cubic term
+    "hybrid": (0.75, (2 * 32 + 8) / 16),
 }
 
 
@@ -84,6 +96,15 @@ def observations(n: int) -> np.ndarray:
     return np.random.default_rng(42).normal(20.0, 2.0, n).astype(np.float32)
 
 
+def host_cores() -> int:
+    """Cores this process may run on (torchrun exports OMP_NUM_THREADS=1, which says nothing about
+    the box)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def measured_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -93,6 +114,18 @@ def measured_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+def measured_traffic(workload: str, world: int):
+    try:
+        table = json.load(open(TRAFFIC_FILE))
+        row = table.get(f"{workload}|{world}")
+        if row:
+            return float(row["bytes_per_launch"]), row.get("source", os.path.basename(TRAFFIC_FILE))
+    except Exception:
+        pass
+    return None, ("no ncu dram capture for this (workload, n_gpus) in profiles/r02_dram_traffic.json; "
+                  "algorithmic traffic is 4 B per cell written, nothing read")
 
 
 # ---------------------------------------------------------------------------------------
@@ -143,6 +176,7 @@ class ClockSampler:
         if self.ok:
             self._thr = threading.Thread(target=self._run, daemon=True)
             self._thr.start()
+        return self
 
     def stop(self):
         if self._thr:
@@ -158,14 +192,22 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference algorithm on the host cores
 # ---------------------------------------------------------------------------------------
+def oracle_all_cores():
+    """The oracle library with its OpenMP team set to every core of the box, whatever
+    OMP_NUM_THREADS says; returns (module, cores)."""
+    import oracle
+    cores = host_cores()
+    oracle.lib().oracle_set_num_threads(cores)
+    return oracle, int(oracle.lib().oracle_num_threads())
+
+
 def cpu_rate_sample(N, n, mode, target_seconds, max_rows=None):
     """Times the oracle (reference numerics: f32 pdf, f64 tree product; f64 log-space for the
     log workload) on a contiguous block of mu rows centred on the posterior peak, all host
     threads.  Returns (evals_per_s, seconds, rows, cores)."""
-    import oracle
+    oracle, cores = oracle_all_cores()
     numerics = oracle.NUM_LOG if mode == 1 else oracle.NUM_REF
     obs = observations(n)
-    cores = int(oracle.lib().oracle_num_threads())
     centre = int((19.55 - MU_RANGE[0]) / (MU_RANGE[1] - MU_RANGE[0]) * (N - 1))
     probe_rows = max(1, min(N, max(cores, 4)))
     if N * n * probe_rows > 4e8:
@@ -218,18 +260,17 @@ def run_reference(args):
     if rank != 0:
         return 0
     N, n, mode = WORKLOADS[args.workload]
-    import oracle
+    oracle, cores = oracle_all_cores()
     numerics = oracle.NUM_LOG if mode == 1 else oracle.NUM_REF
     obs = observations(n)
-    cores = int(oracle.lib().oracle_num_threads())
     # size one step to ~args.ref_step_seconds of CPU work
     rate, _, _, _ = cpu_rate_sample(N, n, mode, 1.0)
     rows = int(max(1, min(N, args.ref_step_seconds * rate / (N * n))))
     centre = int((19.55 - MU_RANGE[0]) / (MU_RANGE[1] - MU_RANGE[0]) * (N - 1))
     rb = max(0, min(N - rows, centre - rows // 2))
     steps, warmup = args.steps, max(args.warmup, 1)
-    if args.steps_defaulted:
-        steps, warmup = 10, 3
+    if args.steps_defaulted or steps * args.ref_step_seconds > 240:
+        steps, warmup = min(steps, 10), min(warmup, 3)   # the whole run ends within minutes
     for _ in range(warmup):
         oracle.bench_rows(obs, N, *MU_RANGE, *SIGMA_RANGE, numerics, rb, rb + rows)
     t0 = time.perf_counter()
@@ -247,7 +288,7 @@ def run_reference(args):
         "steps": steps, "warmup": warmup, "ms_per_step": dt / steps * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64" if mode == 1 else "f32", "data": "synthetic",
-        "config": workload_config(args.workload, args.gpus),
+        "config": workload_config(args.workload),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -258,244 +299,352 @@ def run_reference(args):
     return 0
 
 
-def workload_config(name, gpus):
+def workload_config(name):
+    """Identical in both arms (the driver compares them); what differs per run -- the GPU count,
+    the exchange -- is in top-level keys of the line."""
     N, n, mode = WORKLOADS[name]
     return {
         "workload": f"{N}x{N} grid x {n} obs, " + ("log-space float64" if mode else "float32 product path"),
         "grid_size": N, "n_obs": n, "mode": "logspace" if mode else "product_f32",
         "mu_range": list(MU_RANGE), "sigma_range": list(SIGMA_RANGE),
         "observations": "N(20,2) seed 42 (README recipe)" if n == 50 else "N(20,2) default_rng(42)",
-        "sharding": f"mu rows split over {gpus} GPU(s); one all-reduce of N+2 float64" if gpus > 1
-                    else "single GPU",
+        "sharding": "mu rows split evenly over the GPUs; one exchange of N+2 float64 per step",
         "posterior": "float32 [mu][sigma], device-resident",
-        "l2": f"posterior written per step is {N * N * 4 / gpus / 1e6:.0f} MB per GPU "
-              + ("(> 126 MB L2: no flush needed)" if N * N * 4 / gpus > 126e6 else
-                 "(fits L2: a 256 MB L2 flush runs between timed steps, outside the per-step event "
-                 "pairs that ms_per_step sums)"),
+        "l2": "a shard whose posterior fits the 126 MB L2 gets a 256 MB L2 flush between timed steps "
+              "(outside the per-step event pairs); larger shards overwrite L2 every step",
     }
 
 
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+class Harness:
+    """Process-group plumbing shared by the measurements of one run."""
 
-    import cuda_grid_estimation_b200 as cge
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world != args.gpus:
+            log(f"warning: --gpus {args.gpus} but WORLD_SIZE={self.world}; using WORLD_SIZE")
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback "
+                             "(use --impl reference for the CPU arm)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        self.cpu_group = None
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=self.dev)
+            self.cpu_group = dist.new_group(backend="gloo")   # host-side barriers (no GPU spin)
+        self.flush_buf = None
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        log(f"warning: --gpus {args.gpus} but WORLD_SIZE={world}; using WORLD_SIZE")
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback "
-                         "(use --impl reference for the CPU arm)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
 
-    N, n, mode = WORKLOADS[args.workload]
-    steps, warmup = args.steps, max(args.warmup, 3)
-    ctx = cge.Context(local)
-    info = ctx.device_info()
-    obs_host = torch.from_numpy(observations(n)).pin_memory()
-    obs_dev = obs_host.to(dev)
-    sh = cge.ShardedGridPosterior(ctx, N, MU_RANGE, SIGMA_RANGE, n, mode, exchange=args.exchange)
+    def host_barrier(self):
+        self.torch.cuda.synchronize()
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu_group)
+
+    def max_over_ranks(self, x: float) -> float:
+        if self.world == 1:
+            return x
+        t = self.torch.tensor([x], dtype=self.torch.float64, device=self.dev)
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def flush(self):
+        if self.flush_buf is None:
+            self.flush_buf = self.torch.empty(256 * 1024 * 1024 // 4, dtype=self.torch.float32,
+                                              device=self.dev)
+        self.flush_buf.add_(1.0)
+
+
+def measure_device(h: Harness, ctx, cge, workload, steps, warmup, exchange, sample_clocks=False,
+                   min_seconds=0.0):
+    """Device-resident throughput of one workload at this world size: observations and posterior
+    already in HBM, `steps` steps between two events on the launching stream, max over ranks.
+    With min_seconds the step count is raised so that the timed region lasts at least that long."""
+    torch = h.torch
+    N, n, mode = WORKLOADS[workload]
+    obs_dev = torch.from_numpy(observations(n)).to(h.dev)
+    sh = cge.ShardedGridPosterior(ctx, N, MU_RANGE, SIGMA_RANGE, n, mode, exchange=exchange)
     post = sh.alloc_posterior()
     cells_local = sh.rows_local * N
     need_flush = cells_local * 4 <= 126e6
-    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev) if need_flush else None
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def one_step():
-        if flush_buf is not None:
-            flush_buf.add_(1.0)
-        sh.step(obs_dev, post)
-
     for _ in range(warmup):
-        one_step()
-    barrier()
-
-    sampler = ClockSampler(local)
+        if need_flush:
+            h.flush()
+        sh.step(obs_dev, post)
+    h.barrier()
+    if min_seconds > 0.0:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            sh.step(obs_dev, post)
+        e1.record()
+        torch.cuda.synchronize()
+        per = h.max_over_ranks(e0.elapsed_time(e1) / 3.0)
+        steps = max(steps, int(min_seconds * 1e3 / per) + 1)
+        h.barrier()
+    sampler = ClockSampler(h.local) if sample_clocks else None
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     # workloads that fit L2 get a flush between steps; it must not be part of the step time, so
     # those steps are bracketed one by one (events on the same stream) and their times summed
     step_evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
                 for _ in range(steps)] if need_flush else None
-    ctx.profile_begin(steps)
-    sampler.start()
-    barrier()
+    prof_steps = min(steps, 200)
+    ctx.profile_begin(prof_steps)
+    if sampler:
+        sampler.start()
+    h.barrier()
     ev0.record()
     for i in range(steps):
         if step_evs is None:
             sh.step(obs_dev, post)
         else:
-            flush_buf.add_(1.0)
+            h.flush()
             step_evs[i][0].record()
             sh.step(obs_dev, post)
             step_evs[i][1].record()
     ev1.record()
-    barrier()
-    clocks = sampler.stop()
+    h.barrier()
+    clocks = sampler.stop() if sampler else None
     elapsed_ms = ev0.elapsed_time(ev1)
     if step_evs is not None:
         elapsed_ms = sum(a.elapsed_time(b) for a, b in step_evs)
     phase, captured = ctx.profile_end()
-    if world > 1:
-        t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        elapsed_ms = float(t.item())
-    launches_per_step = ctx.launch_count()
+    elapsed_ms = h.max_over_ranks(elapsed_ms)
     ex, mm, ms_, z = sh.results()
-    total_evals = float(N) * N * n
-    value = total_evals * steps / (elapsed_ms * 1e-3) / 1e9
+    res = {
+        "workload": workload, "N": N, "n": n, "mode": mode, "steps": steps,
+        "ms_per_step": elapsed_ms / steps,
+        "value": float(N) * N * n * steps / (elapsed_ms * 1e-3) / 1e9,
+        "phases_ms": {k: phase[k] for k in ("setup_ms", "likelihood_ms", "reduce_ms", "scale_ms", "total_ms")},
+        "phase_steps_captured": captured, "launches_per_step": ctx.launch_count(),
+        "rows_local": sh.rows_local, "exchange": sh.exchange, "clocks": clocks,
+        "check": {"E_mu": float(ex[0]), "E_sigma": float(ex[1]), "Z": float(z)},
+        "l2_flush_between_steps": bool(need_flush),
+    }
+    sh.close()
+    del post, obs_dev
+    torch.cuda.empty_cache()
+    return res
 
-    # ---- end to end through the public API: host observations in, expectations+marginals out
-    e2e_steps = max(3, min(steps, 50))
-    h2d = obs_host.numel() * 4
-    d2h = 16 + 2 * N * 8 + 8
-    if world == 1:
-        obs_np = obs_host.numpy()
-        for _ in range(3):
-            ctx.grid_posterior(obs_np, N, MU_RANGE, SIGMA_RANGE, mode=mode, posterior=post,
+
+def measure_e2e_single(h, ctx, workload, steps):
+    """N = 1: cge_grid_posterior with HOST observations in and host expectations + marginals out,
+    every step; wall clock around synchronous calls.  Also the variant that brings the posterior
+    to (pinned) host memory."""
+    torch = h.torch
+    N, n, mode = WORKLOADS[workload]
+    obs_np = observations(n)
+    post = torch.empty((N, N), dtype=torch.float32, device=h.dev)
+    for _ in range(3):
+        ctx.grid_posterior(obs_np, N, MU_RANGE, SIGMA_RANGE, mode=mode, posterior=post, want_timing=False)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        r = ctx.grid_posterior(obs_np, N, MU_RANGE, SIGMA_RANGE, mode=mode, posterior=post,
                                want_timing=False)
-        torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    total = float(N) * N * n
+    out = {"value": total * steps / secs / 1e9, "unit": UNIT, "h2d_bytes_per_step": n * 4,
+           "d2h_bytes_per_step": 32 + 2 * N * 8, "steps": steps, "ms_per_step": secs / steps * 1e3,
+           "api": "cge_grid_posterior (C ABI; host observations in; E, both marginals to host; the "
+                  "posterior stays on the device like the reference's device_vector)",
+           "check_E": r.expectations.tolist()}
+    full = None
+    if N * N * 4 <= 4.5e9:
+        pinned = torch.empty((N, N), dtype=torch.float32).pin_memory()
+        host_np = pinned.numpy()
+        fs_steps = max(2, min(steps, 10))
+        ctx.grid_posterior(obs_np, N, MU_RANGE, SIGMA_RANGE, mode=mode, posterior=host_np, want_timing=False)
         t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            r = ctx.grid_posterior(obs_np, N, MU_RANGE, SIGMA_RANGE, mode=mode, posterior=post,
-                                   want_timing=False)
-        e2e_s = time.perf_counter() - t0
-        e2e_check = r.expectations.tolist()
-        # the same call with the posterior ALSO copied to (pinned) host memory every step
-        e2e_full = None
-        if cells_local * 4 <= 4.5e9:
-            pinned = torch.empty((N, N), dtype=torch.float32).pin_memory()
-            host_np = pinned.numpy()
-            full_steps = max(2, min(e2e_steps, 10))
+        for _ in range(fs_steps):
             ctx.grid_posterior(obs_np, N, MU_RANGE, SIGMA_RANGE, mode=mode, posterior=host_np,
                                want_timing=False)
+        fs = time.perf_counter() - t0
+        full = {"value": total * fs_steps / fs / 1e9, "unit": UNIT, "ms_per_step": fs / fs_steps * 1e3,
+                "steps": fs_steps, "d2h_bytes_per_step": 32 + 2 * N * 8 + N * N * 4,
+                "pcie_floor_ms": N * N * 4 / 55e9 * 1e3,
+                "note": "posterior (float32 N*N) also copied to pinned host memory inside the timed "
+                        "region; PCIe-bound (floor quoted at 55 GB/s)"}
+        del pinned, host_np
+    del post
+    torch.cuda.empty_cache()
+    return out, full
+
+
+def measure_e2e_multi(h, cge, workload, steps):
+    """N > 1: rank 0 alone drives all N GPUs through the single-process C entry
+    cge_grid_posterior_multi -- host observations in, expectations and marginals out -- while the
+    other ranks wait on a host-side barrier with their GPUs idle."""
+    N, n, mode = WORKLOADS[workload]
+    out = None
+    h.host_barrier()
+    if h.rank == 0:
+        obs_np = observations(n)
+        with cge.MultiContext(list(range(h.world))) as mc:
+            for _ in range(3):
+                mc.grid_posterior(obs_np, N, MU_RANGE, SIGMA_RANGE, mode=mode, posterior=None)
             t0 = time.perf_counter()
-            for _ in range(full_steps):
-                ctx.grid_posterior(obs_np, N, MU_RANGE, SIGMA_RANGE, mode=mode, posterior=host_np,
-                                   want_timing=False)
-            fs = time.perf_counter() - t0
-            e2e_full = {"value": total_evals * full_steps / fs / 1e9, "unit": UNIT,
-                        "ms_per_step": fs / full_steps * 1e3, "steps": full_steps,
-                        "d2h_bytes_per_step": d2h + N * N * 4,
-                        "note": "posterior (float32 N*N) copied to pinned host memory inside the "
-                                "timed region as well; PCIe-bound"}
-            del pinned, host_np
+            for _ in range(steps):
+                r = mc.grid_posterior(obs_np, N, MU_RANGE, SIGMA_RANGE, mode=mode, posterior=None)
+            secs = time.perf_counter() - t0
+        out = {"value": float(N) * N * n * steps / secs / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": n * 4 * h.world, "d2h_bytes_per_step": 32 + 2 * N * 8,
+               "steps": steps, "ms_per_step": secs / steps * 1e3,
+               "api": f"cge_grid_posterior_multi (C ABI; ONE process, one host thread, {h.world} GPUs; "
+                      "host observations in; E, both marginals to host; posterior shards stay on "
+                      "their devices)",
+               "check_E": r.expectations.tolist()}
+    h.host_barrier()
+    return out
+
+
+def run_ours(args):
+    import cuda_grid_estimation_b200 as cge
+
+    h = Harness(args)
+    torch = h.torch
+    world, rank = h.world, h.rank
+    N, n, mode = WORKLOADS[args.workload]
+    steps, warmup = args.steps, max(args.warmup, 3)
+    ctx = cge.Context(h.local)
+    info = ctx.device_info()
+
+    # ---- the headline: device-resident, `steps` steps
+    main = measure_device(h, ctx, cge, args.workload, steps, warmup, args.exchange, sample_clocks=True)
+    sinfo = ctx.scale_info() if rank == 0 else None
+
+    # ---- sustained: the same step back to back for >= 3 s, clocks sampled throughout
+    sustained = None
+    if not args.quick:
+        s = measure_device(h, ctx, cge, args.workload, steps, 3, args.exchange, sample_clocks=True,
+                           min_seconds=args.sustained_seconds)
+        sustained = {"seconds": s["ms_per_step"] * s["steps"] / 1e3, "steps": s["steps"],
+                     "value": s["value"], "unit": UNIT, "ms_per_step": s["ms_per_step"],
+                     "likelihood_ms": s["phases_ms"]["likelihood_ms"], "clocks": s["clocks"]}
+
+    # ---- the 65536^2 grid at this N (north_star: >= 7x at 8 GPUs is quoted on it)
+    scaling_65536 = None
+    if not args.quick and args.workload == DEFAULT_WORKLOAD:
+        free_b, _ = torch.cuda.mem_get_info()
+        need = 65536 * 65536 * 4 / world * 1.05 + (1 << 30)
+        if free_b > need:
+            s = measure_device(h, ctx, cge, "65536x50", 5, 3, args.exchange)
+            scaling_65536 = {k: s[k] for k in ("value", "ms_per_step", "phases_ms", "steps", "rows_local",
+                                               "exchange", "check")}
+            scaling_65536["unit"] = UNIT
+            scaling_65536["workload"] = workload_config("65536x50")["workload"]
+        else:
+            scaling_65536 = {"value": None, "why": f"{free_b / 1e9:.0f} GB free < {need / 1e9:.0f} GB needed"}
+
+    # ---- N = 1: the log-space workload (BASELINE configs[4]) as an extra block
+    logspace = None
+    if not args.quick and world == 1 and args.workload == DEFAULT_WORKLOAD:
+        s = measure_device(h, ctx, cge, "16384x10k-log", 5, 3, args.exchange)
+        logspace = {k: s[k] for k in ("value", "ms_per_step", "phases_ms", "steps", "check")}
+        logspace["unit"] = UNIT
+        logspace["workload"] = workload_config("16384x10k-log")["workload"]
+
+    # ---- end to end through the C ABI with host buffers
+    e2e_steps = max(3, min(steps, 50))
+    e2e_full = None
+    if world == 1:
+        e2e, e2e_full = measure_e2e_single(h, ctx, args.workload, e2e_steps)
     else:
-        e2e_full = None
-        def e2e_once():
-            obs_dev.copy_(obs_host, non_blocking=True)
-            sh.step(obs_dev, post)
-            return sh.results()
-        for _ in range(3):
-            e2e_once()
-        barrier()
-        t0 = time.perf_counter()
-        for _ in range(e2e_steps):
-            r = e2e_once()
-        torch.cuda.synchronize()
-        e2e_s = time.perf_counter() - t0
-        t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-        e2e_check = r[0].tolist()
-    e2e_value = total_evals * e2e_steps / e2e_s / 1e9
+        e2e = measure_e2e_multi(h, cge, args.workload, e2e_steps)
 
     # ---- rooflines (rank 0's kernels; every rank runs the same shapes)
-    hbm_peak, hbm_src, peaks_doc = measured_peaks()
+    hbm_peak, hbm_src, _ = measured_peaks()
     out = None
     if rank == 0:
         ex2_peak = ctx.microbench(0)
         ffma_peak = ctx.microbench(1)
         dfma_peak = ctx.microbench(2)
         ffma2_peak = ctx.microbench(3)
+        phase = main["phases_ms"]
         like_s = phase["likelihood_ms"] * 1e-3
-        evals_per_launch = float(sh.rows_local) * N * n
-        ach = evals_per_launch / like_s
-        sinfo = ctx.scale_info()
-        traffic = NCU_TRAFFIC.get((args.workload, world))
+        cells_local = float(main["rows_local"]) * N
+        ach = cells_local * n / like_s
+        traffic, traffic_src = measured_traffic(args.workload, world)
+
+        def pipe_roofline(rate, path):
+            mufu_pe, fma_pe = PIPE_OPS.get(path, PIPE_OPS["hybrid"])
+            mufu_util, fma_util = mufu_pe * rate / ex2_peak, fma_pe * rate / ffma_peak
+            return mufu_pe, fma_pe, mufu_util, fma_util
+
         if mode == 0:
-            # executed op counts per pdf-eval of the path that ran (SASS of the inner loop):
-            #   paired rows: 8 MUFU.EX2 + 27 packed (2 lane-ops each) per 16 evals
-            #   hybrid     : 12 MUFU.EX2 + 8 + 8 packed (exponent, product) + 2 x 8 packed
-            #                (polynomial) + 8 scalar per 16 evals
-            #   paired, degree 3: 4 more packed per 16 evals
             path = sinfo["product_path"]
-            mufu_pe, fma_pe = {"paired": (0.5, 54 / 16), "paired3": (0.5, 62 / 16)}.get(
-                path, (0.75, (2 * 32 + 8) / 16))
-            roof = {"bound": "mufu", "achieved": ach / 1e9, "peak": ex2_peak / 1e9, "unit": "Gop/s",
-                    "frac": ach / ex2_peak, "traffic": traffic,
-                    "kernel": "grid_likelihood_select_kernel<ProductPaired deg 2, ProductPaired deg 3, "
-                              "ProductHybrid> -> " + path,
-                    "algorithmic": "1 ex2 per pdf-eval (SURVEY 8(d)); evals per launch = rows*N*n",
-                    "note": "frac > 1 is by design: the kernel takes " + str(mufu_pe) + " of its "
-                            "exponentials per eval from MUFU.EX2 and forms the rest on the FMA pipe "
-                            "(paired rows: e*2^u with a degree-2 polynomial; hybrid: degree-5 "
-                            "polynomial), so neither pipe alone bounds it; `executed` gives the "
-                            "utilisation of each pipe by the instructions actually issued, and "
-                            "variant 1 (MUFU-only) is the plain MUFU-roofline kernel",
+            mufu_pe, fma_pe, mufu_util, fma_util = pipe_roofline(ach, path)
+            binding = "mufu" if mufu_util >= fma_util else "fp32"
+            roof = {"bound": binding,
+                    "achieved": (mufu_pe if binding == "mufu" else fma_pe) * ach / 1e9,
+                    "peak": (ex2_peak if binding == "mufu" else ffma_peak) / 1e9,
+                    "unit": "Gop/s (MUFU.EX2)" if binding == "mufu" else "Gop/s (FP32 lane-ops)",
+                    "frac": max(mufu_util, fma_util),
+                    "frac_vs_survey_count": ach / ex2_peak,
+                    "traffic": traffic, "traffic_note": traffic_src,
+                    "kernel": "grid_likelihood_kernel<ProductPaired<2>, ProductPaired<3>, ProductHybrid> -> " + path,
+                    "algorithmic": f"{mufu_pe} MUFU.EX2 + {fma_pe:.3f} FP32 lane-ops issued per pdf-eval "
+                                   "(SASS count of the inner loop); evals per launch = rows*N*n; "
+                                   "frac = utilisation of the busier of the two pipes against its "
+                                   "micro-benchmarked peak; frac_vs_survey_count keeps SURVEY 8(d)'s "
+                                   "'1 ex2 per eval' count, which this kernel undercuts by deriving "
+                                   "every other row's factor from its neighbour's on the FMA pipe",
                     "executed": {"mufu_per_eval": mufu_pe, "fma_lane_ops_per_eval": fma_pe,
-                                 "mufu_util": mufu_pe * ach / ex2_peak,
-                                 "fma_util": fma_pe * ach / ffma_peak},
+                                 "mufu_util": mufu_util, "fma_util": fma_util},
+                    "evals_per_s": ach,
                     "umax": sinfo["umax"], "paired_umax": sinfo["paired_umax"],
                     "paired3_umax": sinfo["paired3_umax"],
-                    "peak_source": "ex2.approx.ftz micro-benchmark in this run (cge_microbench 0)",
-                    "peak_nominal": 16 * info["sm_count"] * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9}
+                    "peak_source": "ex2.approx.ftz / FFMA micro-benchmarks in this run (cge_microbench 0, 1)",
+                    "peak_nominal": 16 * info["sm_count"] * ((main["clocks"] or {}).get("sm_max_mhz") or 1965.0) * 1e6 / 1e9}
         else:
-            roof = {"bound": "fp32", "achieved": ach / 1e9, "peak": ffma_peak / 1e9, "unit": "Gop/s",
-                    "frac": ach / ffma_peak, "traffic": traffic,
+            roof = {"bound": "fp32", "achieved": 1.125 * ach / 1e9, "peak": ffma_peak / 1e9,
+                    "unit": "Gop/s (FP32 lane-ops)", "frac": 1.125 * ach / ffma_peak,
+                    "traffic": traffic, "traffic_note": traffic_src,
                     "kernel": "grid_likelihood_kernel<LogSpaceTiled<256>>",
-                    "algorithmic": "1 FMA per pdf-eval; evals per launch = rows*N*n",
-                    "executed": {"fma_lane_ops_per_eval": 1.125,
-                                 "fma_util": 1.125 * ach / ffma_peak},
+                    "algorithmic": "1 packed-half FMA per pdf-eval + 1 scalar FMA per 8; evals per launch = rows*N*n",
+                    "executed": {"fma_lane_ops_per_eval": 1.125, "fma_util": 1.125 * ach / ffma_peak},
+                    "evals_per_s": ach,
                     "peak_source": "FFMA micro-benchmark in this run (cge_microbench 1)"}
         scale_s = phase["scale_ms"] * 1e-3
-        hbm = {"bound": "hbm", "kernel": "scale_posterior_kernel",
+        hbm = {"bound": "hbm", "kernel": "finish_kernel (marginals, expectations, posterior *= 1/Z)",
                "achieved": 8.0 * cells_local / scale_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                "frac": 8.0 * cells_local / scale_s / 1e9 / hbm_peak, "traffic": None,
                "algorithmic": "4 B read + 4 B written per cell", "peak_source": hbm_src}
-        fp32 = {"bound": "fp32", "achieved": 4 * ach / 1e9, "peak": ffma_peak / 1e9,
-                "unit": "G lane-instr/s", "frac": 4 * ach / ffma_peak,
-                "algorithmic": "4 FP32 instr per pdf-eval (SURVEY 8(d)'s count for the product "
-                               "path; see roofline.executed for what the kernel issues)"}
         out = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
-            "warmup": warmup, "ms_per_step": elapsed_ms / steps, "higher_is_better": True,
+            "metric": METRIC, "value": main["value"], "unit": UNIT, "n_gpus": world, "steps": steps,
+            "warmup": warmup, "ms_per_step": main["ms_per_step"], "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64" if mode else "f32",
-            "data": "synthetic", "config": dict(workload_config(args.workload, world),
-                           exchange=("none" if world == 1 else
-                                     "peer loads over NVLink fused into the results kernel (CUDA IPC)"
-                                     if sh.exchange == "p2p" else "NCCL all_reduce")),
-            "clocks": clocks,
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "ms_per_step": e2e_s / e2e_steps * 1e3,
-                    "api": "cge_grid_posterior (host obs in; E, marginals to host; posterior stays "
-                           "on the device like the reference's device_vector)" if world == 1 else
-                           "pinned obs -> device, ShardedGridPosterior.step, cge_read_results"},
-            "e2e_posterior_to_host": e2e_full,
-            "gpu_launches": launches_per_step * steps,
-            "launches_per_step": launches_per_step,
-            "roofline": roof, "roofline_hbm": hbm, "roofline_fp32": fp32,
-            "phases_ms": {k: phase[k] for k in ("setup_ms", "likelihood_ms", "reduce_ms", "scale_ms", "total_ms")},
-            "phase_steps_captured": captured,
+            "data": "synthetic", "config": workload_config(args.workload),
+            "exchange": ("none" if world == 1 else
+                         "peer loads over NVLink fused into the finish kernel (CUDA IPC)"
+                         if main["exchange"] == "p2p" else "NCCL all_reduce"),
+            "clocks": main["clocks"],
+            "e2e": e2e, "e2e_posterior_to_host": e2e_full,
+            "gpu_launches": main["launches_per_step"] * steps,
+            "launches_per_step": main["launches_per_step"],
+            "roofline": roof, "roofline_hbm": hbm,
+            "phases_ms": phase, "phase_steps_captured": main["phase_steps_captured"],
+            "sustained": sustained, "scaling_65536": scaling_65536, "logspace_16384x10k": logspace,
             "pipe_peaks": {"mufu_ex2_Gops": ex2_peak / 1e9, "ffma_Gops": ffma_peak / 1e9,
                            "dfma_Gops": dfma_peak / 1e9, "ffma2_Glaneops": ffma2_peak / 1e9,
                            "sm_count": info["sm_count"]},
-            "check": {"E_mu": float(ex[0]), "E_sigma": float(ex[1]), "Z": float(z), "e2e_E": e2e_check},
+            "check": main["check"],
         }
+        if logspace is not None:
+            lrate = 16384.0 * 16384 * 10000 / (logspace["phases_ms"]["likelihood_ms"] * 1e-3)
+            logspace["likelihood_evals_per_s"] = lrate
+            logspace["fma_util"] = 1.125 * lrate / ffma_peak
         if world == 1 and not args.no_cpu_baseline:
             try:
                 rate, secs, rows, cores = cpu_rate_sample(N, n, mode, args.cpu_seconds)
@@ -507,10 +656,9 @@ def run_ours(args):
             except Exception as e:  # the oracle is test infrastructure; never fail the GPU number on it
                 out["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": None, "kind": "port",
                                        "sample": f"unavailable: {e!r}"}
-    sh.close()
+    h.host_barrier()
     if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        h.dist.destroy_process_group()
     ctx.close()
     if out is not None:
         emit(out)
@@ -526,7 +674,10 @@ def main():
     ap.add_argument("--workload", choices=sorted(WORKLOADS), default=DEFAULT_WORKLOAD)
     ap.add_argument("--cpu-seconds", type=float, default=10.0)
     ap.add_argument("--ref-step-seconds", type=float, default=4.0)
+    ap.add_argument("--sustained-seconds", type=float, default=3.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--quick", action="store_true",
+                    help="headline + e2e only (no sustained / 65536 / log-space blocks): for ncu runs")
     ap.add_argument("--exchange", choices=["auto", "p2p", "nccl"], default="auto",
                     help="N>1: how the N+2 float64 partial vector is summed over ranks")
     args = ap.parse_args()

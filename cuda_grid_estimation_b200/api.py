@@ -396,16 +396,14 @@ def _scale_info(self, stream=None) -> dict:
 
 
 def band_columns(grid_size: int) -> int:
-    """Sigma columns per CTA column band (mirrors make_plan in cge_api.cu: 128 columns per warp
-    strip, 8 / 4 / 2 / 1 strips per CTA depending on the grid width)."""
-    ncw = (grid_size + 127) // 128
-    wn = 8 if ncw >= 8 else 4 if ncw >= 4 else 2 if ncw >= 2 else 1
-    return wn * 128
+    """Sigma columns per warp column strip of the product kernels (32 lanes x 4 columns): the
+    granularity at which the default kernel chooses its arithmetic (cge::strip_umax)."""
+    return 128
 
 
 def band_paths(info: dict, sigma: np.ndarray) -> list:
     """Which product policy each column band takes, from scale_info() and the sigma table:
-    mirrors cge::band_scale (|a_j| = 0.5*log2(e)/sigma_j^2 at the band's two ends)."""
+    mirrors cge::strip_umax (|a_j| = 0.5*log2(e)/sigma_j^2 at the band's two ends)."""
     out = []
     band_cols = band_columns(len(sigma))
     for j0 in range(0, len(sigma), band_cols):

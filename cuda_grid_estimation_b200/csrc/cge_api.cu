@@ -130,6 +130,7 @@ struct cge_context {
   bool knob_no_pdl = false;      // CGE_NO_PDL: ordinary stream-ordered launches
   // resident CTAs per SM of each likelihood kernel at its shared-memory size (occupancy query)
   std::map<std::pair<const void *, size_t>, int> occupancy;
+  std::map<const void *, size_t> smem_optin;  // largest dynamic shared memory each kernel was opted in for
   // per-step event capture: 6 marks per step
   //   0 start | 1 after the streamed set-up (== 0 otherwise) | 2 after likelihood |
   //   3 after fold + publish | 4 before finish | 5 after finish
@@ -151,6 +152,8 @@ namespace {
 int bind(cge_context *ctx) {
   if (!ctx) return set_error(CGE_ERR_BAD_ARG, "context is NULL");
   CK(cudaSetDevice(ctx->device));
+  cudaGetLastError();  // a non-sticky error left by an unrelated earlier call must not be blamed on
+                       // the first launch check of this one
   return CGE_OK;
 }
 
@@ -251,10 +254,15 @@ size_t like_smem(const Plan &pl, const cge_host::KernelChoice &kc) {
 int size_grid(cge_context *ctx, Plan *pl, const cge_host::KernelChoice &kc, int max_ctas) {
   pl->smem = like_smem(*pl, kc);
   const auto key = std::make_pair(kc.fn, pl->smem);
+  if (pl->smem > 40 * 1024) {  // static + dynamic beyond 48 KB needs the opt-in; it only ever grows
+    size_t &have = ctx->smem_optin[kc.fn];  // (a smaller value set later would make a cached larger
+    if (pl->smem > have) {                  // launch shape invalid)
+      CK(cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
+      have = pl->smem;
+    }
+  }
   auto it = ctx->occupancy.find(key);
   if (it == ctx->occupancy.end()) {
-    if (pl->smem > 40 * 1024)  // static + dynamic beyond 48 KB needs the opt-in
-      CK(cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)pl->smem));
     int per_sm = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kc.fn, kc.threads, pl->smem));
     if (per_sm < 1)
@@ -1324,12 +1332,13 @@ CGE_EXPORT int cge_debug_times(cge_context *ctx, unsigned long long *out, int ma
 // ---------------------------------------------------------------------------------------
 CGE_EXPORT int cge_microbench(cge_context *ctx, int kind, double *ops_per_second) {
   CKRC(bind(ctx));
-  if (!ops_per_second || kind < 0 || kind > 10)
+  if (!ops_per_second || kind < 0 || kind > 12)
     return set_error(CGE_ERR_BAD_ARG, "microbench: bad argument");
   CKRC(ctx->sink.reserve(4));
   const int iters = 4096, chains = 8;
   // kinds 8, 9, 10: the 6 FFMA2 + 2 MUFU mix at 2, 3 and 4 CTAs per SM (8, 12, 16 warps per SM)
-  const int blocks = ctx->sm_count * (kind == 8 ? 2 : kind == 9 ? 3 : kind == 10 ? 4 : 8), threads = 256;
+  // kinds 11, 12: the 10 FFMA2 + 2 MUFU mix at 64 and at 24 resident warps per SM
+  const int blocks = ctx->sm_count * (kind == 8 ? 2 : kind == 9 || kind == 12 ? 3 : kind == 10 ? 4 : 8), threads = 256;
   cudaStream_t st = ctx->stream;
   auto launch = [&]() {
     switch (kind) {
@@ -1341,6 +1350,7 @@ CGE_EXPORT int cge_microbench(cge_context *ctx, int kind, double *ops_per_second
       case 5: cge::microbench_kernel<5><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
       case 6: cge::microbench_kernel<6><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
       case 7: cge::microbench_kernel<7><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
+      case 11: case 12: cge::microbench_kernel<11><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
       default: cge::microbench_kernel<6><<<blocks, threads, 0, st>>>(ctx->sink.ptr, iters, 0.5f); break;
     }
   };
@@ -1359,8 +1369,8 @@ CGE_EXPORT int cge_microbench(cge_context *ctx, int kind, double *ops_per_second
   CK(cudaGetLastError());
   // kinds 0-3: one instruction class, 8 chains; kinds 4-7: FMA lane-ops of the mix per iteration
   // (packed count as 2; the MUFU chains' bounding FFMA counts as 1; MUFU ops are not counted)
-  static const double per_iter[11] = {8, 8, 8, 16, 4 * 2 + 4, 4 * 2 + 8, 6 * 2 + 2, 4 * 2 + 4 + 2,
-                                      6 * 2 + 2, 6 * 2 + 2, 6 * 2 + 2};
+  static const double per_iter[13] = {8, 8, 8, 16, 4 * 2 + 4, 4 * 2 + 8, 6 * 2 + 2, 4 * 2 + 4 + 2,
+                                      6 * 2 + 2, 6 * 2 + 2, 6 * 2 + 2, 10 * 2 + 2, 10 * 2 + 2};
   (void)chains;
   double ops = (double)blocks * threads * (double)iters * per_iter[kind];
   *ops_per_second = ops / (best * 1e-3);

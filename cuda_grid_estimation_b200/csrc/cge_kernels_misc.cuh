@@ -548,7 +548,8 @@ __global__ void __launch_bounds__(256) microbench_kernel(float *out, int iters, 
     // do packed (heavy half of the FMA pipe only) and scalar (either half) instructions add up to
     // more than either alone, and how much FMA work fits beside a saturated XU pipe?
     //   4: 4 FFMA2 + 4 FFMA    5: 4 FFMA2 + 8 FFMA    6: 6 FFMA2 + 2 MUFU    7: 4 FFMA2 + 4 FFMA + 2 MUFU
-    constexpr int NP = KIND == 6 ? 6 : 4;
+    //   11: 10 FFMA2 + 2 MUFU (the mix of one exponential per three rows)
+    constexpr int NP = KIND == 11 ? 10 : KIND == 6 ? 6 : 4;
     constexpr int NS = KIND == 4 ? 4 : KIND == 5 ? 8 : KIND == 7 ? 4 : 0;
     constexpr int NM = KIND >= 6 ? 2 : 0;
     unsigned long long v[NP];

@@ -218,6 +218,7 @@ CGE_EXPORT int cge_destroy_multi(cge_multi *m) {
     for (int i = 0; i < m->n; ++i)
       if (m->ctx[i]) cge_internal_peer_detach(m->ctx[i]);
   for (int i = 0; i < m->n; ++i) {
+    if (!m->ctx[i]) continue;  // (creation failed before this entry: nothing was allocated on it)
     cudaSetDevice(m->devices[i]);
     if (m->post[i]) cudaFree(m->post[i]);
     if (m->obs_dev[i]) cudaFree(m->obs_dev[i]);
@@ -231,6 +232,7 @@ CGE_EXPORT int cge_destroy_multi(cge_multi *m) {
   }
   if (m->obs_pinned) cudaFreeHost(m->obs_pinned);
   if (m->res_pinned) cudaFreeHost(m->res_pinned);
+  cudaGetLastError();
   delete m;
   return CGE_OK;
 }
