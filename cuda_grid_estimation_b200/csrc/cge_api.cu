@@ -216,18 +216,21 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->row_begin = rb;
   pl->row_end = re;
   pl->rows_local = re - rb;
-  // columns per warp strip: 32 lanes x Policy::kCols (log-space keeps 8 columns per thread)
+  // columns per warp strip: 32 lanes x Policy::kCols (log-space keeps 8 columns per thread); rows
+  // per group: Policy::kRows
   pl->kcols = p->mode == CGE_MODE_LOGSPACE ? 8 : 4;
+  pl->krows = p->mode == CGE_MODE_LOGSPACE ? cge::kRowsLog : cge::kRowsProduct;
   const int strip = 32 * pl->kcols;
   pl->ncw = (pl->N + strip - 1) / strip;
-  // row groups start at a multiple of kRM rows (see run_strip)
-  const int span = re - (rb & ~(cge::kRM - 1));
-  const int groups = (span + cge::kRM - 1) / cge::kRM;
+  // row groups start at a multiple of krows rows (see run_strip)
+  const int span = re - (rb - rb % pl->krows);
+  const int groups = (span + pl->krows - 1) / pl->krows;
   pl->groups = groups;
-  // fixed-point column sums: at most `groups` addends per column (col_fixed_shift)
+  // fixed-point column sums: at most `groups` addends per column, each a krows-row sum
+  // (col_fixed_shift)
   int lc = 0;
   while ((1ll << lc) < (long long)groups + 1) ++lc;
-  pl->fixed_bits = 58 - lc;
+  pl->fixed_bits = 58 - lc - (pl->krows > 4 ? 1 : 0);
   pl->nb_col = (pl->N + 255) / 256;
   pl->nb_row = (pl->rows_local + 7) / 8;
   pl->nb_res = (pl->N + 255) / 256;
@@ -250,7 +253,7 @@ size_t like_smem(const Plan &pl, const cge_host::KernelChoice &kc) {
 }
 
 // fixes the persistent grid: one CTA per resident slot of the device (occupancy of this kernel at
-// this shared-memory size), never more than there are items for; and the item size
+// this shared-memory size), never more than there are groups for; and the claim size
 int size_grid(cge_context *ctx, Plan *pl, const cge_host::KernelChoice &kc, int max_ctas) {
   pl->smem = like_smem(*pl, kc);
   const auto key = std::make_pair(kc.fn, pl->smem);
@@ -274,21 +277,31 @@ int size_grid(cge_context *ctx, Plan *pl, const cge_host::KernelChoice &kc, int 
   if (ctx->knob_ctas_per_sm > 0 && ctx->knob_ctas_per_sm < per_sm) per_sm = ctx->knob_ctas_per_sm;
   long long P = (long long)ctx->sm_count * per_sm * ctx->knob_grid_mult;
   if (max_ctas > 0 && P > max_ctas) P = max_ctas;
-  // item size: ~32 items per worker (a warp; a whole CTA when the observations are streamed) so
-  // that the last item of the slowest worker is a small tail, at most 8 row groups so that a claim
-  // (one atomic, hidden behind the item) stays far below 1 % of an item
-  const long long per_item = pl->streamed ? cge::kWarps : 1;  // groups one chunk step covers
   const long long total = (long long)pl->ncw * pl->groups;
-  const long long workers = P * (pl->streamed ? 1 : cge::kWarps);
-  long long chunk = total / (workers * 32 * per_item);
-  if (chunk < 1) chunk = 1;
-  if (chunk > 8) chunk = 8;
-  if (ctx->knob_chunk > 0) chunk = ctx->knob_chunk < 8 ? ctx->knob_chunk : 8;  // (run_strip: one lane per row of an item)
-  pl->chunk = (int)chunk;
-  pl->items_per_strip = (int)((pl->groups + chunk * per_item - 1) / (chunk * per_item));
-  const long long items = (long long)pl->ncw * pl->items_per_strip;
-  const long long useful = pl->streamed ? items : (items + cge::kWarps - 1) / cge::kWarps;
-  if (P > useful) P = useful;
+  if (!pl->streamed) {
+    // every CTA owns total / P groups (its pool) and its 8 warps take `chunk` of them at a time from
+    // a shared-memory counter: ~48 claims per warp, so that the last claim of the slowest warp is a
+    // small tail; a claim covers at most 32 rows (run_strip: one range value per lane)
+    if (P > total) P = total;
+    long long chunk = total / (P * cge::kWarps * 48);
+    const long long cap = 32 / pl->krows;
+    if (chunk < 1) chunk = 1;
+    if (chunk > cap) chunk = cap;
+    if (ctx->knob_chunk > 0) chunk = ctx->knob_chunk < cap ? ctx->knob_chunk : cap;
+    pl->chunk = (int)chunk;
+    pl->items_per_strip = 0;
+  } else {
+    // streamed observations: the CTA is the worker; items of 8 * chunk groups of one strip are
+    // claimed from the strip's counter in global memory (a step is hundreds of microseconds there)
+    long long chunk = total / (P * 32 * cge::kWarps);
+    const long long cap = 32 / pl->krows;
+    if (chunk < 1) chunk = 1;
+    if (chunk > cap) chunk = cap;
+    pl->chunk = (int)chunk;
+    pl->items_per_strip = (int)((pl->groups + chunk * cge::kWarps - 1) / (chunk * cge::kWarps));
+    const long long items = (long long)pl->ncw * pl->items_per_strip;
+    if (P > items) P = items;
+  }
   pl->nctas = (int)P;
   return CGE_OK;
 }

@@ -33,8 +33,9 @@ struct Plan {
   int row_begin = 0, row_end = 0, rows_local = 0;
   int kcols = 4;           // columns per thread: a warp's strip is 32 * kcols columns
   int ncw = 0;             // strips per row
-  int groups = 0;          // row groups (kRM rows) that cover the shard's rows
-  int chunk = 1;           // row groups per claimed item
+  int krows = 4;           // rows per group (Policy::kRows)
+  int groups = 0;          // row groups that cover the shard's rows
+  int chunk = 1;           // row groups per claim
   int items_per_strip = 0;
   int fixed_bits = 0;      // 58 - ceil(log2(addends per column))
   int nctas = 0;           // P: persistent CTAs (resident slots of the device)
@@ -54,8 +55,8 @@ struct KernelChoice {
 };
 
 // the default product policies
-using DefaultFine = cge::ProductPaired<2>;    // degree-2 polynomial, band umax <= 0.011
-using DefaultMid = cge::ProductPaired<3>;     // degree-3 polynomial, band umax <= 0.05
+using DefaultFine = cge::ProductNeighbour<2>;  // degree-2 polynomial, strip umax <= 0.011
+using DefaultMid = cge::ProductNeighbour<3>;   // degree-3 polynomial, strip umax <= 0.05
 using DefaultCoarse = cge::ProductHybrid;
 constexpr int kDefaultMinB = 3;  // <= 80 registers: three 256-thread CTAs (24 warps) per SM
 

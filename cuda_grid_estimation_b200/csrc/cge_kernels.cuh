@@ -37,8 +37,10 @@ namespace cge {
 // 166 bits (1e-50 relative to the peak) below it before a cell flushes to zero.
 constexpr double kPeakLog2 = 40.0;
 
-constexpr int kRM = 4;            // register patch rows (mu) per thread; also the row alignment of
-                                  // every unit of work
+constexpr int kRowsProduct = 6;   // register patch rows (mu) per thread of the product policies: two
+                                  // triples, the middle row of each on MUFU.EX2 (see ProductNeighbour)
+constexpr int kRowsLog = 4;       // ... of the log-space policies
+                                  // (a policy's kRows is also the row alignment of every unit of work)
 constexpr int kRN = 4;            // columns (sigma) per float4 store; a policy owns
                                   // Policy::kCols = 4 or 8 columns = 1 or 2 such groups
 constexpr int kGroupCols = 32 * kRN;  // 128 columns: one float4 per lane across a warp
@@ -71,28 +73,32 @@ struct RangeArgs {
   float mu0, mu1, sg0, sg1;
 };
 
-// Work decomposition of the likelihood kernel.  A GROUP is kRM rows of one warp-wide column STRIP
-// (32 * kCols columns); an ITEM is `chunk` consecutive groups of one strip.  Items are not
-// assigned, they are CLAIMED, and the worker is the WARP, not the CTA: every strip has a counter,
-// a warp starts on its home strip (the warps of the grid are spread evenly over the strips), takes
-// items from that strip's counter until it runs out and then moves on to the next strip.  After
-// the set-up the warps of a CTA never synchronise again.  Two measured reasons (B200, 16384^2 x 50):
-//   * the warp scheduler does not share an SM fairly between resident CTAs -- with equal static
-//     shares some CTAs finished in 0.95 ms and others in 1.82 ms, the tail running at a third of
-//     the occupancy -- so the balance has to be dynamic;
+// Work decomposition of the likelihood kernel.  A GROUP is Policy::kRows rows of one warp-wide
+// column STRIP (32 * kCols columns); groups are numbered strip-major, u = strip * groups + group.
+// The grid is persistent (one CTA per resident slot of the device).  Every CTA owns an equal,
+// contiguous share of the groups -- its POOL -- and the worker is the WARP, not the CTA: the warps
+// of a CTA take `chunk` consecutive groups at a time from the pool through a shared-memory counter
+// and never synchronise after the set-up.  Measured reasons (B200, 16384^2 x 50):
+//   * the warp scheduler does not share an SM fairly between its warps, so equal static shares per
+//     warp leave some warps finished early and the rest running at lower occupancy; a counter in
+//     shared memory balances the warps of a CTA at the cost of one ~100-cycle atomic per claim;
+//   * claims from per-strip counters in GLOBAL memory (the first design) cost an L2 round trip each,
+//     and the warp could not hide it: with one group per claim the kernel took 2.48 ms instead of
+//     1.83 ms, and small shards (2048 rows, one of 8 GPUs) ran at 63 % of the full grid's rate;
 //   * warps that move in lock step all reach the epilogue (stores, shuffles, float64) together and
-//     all return to the MUFU-bound loop together; independent warps drift apart and the epilogue
-//     of one hides behind the exponentials of the others.
+//     all return to the pipe-bound loop together; independent warps drift apart and the epilogue
+//     of one hides behind the arithmetic of the others.
 //
 // Results must not depend on who computed what.  Cells and partial row sums go to fixed places.
-// Column sums cross items, so they are accumulated EXACTLY: every thread's 4-row float32 sum is
+// Column sums cross pools, so they are accumulated EXACTLY: every thread's kRows-row float32 sum is
 // scaled by a power of two chosen per column -- from the closed-form largest cell of that column,
 // colmax_j = 2^(a_j S_min + n c0_j + shift), so that the shard's total stays below 2^62 -- rounded
-// to an integer and added in int64: per CTA in shared memory, then once per band with integer
-// atomics into colacc[N].  Integer addition is associative: the sums are bit-identical whatever the
-// order, with a resolution of colmax_j * 2^-(58 - log2(rows/4)), i.e. ~2^-46 relative to the
-// column's own largest cell at 16384 rows (finer than the float64 partial sums it replaces for the
-// columns that matter, and scaled per column, so the far tails keep their relative precision).
+// to an integer and added in int64: per warp in shared memory, then once per strip visit with
+// integer atomics into colacc[N].  Integer addition is associative: the sums are bit-identical
+// whatever the order, with a resolution of colmax_j * 2^-(57 - log2(rows/kRows)), i.e. ~2^-45
+// relative to the column's own largest cell at 16384 rows (finer than the float64 partial sums it
+// replaces for the columns that matter, and scaled per column, so the far tails keep their
+// relative precision).
 struct LikeArgs {
   // Observations: fused set-up (scale_in == NULL): the caller's n floats, any alignment, device
   // or mapped host memory; every CTA stages them and derives the statistics itself.  Streamed
@@ -112,13 +118,14 @@ struct LikeArgs {
   float *post;      // shard base (row `row_begin` at offset 0)
   double *rowpart;  // [rows_local][ncw]
   unsigned long long *colacc;  // [N] fixed-point column sums (zero at launch; the fold kernel clears them)
-  int *strip_next;  // [ncw] next unclaimed item of each strip (zero at launch; the fold kernel clears them)
+  int *strip_next;  // streamed only: [ncw] next unclaimed item of each strip (zero at launch; the fold
+                    // kernel clears them)
   int n, n_pad, N;  // n observations; n_pad staged floats (multiple of 4)
   int row_begin, row_end;
-  int groups;          // row groups that cover the shard's rows
-  int chunk;           // row groups per item
-  int items_per_strip; // ceil(groups / chunk) (streamed: ceil(groups / (8 * chunk)), claimed per CTA)
-  int fixed_bits;      // 58 - ceil(log2(addends per column)): see col_fixed_shift
+  int groups;          // row groups (Policy::kRows rows each) that cover the shard's rows
+  int chunk;           // row groups per claim (at most 32 / kRows: one range value per lane)
+  int items_per_strip; // streamed only: ceil(groups / (8 * chunk)) items per strip, claimed per CTA
+  int fixed_bits;      // 58 - ceil(log2(addends per column)) (- 1 for 6-row groups): see col_fixed_shift
   int ncw;             // column strips per row: ceil(N / (32 * Policy::kCols))
   int vec4;            // N % 4 == 0 and the shard base is 16-byte aligned: float4 stores
   int keep_l2;         // the shard fits in L2: store with the default policy instead of .cs
@@ -130,10 +137,11 @@ struct LikeArgs {
 __device__ __forceinline__ double coef_a(double sd) { return -0.5 * 1.4426950408889634074 / (sd * sd); }
 __device__ __forceinline__ double coef_c0(double sd) { return -log2(sd * 2.5066282746310005024); }
 
-// Fixed-point exponent of column j: its 4-row sums are accumulated as rint(x * 2^s).  The cells of
-// the column are at most 2^e, e = ceil(log2 colmax_j + log2 prior_max) + 1 (one binade of slack
-// for the float32 rounding of the product); a 4-row sum is below 2^(e+2), and with at most
-// 2^(58 - fixed_bits) addends the int64 total stays below 2^62 for s = fixed_bits - e - 2.  The
+// Fixed-point exponent of column j: its kRows-row sums are accumulated as rint(x * 2^s).  The cells
+// of the column are at most 2^e, e = ceil(log2 colmax_j + log2 prior_max) + 1 (one binade of slack
+// for the float32 rounding of the product); a 4-row sum is below 2^(e+2) (a 6-row sum below
+// 2^(e+3): the host takes one more bit off fixed_bits), and with at most 2^(58 - fixed_bits)
+// addends the int64 total stays below 2^62 for s = fixed_bits - e - 2.  The
 // clamp keeps 2^s a float32 normal: columns whose largest cell is below ~2^-70 keep an absolute
 // resolution of 2^-120 (their cells flush to zero at 2^-126 anyway).  Evaluated with identical
 // arithmetic by the likelihood kernel (to scale) and the fold kernel (to scale back).
@@ -285,7 +293,7 @@ __device__ __forceinline__ ScaleInfo setup_scale(const RangeArgs &r, const float
   // Largest exponent step between vertically adjacent cells,
   //   |t_(i+1,j,k) - t_(i,j,k)| = |a_j| |mu_(i+1) - mu_i| |mu_i + mu_(i+1) - 2 x_k|,
   // bounded over the whole grid and every observation.  The row spacing gets 2 ulp of slack for
-  // the float32 rounding of the range values.  ProductPaired is only used below kPairedUmax.
+  // the float32 rounding of the range values.  ProductNeighbour is only used below kPairedUmax.
   {
     const double mlo = fmin((double)mu0, (double)mu1), mhi = fmax((double)mu0, (double)mu1);
     const double reach = fmax(fmax(fabs(xhi - mlo), fabs(xlo - mlo)), fmax(fabs(xhi - mhi), fabs(xlo - mhi)));
@@ -300,7 +308,7 @@ __device__ __forceinline__ ScaleInfo setup_scale(const RangeArgs &r, const float
 
 // ---------------------------------------------------------------------------------------
 // Arithmetic policies of the fused likelihood kernel.  Each owns the per-thread state for a
-// kRM x kCols patch of cells and consumes the observations of one row group.
+// kRows x kCols patch of cells and consumes the observations of one row group.
 //   kSmemDoubles  float64 values per thread the policy keeps in shared memory (element k of
 //                 thread t at own[k * NT]; `own` is already offset by the thread index)
 // ---------------------------------------------------------------------------------------
@@ -315,15 +323,15 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 struct ProductF32 {
   static constexpr double kUmax = 1e300;
   static constexpr bool kColSmem = false;
-  static constexpr int kRows = kRM;
+  static constexpr int kRows = kRowsProduct;
   static constexpr int kCols = 4;
   static constexpr int kSmemDoubles = 0;
   static __device__ __forceinline__ void consume(ProductF32 &pol, const float *xs, int count,
-                                                 const float (&mu)[kRM]) {
+                                                 const float (&mu)[kRows]) {
     consume_scalar_obs(pol, xs, count, mu);
   }
   float a[kRN], c[kRN];
-  float p[kRM][kRN];
+  float p[kRows][kRN];
 
   template <int NT>
   __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
@@ -337,19 +345,19 @@ struct ProductF32 {
   }
   __device__ __forceinline__ void begin_rows() {
 #pragma unroll
-    for (int r = 0; r < kRM; ++r)
+    for (int r = 0; r < kRows; ++r)
 #pragma unroll
       for (int cidx = 0; cidx < kRN; ++cidx) p[r][cidx] = 1.0f;
   }
-  __device__ __forceinline__ void step(float x, const float (&mu)[kRM]) {
-    float dd[kRM];
+  __device__ __forceinline__ void step(float x, const float (&mu)[kRows]) {
+    float dd[kRows];
 #pragma unroll
-    for (int r = 0; r < kRM; ++r) {
+    for (int r = 0; r < kRows; ++r) {
       float d = x - mu[r];  // same f32 rounding as the reference's (x - mu), kernels.h:111
       dd[r] = d * d;
     }
 #pragma unroll
-    for (int r = 0; r < kRM; ++r)
+    for (int r = 0; r < kRows; ++r)
 #pragma unroll
       for (int cidx = 0; cidx < kRN; ++cidx)
         p[r][cidx] *= ex2_approx(fmaf(dd[r], a[cidx], c[cidx]));
@@ -553,22 +561,22 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 // ProductF32 (exponent FMA, 2^t, running product) but
 //   * the per-cell arithmetic runs as packed f32x2 (FFMA2/FMUL2): a thread's 4 columns are two
 //     register pairs; the per-row (x - mu)^2 stays scalar and enters FFMA2 as a broadcast operand;
-//   * of the 8 column pairs a thread updates per observation, 2 take 2^t from the degree-5
+//   * of the 12 column pairs a thread updates per observation, 3 take 2^t from the degree-5
 //     FMA-pipe polynomial (ex2_poly2) instead of MUFU.EX2.  With MUFU-only code the XU pipe is
 //     96 % busy while the FMA pipe idles at 30 % and half the issue slots are free
-//     (profiles/r01_ncu_full_mufu_only_16384x50.csv); moving 4 of 16 exponentials over balances
-//     the two pipes.
+//     (profiles/r01_ncu_full_mufu_only_16384x50.csv); moving a quarter of the exponentials over
+//     balances the two pipes.
 // Which cells use which pipe is fixed at compile time, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------
 struct ProductHybrid {
   static constexpr double kUmax = 1e300;  // any grid
   static constexpr bool kColSmem = false;
-  static constexpr int kRows = kRM;
+  static constexpr int kRows = kRowsProduct;
   static constexpr int kCols = 4;
   static constexpr int kSmemDoubles = 0;
-  static constexpr int kPoly = 2;  // (row, pair) slots per observation on the polynomial
+  static constexpr int kPoly = 3;  // (row, pair) slots per observation on the polynomial
   f32x2 a2[kRN / 2], c2[kRN / 2];
-  f32x2 p2[kRM][kRN / 2];
+  f32x2 p2[kRows][kRN / 2];
 
   template <int NT>
   __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
@@ -589,22 +597,22 @@ struct ProductHybrid {
   __device__ __forceinline__ void begin_rows() {
     const f32x2 one = pack2(1.0f, 1.0f);
 #pragma unroll
-    for (int r = 0; r < kRM; ++r)
+    for (int r = 0; r < kRows; ++r)
 #pragma unroll
       for (int h = 0; h < kRN / 2; ++h) p2[r][h] = one;
   }
-  __device__ __forceinline__ void step(float x, const float (&mu)[kRM]) {
+  __device__ __forceinline__ void step(float x, const float (&mu)[kRows]) {
 #pragma unroll
-    for (int r = 0; r < kRM; ++r) {
+    for (int r = 0; r < kRows; ++r) {
       const float d = x - mu[r];  // same f32 rounding as the reference's (x - mu), kernels.h:111
       const float dd = d * d;
       const f32x2 dd2 = pack2(dd, dd);  // becomes a scalar-broadcast operand of FFMA2
 #pragma unroll
       for (int h = 0; h < kRN / 2; ++h) {
         const f32x2 t2 = fma2(dd2, a2[h], c2[h]);
-        // spread the polynomial slots over the rows: (r, h) = (0,0),(1,1),(2,0),(3,1), then the rest
-        const int slot = ((h + r) & 1) * kRM + r;
-        const f32x2 e2 = slot < kPoly ? ex2_poly2(t2) : ex2_mufu2(t2);
+        // the polynomial slots, spread over the rows and both pairs: (r, h) = (0,0), (2,1), (4,0)
+        const bool poly = (r == 0 && h == 0) || (r == 2 && h == 1) || (r == 4 && h == 0);
+        const f32x2 e2 = poly ? ex2_poly2(t2) : ex2_mufu2(t2);
         p2[r][h] = mul2(p2[r][h], e2);
       }
     }
@@ -616,35 +624,42 @@ struct ProductHybrid {
     return (cidx & 1) ? hi : lo;
   }
   static __device__ __forceinline__ void consume(ProductHybrid &pol, const float *xs, int count,
-                                                 const float (&mu)[kRM]) {
+                                                 const float (&mu)[kRows]) {
 #pragma unroll 1
     for (int k = 0; k < count; ++k) pol.step(xs[k], mu);
   }
 };
 
 // ---------------------------------------------------------------------------------------
-// float32 product path, paired rows: of every two vertically adjacent cells (mu_i, mu_(i+1) at
-// the same sigma_j) one takes its factor from MUFU.EX2 and the other derives its own from it,
-//   pdf(x_k; mu_(i+1), sigma_j) = pdf(x_k; mu_i, sigma_j) * 2^u,
-//   u = a_j * g_ik,   g_ik = (mu_(i+1) - mu_i) * (mu_i + mu_(i+1) - 2 x_k)      (exact identity)
+// float32 product path, neighbour rows: of every three vertically adjacent cells (mu_(m-1), mu_m,
+// mu_(m+1) at the same sigma_j) the middle one takes its factor from MUFU.EX2 and the two others
+// derive theirs from it,
+//   pdf(x_k; mu_r, sigma_j) = pdf(x_k; mu_m, sigma_j) * 2^u,
+//   u = a_j * g_rk,   g_rk = (mu_r - mu_m) * (mu_m + mu_r - 2 x_k)      (exact identity, r = m -+ 1)
 // with 2^u - 1 from a degree-2 polynomial on the FMA pipe: on a fine grid |u| is tiny (6e-3 at
 // 16384 rows for the README ranges), so no range reduction is needed.  Every pdf-eval still forms
 // its own factor and multiplies it into its own running product; what changes is the pipe mix:
 //   MUFU row   : FFMA2 (exponent), 2 MUFU.EX2, FMUL2 (product)            per column pair
 //   derived row: FFMA2 (a_j k1 + g a_j^2 k2), FMUL2 (* g), FFMA2 (e + e v), FMUL2 (product)
-// i.e. half the MUFU work of ProductF32 for ~3 packed FMA-pipe instructions more per 4 evals;
-// ncu showed the MUFU-only kernel with the XU pipe 97 % busy and the FMA pipe at 30 %.
+// i.e. per 6 evals 2 MUFU.EX2 and 10 packed FMA-pipe instructions (20 lane-ops).  History of the
+// mix on B200 (16 MUFU lanes and 128 FMA lanes per SM and clock):
+//   every exponential on MUFU         1 MUFU + 2 lane-ops per eval   XU-bound   (r01: XU 97 %)
+//   pairs (one derived row of two)  1/2 MUFU + 3 lane-ops            XU-bound, FMA 84 % of XU time:
+//                                    both pipes throttle each other, XU stuck at 79-87 %
+//   triples (two derived of three)  1/3 MUFU + 3.33 lane-ops         FMA-bound, XU at 2/3 of it
+// (+ the per-row scalars).  The pipe micro-benchmark (tools/pipe_mix.py) puts the triple mix at
+// 32 T lane-ops/s with 24 warps per SM (88 % of the FFMA peak) against 28 T for the pair mix.
 // Polynomial: 2^u = 1 + u (k1 + k2 u) with k2 = ln(2)^2/2 and the cubic term folded into
-// k1 = ln 2 + (ln(2)^3/6)(3/4) U^2 (Chebyshev economisation on [-U, U], U = the band's umax):
+// k1 = ln 2 + (ln(2)^3/6)(3/4) U^2 (Chebyshev economisation on [-U, U], U = the strip's umax):
 // error <= 0.0139 U^3 = 1.8e-8 at the eligibility bound kPairedUmax, below the float32 rounding
 // of the factor itself.  The derived factor is e*(1+v) evaluated as fma(e, v, e): one rounding.
 // DEG = 3 adds the cubic term, 2^u - 1 = u (k1 + u (k2 + u k3)), k3 = ln(2)^3/6 and the quartic
 // folded into k2 = ln(2)^2/2 + (ln(2)^4/24) U^2: error <= 0.0024 U^4 = 1.5e-8 at its bound
 // kPairedUmax3 = 0.05, which takes grids 4.5x coarser (README ranges: N >= 690) for one more
 // FFMA2 per derived pair.  Grids too coarse for that run ProductHybrid instead (chosen on the
-// device per column band); which rows are MUFU rows depends on the global row index only.
-// Four observations per loop iteration (one LDS.128), the two row pairs' scalars packed; the
-// tile's float64 column sums live in shared memory, which is what lets the kernel fit 80 registers.
+// device per column strip); which rows are MUFU rows depends on the global row index only
+// (row % 3 == 1).  Four observations per loop iteration (one LDS.128), the per-row scalars of the
+// two triples packed.
 // ---------------------------------------------------------------------------------------
 #ifndef CGE_Q_UNROLL
 #define CGE_Q_UNROLL 1
@@ -654,18 +669,20 @@ constexpr double kPairedUmax = 0.011;
 constexpr double kPairedUmax3 = 0.05;
 
 template <int DEG = 2>
-struct ProductPaired {
+struct ProductNeighbour {
   static_assert(DEG == 2 || DEG == 3, "polynomial degree of 2^u - 1");
   static constexpr double kUmax = DEG == 2 ? kPairedUmax : kPairedUmax3;  // eligibility bound
   static constexpr bool kColSmem = true;
-  static constexpr int kRows = kRM;
+  static constexpr int kRows = kRowsProduct;
   static constexpr int kCols = 4;
   static constexpr int kSmemDoubles = 0;
   static constexpr int kPairs = kCols / 2;
+  static constexpr int kTriples = kRows / 3;
+  static_assert(kRows == 6, "two triples: the per-row scalars are packed pairwise");
   f32x2 a2[kPairs], c2[kPairs];    // exponent coefficients of the MUFU rows
   f32x2 k1a[kPairs], k2a[kPairs];  // a_j k1, a_j^2 k2 of the derived rows
   f32x2 k3a[DEG == 3 ? kPairs : 1];  // a_j^3 k3
-  f32x2 p2[kRM][kPairs];
+  f32x2 p2[kRows][kPairs];
 
   template <int NT>
   __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
@@ -697,33 +714,42 @@ struct ProductPaired {
   __device__ __forceinline__ void begin_rows() {
     const f32x2 one = pack2(1.0f, 1.0f);
 #pragma unroll
-    for (int r = 0; r < kRM; ++r)
+    for (int r = 0; r < kRows; ++r)
 #pragma unroll
       for (int h = 0; h < kPairs; ++h) p2[r][h] = one;
   }
-  // one observation: rows (0,1) and (2,3) of the patch are the pairs; gm/gb give g = x*gm + gb
-  __device__ __forceinline__ void step(float x, const float (&mu)[kRM], const float (&gm)[kRM / 2],
-                                       const float (&gb)[kRM / 2]) {
-    float ddv[kRM / 2], ggv[kRM / 2];
-    {  // the two row pairs' scalars as one packed FADD2 / FMUL2 / FFMA2 each
+  // one observation.  mid2 = {mu_1, mu_4} (the MUFU rows); gmL/gbL give g = x*gm + gb of the rows
+  // below them (0, 3), gmU/gbU of the rows above (2, 5), each as one packed pair over the triples.
+  __device__ __forceinline__ void step(float x, f32x2 mid2, f32x2 gmL, f32x2 gbL, f32x2 gmU, f32x2 gbU) {
+    float ddv[kTriples], glo[kTriples], gup[kTriples];
+    {
       const f32x2 x2 = pack2(x, x);
-      const f32x2 d2 = sub2(x2, pack2(mu[0], mu[2]));  // same f32 rounding as the reference's (x - mu)
+      const f32x2 d2 = sub2(x2, mid2);  // same f32 rounding as the reference's (x - mu)
       unpack2(mul2(d2, d2), ddv[0], ddv[1]);
-      unpack2(fma2(x2, pack2(gm[0], gm[1]), pack2(gb[0], gb[1])), ggv[0], ggv[1]);
+      unpack2(fma2(x2, gmL, gbL), glo[0], glo[1]);
+      unpack2(fma2(x2, gmU, gbU), gup[0], gup[1]);
     }
 #pragma unroll
-    for (int rp = 0; rp < kRM / 2; ++rp) {
-      const float dd = ddv[rp], gg = ggv[rp];
-      const f32x2 dd2 = pack2(dd, dd);
-      const f32x2 g2 = pack2(gg, gg);
+    for (int t = 0; t < kTriples; ++t) {
+      const f32x2 dd2 = pack2(ddv[t], ddv[t]);  // (scalar-broadcast operands of the packed instructions)
+      const f32x2 gl2 = pack2(glo[t], glo[t]);
+      const f32x2 gu2 = pack2(gup[t], gup[t]);
 #pragma unroll
       for (int h = 0; h < kPairs; ++h) {
         const f32x2 e2 = ex2_mufu2(fma2(dd2, a2[h], c2[h]));
-        p2[2 * rp][h] = mul2(p2[2 * rp][h], e2);
-        const f32x2 q2 = DEG == 3 ? fma2(g2, k3a[h], k2a[h]) : k2a[h];
-        const f32x2 v2 = mul2(g2, fma2(g2, q2, k1a[h]));  // 2^u - 1
-        const f32x2 f2 = fma2(e2, v2, e2);                    // neighbour's factor
-        p2[2 * rp + 1][h] = mul2(p2[2 * rp + 1][h], f2);
+        p2[3 * t + 1][h] = mul2(p2[3 * t + 1][h], e2);
+        {
+          const f32x2 q2 = DEG == 3 ? fma2(gl2, k3a[h], k2a[h]) : k2a[h];
+          const f32x2 v2 = mul2(gl2, fma2(gl2, q2, k1a[h]));  // 2^u - 1
+          const f32x2 f2 = fma2(e2, v2, e2);                   // the lower neighbour's factor
+          p2[3 * t][h] = mul2(p2[3 * t][h], f2);
+        }
+        {
+          const f32x2 q2 = DEG == 3 ? fma2(gu2, k3a[h], k2a[h]) : k2a[h];
+          const f32x2 v2 = mul2(gu2, fma2(gu2, q2, k1a[h]));
+          const f32x2 f2 = fma2(e2, v2, e2);                   // the upper neighbour's factor
+          p2[3 * t + 2][h] = mul2(p2[3 * t + 2][h], f2);
+        }
       }
     }
   }
@@ -733,31 +759,38 @@ struct ProductPaired {
     unpack2(p2[r][cidx >> 1], lo, hi);
     return (cidx & 1) ? hi : lo;
   }
-  static __device__ __forceinline__ void consume(ProductPaired &pol, const float *xs, int count,
-                                                 const float (&mu)[kRM]) {
-    float gm[kRM / 2], gb[kRM / 2];
+  static __device__ __forceinline__ void consume(ProductNeighbour &pol, const float *xs, int count,
+                                                 const float (&mu)[kRows]) {
+    // g of row r against its triple's middle row m: (mu_r - mu_m) * (mu_m + mu_r - 2 x)
+    float gm[kRows], gb[kRows];
 #pragma unroll
-    for (int rp = 0; rp < kRM / 2; ++rp) {
-      const float delta = __fsub_rn(mu[2 * rp + 1], mu[2 * rp]);  // exact (adjacent range values)
-      gm[rp] = -2.0f * delta;
-      gb[rp] = __fmul_rn(delta, __fadd_rn(mu[2 * rp], mu[2 * rp + 1]));
-    }
+    for (int t = 0; t < kTriples; ++t)
+#pragma unroll
+      for (int s = 0; s < 3; s += 2) {
+        const int r = 3 * t + s, m = 3 * t + 1;
+        const float delta = __fsub_rn(mu[r], mu[m]);  // exact (adjacent range values)
+        gm[r] = -2.0f * delta;
+        gb[r] = __fmul_rn(delta, __fadd_rn(mu[m], mu[r]));
+      }
+    const f32x2 mid2 = pack2(mu[1], mu[4]);
+    const f32x2 gmL = pack2(gm[0], gm[3]), gbL = pack2(gb[0], gb[3]);
+    const f32x2 gmU = pack2(gm[2], gm[5]), gbU = pack2(gb[2], gb[5]);
     const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
     const int n4 = count >> 2;
 #pragma unroll kObsLoopUnroll
     for (int q = 0; q < n4; ++q) {
       const float4 x = xs4[q];
-      pol.step(x.x, mu, gm, gb);
-      pol.step(x.y, mu, gm, gb);
-      pol.step(x.z, mu, gm, gb);
-      pol.step(x.w, mu, gm, gb);
+      pol.step(x.x, mid2, gmL, gbL, gmU, gbU);
+      pol.step(x.y, mid2, gmL, gbL, gmU, gbU);
+      pol.step(x.z, mid2, gmL, gbL, gmU, gbU);
+      pol.step(x.w, mid2, gmL, gbL, gmU, gbU);
     }
     if (count & 2) {  // the tail as one LDS.64 and at most one scalar load
       const float2 x = *reinterpret_cast<const float2 *>(xs + (n4 << 2));
-      pol.step(x.x, mu, gm, gb);
-      pol.step(x.y, mu, gm, gb);
+      pol.step(x.x, mid2, gmL, gbL, gmU, gbU);
+      pol.step(x.y, mid2, gmL, gbL, gmU, gbU);
     }
-    if (count & 1) pol.step(xs[count - 1], mu, gm, gb);
+    if (count & 1) pol.step(xs[count - 1], mid2, gmL, gbL, gmU, gbU);
   }
 };
 
@@ -765,12 +798,12 @@ struct ProductPaired {
 // Shared-memory layout of the likelihood kernels (dynamic):
 //   [0, 16)    two mbarriers (streamed observations only)
 //   [16, 96)   ScaleInfo of this step (written once per CTA by the set-up)
-//   [96, 128)  two claim slots (the item a CTA takes next)
+//   [96, 128)  claim slots: [0..2] the item a CTA takes next (streamed), [4] the pool counter
 //   [128, ...) observation stage: n_pad floats, or two chunks of kObsChunk when streamed
 //   then       per-thread slots [k][NT]: kCols int64 column accumulators (as 16-byte pairs), kCols
 //              float32 column scales 2^s_j (as 8-byte pairs), the policy's own float64 values, and
-//              4 floats per thread of row-sum transposition buffer (512 bytes per warp); during the
-//              set-up the same bytes serve as the sort scratch
+//              kRows floats per thread of row-sum transposition buffer (kRows * 128 bytes per
+//              warp); during the set-up the same bytes serve as the sort scratch
 // ---------------------------------------------------------------------------------------
 constexpr int kSmemHeader = 128;
 __host__ __device__ __forceinline__ size_t stage_bytes(int n_pad) {
@@ -779,7 +812,7 @@ __host__ __device__ __forceinline__ size_t stage_bytes(int n_pad) {
 // bytes per thread behind the observation stage
 template <class Policy>
 constexpr int policy_smem_bytes() {
-  return Policy::kCols * 8 + Policy::kCols * 4 + Policy::kSmemDoubles * 8 + 16;
+  return Policy::kCols * 8 + Policy::kCols * 4 + Policy::kSmemDoubles * 8 + Policy::kRows * 4;
 }
 
 // thread 0 only: start the bulk copy of chunk `ch` of the streamed observations into stage `st`
@@ -795,33 +828,38 @@ constexpr int kWarps = 8;             // warps per CTA of every likelihood kerne
 constexpr int kThreads = kWarps * 32;
 
 // ---------------------------------------------------------------------------------------
-// run_strip: everything this warp does in column strip `cw`, starting with item `item` (already
-// claimed) and claiming further items of the strip until none are left -- K1-K5 fused.
+// run_strip: everything this warp does in column strip `cw` -- K1-K5 fused.
 //   The warp owns the strip's 32*kCols sigma columns (lane -> kCols/4 groups of 4 adjacent
-//   columns, one 16-byte store per group and row) and walks its items' row groups kRM rows at a
-//   time.  Per row group it emits its partial row sums (fixed-order shuffle tree) and adds its
-//   4-row column sums into its fixed-point accumulators (shared memory); when the strip is left
-//   they go to colacc[] with one integer atomic per column.  No floating-point atomics.
-//   STREAMED (more than 16384 observations): the CTA moves as one -- thread 0 claims for all 8
-//   warps, which take interleaved groups of the same strip and consume each 32 KB chunk of
-//   observations together (the chunks arrive by TMA bulk copy into two shared-memory stages).
+//   columns, one 16-byte store per group and row) and walks row groups kRows rows at a time.  Per
+//   row group it emits its partial row sums (fixed-order shuffle tree) and adds its kRows-row
+//   column sums into its fixed-point accumulators (shared memory); when the strip is left they go
+//   to colacc[] with one integer atomic per column.  No floating-point atomics.
+//   Pooled (not STREAMED): [u0, u1) is the claim the warp holds (global group numbers, u0 inside
+//   this strip); it works it off, takes further claims from the CTA's pool counter while they
+//   start in this strip, and returns in [u0, u1) the first claim (or remainder of one) that does
+//   not -- u0 >= pool_end when the pool is exhausted.
+//   STREAMED (more than 16384 observations): the CTA moves as one -- u0 is the item of strip `cw`
+//   it holds; thread 0 claims for all 8 warps from the strip's global counter; the warps take
+//   interleaved groups of the same strip and consume each 32 KB chunk of observations together
+//   (the chunks arrive by TMA bulk copy into two shared-memory stages).
 // ---------------------------------------------------------------------------------------
 template <class Policy, bool STREAMED>
-__device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc, int cw, int item,
-                                          uint64_t *bars, float *obs_s, unsigned char *tsm_raw,
-                                          volatile int *claim, int &claim_par, int &streams) {
+__device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc, int cw, int &u0,
+                                          int &u1, int pool_end, uint64_t *bars, float *obs_s,
+                                          unsigned char *tsm_raw, volatile int *claim,
+                                          int &claim_par, int &streams) {
   constexpr int NT = kThreads;
   constexpr int kRows = Policy::kRows;
   constexpr int kCols = Policy::kCols;
   constexpr int kGroups = kCols / kRN;
-  static_assert(kRows == kRM, "row groups are kRM rows");
+  static_assert(kRows == 4 || kRows == 6, "the epilogue is written for 4- and 6-row patches");
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   const int j0 = cw * (32 * kCols) + lane * kRN;  // first column; group g starts 128*g further
-  // row groups start at a multiple of kRM below row_begin, so a cell's position inside the register
-  // patch (hence which exponential path it takes) depends on its GLOBAL row only: a row shard
-  // computes bit-identical unnormalised cells to the single-GPU run
-  const int row_base = g.row_begin & ~(kRM - 1);
+  // row groups start at a multiple of kRows below row_begin, so a cell's position inside the
+  // register patch (hence which exponential path it takes) depends on its GLOBAL row only: a row
+  // shard computes bit-identical unnormalised cells to the single-GPU run
+  const int row_base = g.row_begin - g.row_begin % kRows;
 
   // per-thread shared-memory slots, element k of thread t at [k * NT + t]
   // (the column accumulators and scales are kept as pairs: one 16-byte / 8-byte access per pair)
@@ -853,10 +891,10 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
   int row = 0;
   bool rows_any = false;
 
-  // The range values of an item's rows (at most 8 groups x 4 rows = one per lane) are evaluated
-  // once per item, lane l taking row first_row + l (rows past the end repeat the last value; they
-  // are masked in the epilogue); a group then takes its four by shuffle: the reference's float32
-  // divide is paid once per item, not once per group.
+  // The range values of a claim's rows (at most 32 / kRows groups: one row per lane) are evaluated
+  // once per claim, lane l taking row first_row + l (rows past the end repeat the last value; they
+  // are masked in the epilogue); a group then takes its kRows by shuffle: the reference's float32
+  // divide is paid once per claim, not once per group.
   float mu_item = 0.0f;
   int item_row0 = 0;
   auto begin_item = [&](int grp0) {
@@ -873,10 +911,8 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
   };
 
   // Epilogue of one row group: store the kRows x kCols patch, add it into the row / column sums.
-  // Within the patch the sums are float32 in a fixed pairwise order (4 or 8 terms).  The kRows row
-  // sums of a warp are reduced together in float64 by a transposing butterfly (12 shuffles instead
-  // of 40): lane 8*q ends up with the total of row q.  The column sums go to the fixed-point
-  // accumulators.
+  // Within the patch the sums are float32 in a fixed pairwise order; the column sums go to the
+  // fixed-point accumulators, the row sums of the warp are reduced in float64 in a fixed order.
   auto end_group = [&]() {
     if (!rows_any) return;  // warp-uniform
     float v[kRows][kCols];
@@ -963,10 +999,14 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
       }
     }
     // column sums over the patch rows (float32, pairwise), scaled by 2^s_j and added as integers
+    auto colsum = [&](int cidx) {
+      float t = (v[0][cidx] + v[1][cidx]) + (v[2][cidx] + v[3][cidx]);
+      if (kRows == 6) t += v[kRows - 2][cidx] + v[kRows - 1][cidx];
+      return t;
+    };
 #pragma unroll
     for (int h = 0; h < kPairs; ++h) {
-      const float c0 = (v[0][2 * h] + v[1][2 * h]) + (v[2][2 * h] + v[3][2 * h]);
-      const float c1 = (v[0][2 * h + 1] + v[1][2 * h + 1]) + (v[2][2 * h + 1] + v[3][2 * h + 1]);
+      const float c0 = colsum(2 * h), c1 = colsum(2 * h + 1);
       const float2 sc2 = colscale_s[h * NT];
       longlong2 acc = colacc_s[h * NT];
       acc.x += __float2ll_rn(c0 * sc2.x);
@@ -974,10 +1014,10 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
       colacc_s[h * NT] = acc;
     }
     // row sums over the patch columns (float32, pairwise), then across the warp in float64 in a
-    // fixed order: every lane parks its kRows sums in the warp's shared [row][lane] buffer, lane l
+    // fixed order: every lane parks its kRows sums in the warp's shared [row][lane] buffer; lane l
     // takes back 4 adjacent lanes' sums of row l / 8 (one LDS.128), adds them, and three shuffles
-    // finish the row inside its group of 8 lanes -- 6 SHFL instead of the 12 (+ selects) of a
-    // transposing butterfly on float64 values
+    // finish rows 0..3 inside groups of 8 lanes; with 6 rows, lane l also takes 2 adjacent lanes'
+    // sums of row 4 + l / 16 (one LDS.64) and four shuffles finish rows 4, 5 inside groups of 16
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
       float t = (v[r][0] + v[r][1]) + (v[r][2] + v[r][3]);
@@ -986,6 +1026,8 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
     }
     __syncwarp();
     const float4 q = *reinterpret_cast<const float4 *>(rowbuf + lane * 4);  // row lane/8, lanes 4*(lane%8)..+3
+    float2 w = make_float2(0.0f, 0.0f);
+    if (kRows == 6) w = *reinterpret_cast<const float2 *>(rowbuf + 128 + lane * 2);  // row 4 + lane/16
     __syncwarp();
     double tot = ((double)q.x + (double)q.y) + ((double)q.z + (double)q.w);
     tot += __shfl_xor_sync(0xffffffffu, tot, 4);
@@ -994,26 +1036,44 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
     const int rq = row + (lane >> 3);  // lanes 0, 8, 16, 24 publish rows 0..3 of the patch
     if ((lane & 7) == 0 && rq >= g.row_begin && rq < g.row_end)
       g.rowpart[(size_t)(rq - g.row_begin) * (size_t)g.ncw + cw] = tot;
+    if (kRows == 6) {
+      double tot2 = (double)w.x + (double)w.y;
+      tot2 += __shfl_xor_sync(0xffffffffu, tot2, 8);
+      tot2 += __shfl_xor_sync(0xffffffffu, tot2, 4);
+      tot2 += __shfl_xor_sync(0xffffffffu, tot2, 2);
+      tot2 += __shfl_xor_sync(0xffffffffu, tot2, 1);
+      const int rq2 = row + 4 + (lane >> 4);  // lanes 0, 16 publish rows 4, 5
+      if ((lane & 15) == 0 && rq2 >= g.row_begin && rq2 < g.row_end)
+        g.rowpart[(size_t)(rq2 - g.row_begin) * (size_t)g.ncw + cw] = tot2;
+    }
   };
 
   if (!STREAMED) {
-    while (item < g.items_per_strip) {
-      const int g0 = item * g.chunk, g1 = min(g.groups, g0 + g.chunk);
-      // the next item of this strip is claimed now and looked at after this one is done: the
-      // atomic's round trip hides behind the arithmetic
-      int next_item = 0;
-      if (lane == 0) next_item = atomicAdd(g.strip_next + cw, 1);
-      begin_item(g0);
-      for (int grp = g0; grp < g1; ++grp) {
+    const int strip_first = cw * g.groups, strip_last = strip_first + g.groups;
+    int *pool_next = const_cast<int *>(claim) + 4;
+    while (true) {
+      const int e = min(u1, strip_last);
+      const bool whole = u1 <= strip_last;  // the claim ends in this strip: take the next one now and
+      int nxt = 0;                          // look at it after this one is done
+      if (whole && lane == 0) nxt = atomicAdd(pool_next, g.chunk);
+      begin_item(u0 - strip_first);
+      for (int grp = u0 - strip_first; grp < e - strip_first; ++grp) {
         begin_group(grp);
         // (no skip for groups or columns outside the grid: they are masked in the epilogue, and a
         // single control path keeps the patch initialisation from being emitted per branch)
         Policy::consume(pol, obs_s, g.n, mu);
         end_group();
       }
-      item = __shfl_sync(0xffffffffu, next_item, 0);
+      if (!whole) {  // the rest of the claim lies in the next strip
+        u0 = strip_last;
+        break;
+      }
+      u0 = __shfl_sync(0xffffffffu, nxt, 0);
+      u1 = min(u0 + g.chunk, pool_end);
+      if (u0 >= pool_end || u0 >= strip_last) break;
     }
   } else {
+    int item = u0;
     const int nchunks = (g.n_pad + kObsChunk - 1) / kObsChunk;
     while (item < g.items_per_strip) {
       const int g0 = item * g.chunk * kWarps, g1 = min(g.groups, g0 + g.chunk * kWarps);
@@ -1069,8 +1129,8 @@ __device__ __forceinline__ double strip_umax(const RangeArgs &r, int cw, int str
 
 // ---------------------------------------------------------------------------------------
 // likelihood_cta: everything CTA `cta` of `nctas` does in the likelihood phase.
-//   SELECT: the policy is chosen per column strip on the device -- Fine (ProductPaired, degree 2)
-//   where the strip's umax allows it, Mid (degree 3) up to 4.5x coarser, Coarse (ProductHybrid)
+//   SELECT: the policy is chosen per column strip on the device -- Fine (ProductNeighbour, degree
+//   2) where the strip's umax allows it, Mid (degree 3) up to 4.5x coarser, Coarse (ProductHybrid)
 //   otherwise.  The choice depends on (ranges, N, observations, strip) only -- never on the rows,
 //   the shard or the warp -- so every rank of a sharded run takes the same path for the same cells
 //   and results stay bit-reproducible.  !SELECT: Fine everywhere.
@@ -1081,14 +1141,19 @@ template <class Fine, class Mid, class Coarse, bool SELECT, bool PRELOADED, bool
 __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char *smem_raw,
                                                double *scratch, unsigned cta, unsigned nctas) {
   static_assert(Fine::kCols == Coarse::kCols && Fine::kCols == Mid::kCols, "same tiling");
+  static_assert(Fine::kRows == Coarse::kRows && Fine::kRows == Mid::kRows, "same row groups");
   static_assert(!(PRELOADED && STREAMED), "the small-grid kernel stages every observation at once");
   constexpr int kCols = Fine::kCols;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
   ScaleInfo *sc_s = reinterpret_cast<ScaleInfo *>(smem_raw + 16);
   volatile int *claim = reinterpret_cast<volatile int *>(smem_raw + 96);
   float *obs_s = reinterpret_cast<float *>(smem_raw + kSmemHeader);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   unsigned char *after_stage = smem_raw + kSmemHeader + stage_bytes(g.n_pad);
+
+  // this CTA's pool: an equal contiguous share of the groups, strip-major
+  const long long units = (long long)g.ncw * g.groups;
+  const int pool_begin = (int)(units * cta / nctas), pool_end = (int)(units * (cta + 1) / nctas);
 
   if (!PRELOADED) {
     if (!STREAMED) {
@@ -1108,57 +1173,49 @@ __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char 
         *sc_s = *g.scale_in;
       }
     }
-    __syncthreads();
   }
+  if (tid == 0) claim[4] = pool_begin;
+  __syncthreads();
+#ifdef CGE_DEBUG_TIMES
+  if (g.debug && tid == 0) {  // set-up done
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g.debug[4 * cta + 3] = t;
+  }
+#endif
 
   const int strip_cols = 32 * kCols;
   int claim_par = 0, streams = 0;
-  // home strip: the workers (warps; whole CTAs when streamed) are spread evenly over the strips; a
-  // worker takes its home strip's items with everyone else who lives there, then moves on to help
-  // the next strip
-  const long long worker = STREAMED ? (long long)cta : (long long)cta * kWarps + warp;
-  const long long workers = STREAMED ? (long long)nctas : (long long)nctas * kWarps;
-  int cw = (int)((worker * g.ncw) / workers);
+  auto dispatch = [&](int cw, int &u0, int &u1) {
+    ScaleInfo sc = *sc_s;
+    sc.umax = strip_umax(g.range, cw, strip_cols, sc.ustep);  // the strip's own bound
+    if (!SELECT || sc.umax <= Fine::kUmax)
+      run_strip<Fine, STREAMED>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim, claim_par, streams);
+    else if (sc.umax <= Mid::kUmax)
+      run_strip<Mid, STREAMED>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim, claim_par, streams);
+    else
+      run_strip<Coarse, STREAMED>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim, claim_par, streams);
+  };
+
+  if (!STREAMED) {
+    int u0 = 0;
+    if (lane == 0) u0 = atomicAdd(const_cast<int *>(claim) + 4, g.chunk);
+    u0 = __shfl_sync(0xffffffffu, u0, 0);
+    int u1 = min(u0 + g.chunk, pool_end);
+    while (u0 < pool_end) dispatch(u0 / g.groups, u0, u1);
+    return;
+  }
+
+  // streamed: the CTAs are spread evenly over the strips; a CTA takes its home strip's items with
+  // everyone else who lives there, then walks on through the other strips
+  int cw = (int)(((long long)cta * g.ncw) / nctas);
   for (int visited = 0; visited < g.ncw; ++visited) {
-    int item;
-    if (!STREAMED) {
-      item = 0;
-      if (lane == 0) item = atomicAdd(g.strip_next + cw, 1);
-      item = __shfl_sync(0xffffffffu, item, 0);
-    } else {
-      if (tid == 0) claim[2] = atomicAdd(g.strip_next + cw, 1);
-      __syncthreads();
-      item = claim[2];
-      __syncthreads();  // (the slot is rewritten at the next strip)
-    }
-    if (item < g.items_per_strip) {
-      ScaleInfo sc = *sc_s;
-      sc.umax = strip_umax(g.range, cw, strip_cols, sc.ustep);  // the strip's own bound
-      if (!SELECT || sc.umax <= Fine::kUmax)
-        run_strip<Fine, STREAMED>(g, sc, cw, item, bars, obs_s, after_stage, claim, claim_par, streams);
-      else if (sc.umax <= Mid::kUmax)
-        run_strip<Mid, STREAMED>(g, sc, cw, item, bars, obs_s, after_stage, claim, claim_par, streams);
-      else
-        run_strip<Coarse, STREAMED>(g, sc, cw, item, bars, obs_s, after_stage, claim, claim_par, streams);
-    }
-    if (STREAMED) {  // (a step is hundreds of microseconds there: walk the strips one by one)
-      cw = cw + 1 == g.ncw ? 0 : cw + 1;
-      continue;
-    }
-    // this strip is finished: the next one that still has unclaimed items, 32 counters per look
-    // (one L2 round trip instead of one per strip); none left -> this warp is done
-    int step = 0;
-    for (int base = 1; base < g.ncw && step == 0; base += 32) {
-      const int idx = base + lane;
-      int left = 0;
-      if (idx < g.ncw)
-        left = __ldcg(g.strip_next + (cw + idx) % g.ncw) < g.items_per_strip ? 1 : 0;
-      const unsigned has = __ballot_sync(0xffffffffu, left);
-      if (has) step = base + __ffs(has) - 1;
-    }
-    if (step == 0) break;
-    cw = (cw + step) % g.ncw;
-    visited = 0;  // (termination is by the look above finding nothing)
+    if (tid == 0) claim[2] = atomicAdd(g.strip_next + cw, 1);
+    __syncthreads();
+    int item = claim[2], unused = 0;
+    __syncthreads();  // (the slot is rewritten at the next strip)
+    if (item < g.items_per_strip) dispatch(cw, item, unused);
+    cw = cw + 1 == g.ncw ? 0 : cw + 1;
   }
 }
 
@@ -1184,7 +1241,6 @@ __global__ void __launch_bounds__(kThreads, MINB)
     g.debug[4 * blockIdx.x + 0] = t0;
     g.debug[4 * blockIdx.x + 1] = t1;
     g.debug[4 * blockIdx.x + 2] = smid;
-    g.debug[4 * blockIdx.x + 3] = 0;
   }
 #endif
 }

@@ -12,11 +12,11 @@ static KernelChoice pick() {
   return kc;
 }
 
-// product path.  Default: the policy is selected per column strip on the device -- ProductPaired
-// (half the exponentials from MUFU.EX2, the other half derived from the row above by a degree-2
-// FMA-pipe polynomial) where the strip's exponent step allows it (<= kPairedUmax), the same with a
-// degree-3 polynomial up to kPairedUmax3, else ProductHybrid (12 of 16 exponentials from
-// MUFU.EX2, 4 from a degree-5 polynomial with range reduction).  CGE_VARIANT_PAIRED / _PAIRED3 /
+// product path.  Default: the policy is selected per column strip on the device -- ProductNeighbour
+// (a third of the exponentials from MUFU.EX2, the rows above and below each derived from it by a
+// degree-2 FMA-pipe polynomial) where the strip's exponent step allows it (<= kPairedUmax), the
+// same with a degree-3 polynomial up to kPairedUmax3, else ProductHybrid (3/4 of the exponentials
+// from MUFU.EX2, 1/4 from a degree-5 polynomial with range reduction).  CGE_VARIANT_PAIRED / _PAIRED3 /
 // _HYBRID force one of the three, CGE_VARIANT_MUFU_ONLY is the MUFU-roofline case.
 int choose_product(const Plan &pl, KernelChoice *out) {
   switch (pl.variant) {

@@ -14,11 +14,13 @@ from tools._obs import observations  # noqa: E402
 
 N, n = int(sys.argv[1]), int(sys.argv[2])
 mode = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+rows = int(sys.argv[4]) if len(sys.argv) > 4 else N
 dev = torch.device("cuda", 0)
 with cge.Context(0) as ctx:
     obs_t = torch.from_numpy(observations(n)).to(dev)
-    post = torch.empty((N, N), dtype=torch.float32, device=dev)
-    p = cge.make_params(n, N, (18, 22), (1, 3), mode)
+    post = torch.empty((rows, N), dtype=torch.float32, device=dev)
+    rb = (N - rows) // 2 // 4 * 4
+    p = cge.make_params(n, N, (18, 22), (1, 3), mode, (rb, rb + rows))
     for _ in range(3):
         ctx.likelihood_partials(p, obs_t, post, None)
         ctx.finalize(p, post, None)
@@ -30,7 +32,7 @@ with cge.Context(0) as ctx:
     assert lib.cge_debug_times(ctx._h, buf.ctypes.data, 4096, C.byref(cnt)) == 0
     t = buf[:4 * cnt.value].reshape(-1, 4).astype(np.int64)
     t0 = t[:, 0].min()
-    start, end, sm, units = t[:, 0] - t0, t[:, 1] - t0, t[:, 2], t[:, 3]
+    start, end, sm, setup = t[:, 0] - t0, t[:, 1] - t0, t[:, 2], t[:, 3] - t[:, 0]
     dur = end - start
     per_sm = {}
     for s in sm:
@@ -41,7 +43,7 @@ with cge.Context(0) as ctx:
         "end_us": {"min": float(end.min()) / 1e3, "median": float(np.median(end)) / 1e3, "max": float(end.max()) / 1e3,
                    "p10": float(np.percentile(end, 10)) / 1e3, "p90": float(np.percentile(end, 90)) / 1e3},
         "dur_us": {"min": float(dur.min()) / 1e3, "median": float(np.median(dur)) / 1e3, "max": float(dur.max()) / 1e3},
-        "units": {"min": int(units.min()), "max": int(units.max())},
+        "setup_us": {"min": float(setup.min()) / 1e3, "median": float(np.median(setup)) / 1e3, "max": float(setup.max()) / 1e3},
         "ctas_per_sm_hist": {str(k): int(v) for k, v in zip(*np.unique(list(per_sm.values()), return_counts=True))},
         "sms_used": len(per_sm)}))
     order = np.argsort(start)
