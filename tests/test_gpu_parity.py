@@ -756,3 +756,23 @@ def test_cpp_grid_cli(tmp_path, readme_obs):
     # the reference's default run (no arguments) also works: 50 host-drawn observations
     res = subprocess.run([_bin("grid")], capture_output=True, text=True)
     assert res.returncode == 0 and "Inferred mu" in res.stdout
+
+
+def test_cpp_grid_cli_sharded_in_process(tmp_path, readme_obs):
+    """`grid --devices 0,0,0` (cge_create_multi + cge_grid_posterior_multi from the C++ main(), three
+    shards through the peer exchange on one device) prints the single-GPU expectations."""
+    import subprocess
+    obs_file = tmp_path / "obs.bin"
+    readme_obs.tofile(obs_file)
+
+    def run(*extra):
+        res = subprocess.run([_bin("grid"), "--obs-file", str(obs_file), "--grid", "1000", *extra],
+                             capture_output=True, text=True)
+        assert res.returncode == 0, res.stdout + res.stderr
+        lines = res.stdout.splitlines()
+        return float(lines[0].split()[2].rstrip(";")), float(lines[1].split()[2].rstrip(";"))
+
+    one, three = run(), run("--devices", "0,0,0")
+    assert abs(one[0] - three[0]) < 1e-9 and abs(one[1] - three[1]) < 1e-9
+    res = subprocess.run([_bin("grid"), "--gpus", "100000"], capture_output=True, text=True)
+    assert res.returncode != 0 and "Error" in res.stderr
