@@ -27,6 +27,7 @@ VARIANT_PAIRED = 3
 VARIANT_HYBRID = 4
 VARIANT_LOG_F64 = 5
 VARIANT_PAIRED3 = 8
+VARIANT_SLOPE = 9
 VARIANT_UNFUSED = 7
 
 OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_DEGENERATE, ERR_PEER, ERR_SIZE = range(7)
@@ -383,16 +384,28 @@ def _set_prior(self, prior_mu=None, prior_sigma=None, grid_size=0, prior_full=No
 
 def _scale_info(self, stream=None) -> dict:
     """Scale statistics of the last likelihood call (see cge_scale_info)."""
-    out = np.empty(12, np.float64)
-    _check(self._lib.cge_scale_info(self._h, out.ctypes.data, 12, stream))
+    out = np.empty(14, np.float64)
+    _check(self._lib.cge_scale_info(self._h, out.ctypes.data, 14, stream))
     keys = ("log2s", "shift", "m2", "xbar", "ss", "smin", "mu_c", "s_c", "umax", "paired_umax",
-            "paired3_umax", "ustep")
+            "paired3_umax", "ustep", "slope_eps", "slope_err_max")
     d = dict(zip(keys, out.tolist()))
     # product_path: the arithmetic of the most demanding column band (the one at the smallest
     # sigma); bands at larger sigma may run a cheaper policy (see band_paths)
-    d["product_path"] = ("paired" if d["umax"] <= d["paired_umax"] else
-                         "paired3" if d["umax"] <= d["paired3_umax"] else "hybrid")
+    d["product_path"] = _product_path(d, d["umax"], d["slope_eps"])
     return d
+
+
+_K2 = 0.2402265069591007   # ln(2)^2 / 2
+
+
+def _product_path(info: dict, umax: float, eps: float) -> str:
+    """Mirror of the device-side choice (cge::likelihood_cta): the first eligible of slope,
+    paired (degree 2), paired3 (degree 3), hybrid."""
+    if umax <= info["paired_umax"] and _K2 * umax * umax * eps <= info["slope_err_max"]:
+        return "slope"
+    if umax <= info["paired_umax"]:
+        return "paired"
+    return "paired3" if umax <= info["paired3_umax"] else "hybrid"
 
 
 def band_columns(grid_size: int) -> int:
@@ -403,16 +416,19 @@ def band_columns(grid_size: int) -> int:
 
 def band_paths(info: dict, sigma: np.ndarray) -> list:
     """Which product policy each column band takes, from scale_info() and the sigma table:
-    mirrors cge::strip_umax (|a_j| = 0.5*log2(e)/sigma_j^2 at the band's two ends)."""
+    mirrors cge::strip_umax (|a_j| = 0.5*log2(e)/sigma_j^2 at the band's two ends) and
+    cge::strip_slope_eps (4 column steps over the band's smallest sigma)."""
     out = []
-    band_cols = band_columns(len(sigma))
-    for j0 in range(0, len(sigma), band_cols):
-        j1 = min(j0 + band_cols, len(sigma)) - 1
-        a = max(0.5 * 1.4426950408889634 / float(sigma[j0]) ** 2,
-                0.5 * 1.4426950408889634 / float(sigma[j1]) ** 2)
-        u = a * info["ustep"]
-        out.append("paired" if u <= info["paired_umax"] else
-                   "paired3" if u <= info["paired3_umax"] else "hybrid")
+    n = len(sigma)
+    band_cols = band_columns(n)
+    ds = abs(float(sigma[-1]) - float(sigma[0])) / (n - 1) if n > 1 else 0.0
+    for j0 in range(0, n, band_cols):
+        j1 = min(j0 + band_cols, n) - 1
+        s0, s1 = float(sigma[j0]), float(sigma[j1])
+        a = max(0.5 * 1.4426950408889634 / s0 ** 2, 0.5 * 1.4426950408889634 / s1 ** 2)
+        smin = min(abs(s0), abs(s1))
+        eps = 4.0 * ds / smin if smin > 0 and s0 * s1 > 0 else 1e300
+        out.append(_product_path(info, a * info["ustep"], eps))
     return out
 
 

@@ -126,6 +126,7 @@ struct cge_context {
   int knob_ctas_per_sm = 0;  // CGE_CTAS_PER_SM: cap the persistent grid
   int knob_grid_mult = 1;    // CGE_GRID_MULT: CTAs per resident slot (1 = persistent)
   int knob_chunk = 0;        // CGE_ITEM_STEPS: CTA steps per claimed item
+  int knob_cta_warps = 0;    // CGE_CTA_WARPS: 8 or 24 warps per CTA of the product kernel
   bool knob_no_cluster = false;  // CGE_NO_CLUSTER: small grids without the cluster launch
   bool knob_no_pdl = false;      // CGE_NO_PDL: ordinary stream-ordered launches
   // resident CTAs per SM of each likelihood kernel at its shared-memory size (occupancy query)
@@ -175,6 +176,7 @@ int check_params(const cge_params *p, int *rb, int *re) {
   switch (p->variant) {
     case CGE_VARIANT_DEFAULT: case CGE_VARIANT_UNFUSED: break;
     case CGE_VARIANT_MUFU_ONLY: case CGE_VARIANT_PAIRED: case CGE_VARIANT_PAIRED3: case CGE_VARIANT_HYBRID:
+    case CGE_VARIANT_SLOPE:
       if (p->mode != CGE_MODE_PRODUCT_F32)
         return set_error(CGE_ERR_BAD_ARG, "variant %d belongs to the product mode", p->variant);
       break;
@@ -202,6 +204,8 @@ int check_params(const cge_params *p, int *rb, int *re) {
 int centred_obs(const cge_params *p) {
   return (p->mode == CGE_MODE_LOGSPACE && p->variant != CGE_VARIANT_LOG_F64) ? 1 : 0;
 }
+
+constexpr int kDefaultCtaWarps = 8;  // warps per CTA of the default product kernel (CGE_CTA_WARPS)
 
 // CTA shape and unit decomposition for one shard (everything but the persistent grid size, which
 // needs the kernel: size_grid below).  `post` is where the float32 cells go.
@@ -241,6 +245,7 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->streamed = pl->n_pad > cge::kObsSingleMax;
   pl->reorder = p->mode == CGE_MODE_PRODUCT_F32 && pl->n <= cge::kReorderMax;
   pl->cluster = false;
+  pl->cta_warps = ctx->knob_cta_warps > 0 ? ctx->knob_cta_warps : kDefaultCtaWarps;
   pl->nctas = 0;
 }
 
@@ -283,7 +288,8 @@ int size_grid(cge_context *ctx, Plan *pl, const cge_host::KernelChoice &kc, int 
     // a shared-memory counter: ~48 claims per warp, so that the last claim of the slowest warp is a
     // small tail; a claim covers at most 32 rows (run_strip: one range value per lane)
     if (P > total) P = total;
-    long long chunk = total / (P * cge::kWarps * 48);
+    const int warps = kc.threads / 32;
+    long long chunk = total / (P * warps * 48);
     const long long cap = 32 / pl->krows;
     if (chunk < 1) chunk = 1;
     if (chunk > cap) chunk = cap;
@@ -391,7 +397,7 @@ int fill_like_args(cge_context *ctx, const cge_params *p, const Plan &pl, const 
   args->vec4 = pl.vec4 ? 1 : 0;
   args->keep_l2 = pl.keep_l2 ? 1 : 0;
 #ifdef CGE_DEBUG_TIMES
-  CKRC(ctx->debug_times.reserve((size_t)4 * pl.nctas));
+  CKRC(ctx->debug_times.reserve((size_t)(4 + 32) * pl.nctas));
   args->debug = ctx->debug_times.ptr;
 #endif
   return CGE_OK;
@@ -568,6 +574,7 @@ CGE_EXPORT int cge_create(int device, cge_context **out) {
   if (const char *v = std::getenv("CGE_CTAS_PER_SM")) ctx->knob_ctas_per_sm = std::atoi(v);
   if (const char *v = std::getenv("CGE_GRID_MULT")) ctx->knob_grid_mult = std::atoi(v) > 0 ? std::atoi(v) : 1;
   if (const char *v = std::getenv("CGE_ITEM_STEPS")) ctx->knob_chunk = std::atoi(v);
+  if (const char *v = std::getenv("CGE_CTA_WARPS")) ctx->knob_cta_warps = std::atoi(v);
   ctx->knob_no_cluster = std::getenv("CGE_NO_CLUSTER") != nullptr;
   ctx->knob_no_pdl = std::getenv("CGE_NO_PDL") != nullptr;
   cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -1168,9 +1175,9 @@ CGE_EXPORT int cge_scale_info(cge_context *ctx, double *out, int count, void *st
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemcpyAsync(&h, ctx->scale.ptr, sizeof h, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const double v[12] = {h.log2s, h.shift, h.m2, h.xbar, h.ss, h.smin, h.mu_c, h.s_c, h.umax,
-                        cge::kPairedUmax, cge::kPairedUmax3, h.ustep};
-  for (int i = 0; i < count && i < 12; ++i) out[i] = v[i];
+  const double v[14] = {h.log2s, h.shift, h.m2, h.xbar, h.ss, h.smin, h.mu_c, h.s_c, h.umax,
+                        cge::kPairedUmax, cge::kPairedUmax3, h.ustep, h.seps, cge::kSlopeErr};
+  for (int i = 0; i < count && i < 14; ++i) out[i] = v[i];
   return CGE_OK;
 }
 
@@ -1329,12 +1336,15 @@ extern "C" int cge_internal_stream(cge_context *ctx, void **stream, int *sm_coun
 }
 extern "C" int cge_internal_error(int code, const char *msg) { return set_error(code, "%s", msg); }
 #ifdef CGE_DEBUG_TIMES
-// diagnostic build only: per-CTA {start ns, end ns, smid, units} of the last likelihood launch
+// diagnostic build only: per-CTA {start ns, end ns, smid, set-up done ns} of the last likelihood
+// launch, followed by the end time of each of its warps (kWarps per CTA); `out` holds 12 * max_ctas
 CGE_EXPORT int cge_debug_times(cge_context *ctx, unsigned long long *out, int max_ctas, int *nctas) {
   CKRC(bind(ctx));
   CK(cudaDeviceSynchronize());
-  const int n = ctx->plan.nctas < max_ctas ? ctx->plan.nctas : max_ctas;
-  CK(cudaMemcpy(out, ctx->debug_times.ptr, (size_t)4 * n * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (ctx->plan.nctas > max_ctas) return set_error(CGE_ERR_BAD_ARG, "debug_times: buffer too small");
+  const int n = ctx->plan.nctas;
+  CK(cudaMemcpy(out, ctx->debug_times.ptr, (size_t)(4 + 32) * n * sizeof(unsigned long long),
+                cudaMemcpyDeviceToHost));
   *nctas = n;
   return CGE_OK;
 }

@@ -42,6 +42,7 @@ struct Plan {
   int nb_col = 0, nb_row = 0, nb_res = 0;
   bool vec4 = false, keep_l2 = false, streamed = false, reorder = false;
   bool cluster = false;    // small-grid path: launch the grid as one thread-block cluster
+  int cta_warps = 0;       // product path: warps per CTA (8 x 3 CTAs per SM, or one CTA of 24)
   size_t smem = 0;         // dynamic shared memory of the likelihood kernel
 };
 
@@ -54,17 +55,23 @@ struct KernelChoice {
   int kcols = 4;
 };
 
-// the default product policies
+// the default product policies, finest first (chosen per column strip on the device)
+using DefaultFinest = cge::ProductSlope;       // shared-slope neighbours: the finest grids
 using DefaultFine = cge::ProductNeighbour<2>;  // degree-2 polynomial, strip umax <= 0.011
 using DefaultMid = cge::ProductNeighbour<3>;   // degree-3 polynomial, strip umax <= 0.05
 using DefaultCoarse = cge::ProductHybrid;
 constexpr int kDefaultMinB = 3;  // <= 80 registers: three 256-thread CTAs (24 warps) per SM
+#ifndef CGE_WIDE_WARPS
+#define CGE_WIDE_WARPS 24
+#endif
+constexpr int kWideWarps = CGE_WIDE_WARPS;   // ... or one 768-thread CTA per SM: one pool for all its warps
 
-template <class A, class B, class C>
-constexpr int smem_bytes3() {
+template <class A, class B, class C, class D>
+constexpr int smem_bytes4() {
   constexpr int a = cge::policy_smem_bytes<A>(), b = cge::policy_smem_bytes<B>(),
-                c = cge::policy_smem_bytes<C>();
-  return a > b ? (a > c ? a : c) : (b > c ? b : c);
+                c = cge::policy_smem_bytes<C>(), d = cge::policy_smem_bytes<D>();
+  constexpr int ab = a > b ? a : b, cd = c > d ? c : d;
+  return ab > cd ? ab : cd;
 }
 
 // choosers defined in cge_launch_product.cu / cge_launch_logspace.cu / cge_launch_small.cu;

@@ -66,6 +66,7 @@ struct ScaleInfo {
   double s_c;    // log-space: sum_k (x_k - mu_c)^2
   double umax;   // bound on |t_(i+1,j,k) - t_(i,j,k)| over adjacent mu rows, whole grid
   double ustep;  // the same bound per unit |a_j|: umax of a column band = max |a_j| in it * ustep
+  double seps;   // bound on the relative change of a_j over a thread's 4 columns, whole grid (ProductSlope)
 };
 
 struct RangeArgs {
@@ -130,7 +131,7 @@ struct LikeArgs {
   int vec4;            // N % 4 == 0 and the shard base is 16-byte aligned: float4 stores
   int keep_l2;         // the shard fits in L2: store with the default policy instead of .cs
 #ifdef CGE_DEBUG_TIMES
-  unsigned long long *debug;  // per CTA: {start ns, end ns, smid, items}
+  unsigned long long *debug;  // per CTA: {start ns, end ns, smid, set-up done ns}, then per warp: end ns
 #endif
 };
 
@@ -301,6 +302,10 @@ __device__ __forceinline__ ScaleInfo setup_scale(const RangeArgs &r, const float
     const double sdmin = fmin((double)sg0, (double)sg1);
     out.ustep = dmu * 2.0 * reach;
     out.umax = fabs(coef_a(sdmin)) * out.ustep;
+    const double sabs = fmin(fabs((double)sg0), fabs((double)sg1));
+    out.seps = (N > 1 && sabs > 0.0 && (double)sg0 * (double)sg1 > 0.0)
+                   ? 4.0 * fabs((double)sg1 - (double)sg0) / (double)(N - 1) / sabs
+                   : (N > 1 ? 1e300 : 0.0);
   }
   __syncthreads();  // the stage is complete for every thread of the block
   return out;
@@ -321,6 +326,7 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 // by the kRN columns of a row.
 //   factor_k = 2^(a_j*(x_k-mu_i)^2 + c_j),  c_j = c0_j + log2 s   (constants FMA-folded)
 struct ProductF32 {
+  static __device__ __forceinline__ bool eligible(double, double) { return true; }
   static constexpr double kUmax = 1e300;
   static constexpr bool kColSmem = false;
   static constexpr int kRows = kRowsProduct;
@@ -375,6 +381,7 @@ struct ProductF32 {
 // cell after 10^4 observations) and widened once per (row, observation); 8 columns per thread
 // amortise that widening over 8 evaluations.
 struct LogSpaceF64 {
+  static __device__ __forceinline__ bool eligible(double, double) { return true; }
   static constexpr double kUmax = 1e300;
   static constexpr bool kColSmem = false;
   static constexpr int kRows = 4;
@@ -446,6 +453,7 @@ struct LogSpaceF64 {
 // ---------------------------------------------------------------------------------------
 template <int TILE = 256>
 struct LogSpaceTiled {
+  static __device__ __forceinline__ bool eligible(double, double) { return true; }
   static constexpr double kUmax = 1e300;
   static constexpr bool kColSmem = false;
   static constexpr int kRows = 4;
@@ -569,6 +577,7 @@ __device__ __forceinline__ void consume_scalar_obs(Policy &pol, const float *xs,
 // Which cells use which pipe is fixed at compile time, so results stay bit-reproducible.
 // ---------------------------------------------------------------------------------------
 struct ProductHybrid {
+  static __device__ __forceinline__ bool eligible(double, double) { return true; }
   static constexpr double kUmax = 1e300;  // any grid
   static constexpr bool kColSmem = false;
   static constexpr int kRows = kRowsProduct;
@@ -668,10 +677,35 @@ constexpr int kObsLoopUnroll = CGE_Q_UNROLL;  // iterations (of 4 observations) 
 constexpr double kPairedUmax = 0.011;
 constexpr double kPairedUmax3 = 0.05;
 
+// the observation loop of the neighbour-row policies: the per-row scalars of the group
+// (Policy::Rows), then four observations per iteration (one LDS.128)
+template <class Policy>
+__device__ __forceinline__ void neighbour_consume(Policy &pol, const float *xs, int count,
+                                                  const float (&mu)[Policy::kRows]) {
+  const typename Policy::Rows rs = pol.rows(mu);
+  const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
+  const int n4 = count >> 2;
+#pragma unroll kObsLoopUnroll
+  for (int q = 0; q < n4; ++q) {
+    const float4 x = xs4[q];
+    pol.step(x.x, rs);
+    pol.step(x.y, rs);
+    pol.step(x.z, rs);
+    pol.step(x.w, rs);
+  }
+  if (count & 2) {  // the tail as one LDS.64 and at most one scalar load
+    const float2 x = *reinterpret_cast<const float2 *>(xs + (n4 << 2));
+    pol.step(x.x, rs);
+    pol.step(x.y, rs);
+  }
+  if (count & 1) pol.step(xs[count - 1], rs);
+}
+
 template <int DEG = 2>
 struct ProductNeighbour {
   static_assert(DEG == 2 || DEG == 3, "polynomial degree of 2^u - 1");
   static constexpr double kUmax = DEG == 2 ? kPairedUmax : kPairedUmax3;  // eligibility bound
+  static __device__ __forceinline__ bool eligible(double umax, double) { return umax <= kUmax; }
   static constexpr bool kColSmem = true;
   static constexpr int kRows = kRowsProduct;
   static constexpr int kCols = 4;
@@ -718,16 +752,41 @@ struct ProductNeighbour {
 #pragma unroll
       for (int h = 0; h < kPairs; ++h) p2[r][h] = one;
   }
-  // one observation.  mid2 = {mu_1, mu_4} (the MUFU rows); gmL/gbL give g = x*gm + gb of the rows
-  // below them (0, 3), gmU/gbU of the rows above (2, 5), each as one packed pair over the triples.
-  __device__ __forceinline__ void step(float x, f32x2 mid2, f32x2 gmL, f32x2 gbL, f32x2 gmU, f32x2 gbU) {
+  // the per-row scalars of a group: mid2 = {mu_1, mu_4} (the MUFU rows); gmL/gbL give
+  // g = x*gm + gb of the rows below them (0, 3), gmU/gbU of the rows above (2, 5), each as one
+  // packed pair over the triples.  g of row r against its triple's middle row m:
+  // (mu_r - mu_m) * (mu_m + mu_r - 2 x)
+  struct Rows {
+    f32x2 mid2, gmL, gbL, gmU, gbU;
+  };
+  __device__ __forceinline__ Rows rows(const float (&mu)[kRows]) const {
+    float gm[kRows], gb[kRows];
+#pragma unroll
+    for (int t = 0; t < kTriples; ++t)
+#pragma unroll
+      for (int s = 0; s < 3; s += 2) {
+        const int r = 3 * t + s, m = 3 * t + 1;
+        const float delta = __fsub_rn(mu[r], mu[m]);  // exact (adjacent range values)
+        gm[r] = -2.0f * delta;
+        gb[r] = __fmul_rn(delta, __fadd_rn(mu[m], mu[r]));
+      }
+    Rows rs;
+    rs.mid2 = pack2(mu[1], mu[4]);
+    rs.gmL = pack2(gm[0], gm[3]);
+    rs.gbL = pack2(gb[0], gb[3]);
+    rs.gmU = pack2(gm[2], gm[5]);
+    rs.gbU = pack2(gb[2], gb[5]);
+    return rs;
+  }
+  // one observation
+  __device__ __forceinline__ void step(float x, const Rows &rs) {
     float ddv[kTriples], glo[kTriples], gup[kTriples];
     {
       const f32x2 x2 = pack2(x, x);
-      const f32x2 d2 = sub2(x2, mid2);  // same f32 rounding as the reference's (x - mu)
+      const f32x2 d2 = sub2(x2, rs.mid2);  // same f32 rounding as the reference's (x - mu)
       unpack2(mul2(d2, d2), ddv[0], ddv[1]);
-      unpack2(fma2(x2, gmL, gbL), glo[0], glo[1]);
-      unpack2(fma2(x2, gmU, gbU), gup[0], gup[1]);
+      unpack2(fma2(x2, rs.gmL, rs.gbL), glo[0], glo[1]);
+      unpack2(fma2(x2, rs.gmU, rs.gbU), gup[0], gup[1]);
     }
 #pragma unroll
     for (int t = 0; t < kTriples; ++t) {
@@ -761,44 +820,151 @@ struct ProductNeighbour {
   }
   static __device__ __forceinline__ void consume(ProductNeighbour &pol, const float *xs, int count,
                                                  const float (&mu)[kRows]) {
-    // g of row r against its triple's middle row m: (mu_r - mu_m) * (mu_m + mu_r - 2 x)
-    float gm[kRows], gb[kRows];
+    neighbour_consume(pol, xs, count, mu);
+  }
+};
+
+// ---------------------------------------------------------------------------------------
+// float32 product path, neighbour rows with a shared slope (the finest grids): the same triples as
+// ProductNeighbour -- the middle row's factor e from MUFU.EX2, the rows above and below derive
+// theirs, f = e * 2^u, u = a_j g_rk -- but the polynomial is evaluated once per (row, observation)
+// instead of once per cell.  With a_0 the mean |a_j| slope of the thread's four adjacent columns,
+//   2^u - 1 = a_j g (k1 + k2 a_j g) = a_j H_rk + a_j (a_j - a_0) k2 g^2,   H_rk = g (k1 + k2 a_0 g),
+// and the last term is dropped: adjacent sigma columns differ by eps = |a_j - a_0| / |a_j| <=
+// 3 dsigma / sigma, so it is at most k2 U^2 eps (3e-9 on the 16384^2 README grid: a twentieth of
+// the float32 rounding of the factor itself).  The policy is eligible while that bound stays
+// below kSlopeErr and U <= kPairedUmax (cubic term, as ProductNeighbour<2>); coarser strips fall
+// back to ProductNeighbour.  Every pdf-eval still forms its own factor and multiplies it into its
+// own running product:
+//   MUFU row   : FFMA2 (exponent), 2 MUFU.EX2, FMUL2 (product)                  per column pair
+//   shared     : FMUL2 (ea = e * a_j)                                           per triple and pair
+//   derived row: FFMA2 (f = ea * H + e), FMUL2 (product)
+// i.e. per 6 evals 2 MUFU.EX2 and 7 packed instructions instead of 10, plus 6 packed per-row
+// scalars per observation (d, d^2 and the two H, each a Horner quadratic in d).  Per thread and
+// observation: 34 packed FMA-pipe instructions (68 pipe cycles per warp) against 8 MUFU.EX2 (64 XU
+// cycles).
+// ---------------------------------------------------------------------------------------
+constexpr double kSlopeErr = 4.0e-8;
+struct ProductSlope {
+  static constexpr double kUmax = kPairedUmax;
+  static __device__ __forceinline__ bool eligible(double umax, double eps) {
+    return umax <= kPairedUmax && 0.2402265069591007 * umax * umax * eps <= kSlopeErr;
+  }
+  static constexpr bool kColSmem = true;
+  static constexpr int kRows = kRowsProduct;
+  static constexpr int kCols = 4;
+  static constexpr int kSmemDoubles = 0;
+  static constexpr int kPairs = kCols / 2;
+  static constexpr int kTriples = kRows / 3;
+  static_assert(kRows == 6, "two triples: the per-row scalars are packed pairwise");
+  f32x2 a2[kPairs], c2[kPairs];  // exponent coefficients of the MUFU rows (a2 also scales ea)
+  float k1, a0k2;                // k1 and kappa = a_0 k2
+  f32x2 p2[kRows][kPairs];
+
+  template <int NT>
+  __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
+                                               const ColumnCoefs<kCols> &cf, double *) {
+    const double U = sc.umax;
+    const double k2 = 0.24022650695910071233;
+    k1 = (float)(0.69314718055994530942 + 0.0555041086648215799 * 0.75 * U * U);
+    // slope of the thread's columns: the mean of the two middle ones (clamped to the grid, so a
+    // thread that straddles the last column still gets a slope of its own columns)
+    const double s1 = (double)range_value(min(j0 + 1, g.N - 1), g.N, g.range.sg0, g.range.sg1);
+    const double s2 = (double)range_value(min(j0 + 2, g.N - 1), g.N, g.range.sg0, g.range.sg1);
+    a0k2 = (float)(0.5 * (coef_a(s1) + coef_a(s2)) * k2);
+#pragma unroll
+    for (int h = 0; h < kPairs; ++h) {
+      float av[2], cv[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = patch_col(j0, 2 * h + e);
+        av[e] = (float)cf.a[2 * h + e];
+        cv[e] = j < g.N ? (float)(cf.c0[2 * h + e] + sc.log2s) : 0.0f;
+      }
+      a2[h] = pack2(av[0], av[1]);
+      c2[h] = pack2(cv[0], cv[1]);
+    }
+  }
+  __device__ __forceinline__ void begin_rows() {
+    const f32x2 one = pack2(1.0f, 1.0f);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+#pragma unroll
+      for (int h = 0; h < kPairs; ++h) p2[r][h] = one;
+  }
+  // The per-row scalars of a group.  With d = x - mu_m (the MUFU row's own difference, rounded as
+  // the reference rounds it) and delta = mu_r - mu_m, the neighbour's exponent offset is
+  // g = delta (delta - 2 d) and H = g (k1 + kappa g) is a quadratic in d,
+  //   H = [4 kappa delta^2] d^2 - [2 delta (k1 + 2 kappa delta^2)] d + [delta^2 (k1 + kappa delta^2)],
+  // two packed FMAs per observation for the rows below (0, 3) and two for the rows above (2, 5),
+  // with no cancellation (the linear term dominates).
+  struct Rows {
+    f32x2 mid2, aL, bL, cL, aU, bU, cU;
+  };
+  __device__ __forceinline__ Rows rows(const float (&mu)[kRows]) const {
+    float qa[kRows], qb[kRows], qc[kRows];
 #pragma unroll
     for (int t = 0; t < kTriples; ++t)
 #pragma unroll
       for (int s = 0; s < 3; s += 2) {
         const int r = 3 * t + s, m = 3 * t + 1;
         const float delta = __fsub_rn(mu[r], mu[m]);  // exact (adjacent range values)
-        gm[r] = -2.0f * delta;
-        gb[r] = __fmul_rn(delta, __fadd_rn(mu[m], mu[r]));
+        const float kd2 = a0k2 * delta * delta;
+        qa[r] = 4.0f * kd2;
+        qb[r] = -2.0f * delta * fmaf(2.0f, kd2, k1);
+        qc[r] = delta * delta * (k1 + kd2);
       }
-    const f32x2 mid2 = pack2(mu[1], mu[4]);
-    const f32x2 gmL = pack2(gm[0], gm[3]), gbL = pack2(gb[0], gb[3]);
-    const f32x2 gmU = pack2(gm[2], gm[5]), gbU = pack2(gb[2], gb[5]);
-    const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
-    const int n4 = count >> 2;
-#pragma unroll kObsLoopUnroll
-    for (int q = 0; q < n4; ++q) {
-      const float4 x = xs4[q];
-      pol.step(x.x, mid2, gmL, gbL, gmU, gbU);
-      pol.step(x.y, mid2, gmL, gbL, gmU, gbU);
-      pol.step(x.z, mid2, gmL, gbL, gmU, gbU);
-      pol.step(x.w, mid2, gmL, gbL, gmU, gbU);
+    Rows rs;
+    rs.mid2 = pack2(mu[1], mu[4]);
+    rs.aL = pack2(qa[0], qa[3]);
+    rs.bL = pack2(qb[0], qb[3]);
+    rs.cL = pack2(qc[0], qc[3]);
+    rs.aU = pack2(qa[2], qa[5]);
+    rs.bU = pack2(qb[2], qb[5]);
+    rs.cU = pack2(qc[2], qc[5]);
+    return rs;
+  }
+  // one observation
+  __device__ __forceinline__ void step(float x, const Rows &rs) {
+    float ddv[kTriples], hlo[kTriples], hup[kTriples];
+    {
+      const f32x2 d2 = sub2(pack2(x, x), rs.mid2);  // same f32 rounding as the reference's (x - mu)
+      unpack2(mul2(d2, d2), ddv[0], ddv[1]);
+      unpack2(fma2(fma2(d2, rs.aL, rs.bL), d2, rs.cL), hlo[0], hlo[1]);  // H of rows 0, 3
+      unpack2(fma2(fma2(d2, rs.aU, rs.bU), d2, rs.cU), hup[0], hup[1]);  // H of rows 2, 5
     }
-    if (count & 2) {  // the tail as one LDS.64 and at most one scalar load
-      const float2 x = *reinterpret_cast<const float2 *>(xs + (n4 << 2));
-      pol.step(x.x, mid2, gmL, gbL, gmU, gbU);
-      pol.step(x.y, mid2, gmL, gbL, gmU, gbU);
+#pragma unroll
+    for (int t = 0; t < kTriples; ++t) {
+      const f32x2 dd2 = pack2(ddv[t], ddv[t]);  // (scalar-broadcast operands of the packed instructions)
+      const f32x2 hl2 = pack2(hlo[t], hlo[t]);
+      const f32x2 hu2 = pack2(hup[t], hup[t]);
+#pragma unroll
+      for (int h = 0; h < kPairs; ++h) {
+        const f32x2 e2 = ex2_mufu2(fma2(dd2, a2[h], c2[h]));
+        p2[3 * t + 1][h] = mul2(p2[3 * t + 1][h], e2);
+        const f32x2 ea2 = mul2(e2, a2[h]);
+        p2[3 * t][h] = mul2(p2[3 * t][h], fma2(ea2, hl2, e2));          // the lower neighbour's factor
+        p2[3 * t + 2][h] = mul2(p2[3 * t + 2][h], fma2(ea2, hu2, e2));  // the upper neighbour's factor
+      }
     }
-    if (count & 1) pol.step(xs[count - 1], mid2, gmL, gbL, gmU, gbU);
+  }
+  template <int NT>
+  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx, const double *) const {
+    float lo, hi;
+    unpack2(p2[r][cidx >> 1], lo, hi);
+    return (cidx & 1) ? hi : lo;
+  }
+  static __device__ __forceinline__ void consume(ProductSlope &pol, const float *xs, int count,
+                                                 const float (&mu)[kRows]) {
+    neighbour_consume(pol, xs, count, mu);
   }
 };
 
 // ---------------------------------------------------------------------------------------
 // Shared-memory layout of the likelihood kernels (dynamic):
 //   [0, 16)    two mbarriers (streamed observations only)
-//   [16, 96)   ScaleInfo of this step (written once per CTA by the set-up)
-//   [96, 128)  claim slots: [0..2] the item a CTA takes next (streamed), [4] the pool counter
+//   [16, 104)  ScaleInfo of this step (written once per CTA by the set-up)
+//   [104, 128) claim slots: [0..2] the item a CTA takes next (streamed), [4] the pool counter
 //   [128, ...) observation stage: n_pad floats, or two chunks of kObsChunk when streamed
 //   then       per-thread slots [k][NT]: kCols int64 column accumulators (as 16-byte pairs), kCols
 //              float32 column scales 2^s_j (as 8-byte pairs), the policy's own float64 values, and
@@ -806,6 +972,7 @@ struct ProductNeighbour {
 //              warp); during the set-up the same bytes serve as the sort scratch
 // ---------------------------------------------------------------------------------------
 constexpr int kSmemHeader = 128;
+static_assert(16 + sizeof(ScaleInfo) <= 104, "shared-memory header layout");
 __host__ __device__ __forceinline__ size_t stage_bytes(int n_pad) {
   return (((size_t)(n_pad > kObsSingleMax ? 2 * kObsChunk : n_pad) * 4) + 15) & ~(size_t)15;
 }
@@ -843,12 +1010,12 @@ constexpr int kThreads = kWarps * 32;
 //   interleaved groups of the same strip and consume each 32 KB chunk of observations together
 //   (the chunks arrive by TMA bulk copy into two shared-memory stages).
 // ---------------------------------------------------------------------------------------
-template <class Policy, bool STREAMED>
+template <class Policy, bool STREAMED, int NT>
 __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc, int cw, int &u0,
                                           int &u1, int pool_end, uint64_t *bars, float *obs_s,
                                           unsigned char *tsm_raw, volatile int *claim,
                                           int &claim_par, int &streams) {
-  constexpr int NT = kThreads;
+  constexpr int kWarpsCta = NT / 32;
   constexpr int kRows = Policy::kRows;
   constexpr int kCols = Policy::kCols;
   constexpr int kGroups = kCols / kRN;
@@ -1076,11 +1243,11 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
     int item = u0;
     const int nchunks = (g.n_pad + kObsChunk - 1) / kObsChunk;
     while (item < g.items_per_strip) {
-      const int g0 = item * g.chunk * kWarps, g1 = min(g.groups, g0 + g.chunk * kWarps);
+      const int g0 = item * g.chunk * kWarpsCta, g1 = min(g.groups, g0 + g.chunk * kWarpsCta);
       claim_par ^= 1;
       int next_item = 0;
       if (tid == 0) next_item = atomicAdd(g.strip_next + cw, 1);
-      for (int base = g0; base < g1; base += kWarps) {
+      for (int base = g0; base < g1; base += kWarpsCta) {
         // 32 KB chunks through two stages, the next chunk in flight while this one is consumed
         // (stage = parity of the running load count)
         if (tid == 0) issue_chunk(g, bars, obs_s, 0, streams & 1);
@@ -1126,27 +1293,45 @@ __device__ __forceinline__ double strip_umax(const RangeArgs &r, int cw, int str
   const double s1 = (double)range_value(jlast, r.N, r.sg0, r.sg1);
   return fmax(fabs(coef_a(s0)), fabs(coef_a(s1))) * ustep;
 }
+// Bound on |a_j - a_0| / |a_j| inside a thread's four adjacent columns of the strip, a_0 the mean
+// of the two middle ones (ProductSlope): a = -0.72/sigma^2, so one column step changes it by
+// |2 dsigma/sigma| to first order; 1.5 steps to the outer columns, with the second-order term and
+// the float32 rounding of the range values covered by taking 2 steps at the strip's smallest sigma.
+__device__ __forceinline__ double strip_slope_eps(const RangeArgs &r, int cw, int strip_cols) {
+  const int jfirst = cw * strip_cols;
+  const int jlast = min(jfirst + strip_cols, r.N) - 1;
+  const double s0 = (double)range_value(jfirst, r.N, r.sg0, r.sg1);
+  const double s1 = (double)range_value(jlast, r.N, r.sg0, r.sg1);
+  const double ds = r.N > 1 ? fabs((double)r.sg1 - (double)r.sg0) / (double)(r.N - 1) : 0.0;
+  const double smin = fmin(fabs(s0), fabs(s1));
+  return (smin > 0.0 && s0 * s1 > 0.0) ? 4.0 * ds / smin : 1e300;  // (a strip across sigma = 0: never)
+}
 
 // ---------------------------------------------------------------------------------------
 // likelihood_cta: everything CTA `cta` of `nctas` does in the likelihood phase.
-//   SELECT: the policy is chosen per column strip on the device -- Fine (ProductNeighbour, degree
-//   2) where the strip's umax allows it, Mid (degree 3) up to 4.5x coarser, Coarse (ProductHybrid)
-//   otherwise.  The choice depends on (ranges, N, observations, strip) only -- never on the rows,
-//   the shard or the warp -- so every rank of a sharded run takes the same path for the same cells
-//   and results stay bit-reproducible.  !SELECT: Fine everywhere.
+//   SELECT: the policy is chosen per column strip on the device, the first of (Finest, Fine, Mid,
+//   Coarse) whose eligibility bound the strip meets -- by default ProductSlope, ProductNeighbour
+//   of degree 2 and 3 (exponent step up to 0.011 / 0.05), ProductHybrid (any grid).  The choice
+//   depends on (ranges, N, observations, strip) only -- never on the rows, the shard or the warp --
+//   so every rank of a sharded run takes the same path for the same cells and results stay
+//   bit-reproducible.  !SELECT: Finest everywhere.
 //   PRELOADED: the caller (small_grid_kernel) has staged the observations and written the
 //   ScaleInfo slot of shared memory, and synchronised the block.
+//   NT: threads per CTA.
 // ---------------------------------------------------------------------------------------
-template <class Fine, class Mid, class Coarse, bool SELECT, bool PRELOADED, bool STREAMED = false>
+template <class Finest, class Fine, class Mid, class Coarse, bool SELECT, bool PRELOADED,
+          bool STREAMED = false, int NT = kThreads>
 __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char *smem_raw,
                                                double *scratch, unsigned cta, unsigned nctas) {
-  static_assert(Fine::kCols == Coarse::kCols && Fine::kCols == Mid::kCols, "same tiling");
-  static_assert(Fine::kRows == Coarse::kRows && Fine::kRows == Mid::kRows, "same row groups");
+  static_assert(Fine::kCols == Coarse::kCols && Fine::kCols == Mid::kCols && Fine::kCols == Finest::kCols,
+                "same tiling");
+  static_assert(Fine::kRows == Coarse::kRows && Fine::kRows == Mid::kRows && Fine::kRows == Finest::kRows,
+                "same row groups");
   static_assert(!(PRELOADED && STREAMED), "the small-grid kernel stages every observation at once");
   constexpr int kCols = Fine::kCols;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
   ScaleInfo *sc_s = reinterpret_cast<ScaleInfo *>(smem_raw + 16);
-  volatile int *claim = reinterpret_cast<volatile int *>(smem_raw + 96);
+  volatile int *claim = reinterpret_cast<volatile int *>(smem_raw + 104);
   float *obs_s = reinterpret_cast<float *>(smem_raw + kSmemHeader);
   const int tid = threadIdx.x, lane = tid & 31;
   unsigned char *after_stage = smem_raw + kSmemHeader + stage_bytes(g.n_pad);
@@ -1189,12 +1374,15 @@ __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char 
   auto dispatch = [&](int cw, int &u0, int &u1) {
     ScaleInfo sc = *sc_s;
     sc.umax = strip_umax(g.range, cw, strip_cols, sc.ustep);  // the strip's own bound
-    if (!SELECT || sc.umax <= Fine::kUmax)
-      run_strip<Fine, STREAMED>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim, claim_par, streams);
-    else if (sc.umax <= Mid::kUmax)
-      run_strip<Mid, STREAMED>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim, claim_par, streams);
+    const double eps = SELECT ? strip_slope_eps(g.range, cw, strip_cols) : 0.0;
+    if (!SELECT || Finest::eligible(sc.umax, eps))
+      run_strip<Finest, STREAMED, NT>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim, claim_par, streams);
+    else if (Fine::eligible(sc.umax, eps))
+      run_strip<Fine, STREAMED, NT>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim, claim_par, streams);
+    else if (Mid::eligible(sc.umax, eps))
+      run_strip<Mid, STREAMED, NT>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim, claim_par, streams);
     else
-      run_strip<Coarse, STREAMED>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim, claim_par, streams);
+      run_strip<Coarse, STREAMED, NT>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim, claim_par, streams);
   };
 
   if (!STREAMED) {
@@ -1219,8 +1407,9 @@ __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char 
   }
 }
 
-template <class Fine, class Mid, class Coarse, bool SELECT, int MINB = 1, bool STREAMED = false>
-__global__ void __launch_bounds__(kThreads, MINB)
+template <class Finest, class Fine, class Mid, class Coarse, bool SELECT, int MINB = 1,
+          bool STREAMED = false, int WARPS = kWarps>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
     grid_likelihood_kernel(const LikeArgs g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   __shared__ double scratch[32];
@@ -1231,8 +1420,14 @@ __global__ void __launch_bounds__(kThreads, MINB)
   unsigned long long t0 = 0;
   if (g.debug && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
 #endif
-  likelihood_cta<Fine, Mid, Coarse, SELECT, false, STREAMED>(g, smem_raw, scratch, blockIdx.x, gridDim.x);
+  likelihood_cta<Finest, Fine, Mid, Coarse, SELECT, false, STREAMED, WARPS * 32>(g, smem_raw, scratch,
+                                                                               blockIdx.x, gridDim.x);
 #ifdef CGE_DEBUG_TIMES
+  if (g.debug && (threadIdx.x & 31) == 0) {  // per warp: when it ran out of work
+    unsigned long long tw;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw));
+    g.debug[4 * gridDim.x + WARPS * blockIdx.x + (threadIdx.x >> 5)] = tw;
+  }
   if (g.debug && threadIdx.x == 0) {
     unsigned long long t1;
     unsigned smid;
@@ -1308,7 +1503,7 @@ __device__ __forceinline__ void cluster_barrier() {
                    : "memory");
 }
 
-template <class Fine, class Mid, class Coarse, bool SELECT, bool CLUSTER>
+template <class Finest, class Fine, class Mid, class Coarse, bool SELECT, bool CLUSTER>
 __global__ void __launch_bounds__(kThreads)
     small_grid_kernel(const SmallArgs a) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1330,7 +1525,7 @@ __global__ void __launch_bounds__(kThreads)
     }
     __syncthreads();
   }
-  likelihood_cta<Fine, Mid, Coarse, SELECT, true>(g, smem_raw, scratch, cta, nctas);
+  likelihood_cta<Finest, Fine, Mid, Coarse, SELECT, true>(g, smem_raw, scratch, cta, nctas);
   __syncthreads();  // the warps of this CTA worked independently: all of them are done
 
   bool writer;  // the CTA that writes partials / results: the last one, or cluster rank 0

@@ -8,7 +8,7 @@ static KernelChoice pick() {
   KernelChoice kc;
   kc.smem_bytes = cge::policy_smem_bytes<P>();
   kc.kcols = P::kCols;
-  kc.fn = (const void *)cge::grid_likelihood_kernel<P, P, P, false, MINB, STREAMED>;
+  kc.fn = (const void *)cge::grid_likelihood_kernel<P, P, P, P, false, MINB, STREAMED>;
   return kc;
 }
 

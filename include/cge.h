@@ -102,6 +102,8 @@ enum {
                                 from it, e * 2^u with 2^u - 1 a degree-2 FMA-pipe polynomial (only
                                 accurate while the row spacing keeps |u| <= 0.011) */
   CGE_VARIANT_PAIRED3 = 8,   /* paired rows with the degree-3 polynomial, forced (|u| <= 0.05) */
+  CGE_VARIANT_SLOPE = 9,     /* neighbour rows with the polynomial shared by a thread's four adjacent
+                                columns, forced (only accurate on the finest grids) */
   CGE_VARIANT_LOG_F64 = 5,   /* log-space mode only: float64 accumulation, one DFMA per pdf-eval (the
                                 default log-space kernel sums centred terms in float32x2 tiles of 256
                                 observations and folds the tiles into float64) */
