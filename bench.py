@@ -58,9 +58,11 @@ TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
 # arithmetic policy that ran (cge_scale_info "product_path"); counted from the SASS of the inner
 # loop (profiles/r02_sass_inner_loop_*.txt): MUFU.EX2 per eval, FMA-pipe lane-ops per eval
 PIPE_OPS = {
-    "paired": (0.5, 54 / 16),    # per 16 evals: 8 MUFU.EX2 + 27 packed f32x2 (2 lane-ops each)
-    "paired3": (0.5, 62 / 16),   # + 4 packed for the cubic term
-    "hybrid": (0.75, (2 * 32 + 8) / 16),
+    # per thread and observation (6 rows x 4 columns = 24 evals): 8 MUFU.EX2 and
+    "slope": (8 / 24, 2 * 34 / 24),    # 34 packed f32x2 instructions (2 lane-ops each)
+    "paired": (8 / 24, 2 * 44 / 24),   # 44 packed (the polynomial per cell instead of per row)
+    "paired3": (8 / 24, 2 * 52 / 24),  # + 8 packed for the cubic term
+    "hybrid": (18 / 24, 4.5),
 }
 
 
@@ -593,15 +595,23 @@ def run_ours(args):
                     "frac": max(mufu_util, fma_util),
                     "frac_vs_survey_count": ach / ex2_peak,
                     "traffic": traffic, "traffic_note": traffic_src,
-                    "kernel": "grid_likelihood_kernel<ProductPaired<2>, ProductPaired<3>, ProductHybrid> -> " + path,
-                    "algorithmic": f"{mufu_pe} MUFU.EX2 + {fma_pe:.3f} FP32 lane-ops issued per pdf-eval "
+                    "kernel": "grid_likelihood_kernel<ProductSlope, ProductNeighbour<2>, ProductNeighbour<3>, ProductHybrid> -> " + path,
+                    "algorithmic": f"{mufu_pe:.4f} MUFU.EX2 + {fma_pe:.3f} FP32 lane-ops issued per pdf-eval "
                                    "(SASS count of the inner loop); evals per launch = rows*N*n; "
                                    "frac = utilisation of the busier of the two pipes against its "
                                    "micro-benchmarked peak; frac_vs_survey_count keeps SURVEY 8(d)'s "
                                    "'1 ex2 per eval' count, which this kernel undercuts by deriving "
-                                   "every other row's factor from its neighbour's on the FMA pipe",
+                                   "two of every three rows' factors from their neighbour's on the "
+                                   "FMA pipe",
                     "executed": {"mufu_per_eval": mufu_pe, "fma_lane_ops_per_eval": fma_pe,
-                                 "mufu_util": mufu_util, "fma_util": fma_util},
+                                 "mufu_util": mufu_util, "fma_util": fma_util,
+                                 # empirical issue model: a packed f32x2 and a MUFU
+                                 # instruction each hold the warp scheduler's dispatch port for two
+                                 # cycles; fits the measured loop rate of both neighbour-row
+                                 # kernels to 2 %
+                                 "issue_cycles_per_warp_eval": fma_pe + 2 * mufu_pe,
+                                 "issue_util_model": (fma_pe + 2 * mufu_pe) * ach / 32.0 /
+                                 (4 * info["sm_count"] * ((main["clocks"] or {}).get("sm_mhz") or 1965.0) * 1e6)},
                     "evals_per_s": ach,
                     "umax": sinfo["umax"], "paired_umax": sinfo["paired_umax"],
                     "paired3_umax": sinfo["paired3_umax"],

@@ -28,6 +28,7 @@ VARIANT_HYBRID = 4
 VARIANT_LOG_F64 = 5
 VARIANT_PAIRED3 = 8
 VARIANT_SLOPE = 9
+VARIANT_SLOPE_WIDE = 10
 VARIANT_UNFUSED = 7
 
 OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_DEGENERATE, ERR_PEER, ERR_SIZE = range(7)
@@ -384,14 +385,15 @@ def _set_prior(self, prior_mu=None, prior_sigma=None, grid_size=0, prior_full=No
 
 def _scale_info(self, stream=None) -> dict:
     """Scale statistics of the last likelihood call (see cge_scale_info)."""
-    out = np.empty(14, np.float64)
-    _check(self._lib.cge_scale_info(self._h, out.ctypes.data, 14, stream))
+    out = np.empty(15, np.float64)
+    _check(self._lib.cge_scale_info(self._h, out.ctypes.data, 15, stream))
     keys = ("log2s", "shift", "m2", "xbar", "ss", "smin", "mu_c", "s_c", "umax", "paired_umax",
-            "paired3_umax", "ustep", "slope_eps", "slope_err_max")
+            "paired3_umax", "ustep", "slope_eps", "slope_err_max", "wide")
     d = dict(zip(keys, out.tolist()))
-    # product_path: the arithmetic of the most demanding column band (the one at the smallest
-    # sigma); bands at larger sigma may run a cheaper policy (see band_paths)
-    d["product_path"] = _product_path(d, d["umax"], d["slope_eps"])
+    # product_path: "slope8" when the whole grid ran the 8-column wide policy; otherwise the
+    # arithmetic of the most demanding column band (the one at the smallest sigma) -- bands at
+    # larger sigma may run a cheaper policy (see band_paths)
+    d["product_path"] = "slope8" if d["wide"] else _product_path(d, d["umax"], d["slope_eps"])
     return d
 
 
@@ -418,6 +420,8 @@ def band_paths(info: dict, sigma: np.ndarray) -> list:
     """Which product policy each column band takes, from scale_info() and the sigma table:
     mirrors cge::strip_umax (|a_j| = 0.5*log2(e)/sigma_j^2 at the band's two ends) and
     cge::strip_slope_eps (4 column steps over the band's smallest sigma)."""
+    if info.get("wide"):
+        return ["slope8"] * ((len(sigma) + 127) // 128)
     out = []
     n = len(sigma)
     band_cols = band_columns(n)

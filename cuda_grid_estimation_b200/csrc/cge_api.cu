@@ -91,6 +91,8 @@ struct PinnedBuf {
 
 }  // namespace
 
+constexpr int kCopyChunksMax = 32;  // row chunks of a posterior that is copied to the host
+
 struct cge_context {
   int device = 0;
   int sm_count = 0, cc_major = 0, cc_minor = 0;
@@ -98,6 +100,8 @@ struct cge_context {
   cudaStream_t stream = nullptr;
   bool own_stream = true;
   cudaEvent_t ev[10] = {};
+  cudaStream_t copy_stream = nullptr;          // host-posterior path: chunked device-to-host copies
+  cudaEvent_t copy_ev[kCopyChunksMax + 1] = {};
   DevBuf<float> obs_pad, obs_in, posterior, like32;
   DevBuf<double> posterior64;
   DevBuf<double> rowpart, partials, rowsum, zpart, smupart, espart, results, tmp;
@@ -127,6 +131,7 @@ struct cge_context {
   int knob_grid_mult = 1;    // CGE_GRID_MULT: CTAs per resident slot (1 = persistent)
   int knob_chunk = 0;        // CGE_ITEM_STEPS: CTA steps per claimed item
   int knob_cta_warps = 0;    // CGE_CTA_WARPS: 8 or 24 warps per CTA of the product kernel
+  bool knob_no_wide = false;     // CGE_NO_WIDE: never take the 8-column wide product policy
   bool knob_no_cluster = false;  // CGE_NO_CLUSTER: small grids without the cluster launch
   bool knob_no_pdl = false;      // CGE_NO_PDL: ordinary stream-ordered launches
   // resident CTAs per SM of each likelihood kernel at its shared-memory size (occupancy query)
@@ -176,7 +181,7 @@ int check_params(const cge_params *p, int *rb, int *re) {
   switch (p->variant) {
     case CGE_VARIANT_DEFAULT: case CGE_VARIANT_UNFUSED: break;
     case CGE_VARIANT_MUFU_ONLY: case CGE_VARIANT_PAIRED: case CGE_VARIANT_PAIRED3: case CGE_VARIANT_HYBRID:
-    case CGE_VARIANT_SLOPE:
+    case CGE_VARIANT_SLOPE: case CGE_VARIANT_SLOPE_WIDE:
       if (p->mode != CGE_MODE_PRODUCT_F32)
         return set_error(CGE_ERR_BAD_ARG, "variant %d belongs to the product mode", p->variant);
       break;
@@ -205,7 +210,6 @@ int centred_obs(const cge_params *p) {
   return (p->mode == CGE_MODE_LOGSPACE && p->variant != CGE_VARIANT_LOG_F64) ? 1 : 0;
 }
 
-constexpr int kDefaultCtaWarps = 8;  // warps per CTA of the default product kernel (CGE_CTA_WARPS)
 
 // CTA shape and unit decomposition for one shard (everything but the persistent grid size, which
 // needs the kernel: size_grid below).  `post` is where the float32 cells go.
@@ -245,7 +249,10 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->streamed = pl->n_pad > cge::kObsSingleMax;
   pl->reorder = p->mode == CGE_MODE_PRODUCT_F32 && pl->n <= cge::kReorderMax;
   pl->cluster = false;
-  pl->cta_warps = ctx->knob_cta_warps > 0 ? ctx->knob_cta_warps : kDefaultCtaWarps;
+  // one CTA per SM whose warps share a single pool (product: 20 warps, log-space: 16), or with
+  // CGE_CTA_WARPS=8 the earlier shape of several 8-warp CTAs per SM with a pool each (A/B runs;
+  // measured at 16384^2 x 50: 1.60 vs 1.50 ms, log-space 16384^2 x 10k: 112.5 vs 107.6 ms)
+  pl->cta_warps = ctx->knob_cta_warps > 0 ? ctx->knob_cta_warps : 0;
   pl->nctas = 0;
 }
 
@@ -396,8 +403,11 @@ int fill_like_args(cge_context *ctx, const cge_params *p, const Plan &pl, const 
   args->ncw = pl.ncw;
   args->vec4 = pl.vec4 ? 1 : 0;
   args->keep_l2 = pl.keep_l2 ? 1 : 0;
+  args->vec8 = (N % 8 == 0) && ((reinterpret_cast<uintptr_t>(posterior_dev) & 31u) == 0) ? 1 : 0;
+  args->wide = p->variant == CGE_VARIANT_SLOPE_WIDE ? 1 : ctx->knob_no_wide ? -1 : 0;
 #ifdef CGE_DEBUG_TIMES
   CKRC(ctx->debug_times.reserve((size_t)(4 + 32) * pl.nctas));
+  CK(cudaMemset(ctx->debug_times.ptr, 0, (size_t)(4 + 32) * pl.nctas * sizeof(unsigned long long)));
   args->debug = ctx->debug_times.ptr;
 #endif
   return CGE_OK;
@@ -575,6 +585,7 @@ CGE_EXPORT int cge_create(int device, cge_context **out) {
   if (const char *v = std::getenv("CGE_GRID_MULT")) ctx->knob_grid_mult = std::atoi(v) > 0 ? std::atoi(v) : 1;
   if (const char *v = std::getenv("CGE_ITEM_STEPS")) ctx->knob_chunk = std::atoi(v);
   if (const char *v = std::getenv("CGE_CTA_WARPS")) ctx->knob_cta_warps = std::atoi(v);
+  ctx->knob_no_wide = std::getenv("CGE_NO_WIDE") != nullptr;
   ctx->knob_no_cluster = std::getenv("CGE_NO_CLUSTER") != nullptr;
   ctx->knob_no_pdl = std::getenv("CGE_NO_PDL") != nullptr;
   cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
@@ -610,6 +621,9 @@ CGE_EXPORT int cge_destroy(cge_context *ctx) {
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
   for (auto &ev : ctx->prof_events) cudaEventDestroy(ev);
+  for (auto &e : ctx->copy_ev)
+    if (e) cudaEventDestroy(e);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
   if (ctx->stream && ctx->own_stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return CGE_OK;
@@ -778,8 +792,10 @@ CGE_EXPORT int cge_partials(cge_context *ctx, double **partials_dev, size_t *cou
 // ---------------------------------------------------------------------------------------
 // phase 2: (peer sum) + results + scale, one launch
 // ---------------------------------------------------------------------------------------
-CGE_EXPORT int cge_finalize(cge_context *ctx, const cge_params *p, void *posterior_dev,
-                            void *stream) {
+// `scale_cells`: how many cells of the shard this launch scales (0 = all of them; the chunked
+// host-posterior path of cge_grid_posterior scales the rest itself)
+static int finalize_impl(cge_context *ctx, const cge_params *p, void *posterior_dev, void *stream,
+                         size_t scale_cells) {
   CKRC(bind(ctx));
   int rb, re;
   CKRC(check_params(p, &rb, &re));
@@ -807,6 +823,7 @@ CGE_EXPORT int cge_finalize(cge_context *ctx, const cge_params *p, void *posteri
   a.espart = ctx->espart.ptr;
   a.ticket = ctx->tickets.ptr + 1;
   a.cells = (size_t)pl.rows_local * N;
+  if (scale_cells > 0 && scale_cells < a.cells) a.cells = scale_cells;
   if (pl.post_f64) {
     a.post = ctx->like32.ptr;
     a.post64 = static_cast<double *>(posterior_dev);
@@ -832,6 +849,61 @@ CGE_EXPORT int cge_finalize(cge_context *ctx, const cge_params *p, void *posteri
   ctx->launches += 1;
   CKRC(mark(ctx, 5, st));
   if (ctx->prof_on && ctx->prof_step < ctx->prof_cap) ctx->prof_step++;
+  return CGE_OK;
+}
+
+CGE_EXPORT int cge_finalize(cge_context *ctx, const cge_params *p, void *posterior_dev,
+                            void *stream) {
+  return finalize_impl(ctx, p, posterior_dev, stream, 0);
+}
+
+// Phase 2 with the posterior going to host memory: the shard is scaled in row chunks of ~64 MB
+// (the first by the finish kernel, the others by scale_chunk_kernel) and each chunk's PCIe copy,
+// on a second stream, overlaps the scale pass of the next ones.
+static int finalize_to_host(cge_context *ctx, const cge_params *p, void *post_dev, void *post_host,
+                            cudaStream_t st) {
+  const Plan &pl = ctx->plan;
+  const size_t N = pl.N, rows = pl.rows_local, cell_bytes = pl.post_f64 ? sizeof(double) : sizeof(float);
+  size_t chunk_rows = ((size_t)64 << 20) / (N * cell_bytes);
+  if (chunk_rows < 1) chunk_rows = 1;
+  if ((rows + chunk_rows - 1) / chunk_rows > kCopyChunksMax) chunk_rows = (rows + kCopyChunksMax - 1) / kCopyChunksMax;
+  if (chunk_rows >= rows) {  // one chunk: nothing to overlap
+    CKRC(finalize_impl(ctx, p, post_dev, st, 0));
+    CK(cudaMemcpyAsync(post_host, post_dev, rows * N * cell_bytes, cudaMemcpyDeviceToHost, st));
+    return CGE_OK;
+  }
+  if (!ctx->copy_stream) {
+    CK(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    for (auto &e : ctx->copy_ev) CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  }
+  float *src32 = pl.post_f64 ? ctx->like32.ptr : static_cast<float *>(post_dev);
+  double *dst64 = pl.post_f64 ? static_cast<double *>(post_dev) : nullptr;
+  int k = 0;
+  for (size_t r0 = 0; r0 < rows; r0 += chunk_rows, ++k) {
+    const size_t nr = rows - r0 < chunk_rows ? rows - r0 : chunk_rows, off = r0 * N, cells = nr * N;
+    if (k == 0) {
+      CKRC(finalize_impl(ctx, p, post_dev, st, cells));
+    } else {
+      cge::ScaleChunkArgs a = {};
+      a.results = ctx->results.ptr;
+      a.post = src32 + off;
+      a.post64 = dst64 ? dst64 + off : nullptr;
+      a.cells = cells;
+      a.aligned = ((reinterpret_cast<uintptr_t>(a.post) | reinterpret_cast<uintptr_t>(a.post64)) & 15u) == 0;
+      size_t want = a.aligned ? (cells / 4 + 1023) / 1024 : (cells + 255) / 256;
+      const size_t cap = (size_t)ctx->sm_count * 16;
+      if (want > cap) want = cap;
+      CKRC(launch_ex(ctx, (const void *)cge::scale_chunk_kernel, (unsigned)want, 256, 0, st, &a, true, 0));
+      ctx->launches += 1;
+    }
+    CK(cudaEventRecord(ctx->copy_ev[k], st));
+    CK(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_ev[k], 0));
+    CK(cudaMemcpyAsync(static_cast<char *>(post_host) + off * cell_bytes,
+                       static_cast<char *>(post_dev) + off * cell_bytes, cells * cell_bytes,
+                       cudaMemcpyDeviceToHost, ctx->copy_stream));
+  }
+  CK(cudaEventRecord(ctx->copy_ev[kCopyChunksMax], ctx->copy_stream));
+  CK(cudaStreamWaitEvent(st, ctx->copy_ev[kCopyChunksMax], 0));
   return CGE_OK;
 }
 
@@ -1110,14 +1182,15 @@ CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const f
     rc = small_grid_step(ctx, p, obs_dev, static_cast<float *>(post_dev), st, host_out);
   } else {
     rc = cge_likelihood_partials(ctx, p, obs_dev, post_dev, st);
-    if (rc == CGE_OK) rc = cge_finalize(ctx, p, post_dev, st);
+    if (rc == CGE_OK)
+      rc = post_to_host ? finalize_to_host(ctx, p, post_dev, posterior, st) : cge_finalize(ctx, p, post_dev, st);
   }
   if (rc != CGE_OK) {
     if (!was_on) ctx->prof_on = false;
     return rc;
   }
   if (timing) CK(cudaEventRecord(ctx->ev[1], st));
-  if (post_to_host)
+  if (post_to_host && small)
     CK(cudaMemcpyAsync(posterior, post_dev, cells * cell_bytes, cudaMemcpyDeviceToHost, st));
   rc = cge_read_results(ctx, p, expectations, marg_mu, marg_sigma, nullptr, st);
   if (timing) {
@@ -1175,9 +1248,9 @@ CGE_EXPORT int cge_scale_info(cge_context *ctx, double *out, int count, void *st
   cudaStream_t st = (cudaStream_t)stream;
   CK(cudaMemcpyAsync(&h, ctx->scale.ptr, sizeof h, cudaMemcpyDeviceToHost, st));
   CK(cudaStreamSynchronize(st));
-  const double v[14] = {h.log2s, h.shift, h.m2, h.xbar, h.ss, h.smin, h.mu_c, h.s_c, h.umax,
-                        cge::kPairedUmax, cge::kPairedUmax3, h.ustep, h.seps, cge::kSlopeErr};
-  for (int i = 0; i < count && i < 14; ++i) out[i] = v[i];
+  const double v[15] = {h.log2s, h.shift, h.m2, h.xbar, h.ss, h.smin, h.mu_c, h.s_c, h.umax,
+                        cge::kPairedUmax, cge::kPairedUmax3, h.ustep, h.seps, cge::kSlopeErr, h.wide};
+  for (int i = 0; i < count && i < 15; ++i) out[i] = v[i];
   return CGE_OK;
 }
 
@@ -1337,7 +1410,8 @@ extern "C" int cge_internal_stream(cge_context *ctx, void **stream, int *sm_coun
 extern "C" int cge_internal_error(int code, const char *msg) { return set_error(code, "%s", msg); }
 #ifdef CGE_DEBUG_TIMES
 // diagnostic build only: per-CTA {start ns, end ns, smid, set-up done ns} of the last likelihood
-// launch, followed by the end time of each of its warps (kWarps per CTA); `out` holds 12 * max_ctas
+// launch, followed by the end time of each of its warps (32 slots per CTA, unused ones zero);
+// `out` holds 36 * max_ctas
 CGE_EXPORT int cge_debug_times(cge_context *ctx, unsigned long long *out, int max_ctas, int *nctas) {
   CKRC(bind(ctx));
   CK(cudaDeviceSynchronize());

@@ -188,6 +188,18 @@ __device__ __forceinline__ void st_keep_f1(float *p, float a) {
   asm volatile("st.global.f32 [%0], %1;" ::"l"(p), "f"(a) : "memory");
 }
 
+// 32-byte stores (sm_100: STG.256), p 32-byte aligned
+__device__ __forceinline__ void st_stream_f8(float *p, const float (&v)[8]) {
+  asm volatile("st.global.cs.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]),
+               "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+__device__ __forceinline__ void st_keep_f8(float *p, const float (&v)[8]) {
+  asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "f"(v[0]),
+               "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7])
+               : "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // fixed-order reductions: the combination tree depends only on lane / warp indices, never on
 // timing, so every run (and every shard layout with the same tiling) sums in the same order.

@@ -62,9 +62,10 @@ using DefaultMid = cge::ProductNeighbour<3>;   // degree-3 polynomial, strip uma
 using DefaultCoarse = cge::ProductHybrid;
 constexpr int kDefaultMinB = 3;  // <= 80 registers: three 256-thread CTAs (24 warps) per SM
 #ifndef CGE_WIDE_WARPS
-#define CGE_WIDE_WARPS 24
+#define CGE_WIDE_WARPS 16
 #endif
-constexpr int kWideWarps = CGE_WIDE_WARPS;   // ... or one 768-thread CTA per SM: one pool for all its warps
+constexpr int kWideWarps = CGE_WIDE_WARPS;   // ... or one CTA per SM: one pool for all its warps, and up to
+                                             // 102 registers per thread for the 8-column wide policy
 
 template <class A, class B, class C, class D>
 constexpr int smem_bytes4() {

@@ -50,6 +50,11 @@ constexpr int kGroupCols = 32 * kRN;  // 128 columns: one float4 per lane across
 __device__ __forceinline__ int patch_col(int jbase, int cidx) {
   return jbase + (cidx >> 2) * kGroupCols + (cidx & 3);
 }
+// ... or, for a policy whose thread owns kCols ADJACENT columns (one 32-byte store per row)
+template <bool ADJ>
+__device__ __forceinline__ int col_at(int jbase, int cidx) {
+  return ADJ ? jbase + cidx : patch_col(jbase, cidx);
+}
 constexpr int kObsChunk = 8192;   // floats per streamed observation chunk (32 KB)
 constexpr int kObsSingleMax = 16384;  // up to this many (padded) observations live in smem at once
 constexpr int kReorderMax = 1024;     // product mode: observations are re-ordered up to this count
@@ -67,6 +72,7 @@ struct ScaleInfo {
   double umax;   // bound on |t_(i+1,j,k) - t_(i,j,k)| over adjacent mu rows, whole grid
   double ustep;  // the same bound per unit |a_j|: umax of a column band = max |a_j| in it * ustep
   double seps;   // bound on the relative change of a_j over a thread's 4 columns, whole grid (ProductSlope)
+  double wide;   // 1 when the step ran the 8-column wide product policy (reporting only)
 };
 
 struct RangeArgs {
@@ -130,8 +136,10 @@ struct LikeArgs {
   int ncw;             // column strips per row: ceil(N / (32 * Policy::kCols))
   int vec4;            // N % 4 == 0 and the shard base is 16-byte aligned: float4 stores
   int keep_l2;         // the shard fits in L2: store with the default policy instead of .cs
+  int vec8;            // N % 8 == 0 and the shard base is 32-byte aligned: 32-byte stores (wide policy)
+  int wide;            // the 8-column policy of the product kernel: 0 = where eligible, -1 = never, 1 = forced
 #ifdef CGE_DEBUG_TIMES
-  unsigned long long *debug;  // per CTA: {start ns, end ns, smid, set-up done ns}, then per warp: end ns
+  unsigned long long *debug;  // per CTA: {start ns, end ns, smid, set-up done ns}, then 32 slots per CTA: warp end ns
 #endif
 };
 
@@ -157,13 +165,13 @@ __device__ __forceinline__ int col_fixed_shift(double a, double c0, const ScaleI
 
 // per-thread column coefficients in float64: a_j = -0.5*log2(e)/sigma_j^2, c0_j = -log2(sigma_j*sqrt(2 pi)),
 // sigma_j from the reference's float32 range formula
-template <int KC>
+template <int KC, bool ADJ = false>
 struct ColumnCoefs {
   double a[KC], c0[KC];
   __device__ __forceinline__ void compute(const RangeArgs &r, int j0) {
 #pragma unroll
     for (int cidx = 0; cidx < KC; ++cidx) {
-      const int j = patch_col(j0, cidx);
+      const int j = col_at<ADJ>(j0, cidx);
       const double sd = (double)range_value(min(j, r.N - 1), r.N, r.sg0, r.sg1);
       a[cidx] = j < r.N ? coef_a(sd) : 0.0;
       c0[cidx] = j < r.N ? coef_c0(sd) : 0.0;
@@ -303,6 +311,7 @@ __device__ __forceinline__ ScaleInfo setup_scale(const RangeArgs &r, const float
     out.ustep = dmu * 2.0 * reach;
     out.umax = fabs(coef_a(sdmin)) * out.ustep;
     const double sabs = fmin(fabs((double)sg0), fabs((double)sg1));
+    out.wide = 0.0;
     out.seps = (N > 1 && sabs > 0.0 && (double)sg0 * (double)sg1 > 0.0)
                    ? 4.0 * fabs((double)sg1 - (double)sg0) / (double)(N - 1) / sabs
                    : (N > 1 ? 1e300 : 0.0);
@@ -329,6 +338,7 @@ struct ProductF32 {
   static __device__ __forceinline__ bool eligible(double, double) { return true; }
   static constexpr double kUmax = 1e300;
   static constexpr bool kColSmem = false;
+  static constexpr bool kAdjacent = false;
   static constexpr int kRows = kRowsProduct;
   static constexpr int kCols = 4;
   static constexpr int kSmemDoubles = 0;
@@ -384,6 +394,7 @@ struct LogSpaceF64 {
   static __device__ __forceinline__ bool eligible(double, double) { return true; }
   static constexpr double kUmax = 1e300;
   static constexpr bool kColSmem = false;
+  static constexpr bool kAdjacent = false;
   static constexpr int kRows = 4;
   static constexpr int kCols = 8;
   static constexpr int kSmemDoubles = kCols;  // n*c0_j + shift of the thread's columns
@@ -456,6 +467,7 @@ struct LogSpaceTiled {
   static __device__ __forceinline__ bool eligible(double, double) { return true; }
   static constexpr double kUmax = 1e300;
   static constexpr bool kColSmem = false;
+  static constexpr bool kAdjacent = false;
   static constexpr int kRows = 4;
   static constexpr int kCols = 8;
   static constexpr int kSmemDoubles = kCols;  // a_j S_c + n c0_j + shift of the thread's columns
@@ -580,6 +592,7 @@ struct ProductHybrid {
   static __device__ __forceinline__ bool eligible(double, double) { return true; }
   static constexpr double kUmax = 1e300;  // any grid
   static constexpr bool kColSmem = false;
+  static constexpr bool kAdjacent = false;
   static constexpr int kRows = kRowsProduct;
   static constexpr int kCols = 4;
   static constexpr int kSmemDoubles = 0;
@@ -707,6 +720,7 @@ struct ProductNeighbour {
   static constexpr double kUmax = DEG == 2 ? kPairedUmax : kPairedUmax3;  // eligibility bound
   static __device__ __forceinline__ bool eligible(double umax, double) { return umax <= kUmax; }
   static constexpr bool kColSmem = true;
+  static constexpr bool kAdjacent = false;
   static constexpr int kRows = kRowsProduct;
   static constexpr int kCols = 4;
   static constexpr int kSmemDoubles = 0;
@@ -844,15 +858,26 @@ struct ProductNeighbour {
 // observation: 34 packed FMA-pipe instructions (68 pipe cycles per warp) against 8 MUFU.EX2 (64 XU
 // cycles).
 // ---------------------------------------------------------------------------------------
+//
+// KC = 8 is the WIDE form: a thread owns 8 ADJACENT columns (one 32-byte store per row; the warp's
+// strip is 256 columns = two row-partial slots), so the 6 packed row scalars are shared by twice
+// the cells -- 62 packed + 16 MUFU.EX2 per 48 evals instead of 68 + 16 -- and the per-group
+// epilogue (row sums, claims, range values) is paid once per 48 cells.  a_0 is then up to 3.5
+// column steps from a thread's outer columns instead of 1.5, so eps is scaled by 9.5 / 4.
 constexpr double kSlopeErr = 4.0e-8;
-struct ProductSlope {
+template <int KC>
+struct ProductSlopeT {
+  static_assert(KC == 4 || KC == 8, "4 columns (two groups' worth of one float4) or 8 adjacent ones");
   static constexpr double kUmax = kPairedUmax;
+  static constexpr double kEpsScale = KC == 8 ? 9.5 / 4.0 : 1.0;
+  // eps: the strip's (or grid's) bound for 4 adjacent columns (strip_slope_eps / ScaleInfo::seps)
   static __device__ __forceinline__ bool eligible(double umax, double eps) {
-    return umax <= kPairedUmax && 0.2402265069591007 * umax * umax * eps <= kSlopeErr;
+    return umax <= kPairedUmax && 0.2402265069591007 * umax * umax * (eps * kEpsScale) <= kSlopeErr;
   }
   static constexpr bool kColSmem = true;
+  static constexpr bool kAdjacent = KC == 8;
   static constexpr int kRows = kRowsProduct;
-  static constexpr int kCols = 4;
+  static constexpr int kCols = KC;
   static constexpr int kSmemDoubles = 0;
   static constexpr int kPairs = kCols / 2;
   static constexpr int kTriples = kRows / 3;
@@ -863,21 +888,21 @@ struct ProductSlope {
 
   template <int NT>
   __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
-                                               const ColumnCoefs<kCols> &cf, double *) {
+                                               const ColumnCoefs<kCols, kAdjacent> &cf, double *) {
     const double U = sc.umax;
     const double k2 = 0.24022650695910071233;
     k1 = (float)(0.69314718055994530942 + 0.0555041086648215799 * 0.75 * U * U);
     // slope of the thread's columns: the mean of the two middle ones (clamped to the grid, so a
     // thread that straddles the last column still gets a slope of its own columns)
-    const double s1 = (double)range_value(min(j0 + 1, g.N - 1), g.N, g.range.sg0, g.range.sg1);
-    const double s2 = (double)range_value(min(j0 + 2, g.N - 1), g.N, g.range.sg0, g.range.sg1);
+    const double s1 = (double)range_value(min(j0 + kCols / 2 - 1, g.N - 1), g.N, g.range.sg0, g.range.sg1);
+    const double s2 = (double)range_value(min(j0 + kCols / 2, g.N - 1), g.N, g.range.sg0, g.range.sg1);
     a0k2 = (float)(0.5 * (coef_a(s1) + coef_a(s2)) * k2);
 #pragma unroll
     for (int h = 0; h < kPairs; ++h) {
       float av[2], cv[2];
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const int j = patch_col(j0, 2 * h + e);
+        const int j = col_at<kAdjacent>(j0, 2 * h + e);
         av[e] = (float)cf.a[2 * h + e];
         cv[e] = j < g.N ? (float)(cf.c0[2 * h + e] + sc.log2s) : 0.0f;
       }
@@ -954,25 +979,27 @@ struct ProductSlope {
     unpack2(p2[r][cidx >> 1], lo, hi);
     return (cidx & 1) ? hi : lo;
   }
-  static __device__ __forceinline__ void consume(ProductSlope &pol, const float *xs, int count,
+  static __device__ __forceinline__ void consume(ProductSlopeT &pol, const float *xs, int count,
                                                  const float (&mu)[kRows]) {
     neighbour_consume(pol, xs, count, mu);
   }
 };
+using ProductSlope = ProductSlopeT<4>;
+using ProductSlopeWide = ProductSlopeT<8>;
 
 // ---------------------------------------------------------------------------------------
 // Shared-memory layout of the likelihood kernels (dynamic):
 //   [0, 16)    two mbarriers (streamed observations only)
-//   [16, 104)  ScaleInfo of this step (written once per CTA by the set-up)
-//   [104, 128) claim slots: [0..2] the item a CTA takes next (streamed), [4] the pool counter
-//   [128, ...) observation stage: n_pad floats, or two chunks of kObsChunk when streamed
+//   [16, 112)  ScaleInfo of this step (written once per CTA by the set-up)
+//   [128, 160) claim slots: [0..2] the item a CTA takes next (streamed), [4] the pool counter
+//   [160, ...) observation stage: n_pad floats, or two chunks of kObsChunk when streamed
 //   then       per-thread slots [k][NT]: kCols int64 column accumulators (as 16-byte pairs), kCols
 //              float32 column scales 2^s_j (as 8-byte pairs), the policy's own float64 values, and
 //              kRows floats per thread of row-sum transposition buffer (kRows * 128 bytes per
 //              warp); during the set-up the same bytes serve as the sort scratch
 // ---------------------------------------------------------------------------------------
-constexpr int kSmemHeader = 128;
-static_assert(16 + sizeof(ScaleInfo) <= 104, "shared-memory header layout");
+constexpr int kSmemHeader = 160;
+static_assert(16 + sizeof(ScaleInfo) <= 128, "shared-memory header layout");
 __host__ __device__ __forceinline__ size_t stage_bytes(int n_pad) {
   return (((size_t)(n_pad > kObsSingleMax ? 2 * kObsChunk : n_pad) * 4) + 15) & ~(size_t)15;
 }
@@ -1019,10 +1046,15 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
   constexpr int kRows = Policy::kRows;
   constexpr int kCols = Policy::kCols;
   constexpr int kGroups = kCols / kRN;
+  constexpr bool kAdj = Policy::kAdjacent;
+  // float offset between a thread's successive 4-column groups: adjacent, or 128 columns apart
+  constexpr int kGroupStride = kAdj ? kRN : kGroupCols;
   static_assert(kRows == 4 || kRows == 6, "the epilogue is written for 4- and 6-row patches");
+  static_assert(!kAdj || (kCols == 8 && kRows == 6 && !STREAMED), "the adjacent layout is the wide product policy's");
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
-  const int j0 = cw * (32 * kCols) + lane * kRN;  // first column; group g starts 128*g further
+  // first column; group g starts 128*g further (adjacent layout: all kCols columns in a row)
+  const int j0 = cw * (32 * kCols) + lane * (kAdj ? kCols : kRN);
   // row groups start at a multiple of kRows below row_begin, so a cell's position inside the
   // register patch (hence which exponential path it takes) depends on its GLOBAL row only: a row
   // shard computes bit-identical unnormalised cells to the single-GPU run
@@ -1039,7 +1071,7 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
 
   Policy pol;
   {
-    ColumnCoefs<kCols> cf;
+    ColumnCoefs<kCols, kAdj> cf;
     cf.compute(g.range, j0);
     pol.template load_columns<NT>(g, j0, sc, cf, own);
 #pragma unroll
@@ -1088,14 +1120,14 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
 #pragma unroll
       for (int cidx = 0; cidx < kCols; ++cidx) v[r][cidx] = pol.template value<NT>(g, r, cidx, own);
     const bool interior =
-        row >= g.row_begin && row + kRows <= g.row_end && patch_col(j0, kCols - 1) < g.N;
+        row >= g.row_begin && row + kRows <= g.row_end && col_at<kAdj>(j0, kCols - 1) < g.N;
     if (!interior) {  // shard / grid edges: cells outside contribute exactly zero
 #pragma unroll
       for (int r = 0; r < kRows; ++r) {
         const bool rv = row + r >= g.row_begin && row + r < g.row_end;
 #pragma unroll
         for (int cidx = 0; cidx < kCols; ++cidx)
-          if (!(rv && patch_col(j0, cidx) < g.N)) v[r][cidx] = 0.0f;
+          if (!(rv && col_at<kAdj>(j0, cidx) < g.N)) v[r][cidx] = 0.0f;
       }
     }
     if (has_prior) {  // likelihood x prior before normalisation (cuda_functions.h:145-148)
@@ -1107,7 +1139,7 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
       }
 #pragma unroll
       for (int cidx = 0; cidx < kCols; ++cidx) {
-        const int j = patch_col(j0, cidx);
+        const int j = col_at<kAdj>(j0, cidx);
         ps[cidx] = (g.prior_sigma && j < g.N) ? g.prior_sigma[j] : 1.0f;
       }
 #pragma unroll
@@ -1121,14 +1153,30 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
           const float *pf = g.prior_full + (size_t)(row + r - g.row_begin) * (size_t)g.N;
 #pragma unroll
           for (int cidx = 0; cidx < kCols; ++cidx) {
-            const int j = patch_col(j0, cidx);
+            const int j = col_at<kAdj>(j0, cidx);
             if (j < g.N) v[r][cidx] *= pf[j];
           }
         }
       }
     }
     float *rowp = g.post + (ptrdiff_t)(row - g.row_begin) * (ptrdiff_t)g.N + j0;
-    if (g.vec4 && __all_sync(0xffffffffu, interior)) {
+    const bool warp_interior = __all_sync(0xffffffffu, interior);
+    bool stored = false;
+    if constexpr (kAdj) {
+      if (g.vec8 && warp_interior) {
+        // adjacent layout: one 32-byte store per lane and row, a 1 KB run per instruction
+        if (g.keep_l2) {
+#pragma unroll
+          for (int r = 0; r < kRows; ++r, rowp += g.N) st_keep_f8(rowp, v[r]);
+        } else {
+#pragma unroll
+          for (int r = 0; r < kRows; ++r, rowp += g.N) st_stream_f8(rowp, v[r]);
+        }
+        stored = true;
+      }
+    }
+    if (stored) {
+    } else if (g.vec4 && warp_interior) {
       // the whole warp is inside the shard and the grid (all but the edge groups): straight-line
       // stores, one 512-byte run per instruction
       if (g.keep_l2) {
@@ -1136,14 +1184,14 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
         for (int r = 0; r < kRows; ++r, rowp += g.N)
 #pragma unroll
           for (int grp4 = 0; grp4 < kGroups; ++grp4)
-            st_keep_f4(rowp + grp4 * kGroupCols, v[r][4 * grp4], v[r][4 * grp4 + 1],
+            st_keep_f4(rowp + grp4 * kGroupStride, v[r][4 * grp4], v[r][4 * grp4 + 1],
                        v[r][4 * grp4 + 2], v[r][4 * grp4 + 3]);
       } else {
 #pragma unroll
         for (int r = 0; r < kRows; ++r, rowp += g.N)
 #pragma unroll
           for (int grp4 = 0; grp4 < kGroups; ++grp4)
-            st_stream_f4(rowp + grp4 * kGroupCols, v[r][4 * grp4], v[r][4 * grp4 + 1],
+            st_stream_f4(rowp + grp4 * kGroupStride, v[r][4 * grp4], v[r][4 * grp4 + 1],
                          v[r][4 * grp4 + 2], v[r][4 * grp4 + 3]);
       }
     } else {
@@ -1152,15 +1200,15 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
         const bool rv = interior || (row + r >= g.row_begin && row + r < g.row_end);
 #pragma unroll
         for (int grp4 = 0; grp4 < kGroups; ++grp4) {
-          const int jg = j0 + grp4 * kGroupCols;
+          const int jg = j0 + grp4 * kGroupStride;
           if (g.vec4) {
             if (rv && jg < g.N)
-              st_keep_f4(rowp + grp4 * kGroupCols, v[r][4 * grp4], v[r][4 * grp4 + 1],
+              st_keep_f4(rowp + grp4 * kGroupStride, v[r][4 * grp4], v[r][4 * grp4 + 1],
                          v[r][4 * grp4 + 2], v[r][4 * grp4 + 3]);
           } else {
 #pragma unroll
             for (int e = 0; e < kRN; ++e)
-              if (rv && jg + e < g.N) st_keep_f1(rowp + grp4 * kGroupCols + e, v[r][4 * grp4 + e]);
+              if (rv && jg + e < g.N) st_keep_f1(rowp + grp4 * kGroupStride + e, v[r][4 * grp4 + e]);
           }
         }
       }
@@ -1197,21 +1245,35 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
     if (kRows == 6) w = *reinterpret_cast<const float2 *>(rowbuf + 128 + lane * 2);  // row 4 + lane/16
     __syncwarp();
     double tot = ((double)q.x + (double)q.y) + ((double)q.z + (double)q.w);
-    tot += __shfl_xor_sync(0xffffffffu, tot, 4);
+    // (adjacent layout: the warp's 256 columns are two row-partial slots of 128 columns, lanes
+    // 0..15 and 16..31: the tree stops one level early and publishes both halves)
+    if (!kAdj) tot += __shfl_xor_sync(0xffffffffu, tot, 4);
     tot += __shfl_xor_sync(0xffffffffu, tot, 2);
     tot += __shfl_xor_sync(0xffffffffu, tot, 1);
     const int rq = row + (lane >> 3);  // lanes 0, 8, 16, 24 publish rows 0..3 of the patch
-    if ((lane & 7) == 0 && rq >= g.row_begin && rq < g.row_end)
-      g.rowpart[(size_t)(rq - g.row_begin) * (size_t)g.ncw + cw] = tot;
+    if (!kAdj) {
+      if ((lane & 7) == 0 && rq >= g.row_begin && rq < g.row_end)
+        g.rowpart[(size_t)(rq - g.row_begin) * (size_t)g.ncw + cw] = tot;
+    } else {
+      const int slot = 2 * cw + ((lane >> 2) & 1);  // (lanes 0, 4 of every 8)
+      if ((lane & 3) == 0 && rq >= g.row_begin && rq < g.row_end && slot < g.ncw)
+        g.rowpart[(size_t)(rq - g.row_begin) * (size_t)g.ncw + slot] = tot;
+    }
     if (kRows == 6) {
       double tot2 = (double)w.x + (double)w.y;
-      tot2 += __shfl_xor_sync(0xffffffffu, tot2, 8);
+      if (!kAdj) tot2 += __shfl_xor_sync(0xffffffffu, tot2, 8);
       tot2 += __shfl_xor_sync(0xffffffffu, tot2, 4);
       tot2 += __shfl_xor_sync(0xffffffffu, tot2, 2);
       tot2 += __shfl_xor_sync(0xffffffffu, tot2, 1);
       const int rq2 = row + 4 + (lane >> 4);  // lanes 0, 16 publish rows 4, 5
-      if ((lane & 15) == 0 && rq2 >= g.row_begin && rq2 < g.row_end)
-        g.rowpart[(size_t)(rq2 - g.row_begin) * (size_t)g.ncw + cw] = tot2;
+      if (!kAdj) {
+        if ((lane & 15) == 0 && rq2 >= g.row_begin && rq2 < g.row_end)
+          g.rowpart[(size_t)(rq2 - g.row_begin) * (size_t)g.ncw + cw] = tot2;
+      } else {
+        const int slot = 2 * cw + ((lane >> 3) & 1);  // (lanes 0, 8 of every 16)
+        if ((lane & 7) == 0 && rq2 >= g.row_begin && rq2 < g.row_end && slot < g.ncw)
+          g.rowpart[(size_t)(rq2 - g.row_begin) * (size_t)g.ncw + slot] = tot2;
+      }
     }
   };
 
@@ -1275,7 +1337,7 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
 #pragma unroll
     for (int h = 0; h < kPairs; ++h) {
       const longlong2 part = colacc_s[h * NT];
-      const int ja = patch_col(j0, 2 * h), jb = patch_col(j0, 2 * h + 1);
+      const int ja = col_at<kAdj>(j0, 2 * h), jb = col_at<kAdj>(j0, 2 * h + 1);
       if (ja < g.N && part.x != 0) atomicAdd(g.colacc + ja, (unsigned long long)part.x);
       if (jb < g.N && part.y != 0) atomicAdd(g.colacc + jb, (unsigned long long)part.y);
     }
@@ -1320,7 +1382,7 @@ __device__ __forceinline__ double strip_slope_eps(const RangeArgs &r, int cw, in
 //   NT: threads per CTA.
 // ---------------------------------------------------------------------------------------
 template <class Finest, class Fine, class Mid, class Coarse, bool SELECT, bool PRELOADED,
-          bool STREAMED = false, int NT = kThreads>
+          bool STREAMED = false, int NT = kThreads, bool WIDE = false>
 __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char *smem_raw,
                                                double *scratch, unsigned cta, unsigned nctas) {
   static_assert(Fine::kCols == Coarse::kCols && Fine::kCols == Mid::kCols && Fine::kCols == Finest::kCols,
@@ -1328,27 +1390,31 @@ __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char 
   static_assert(Fine::kRows == Coarse::kRows && Fine::kRows == Mid::kRows && Fine::kRows == Finest::kRows,
                 "same row groups");
   static_assert(!(PRELOADED && STREAMED), "the small-grid kernel stages every observation at once");
+  static_assert(!WIDE || (SELECT && !PRELOADED && !STREAMED), "the wide policy belongs to the default product kernel");
   constexpr int kCols = Fine::kCols;
   uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw);
   ScaleInfo *sc_s = reinterpret_cast<ScaleInfo *>(smem_raw + 16);
-  volatile int *claim = reinterpret_cast<volatile int *>(smem_raw + 104);
+  volatile int *claim = reinterpret_cast<volatile int *>(smem_raw + 128);
   float *obs_s = reinterpret_cast<float *>(smem_raw + kSmemHeader);
   const int tid = threadIdx.x, lane = tid & 31;
   unsigned char *after_stage = smem_raw + kSmemHeader + stage_bytes(g.n_pad);
 
-  // this CTA's pool: an equal contiguous share of the groups, strip-major
-  const long long units = (long long)g.ncw * g.groups;
-  const int pool_begin = (int)(units * cta / nctas), pool_end = (int)(units * (cta + 1) / nctas);
-
+  // WIDE: the whole grid runs ProductSlopeWide (strips of 256 columns) when the grid-level bounds
+  // allow it -- a function of (ranges, N, observations) only, like the per-strip choice below
+  bool wide = false;
   if (!PRELOADED) {
     if (!STREAMED) {
       // fused set-up: this CTA's own copy of the observations and of the statistics
       const ScaleInfo sc = setup_scale(g.range, g.obs, obs_s, g.n, g.n_pad, g.centred,
                                        g.reorder ? reinterpret_cast<float *>(after_stage) : nullptr,
                                        scratch);
+      if (WIDE) wide = g.wide > 0 || (g.wide == 0 && ProductSlopeWide::eligible(sc.umax, sc.seps));
       if (tid == 0) {
         *sc_s = sc;
-        if (cta == 0) *g.scale_out = sc;
+        if (cta == 0) {
+          *g.scale_out = sc;
+          g.scale_out->wide = wide ? 1.0 : 0.0;
+        }
       }
     } else {
       if (tid == 0) {
@@ -1359,6 +1425,10 @@ __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char 
       }
     }
   }
+  // this CTA's pool: an equal contiguous share of the groups, strip-major
+  const int ncw_run = wide ? (g.N + 32 * ProductSlopeWide::kCols - 1) / (32 * ProductSlopeWide::kCols) : g.ncw;
+  const long long units = (long long)ncw_run * g.groups;
+  const int pool_begin = (int)(units * cta / nctas), pool_end = (int)(units * (cta + 1) / nctas);
   if (tid == 0) claim[4] = pool_begin;
   __syncthreads();
 #ifdef CGE_DEBUG_TIMES
@@ -1390,6 +1460,18 @@ __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char 
     if (lane == 0) u0 = atomicAdd(const_cast<int *>(claim) + 4, g.chunk);
     u0 = __shfl_sync(0xffffffffu, u0, 0);
     int u1 = min(u0 + g.chunk, pool_end);
+    if constexpr (WIDE) {
+      if (wide) {
+        while (u0 < pool_end) {
+          const int cw = u0 / g.groups;
+          ScaleInfo sc = *sc_s;
+          sc.umax = strip_umax(g.range, cw, 32 * ProductSlopeWide::kCols, sc.ustep);
+          run_strip<ProductSlopeWide, false, NT>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim,
+                                                 claim_par, streams);
+        }
+        return;
+      }
+    }
     while (u0 < pool_end) dispatch(u0 / g.groups, u0, u1);
     return;
   }
@@ -1408,7 +1490,7 @@ __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char 
 }
 
 template <class Finest, class Fine, class Mid, class Coarse, bool SELECT, int MINB = 1,
-          bool STREAMED = false, int WARPS = kWarps>
+          bool STREAMED = false, int WARPS = kWarps, bool WIDE = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
     grid_likelihood_kernel(const LikeArgs g) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -1420,13 +1502,13 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   unsigned long long t0 = 0;
   if (g.debug && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
 #endif
-  likelihood_cta<Finest, Fine, Mid, Coarse, SELECT, false, STREAMED, WARPS * 32>(g, smem_raw, scratch,
-                                                                               blockIdx.x, gridDim.x);
+  likelihood_cta<Finest, Fine, Mid, Coarse, SELECT, false, STREAMED, WARPS * 32, WIDE>(g, smem_raw, scratch,
+                                                                                     blockIdx.x, gridDim.x);
 #ifdef CGE_DEBUG_TIMES
   if (g.debug && (threadIdx.x & 31) == 0) {  // per warp: when it ran out of work
     unsigned long long tw;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tw));
-    g.debug[4 * gridDim.x + WARPS * blockIdx.x + (threadIdx.x >> 5)] = tw;
+    g.debug[4 * gridDim.x + 32 * blockIdx.x + (threadIdx.x >> 5)] = tw;  // (32 slots per CTA)
   }
   if (g.debug && threadIdx.x == 0) {
     unsigned long long t1;

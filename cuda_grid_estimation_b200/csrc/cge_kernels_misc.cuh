@@ -184,6 +184,59 @@ __device__ __forceinline__ double ld_peer(const double *p) {
   return v;
 }
 
+// the scale pass of one launch: post[0..cells) *= 1/Z in place, or post64 = post * (1/Z)
+__device__ __forceinline__ void scale_pass(float *post, double *post64, size_t cells, double inv,
+                                           int aligned) {
+  const int tid = threadIdx.x;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  size_t i = (size_t)blockIdx.x * blockDim.x + tid;
+  if (post64 != nullptr) {  // float32 likelihoods in, float64 posterior out (normalised in float64)
+    if (aligned) {
+      const size_t nvec = cells >> 2;
+      const float4 *s4 = reinterpret_cast<const float4 *>(post);
+      double2 *d2 = reinterpret_cast<double2 *>(post64);
+      for (; i + stride < nvec; i += 2 * stride) {
+        const float4 p = s4[i], q = s4[i + stride];
+        d2[2 * i] = make_double2((double)p.x * inv, (double)p.y * inv);
+        d2[2 * i + 1] = make_double2((double)p.z * inv, (double)p.w * inv);
+        d2[2 * (i + stride)] = make_double2((double)q.x * inv, (double)q.y * inv);
+        d2[2 * (i + stride) + 1] = make_double2((double)q.z * inv, (double)q.w * inv);
+      }
+      for (; i < nvec; i += stride) {
+        const float4 p = s4[i];
+        d2[2 * i] = make_double2((double)p.x * inv, (double)p.y * inv);
+        d2[2 * i + 1] = make_double2((double)p.z * inv, (double)p.w * inv);
+      }
+      if (blockIdx.x == 0 && tid < (int)(cells & 3))
+        post64[(nvec << 2) + tid] = (double)post[(nvec << 2) + tid] * inv;
+    } else {
+      for (; i < cells; i += stride) post64[i] = (double)post[i] * inv;
+    }
+    return;
+  }
+  const float finv = (float)inv;
+  if (aligned) {
+    const size_t nvec = cells >> 2;
+    float4 *p4 = reinterpret_cast<float4 *>(post);
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+      float4 p = p4[i], q = p4[i + stride], r = p4[i + 2 * stride], s = p4[i + 3 * stride];
+      p.x *= finv; p.y *= finv; p.z *= finv; p.w *= finv;
+      q.x *= finv; q.y *= finv; q.z *= finv; q.w *= finv;
+      r.x *= finv; r.y *= finv; r.z *= finv; r.w *= finv;
+      s.x *= finv; s.y *= finv; s.z *= finv; s.w *= finv;
+      p4[i] = p; p4[i + stride] = q; p4[i + 2 * stride] = r; p4[i + 3 * stride] = s;
+    }
+    for (; i < nvec; i += stride) {
+      float4 p = p4[i];
+      p.x *= finv; p.y *= finv; p.z *= finv; p.w *= finv;
+      p4[i] = p;
+    }
+    if (blockIdx.x == 0 && tid < (int)(cells & 3)) post[(nvec << 2) + tid] *= finv;
+  } else {  // a posterior pointer that is not 16-byte aligned (caller-owned sub-buffers)
+    for (; i < cells; i += stride) post[i] *= finv;
+  }
+}
+
 __global__ void __launch_bounds__(256) finish_kernel(const FinishArgs a) {
   __shared__ double scratch[32];
   __shared__ bool is_last;
@@ -264,54 +317,22 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishArgs a) {
     }
   }
 
-  // ---- the scale pass
-  const size_t stride = (size_t)gridDim.x * blockDim.x;
-  size_t i = (size_t)blockIdx.x * blockDim.x + tid;
-  if (a.post64 != nullptr) {  // float32 likelihoods in, float64 posterior out (normalised in float64)
-    if (a.aligned) {
-      const size_t nvec = a.cells >> 2;
-      const float4 *s4 = reinterpret_cast<const float4 *>(a.post);
-      double2 *d2 = reinterpret_cast<double2 *>(a.post64);
-      for (; i + stride < nvec; i += 2 * stride) {
-        const float4 p = s4[i], q = s4[i + stride];
-        d2[2 * i] = make_double2((double)p.x * inv, (double)p.y * inv);
-        d2[2 * i + 1] = make_double2((double)p.z * inv, (double)p.w * inv);
-        d2[2 * (i + stride)] = make_double2((double)q.x * inv, (double)q.y * inv);
-        d2[2 * (i + stride) + 1] = make_double2((double)q.z * inv, (double)q.w * inv);
-      }
-      for (; i < nvec; i += stride) {
-        const float4 p = s4[i];
-        d2[2 * i] = make_double2((double)p.x * inv, (double)p.y * inv);
-        d2[2 * i + 1] = make_double2((double)p.z * inv, (double)p.w * inv);
-      }
-      if (blockIdx.x == 0 && tid < (int)(a.cells & 3))
-        a.post64[(nvec << 2) + tid] = (double)a.post[(nvec << 2) + tid] * inv;
-    } else {
-      for (; i < a.cells; i += stride) a.post64[i] = (double)a.post[i] * inv;
-    }
-    return;
-  }
-  const float finv = (float)inv;
-  if (a.aligned) {
-    const size_t nvec = a.cells >> 2;
-    float4 *p4 = reinterpret_cast<float4 *>(a.post);
-    for (; i + 3 * stride < nvec; i += 4 * stride) {
-      float4 p = p4[i], q = p4[i + stride], r = p4[i + 2 * stride], s = p4[i + 3 * stride];
-      p.x *= finv; p.y *= finv; p.z *= finv; p.w *= finv;
-      q.x *= finv; q.y *= finv; q.z *= finv; q.w *= finv;
-      r.x *= finv; r.y *= finv; r.z *= finv; r.w *= finv;
-      s.x *= finv; s.y *= finv; s.z *= finv; s.w *= finv;
-      p4[i] = p; p4[i + stride] = q; p4[i + 2 * stride] = r; p4[i + 3 * stride] = s;
-    }
-    for (; i < nvec; i += stride) {
-      float4 p = p4[i];
-      p.x *= finv; p.y *= finv; p.z *= finv; p.w *= finv;
-      p4[i] = p;
-    }
-    if (blockIdx.x == 0 && tid < (int)(a.cells & 3)) a.post[(nvec << 2) + tid] *= finv;
-  } else {  // a posterior pointer that is not 16-byte aligned (caller-owned sub-buffers)
-    for (; i < a.cells; i += stride) a.post[i] *= finv;
-  }
+  scale_pass(a.post, a.post64, a.cells, inv, a.aligned);
+}
+
+// Further row chunks of the same posterior (cge_grid_posterior with a host posterior scales and
+// copies chunk by chunk, so the PCIe copy of one chunk overlaps the scale pass of the next)
+struct ScaleChunkArgs {
+  const double *results;  // results[3] = 1/Z, written by the finish kernel
+  float *post;
+  double *post64;
+  size_t cells;
+  int aligned;
+};
+__global__ void __launch_bounds__(256) scale_chunk_kernel(const ScaleChunkArgs a) {
+  pdl_trigger();
+  pdl_wait();
+  scale_pass(a.post, a.post64, a.cells, a.results[3], a.aligned);
 }
 
 // largest |v| of a float array as the bit pattern of a non-negative float (which orders like the

@@ -3,12 +3,13 @@
 
 namespace cge_host {
 
-template <class P, int MINB, bool STREAMED>
+template <class P, int MINB, bool STREAMED, int WARPS = cge::kWarps>
 static KernelChoice pick() {
   KernelChoice kc;
   kc.smem_bytes = cge::policy_smem_bytes<P>();
   kc.kcols = P::kCols;
-  kc.fn = (const void *)cge::grid_likelihood_kernel<P, P, P, P, false, MINB, STREAMED>;
+  kc.threads = WARPS * 32;
+  kc.fn = (const void *)cge::grid_likelihood_kernel<P, P, P, P, false, MINB, STREAMED, WARPS>;
   return kc;
 }
 
@@ -20,7 +21,11 @@ int choose_logspace(const Plan &pl, KernelChoice *out) {
   if (pl.variant == CGE_VARIANT_LOG_F64)
     *out = pl.streamed ? pick<cge::LogSpaceF64, 1, true>() : pick<cge::LogSpaceF64, 1, false>();
   else
-    *out = pl.streamed ? pick<cge::LogSpaceTiled<256>, 2, true>() : pick<cge::LogSpaceTiled<256>, 2, false>();
+    // (<= 128 registers either way: two 8-warp CTAs per SM, or -- like the product kernel -- one
+    // 16-warp CTA whose warps share a single pool)
+    *out = pl.streamed ? pick<cge::LogSpaceTiled<256>, 2, true>()
+           : pl.cta_warps != 8 ? pick<cge::LogSpaceTiled<256>, 1, false, 16>()
+                                        : pick<cge::LogSpaceTiled<256>, 2, false>();
   return CGE_OK;
 }
 

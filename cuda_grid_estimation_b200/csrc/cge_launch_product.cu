@@ -3,13 +3,16 @@
 
 namespace cge_host {
 
-template <class Finest, class Fine, class Mid, class Coarse, bool SELECT, int MINB, int WARPS = cge::kWarps>
+template <class Finest, class Fine, class Mid, class Coarse, bool SELECT, int MINB, int WARPS = cge::kWarps,
+          bool WIDE = false>
 static KernelChoice pick() {
   KernelChoice kc;
   kc.smem_bytes = smem_bytes4<Finest, Fine, Mid, Coarse>();
+  if (WIDE && cge::policy_smem_bytes<cge::ProductSlopeWide>() > kc.smem_bytes)
+    kc.smem_bytes = cge::policy_smem_bytes<cge::ProductSlopeWide>();
   kc.kcols = Fine::kCols;
   kc.threads = WARPS * 32;
-  kc.fn = (const void *)cge::grid_likelihood_kernel<Finest, Fine, Mid, Coarse, SELECT, MINB, false, WARPS>;
+  kc.fn = (const void *)cge::grid_likelihood_kernel<Finest, Fine, Mid, Coarse, SELECT, MINB, false, WARPS, WIDE>;
   return kc;
 }
 
@@ -39,10 +42,12 @@ int choose_product(const Plan &pl, KernelChoice *out) {
       *out = pick<DefaultCoarse, DefaultCoarse, DefaultCoarse, DefaultCoarse, false, 1>();
       break;
     default:
-      if (pl.cta_warps == kWideWarps)
-        *out = pick<DefaultFinest, DefaultFine, DefaultMid, DefaultCoarse, true, 1, kWideWarps>();
-      else
+      // one CTA per SM (a single pool for all its warps) that also holds the 8-column wide policy;
+      // CGE_CTA_WARPS=8: the three-CTA shape without it (A/B runs)
+      if (pl.cta_warps == 8)
         *out = pick<DefaultFinest, DefaultFine, DefaultMid, DefaultCoarse, true, kDefaultMinB>();
+      else
+        *out = pick<DefaultFinest, DefaultFine, DefaultMid, DefaultCoarse, true, 1, kWideWarps, true>();
       break;
   }
   return CGE_OK;

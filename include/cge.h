@@ -104,6 +104,9 @@ enum {
   CGE_VARIANT_PAIRED3 = 8,   /* paired rows with the degree-3 polynomial, forced (|u| <= 0.05) */
   CGE_VARIANT_SLOPE = 9,     /* neighbour rows with the polynomial shared by a thread's four adjacent
                                 columns, forced (only accurate on the finest grids) */
+  CGE_VARIANT_SLOPE_WIDE = 10, /* the same with eight adjacent columns per thread (32-byte stores),
+                                forced; the default kernel takes it for the whole grid when the
+                                grid-level bounds allow it */
   CGE_VARIANT_LOG_F64 = 5,   /* log-space mode only: float64 accumulation, one DFMA per pdf-eval (the
                                 default log-space kernel sums centred terms in float32x2 tiles of 256
                                 observations and folds the tiles into float64) */
@@ -318,8 +321,11 @@ int cge_quantiles(cge_context *ctx, const double *marginal_dev, int n, const dou
  * likelihood on the grid, sample mean, sum of squared deviations, min_i sum_k (x_k - mu_i)^2,
  * log-space centre mu_c, sum_k (x_k - mu_c)^2, umax (largest exponent step between vertically
  * adjacent cells, over the whole grid), the bounds on umax below which the paired-rows product
- * kernel runs with its degree-2 and degree-3 polynomial, and ustep (umax per unit |a_j|: a column
- * band's own bound is max |a_j| over the band times ustep -- the kernel chooses per band). */
+ * kernel runs with its degree-2 and degree-3 polynomial, ustep (umax per unit |a_j|: a column
+ * band's own bound is max |a_j| over the band times ustep -- the kernel chooses per band),
+ * out[12..14] = the grid's bound on the relative change of a_j over four adjacent columns, the
+ * largest shared-slope error term the slope policies accept, and 1 when the step ran the
+ * 8-column wide policy. */
 int cge_scale_info(cge_context *ctx, double *out, int count, void *stream);
 
 /* ---- roofline micro-benchmarks (bench.py): measured pipe peaks on this device ------------

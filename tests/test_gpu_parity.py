@@ -220,11 +220,12 @@ def test_single_launch_small_grids(ctx, readme_obs, N):
 
 
 def test_single_launch_fine_small_grid_and_prior(ctx, readme_obs):
-    """The one-launch path also picks paired rows on a fine small grid, and honours a prior."""
+    """The one-launch path also picks neighbour rows (the shared-slope policy) on a fine small grid,
+    and honours a prior."""
     mu_r, sg_r = (19.4, 19.7), (1.7, 2.1)
     one = ctx.grid_posterior(readme_obs, 250, mu_r, sg_r)
-    assert one.launches == 1 and ctx.scale_info()["product_path"] == "paired"
-    forced = ctx.grid_posterior(readme_obs, 250, mu_r, sg_r, variant=api.VARIANT_PAIRED)
+    assert one.launches == 1 and ctx.scale_info()["product_path"] == "slope"
+    forced = ctx.grid_posterior(readme_obs, 250, mu_r, sg_r, variant=api.VARIANT_SLOPE)
     nz = forced.posterior > 0
     assert (np.abs(one.posterior - forced.posterior)[nz] / forced.posterior[nz]).max() < 2.5e-7
     N = 128
@@ -376,10 +377,11 @@ def _ref_4096(readme_obs):
     return _REF_4096["f64"]
 
 
-@pytest.mark.parametrize("variant", [0, 3, 8, 4, 1])
+@pytest.mark.parametrize("variant", [0, 9, 10, 3, 8, 4, 1])
 def test_paired_rows_variants_4096(ctx, readme_obs, variant):
-    """README ranges at N=4096: |u| <= 0.0084, inside the paired kernel's bound (0.011).  Every
-    paired variant (and the hybrid one it replaces here) against the float64 oracle."""
+    """README ranges at N=4096: |u| <= 0.0084, inside the neighbour-row kernels' bound (0.011), and
+    the shared-slope term at 3.3e-8 (bound 4e-8).  Every neighbour-row variant (and the hybrid one
+    they replace here) against the float64 oracle."""
     res = ctx.grid_posterior(readme_obs, 4096, (18, 22), (1, 3), variant=variant)
     d = check_against(res, _ref_4096(readme_obs), what=f"variant {variant} N=4096 vs F64")
     assert d < 1e-6
@@ -387,13 +389,15 @@ def test_paired_rows_variants_4096(ctx, readme_obs, variant):
 
 def test_default_picks_the_path_on_the_device(ctx, readme_obs):
     """The default kernel chooses its arithmetic from ScaleInfo::umax (ranges, N and the
-    observations, all on the device).  README ranges: N=512 is too coarse for paired rows
-    (|u| <= 0.067 -> hybrid), N=1024 takes the degree-3 polynomial (0.034), N=4096 the degree-2
-    one (0.0084); each is bit-identical to the corresponding forced variant and differs from the
+    observations, all on the device).  README ranges: N=512 is too coarse for neighbour rows
+    (|u| <= 0.067 -> hybrid), N=1024 takes the degree-3 polynomial (0.034), N=3300 the degree-2
+    one (0.0105, shared-slope term 6.4e-8 > 4e-8), N=4096 the shared-slope policy (0.0084,
+    3.3e-8); each is bit-identical to the corresponding forced variant and differs from the
     others.  A far-out observation raises |u| and moves N=4096 to the degree-3 polynomial."""
-    forced = {"hybrid": api.VARIANT_HYBRID, "paired3": api.VARIANT_PAIRED3, "paired": api.VARIANT_PAIRED}
+    forced = {"hybrid": api.VARIANT_HYBRID, "paired3": api.VARIANT_PAIRED3, "paired": api.VARIANT_PAIRED,
+              "slope": api.VARIANT_SLOPE}
     bw = api.band_columns(0)
-    for N, want in ((512, "hybrid"), (1024, "paired3"), (4096, "paired")):
+    for N, want in ((512, "hybrid"), (1024, "paired3"), (3300, "paired"), (4096, "slope")):
         d = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_UNFUSED)
         info = ctx.scale_info()
         assert info["product_path"] == want
@@ -409,19 +413,21 @@ def test_default_picks_the_path_on_the_device(ctx, readme_obs):
                 ratio = d.posterior[row, sl].astype(np.float64) / f.posterior[row, sl].astype(np.float64)
                 if took == name:
                     assert np.ptp(ratio) < 3e-7, (N, b, name, np.ptp(ratio))
-                elif b == 0:   # (far strips: the degree-2 and degree-3 factors agree to rounding)
+                elif b == 0 and N <= 1024:
+                    # (far strips and finer grids: the policies agree to rounding)
                     assert np.ptp(ratio) > 3e-7, (N, b, name, took, np.ptp(ratio))
     # The choice is per column band (|u| scales with 0.72 / sigma^2).  A far-out observation
     # (reach 12 instead of ~5: |u| <= 0.017 at sigma = 1) moves only the band at the smallest
-    # sigma of the N=4096 grid to the degree-3 polynomial; the other three stay on degree 2.
+    # sigma of the N=4096 grid to the degree-3 polynomial; the next ones take degree 2 and, as
+    # sigma grows, the shared-slope policy.
     far = readme_obs.copy()
     far[0] = 30.0
     d = ctx.grid_posterior(far, 4096, (18, 22), (1, 3))
     info = ctx.scale_info()
     assert info["product_path"] == "paired3"
     paths = api.band_paths(info, oracle.linspace(4096, 1, 3))
-    assert paths[0] == "paired3" and paths[-1] == "paired" and "hybrid" not in paths
-    for name in ("paired", "paired3"):
+    assert paths[0] == "paired3" and paths[-1] == "slope" and "hybrid" not in paths
+    for name in ("paired", "paired3", "slope"):
         f = ctx.grid_posterior(far, 4096, (18, 22), (1, 3), variant=forced[name])
         for b, want in enumerate(paths):
             same = d.posterior[:, b * bw:(b + 1) * bw].tobytes() == f.posterior[:, b * bw:(b + 1) * bw].tobytes()
@@ -434,20 +440,39 @@ def test_default_picks_the_path_on_the_device(ctx, readme_obs):
     # a wide sigma range: hybrid only where sigma is small, paired rows in the other bands
     d = ctx.grid_posterior(readme_obs, 4096, (18, 22), (0.4, 3))
     paths = api.band_paths(ctx.scale_info(), oracle.linspace(4096, 0.4, 3))
-    assert paths[0] != "paired" and paths[-1] == "paired", paths
+    assert paths[0] not in ("paired", "slope") and paths[-1] == "slope", paths
     check_against(d, oracle.grid_posterior(readme_obs, 4096, 18, 22, 0.4, 3, oracle.NUM_F64),
                   what="wide sigma range, N=4096")
 
 
 @pytest.mark.parametrize("N", [2, 3, 64, 130, 301, 700, 1026])
 def test_paired_rows_on_small_fine_grids(ctx, readme_obs, N):
-    """Narrow ranges make a small grid fine enough for the paired kernel, so it also runs in the
-    narrow tile shapes, with odd N (last row has no partner) and N not a multiple of 4."""
+    """Narrow ranges make a small grid fine enough for the neighbour-row kernels, so they also run
+    in the narrow tile shapes, with odd N (last row has no partner) and N not a multiple of 4."""
     mu_r, sg_r = ((19.4, 19.7) if N > 64 else (19.5, 19.5 + 2e-3 * (N - 1))), (1.7, 2.1)
     d = ctx.grid_posterior(readme_obs, N, mu_r, sg_r)
-    forced = ctx.grid_posterior(readme_obs, N, mu_r, sg_r, variant=api.VARIANT_PAIRED)
-    assert d.posterior.tobytes() == forced.posterior.tobytes()
+    info = ctx.scale_info()
+    took = info["product_path"]
+    assert took in ("slope8", "slope", "paired")   # (small N: the sigma columns are too far apart for "slope")
+    variants = {"slope8": api.VARIANT_SLOPE_WIDE, "slope": api.VARIANT_SLOPE, "paired": api.VARIANT_PAIRED}
+    paths = api.band_paths(info, oracle.linspace(N, *sg_r))
+    assert set(paths) <= set(variants)
+    if len(set(paths)) == 1:
+        forced = ctx.grid_posterior(readme_obs, N, mu_r, sg_r, variant=variants[took])
+        assert d.posterior.tobytes() == forced.posterior.tobytes()
+    else:   # the column bands differ (N = 130: the two columns of the second band are eligible for
+            # "slope", the first band is not): same arithmetic in a band <=> a constant ratio
+        bw = api.band_columns(N)
+        for b, name in enumerate(paths):
+            f = ctx.grid_posterior(readme_obs, N, mu_r, sg_r, variant=variants[name])
+            sl = slice(b * bw, min((b + 1) * bw, N))
+            ratio = d.posterior[N // 2, sl].astype(np.float64) / f.posterior[N // 2, sl].astype(np.float64)
+            assert np.ptp(ratio) < 3e-7, (N, b, name, np.ptp(ratio))
     ref = oracle.grid_posterior(readme_obs, N, *mu_r, *sg_r, oracle.NUM_F64)
+    for name, variant in variants.items():
+        if name != took:
+            other = ctx.grid_posterior(readme_obs, N, mu_r, sg_r, variant=variant)
+            check_against(other, ref, what=f"narrow ranges N={N}, forced {name}")
     check_against(d, ref, what=f"narrow ranges N={N}")
 
 
@@ -458,10 +483,14 @@ def test_paired_rows_observation_counts(ctx, n):
     obs = oracle.readme_observations(n=n, seed=7)
     for N, mu_r in ((200, (19.9, 20.1)), (1100, (19.6, 20.4))):
         sg_r = (1.6, 2.4)
-        res = ctx.grid_posterior(obs, N, mu_r, sg_r)
-        assert ctx.scale_info()["product_path"] == "paired"
         ref = oracle.grid_posterior(obs, N, *mu_r, *sg_r, oracle.NUM_F64)
-        check_against(res, ref, what=f"paired n={n} N={N}")
+        res = ctx.grid_posterior(obs, N, mu_r, sg_r)
+        # (the single launch at N = 200 has the 4-column policies only; N = 1100 runs the wide one)
+        assert ctx.scale_info()["product_path"] == ("slope" if N == 200 else "slope8")
+        check_against(res, ref, what=f"default n={n} N={N}")
+        for variant in (api.VARIANT_PAIRED, api.VARIANT_SLOPE, api.VARIANT_SLOPE_WIDE):
+            res = ctx.grid_posterior(obs, N, mu_r, sg_r, variant=variant)
+            check_against(res, ref, what=f"variant {variant} n={n} N={N}")
 
 
 def test_descending_and_sign_crossing_ranges(ctx):
@@ -476,7 +505,7 @@ def test_descending_and_sign_crossing_ranges(ctx):
                 ref = oracle.grid_posterior(obs, N, *mu_r, *sg_r, num)
                 check_against(res, ref, what=f"N={N} mu={mu_r} sigma={sg_r} mode={mode}")
     res = ctx.grid_posterior(obs, 2048, (0.6, -0.4), (0.7, 1.5))
-    assert ctx.scale_info()["product_path"] in ("paired", "paired3")
+    assert ctx.scale_info()["product_path"] in ("slope8", "slope", "paired", "paired3")
 
 
 def test_paired_rows_at_the_eligibility_bound(ctx, readme_obs):
@@ -487,6 +516,12 @@ def test_paired_rows_at_the_eligibility_bound(ctx, readme_obs):
         res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_PAIRED)
         ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_F64)
         check_against(res, ref, post_rel=rel_max, what=f"forced paired N={N}")
+    # shared slope: the dropped term is k2 u^2 eps = 3.3e-8 per factor at N = 4096 (the bound is
+    # 4e-8), 1.3e-7 at N = 2600
+    for N, rel_max in ((4096, 3e-5), (2600, 1e-4)):
+        res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_SLOPE)
+        ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_F64)
+        check_against(res, ref, post_rel=rel_max, what=f"forced slope N={N}")
     for N, rel_max in ((700, 3e-5), (560, 1e-4)):  # degree 3: |u| <= 0.0495, 0.062
         res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_PAIRED3)
         ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_F64)
@@ -568,7 +603,7 @@ def test_65536_product_properties(ctx, readme_obs):
     dev = torch.device("cuda", 0)
     ranges = (18.0, 22.0, 1.0, 3.0)
     res = ctx.grid_posterior(readme_obs, N, ranges[:2], ranges[2:], posterior="device")
-    assert ctx.scale_info()["product_path"] == "paired"
+    assert ctx.scale_info()["product_path"] == "slope8"
     ptr, cnt = ctx.posterior_ptr()
     post = cge.device_tensor(ptr, cnt, "float32", 0).view(N, N)
     mu = torch.from_numpy(oracle.linspace(N, *ranges[:2]).astype(np.float64)).to(dev)

@@ -168,3 +168,22 @@ def test_step_is_three_launches(ctx, readme_obs):
     big = oracle.readme_observations(n=17000, seed=2)
     res = ctx.grid_posterior(big, 64, (19.9, 20.1), (1.9, 2.1), mode=cge.MODE_LOGSPACE)
     assert res.launches == 4     # + the staging of > 16384 observations
+
+
+@pytest.mark.parametrize("N,dtype", [(4100, "f32"), (3001, "f64")])
+def test_host_posterior_is_copied_in_row_chunks(ctx, readme_obs, N, dtype):
+    """A posterior that goes to host memory and is larger than 64 MB is scaled and copied in row
+    chunks (the finish kernel scales the first, scale_chunk_kernel the others, the copies run on a
+    second stream): same bits as the posterior left on the device, N odd-sized so the chunks are
+    not 16-byte aligned in the float32 case."""
+    import torch
+    f64 = dtype == "f64"
+    kw = dict(posterior_dtype=api.POSTERIOR_F64) if f64 else {}
+    host = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), **kw)   # posterior -> numpy
+    assert host.launches > 3   # likelihood, fold, finish + one scale launch per further chunk
+    dev = torch.empty((N, N), dtype=torch.float64 if f64 else torch.float32, device="cuda:0")
+    res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), posterior=dev, **kw)
+    assert res.launches == 3
+    assert dev.cpu().numpy().tobytes() == host.posterior.tobytes()
+    assert res.expectations.tobytes() == host.expectations.tobytes()
+    assert abs(host.posterior.astype(np.float64).sum() - 1.0) <= 1e-6

@@ -25,14 +25,15 @@ with cge.Context(0) as ctx:
         ctx.likelihood_partials(p, obs_t, post, None)
         ctx.finalize(p, post, None)
     torch.cuda.synchronize()
-    buf = np.zeros(12 * 4096, np.uint64)
+    buf = np.zeros(36 * 4096, np.uint64)
     cnt = C.c_int()
     lib = cge.load_library()
     lib.cge_debug_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
     assert lib.cge_debug_times(ctx._h, buf.ctypes.data, 4096, C.byref(cnt)) == 0
     t = buf[:4 * cnt.value].reshape(-1, 4).astype(np.int64)
     t0 = t[:, 0].min()
-    wend = buf[4 * cnt.value:12 * cnt.value].reshape(-1, 8).astype(np.int64) - t0
+    wend = buf[4 * cnt.value:36 * cnt.value].reshape(-1, 32).astype(np.int64)
+    wend = wend[:, (wend != 0).any(axis=0)] - t0   # (32 slots per CTA; a CTA has 8, 16 or 20 warps)
     kend = wend.max()
     print(json.dumps({"warp_end_us": {"min": float(wend.min()) / 1e3, "p10": float(np.percentile(wend, 10)) / 1e3,
                                       "median": float(np.median(wend)) / 1e3, "p90": float(np.percentile(wend, 90)) / 1e3,
