@@ -400,10 +400,18 @@ def _scale_info(self, stream=None) -> dict:
 _K2 = 0.2402265069591007   # ln(2)^2 / 2
 
 
-def _product_path(info: dict, umax: float, eps: float) -> str:
+def slope_error_bound(umax: float, rstep: float, steps: float = 1.5) -> float:
+    """Largest shared-slope term per factor (cge::ProductSlopeT::eligible): k2 U^2 eps, with
+    eps = 2x(1 + 1.5x), x = steps * relative sigma step (1.5 columns for the 4-column policy, 3.5
+    for the wide one), 1 % on top."""
+    x = steps * rstep * 1.01
+    return _K2 * umax * umax * 2.0 * x * (1.0 + 1.5 * x)
+
+
+def _product_path(info: dict, umax: float, rstep: float) -> str:
     """Mirror of the device-side choice (cge::likelihood_cta): the first eligible of slope,
     paired (degree 2), paired3 (degree 3), hybrid."""
-    if umax <= info["paired_umax"] and _K2 * umax * umax * eps <= info["slope_err_max"]:
+    if umax <= info["paired_umax"] and slope_error_bound(umax, rstep) <= info["slope_err_max"]:
         return "slope"
     if umax <= info["paired_umax"]:
         return "paired"
@@ -419,7 +427,7 @@ def band_columns(grid_size: int) -> int:
 def band_paths(info: dict, sigma: np.ndarray) -> list:
     """Which product policy each column band takes, from scale_info() and the sigma table:
     mirrors cge::strip_umax (|a_j| = 0.5*log2(e)/sigma_j^2 at the band's two ends) and
-    cge::strip_slope_eps (4 column steps over the band's smallest sigma)."""
+    cge::strip_sigma_step (the column step over the band's smallest sigma)."""
     if info.get("wide"):
         return ["slope8"] * ((len(sigma) + 127) // 128)
     out = []
@@ -431,7 +439,7 @@ def band_paths(info: dict, sigma: np.ndarray) -> list:
         s0, s1 = float(sigma[j0]), float(sigma[j1])
         a = max(0.5 * 1.4426950408889634 / s0 ** 2, 0.5 * 1.4426950408889634 / s1 ** 2)
         smin = min(abs(s0), abs(s1))
-        eps = 4.0 * ds / smin if smin > 0 and s0 * s1 > 0 else 1e300
+        eps = ds / smin if smin > 0 and s0 * s1 > 0 else 1e300
         out.append(_product_path(info, a * info["ustep"], eps))
     return out
 

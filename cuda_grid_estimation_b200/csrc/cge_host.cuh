@@ -42,7 +42,7 @@ struct Plan {
   int nb_col = 0, nb_row = 0, nb_res = 0;
   bool vec4 = false, keep_l2 = false, streamed = false, reorder = false;
   bool cluster = false;    // small-grid path: launch the grid as one thread-block cluster
-  int cta_warps = 0;       // product path: warps per CTA (8 x 3 CTAs per SM, or one CTA of 24)
+  int cta_warps = 0;       // CGE_CTA_WARPS knob (0 = the default CTA shape)
   size_t smem = 0;         // dynamic shared memory of the likelihood kernel
 };
 

@@ -71,7 +71,7 @@ struct ScaleInfo {
   double s_c;    // log-space: sum_k (x_k - mu_c)^2
   double umax;   // bound on |t_(i+1,j,k) - t_(i,j,k)| over adjacent mu rows, whole grid
   double ustep;  // the same bound per unit |a_j|: umax of a column band = max |a_j| in it * ustep
-  double seps;   // bound on the relative change of a_j over a thread's 4 columns, whole grid (ProductSlope)
+  double seps;   // relative sigma step |dsigma| / min |sigma| of the whole grid (slope policies' eligibility)
   double wide;   // 1 when the step ran the 8-column wide product policy (reporting only)
 };
 
@@ -313,7 +313,7 @@ __device__ __forceinline__ ScaleInfo setup_scale(const RangeArgs &r, const float
     const double sabs = fmin(fabs((double)sg0), fabs((double)sg1));
     out.wide = 0.0;
     out.seps = (N > 1 && sabs > 0.0 && (double)sg0 * (double)sg1 > 0.0)
-                   ? 4.0 * fabs((double)sg1 - (double)sg0) / (double)(N - 1) / sabs
+                   ? fabs((double)sg1 - (double)sg0) / (double)(N - 1) / sabs
                    : (N > 1 ? 1e300 : 0.0);
   }
   __syncthreads();  // the stage is complete for every thread of the block
@@ -476,11 +476,13 @@ struct LogSpaceTiled {
   f32x2 a2[kPairs];
   double acc[kRows][kCols];
   double mu_c_;
+  bool vec_;  // always true, but only known at run time (see consume)
 
   template <int NT>
   __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
                                                const ColumnCoefs<kCols> &cf, double *own) {
     mu_c_ = sc.mu_c;
+    vec_ = g.n >= 0;
 #pragma unroll
     for (int h = 0; h < kPairs; ++h) a2[h] = pack2((float)cf.a[2 * h], (float)cf.a[2 * h + 1]);
 #pragma unroll
@@ -524,8 +526,13 @@ struct LogSpaceTiled {
 #pragma unroll
     for (int r = 0; r < kRows; ++r) {
       const float m = (float)((double)mu[r] - pol.mu_c_);
-      gm[r] = -2.0f * m;
-      gb[r] = m * m;
+      // The rows are warp-uniform, and ptxas keeps warp-uniform scalars in uniform registers --
+      // from where each FFMA below (two such operands) needs a MOV first: 12 of the loop's 99
+      // instructions.  A select against a lane-dependent value (never taken) makes them ordinary
+      // vector registers.
+      const float lane_val = __int_as_float((int)threadIdx.x);
+      gm[r] = pol.vec_ ? -2.0f * m : lane_val;
+      gb[r] = pol.vec_ ? m * m : lane_val;
     }
     f32x2 t2[kRows][kPairs];
     const f32x2 zero = pack2(0.0f, 0.0f);
@@ -844,11 +851,12 @@ struct ProductNeighbour {
 // theirs, f = e * 2^u, u = a_j g_rk -- but the polynomial is evaluated once per (row, observation)
 // instead of once per cell.  With a_0 the mean |a_j| slope of the thread's four adjacent columns,
 //   2^u - 1 = a_j g (k1 + k2 a_j g) = a_j H_rk + a_j (a_j - a_0) k2 g^2,   H_rk = g (k1 + k2 a_0 g),
-// and the last term is dropped: adjacent sigma columns differ by eps = |a_j - a_0| / |a_j| <=
-// 3 dsigma / sigma, so it is at most k2 U^2 eps (3e-9 on the 16384^2 README grid: a twentieth of
-// the float32 rounding of the factor itself).  The policy is eligible while that bound stays
-// below kSlopeErr and U <= kPairedUmax (cubic term, as ProductNeighbour<2>); coarser strips fall
-// back to ProductNeighbour.  Every pdf-eval still forms its own factor and multiplies it into its
+// and the last term is dropped.  a = -0.72/sigma^2, so a column `s` steps from the one a_0 belongs to
+// has |a_j - a_0| / |a_j| <= eps(s) = 2 x (1 + 1.5 x), x = s |dsigma| / sigma_min, and the dropped
+// term is at most k2 U^2 eps (1e-9 on the 16384^2 README grid).  The policy is eligible while that
+// bound stays below kSlopeErr = 2^-24 -- the float32 rounding unit of the factor itself -- and
+// U <= kPairedUmax (cubic term, as ProductNeighbour<2>); coarser strips fall back to
+// ProductNeighbour.  Every pdf-eval still forms its own factor and multiplies it into its
 // own running product:
 //   MUFU row   : FFMA2 (exponent), 2 MUFU.EX2, FMUL2 (product)                  per column pair
 //   shared     : FMUL2 (ea = e * a_j)                                           per triple and pair
@@ -863,16 +871,18 @@ struct ProductNeighbour {
 // strip is 256 columns = two row-partial slots), so the 6 packed row scalars are shared by twice
 // the cells -- 62 packed + 16 MUFU.EX2 per 48 evals instead of 68 + 16 -- and the per-group
 // epilogue (row sums, claims, range values) is paid once per 48 cells.  a_0 is then up to 3.5
-// column steps from a thread's outer columns instead of 1.5, so eps is scaled by 9.5 / 4.
-constexpr double kSlopeErr = 4.0e-8;
+// column steps from a thread's outer columns instead of 1.5.
+constexpr double kSlopeErr = 5.9604644775390625e-8;  // 2^-24
 template <int KC>
 struct ProductSlopeT {
   static_assert(KC == 4 || KC == 8, "4 columns (two groups' worth of one float4) or 8 adjacent ones");
   static constexpr double kUmax = kPairedUmax;
-  static constexpr double kEpsScale = KC == 8 ? 9.5 / 4.0 : 1.0;
-  // eps: the strip's (or grid's) bound for 4 adjacent columns (strip_slope_eps / ScaleInfo::seps)
-  static __device__ __forceinline__ bool eligible(double umax, double eps) {
-    return umax <= kPairedUmax && 0.2402265069591007 * umax * umax * (eps * kEpsScale) <= kSlopeErr;
+  static constexpr double kSteps = KC == 8 ? 3.5 : 1.5;  // columns between a_0 and the outermost one
+  // rstep: the strip's (or grid's) relative sigma step (strip_sigma_step / ScaleInfo::seps); 1 %
+  // on top for the float32 rounding of the range values
+  static __device__ __forceinline__ bool eligible(double umax, double rstep) {
+    const double x = kSteps * rstep * 1.01;
+    return umax <= kPairedUmax && 0.2402265069591007 * umax * umax * (2.0 * x * (1.0 + 1.5 * x)) <= kSlopeErr;
   }
   static constexpr bool kColSmem = true;
   static constexpr bool kAdjacent = KC == 8;
@@ -1355,18 +1365,15 @@ __device__ __forceinline__ double strip_umax(const RangeArgs &r, int cw, int str
   const double s1 = (double)range_value(jlast, r.N, r.sg0, r.sg1);
   return fmax(fabs(coef_a(s0)), fabs(coef_a(s1))) * ustep;
 }
-// Bound on |a_j - a_0| / |a_j| inside a thread's four adjacent columns of the strip, a_0 the mean
-// of the two middle ones (ProductSlope): a = -0.72/sigma^2, so one column step changes it by
-// |2 dsigma/sigma| to first order; 1.5 steps to the outer columns, with the second-order term and
-// the float32 rounding of the range values covered by taking 2 steps at the strip's smallest sigma.
-__device__ __forceinline__ double strip_slope_eps(const RangeArgs &r, int cw, int strip_cols) {
+// Relative sigma step of the strip, |dsigma| / min |sigma| (the slope policies' eligibility)
+__device__ __forceinline__ double strip_sigma_step(const RangeArgs &r, int cw, int strip_cols) {
   const int jfirst = cw * strip_cols;
   const int jlast = min(jfirst + strip_cols, r.N) - 1;
   const double s0 = (double)range_value(jfirst, r.N, r.sg0, r.sg1);
   const double s1 = (double)range_value(jlast, r.N, r.sg0, r.sg1);
   const double ds = r.N > 1 ? fabs((double)r.sg1 - (double)r.sg0) / (double)(r.N - 1) : 0.0;
   const double smin = fmin(fabs(s0), fabs(s1));
-  return (smin > 0.0 && s0 * s1 > 0.0) ? 4.0 * ds / smin : 1e300;  // (a strip across sigma = 0: never)
+  return (smin > 0.0 && s0 * s1 > 0.0) ? ds / smin : 1e300;  // (a strip across sigma = 0: never)
 }
 
 // ---------------------------------------------------------------------------------------
@@ -1444,7 +1451,7 @@ __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char 
   auto dispatch = [&](int cw, int &u0, int &u1) {
     ScaleInfo sc = *sc_s;
     sc.umax = strip_umax(g.range, cw, strip_cols, sc.ustep);  // the strip's own bound
-    const double eps = SELECT ? strip_slope_eps(g.range, cw, strip_cols) : 0.0;
+    const double eps = SELECT ? strip_sigma_step(g.range, cw, strip_cols) : 0.0;
     if (!SELECT || Finest::eligible(sc.umax, eps))
       run_strip<Finest, STREAMED, NT>(g, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim, claim_par, streams);
     else if (Fine::eligible(sc.umax, eps))

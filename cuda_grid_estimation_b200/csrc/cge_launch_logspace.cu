@@ -1,6 +1,9 @@
 // cge_launch_logspace.cu -- instantiations of the log-space likelihood kernels
 #include "cge_host.cuh"
 
+#ifndef CGE_LOG_WARPS
+#define CGE_LOG_WARPS 16
+#endif
 namespace cge_host {
 
 template <class P, int MINB, bool STREAMED, int WARPS = cge::kWarps>
@@ -24,7 +27,7 @@ int choose_logspace(const Plan &pl, KernelChoice *out) {
     // (<= 128 registers either way: two 8-warp CTAs per SM, or -- like the product kernel -- one
     // 16-warp CTA whose warps share a single pool)
     *out = pl.streamed ? pick<cge::LogSpaceTiled<256>, 2, true>()
-           : pl.cta_warps != 8 ? pick<cge::LogSpaceTiled<256>, 1, false, 16>()
+           : pl.cta_warps != 8 ? pick<cge::LogSpaceTiled<256>, 1, false, CGE_LOG_WARPS>()
                                         : pick<cge::LogSpaceTiled<256>, 2, false>();
   return CGE_OK;
 }

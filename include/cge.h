@@ -323,9 +323,8 @@ int cge_quantiles(cge_context *ctx, const double *marginal_dev, int n, const dou
  * adjacent cells, over the whole grid), the bounds on umax below which the paired-rows product
  * kernel runs with its degree-2 and degree-3 polynomial, ustep (umax per unit |a_j|: a column
  * band's own bound is max |a_j| over the band times ustep -- the kernel chooses per band),
- * out[12..14] = the grid's bound on the relative change of a_j over four adjacent columns, the
- * largest shared-slope error term the slope policies accept, and 1 when the step ran the
- * 8-column wide policy. */
+ * out[12..14] = the grid's relative sigma step |dsigma| / min |sigma|, the largest shared-slope
+ * error term the slope policies accept (2^-24), and 1 when the step ran the 8-column wide policy. */
 int cge_scale_info(cge_context *ctx, double *out, int count, void *stream);
 
 /* ---- roofline micro-benchmarks (bench.py): measured pipe peaks on this device ------------

@@ -380,31 +380,34 @@ def _ref_4096(readme_obs):
 @pytest.mark.parametrize("variant", [0, 9, 10, 3, 8, 4, 1])
 def test_paired_rows_variants_4096(ctx, readme_obs, variant):
     """README ranges at N=4096: |u| <= 0.0084, inside the neighbour-row kernels' bound (0.011), and
-    the shared-slope term at 3.3e-8 (bound 4e-8).  Every neighbour-row variant (and the hybrid one
-    they replace here) against the float64 oracle."""
+    the shared-slope term at 5.85e-8 for 8 columns (bound 2^-24 = 5.96e-8).  Every neighbour-row
+    variant (and the hybrid one they replace here) against the float64 oracle."""
     res = ctx.grid_posterior(readme_obs, 4096, (18, 22), (1, 3), variant=variant)
     d = check_against(res, _ref_4096(readme_obs), what=f"variant {variant} N=4096 vs F64")
     assert d < 1e-6
 
 
 def test_default_picks_the_path_on_the_device(ctx, readme_obs):
-    """The default kernel chooses its arithmetic from ScaleInfo::umax (ranges, N and the
-    observations, all on the device).  README ranges: N=512 is too coarse for neighbour rows
-    (|u| <= 0.067 -> hybrid), N=1024 takes the degree-3 polynomial (0.034), N=3300 the degree-2
-    one (0.0105, shared-slope term 6.4e-8 > 4e-8), N=4096 the shared-slope policy (0.0084,
-    3.3e-8); each is bit-identical to the corresponding forced variant and differs from the
-    others.  A far-out observation raises |u| and moves N=4096 to the degree-3 polynomial."""
+    """The default kernel chooses its arithmetic from ScaleInfo (ranges, N and the observations,
+    all on the device).  mu in [18, 22]: N=512 is too coarse for neighbour rows (|u| <= 0.067 ->
+    hybrid), N=1024 takes the degree-3 polynomial (0.034); N=3300 (0.0105) the degree-2 one when
+    the sigma columns are far apart (sigma in [1, 4]: shared-slope term 7.3e-8 > 2^-24) and the
+    shared-slope policy on sigma in [1, 3] (5.8e-8 for 4 columns, too much for 8); N=4096 runs
+    the 8-column wide policy on the whole grid.  Each is bit-identical to the corresponding forced
+    variant and differs from the others.  A far-out observation raises |u| and moves N=4096 to
+    the degree-3 polynomial."""
     forced = {"hybrid": api.VARIANT_HYBRID, "paired3": api.VARIANT_PAIRED3, "paired": api.VARIANT_PAIRED,
-              "slope": api.VARIANT_SLOPE}
+              "slope": api.VARIANT_SLOPE, "slope8": api.VARIANT_SLOPE_WIDE}
     bw = api.band_columns(0)
-    for N, want in ((512, "hybrid"), (1024, "paired3"), (3300, "paired"), (4096, "slope")):
-        d = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_UNFUSED)
+    for N, sg_r, want in ((512, (1, 3), "hybrid"), (1024, (1, 3), "paired3"), (3300, (1, 4), "paired"),
+                          (3300, (1, 3), "slope"), (4096, (1, 3), "slope8")):
+        d = ctx.grid_posterior(readme_obs, N, (18, 22), sg_r, variant=api.VARIANT_UNFUSED)
         info = ctx.scale_info()
-        assert info["product_path"] == want
-        paths = api.band_paths(info, oracle.linspace(N, 1, 3))
+        assert info["product_path"] == want, (N, sg_r, info)
+        paths = api.band_paths(info, oracle.linspace(N, *sg_r))
         assert paths[0] == want   # the strip at the smallest sigma is the most demanding one
         for name, variant in forced.items():
-            f = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=variant)
+            f = ctx.grid_posterior(readme_obs, N, (18, 22), sg_r, variant=variant)
             # same arithmetic in a strip <=> same unnormalised cells; the normaliser differs in the
             # last bits when other strips took another path, so compare ratios along a row
             for b, took in enumerate(paths):
@@ -516,12 +519,13 @@ def test_paired_rows_at_the_eligibility_bound(ctx, readme_obs):
         res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_PAIRED)
         ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_F64)
         check_against(res, ref, post_rel=rel_max, what=f"forced paired N={N}")
-    # shared slope: the dropped term is k2 u^2 eps = 3.3e-8 per factor at N = 4096 (the bound is
-    # 4e-8), 1.3e-7 at N = 2600
+    # shared slope: the dropped term is k2 u^2 eps per factor -- 4 columns: 2.5e-8 at N = 4096,
+    # 9.7e-8 at N = 2600; 8 columns: 5.85e-8 at N = 4096 (the bound is 2^-24 = 5.96e-8), 2.3e-7 at 2600
     for N, rel_max in ((4096, 3e-5), (2600, 1e-4)):
-        res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_SLOPE)
         ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_F64)
-        check_against(res, ref, post_rel=rel_max, what=f"forced slope N={N}")
+        for variant in (api.VARIANT_SLOPE, api.VARIANT_SLOPE_WIDE):
+            res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=variant)
+            check_against(res, ref, post_rel=rel_max, what=f"forced variant {variant} N={N}")
     for N, rel_max in ((700, 3e-5), (560, 1e-4)):  # degree 3: |u| <= 0.0495, 0.062
         res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_PAIRED3)
         ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_F64)

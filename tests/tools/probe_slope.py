@@ -31,5 +31,6 @@ with cge.Context(0) as ctx:
                 row["path"] = info["product_path"]
                 row["umax"] = info["umax"]
                 row["slope_eps"] = info["slope_eps"]
-                row["bound"] = 0.24 * info["umax"] ** 2 * info["slope_eps"]
+                row["bound4"] = api.slope_error_bound(info["umax"], info["slope_eps"], 1.5)
+                row["bound8"] = api.slope_error_bound(info["umax"], info["slope_eps"], 3.5)
         print(json.dumps(row), flush=True)
