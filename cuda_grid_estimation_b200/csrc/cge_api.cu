@@ -379,6 +379,7 @@ int fill_like_args(cge_context *ctx, const cge_params *p, const Plan &pl, const 
   args->rowpart = ctx->rowpart.ptr;
   args->colacc = ctx->colacc.ptr;
   args->strip_next = ctx->strip_next.ptr;
+  args->tickets = ctx->tickets.ptr;
   args->prior_log2max = 0.0f;
   if (args->prior_mu || args->prior_sigma || args->prior_full) {
     const size_t cells = (size_t)pl.rows_local * N;

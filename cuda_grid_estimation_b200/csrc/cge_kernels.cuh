@@ -7,9 +7,9 @@
 //   (inc/kernels.h:208-259), K8 computeExpectationsCuda (inc/cuda_functions.h:185-221).
 //
 // A step is THREE launches chained by programmatic dependent launch (one for grids up to 256^2):
-//   1. grid_likelihood_kernel  K1-K5 fused, persistent: one CTA per resident slot claims
-//                              (column band, row chunk) items from per-band counters until the
-//                              grid is done.  Each CTA derives the scale statistics and its own
+//   1. grid_likelihood_kernel  K1-K5 fused, persistent: one CTA per SM, its warps claiming row
+//                              groups from the CTA's pool until the grid is done (see "Work
+//                              decomposition").  Each CTA derives the scale statistics and its own
 //                              range values and column coefficients itself (no set-up launch, no
 //                              tables in HBM), writes the unnormalised cells, fixed-order partial
 //                              row sums, and column sums accumulated in exact fixed point.
@@ -82,19 +82,26 @@ struct RangeArgs {
 
 // Work decomposition of the likelihood kernel.  A GROUP is Policy::kRows rows of one warp-wide
 // column STRIP (32 * kCols columns); groups are numbered strip-major, u = strip * groups + group.
-// The grid is persistent (one CTA per resident slot of the device).  Every CTA owns an equal,
-// contiguous share of the groups -- its POOL -- and the worker is the WARP, not the CTA: the warps
-// of a CTA take `chunk` consecutive groups at a time from the pool through a shared-memory counter
-// and never synchronise after the set-up.  Measured reasons (B200, 16384^2 x 50):
+// The grid is persistent: ONE CTA PER SM (16 warps for the default product and log-space kernels).
+// Every CTA owns an equal, contiguous share of the groups -- its POOL -- and the worker is the
+// WARP, not the CTA: the warps of a CTA take `chunk` consecutive groups at a time from the pool
+// through a shared-memory counter (one claim ahead, so the atomic's latency is hidden) and never
+// synchronise after the set-up.  Measured reasons (B200, 16384^2 x 50; %globaltimer timelines in
+// profiles/r02_cta_timeline_*.log):
 //   * the warp scheduler does not share an SM fairly between its warps, so equal static shares per
 //     warp leave some warps finished early and the rest running at lower occupancy; a counter in
 //     shared memory balances the warps of a CTA at the cost of one ~100-cycle atomic per claim;
+//   * the same holds between CTAs: three 8-warp CTAs per SM with a pool each finished at 0.89,
+//     1.37 and 1.86 ms (mean warp residency 0.74); one CTA per SM with a single pool keeps every
+//     warp busy to the end (all CTAs within 1.1 % of each other, residency 0.98);
 //   * claims from per-strip counters in GLOBAL memory (the first design) cost an L2 round trip each,
-//     and the warp could not hide it: with one group per claim the kernel took 2.48 ms instead of
-//     1.83 ms, and small shards (2048 rows, one of 8 GPUs) ran at 63 % of the full grid's rate;
+//     and the warp could not hide it: with one group per claim the kernel took 2.48 ms, and small
+//     shards (2048 rows, one of 8 GPUs) ran at 63 % of the full grid's rate;
 //   * warps that move in lock step all reach the epilogue (stores, shuffles, float64) together and
 //     all return to the pipe-bound loop together; independent warps drift apart and the epilogue
-//     of one hides behind the arithmetic of the others.
+//     of one hides behind the arithmetic of the others;
+//   * leaving warps out so that a pool divides evenly among the rest does not pay: throughput
+//     falls by ~1.5 % per missing warp (profiles/r02_negative_working_warps_per_pool.jsonl).
 //
 // Results must not depend on who computed what.  Cells and partial row sums go to fixed places.
 // Column sums cross pools, so they are accumulated EXACTLY: every thread's kRows-row float32 sum is
@@ -127,6 +134,8 @@ struct LikeArgs {
   unsigned long long *colacc;  // [N] fixed-point column sums (zero at launch; the fold kernel clears them)
   int *strip_next;  // streamed only: [ncw] next unclaimed item of each strip (zero at launch; the fold
                     // kernel clears them)
+  unsigned int *tickets;  // "last block" tickets of the fold [0] and finish [1] kernels of this step:
+                          // zeroed here, so a step that failed half-way cannot poison the next one
   int n, n_pad, N;  // n observations; n_pad staged floats (multiple of 4)
   int row_begin, row_end;
   int groups;          // row groups (Policy::kRows rows each) that cover the shard's rows
@@ -1505,6 +1514,7 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
   pdl_trigger();  // the fold kernel may be made resident as this grid's CTAs retire
   pdl_wait();     // the previous step's finish kernel still reads the posterior this one overwrites,
                   // and the caller's kernels may have produced the observations
+  if (blockIdx.x == 0 && threadIdx.x < 2 && g.tickets) g.tickets[threadIdx.x] = 0u;
 #ifdef CGE_DEBUG_TIMES
   unsigned long long t0 = 0;
   if (g.debug && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));

@@ -203,6 +203,12 @@ int cge_peer_disconnect(cge_context *ctx);
 
 int cge_likelihood_partials(cge_context *ctx, const cge_params *p, const float *obs_dev,
                             void *posterior_dev, void *stream);
+/* Lifetime of the device pointers returned by cge_partials, cge_results and cge_posterior_dev:
+ * they point into the context's grow-only scratch and stay valid until the next call on this
+ * context with a LARGER grid, shard or observation count (which may re-allocate), cge_set_prior,
+ * or cge_destroy.  Their CONTENTS are overwritten by the next step.  One step at a time per
+ * context: the phase calls of two steps must not overlap on different streams (the context's
+ * scratch, accumulators and tickets are shared). */
 int cge_partials(cge_context *ctx, double **partials_dev, size_t *count);
 int cge_finalize(cge_context *ctx, const cge_params *p, void *posterior_dev, void *stream);
 /* result block on device: {E[mu], E[sigma], Z, 1/Z} then marg_sigma[N] then marg_mu[N]
