@@ -623,7 +623,7 @@ def run_ours(args):
                     "unit": "Gop/s (FP32 lane-ops)", "frac": 1.125 * ach / ffma_peak,
                     "traffic": traffic, "traffic_note": traffic_src,
                     "kernel": "grid_likelihood_kernel<LogSpaceTiled<256>>",
-                    "algorithmic": "1 packed-half FMA per pdf-eval + 1 scalar FMA per 8; evals per launch = rows*N*n",
+                    "algorithmic": "1 packed-half FMA per pdf-eval + 1 more per 8 (the per-row term, also packed); evals per launch = rows*N*n",
                     "executed": {"fma_lane_ops_per_eval": 1.125, "fma_util": 1.125 * ach / ffma_peak},
                     "evals_per_s": ach,
                     "peak_source": "FFMA micro-benchmark in this run (cge_microbench 1)"}

@@ -468,8 +468,8 @@ struct LogSpaceF64 {
 // small wherever the posterior is not negligible (|mu'| <= ~sqrt(66 / (n |a|)) for cells within
 // 1e-20 of the peak), so float32 tile sums (TILE = 256 observations) folded into float64 lose
 // ~7e-6 relative on a cell at n = 10^4 -- a plain float32 sum of a_j (x - mu)^2 would lose 1e-4.
-// Per (row, observation): one scalar FFMA (e = x' * (-2 mu') + mu'^2) shared by the 8 columns,
-// then 4 FFMA2.
+// Per (row, pair of observations): one FFMA2 (e = x' * (-2 mu') + mu'^2 of both) shared by the 8
+// columns, then 8 FFMA2 -- an all-packed stream, 72 FFMA2 per 4 observations.
 // ---------------------------------------------------------------------------------------
 template <int TILE = 256>
 struct LogSpaceTiled {
@@ -516,6 +516,27 @@ struct LogSpaceTiled {
       for (int h = 0; h < kPairs; ++h) t2[r][h] = fma2(e2, a2[h], t2[r][h]);
     }
   }
+  // two observations: the per-row terms e of both as one packed FMA (an all-packed instruction
+  // stream: 72 FFMA2 per 4 observations, measured 1.6 % faster than 16 FFMA + 64 FFMA2)
+  __device__ __forceinline__ void step2(f32x2 xc2, const float (&gm)[kRows], const float (&gb)[kRows],
+                                        f32x2 (&t2)[kRows][kPairs]) {
+    float e0[kRows], e1[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+      unpack2(fma2(xc2, pack2(gm[r], gm[r]), pack2(gb[r], gb[r])), e0[r], e1[r]);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const f32x2 ea = pack2(e0[r], e0[r]);
+#pragma unroll
+      for (int h = 0; h < kPairs; ++h) t2[r][h] = fma2(ea, a2[h], t2[r][h]);
+    }
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const f32x2 eb = pack2(e1[r], e1[r]);
+#pragma unroll
+      for (int h = 0; h < kPairs; ++h) t2[r][h] = fma2(eb, a2[h], t2[r][h]);
+    }
+  }
   __device__ __forceinline__ void fold(f32x2 (&t2)[kRows][kPairs]) {
     const f32x2 zero = pack2(0.0f, 0.0f);
 #pragma unroll
@@ -536,8 +557,8 @@ struct LogSpaceTiled {
     for (int r = 0; r < kRows; ++r) {
       const float m = (float)((double)mu[r] - pol.mu_c_);
       // The rows are warp-uniform, and ptxas keeps warp-uniform scalars in uniform registers --
-      // from where each FFMA below (two such operands) needs a MOV first: 12 of the loop's 99
-      // instructions.  A select against a lane-dependent value (never taken) makes them ordinary
+      // from where each FMA below (two such operands) needs a MOV first: 12 of the loop's 99
+      // instructions at the time.  A select against a lane-dependent value (never taken) makes them ordinary
       // vector registers.
       const float lane_val = __int_as_float((int)threadIdx.x);
       gm[r] = pol.vec_ ? -2.0f * m : lane_val;
@@ -556,10 +577,8 @@ struct LogSpaceTiled {
 #pragma unroll 1
       for (int q = 0; q < kTile / 4; ++q) {  // 4 observations x 16 independent FFMA2 chains
         const float4 x = xs4[tIdx * (kTile / 4) + q];
-        pol.step(x.x, gm, gb, t2);
-        pol.step(x.y, gm, gb, t2);
-        pol.step(x.z, gm, gb, t2);
-        pol.step(x.w, gm, gb, t2);
+        pol.step2(pack2(x.x, x.y), gm, gb, t2);
+        pol.step2(pack2(x.z, x.w), gm, gb, t2);
       }
       pol.fold(t2);
     }
