@@ -110,6 +110,7 @@ struct cge_context {
   float prior_mu_max = 1.0f, prior_sigma_max = 1.0f, prior_full_max = 1.0f;  // largest |factor| of each piece
   size_t prior_full_cells = 0;        // cells of the full table prior_full_max was measured over
   DevBuf<unsigned int> tickets;  // [0] fold, [1] finish, [2] small-grid kernel; zero between steps
+  DevBuf<unsigned long long> zbcast;  // peer exchange: {step flag, Z, Smu} the finish kernel's block 0 publishes
   DevBuf<float> prior_mu, prior_sigma;   // owned copies of the separable prior factors
   bool has_prior_mu = false, has_prior_sigma = false;
   int prior_n = 0;
@@ -339,6 +340,10 @@ int reserve_step_buffers(cge_context *ctx, const Plan &pl, cudaStream_t st) {
   if (!ctx->tickets.ptr) {
     CKRC(ctx->tickets.reserve(3));
     CK(cudaMemsetAsync(ctx->tickets.ptr, 0, 3 * sizeof(unsigned int), st));
+  }
+  if (!ctx->zbcast.ptr) {
+    CKRC(ctx->zbcast.reserve(4));
+    CK(cudaMemsetAsync(ctx->zbcast.ptr, 0, 4 * sizeof(unsigned long long), st));
   }
   CKRC(ctx->rowpart.reserve((size_t)pl.rows_local * pl.ncw));
   if ((size_t)N > ctx->colacc.cap) {   // (re)allocated zeroed; every step leaves it zeroed
@@ -611,7 +616,7 @@ CGE_EXPORT int cge_destroy(cge_context *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaDeviceSynchronize();
   peer_release(ctx);
-  ctx->obs_pad.release(); ctx->obs_in.release(); ctx->espart.release(); ctx->tickets.release();
+  ctx->obs_pad.release(); ctx->obs_in.release(); ctx->espart.release(); ctx->tickets.release(); ctx->zbcast.release();
   ctx->prior_mu.release(); ctx->prior_sigma.release(); ctx->posterior.release();
   ctx->like32.release(); ctx->posterior64.release(); ctx->rowpart.release();
   ctx->colacc.release(); ctx->strip_next.release(); ctx->partials.release(); ctx->rowsum.release(); ctx->zpart.release();
@@ -823,6 +828,7 @@ static int finalize_impl(cge_context *ctx, const cge_params *p, void *posterior_
   a.results = ctx->results.ptr;
   a.espart = ctx->espart.ptr;
   a.ticket = ctx->tickets.ptr + 1;
+  a.bcast = ctx->zbcast.ptr;
   a.cells = (size_t)pl.rows_local * N;
   if (scale_cells > 0 && scale_cells < a.cells) a.cells = scale_cells;
   if (pl.post_f64) {
@@ -912,6 +918,16 @@ static int finalize_to_host(cge_context *ctx, const cge_params *p, void *post_de
 // peer exchange: CUDA IPC (one process per GPU, one node) or plain peer pointers (one process)
 // ---------------------------------------------------------------------------------------
 namespace {
+// the finish kernel's local {flag, Z, Smu} word counts steps like peer_step: restart it with it
+void reset_bcast(cge_context *ctx) {
+  if (!ctx->zbcast.ptr) return;
+  int cur = -1;
+  cudaGetDevice(&cur);
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaMemset(ctx->zbcast.ptr, 0, 4 * sizeof(unsigned long long));
+  if (cur >= 0) cudaSetDevice(cur);
+}
 int peer_release(cge_context *ctx) {
   for (int r = 0; r < cge::kMaxPeers; ++r) {
     if (!ctx->peer_block[r]) continue;
@@ -925,6 +941,7 @@ int peer_release(cge_context *ctx) {
   ctx->peer_rank = 0;
   ctx->peer_cap = 0;
   ctx->peer_step = 0;
+  reset_bcast(ctx);  // the local flag counts steps too
   return CGE_OK;
 }
 
@@ -983,6 +1000,7 @@ CGE_EXPORT int cge_peer_connect(cge_context *ctx, int rank, int world, const voi
   }
   ctx->peer_world = world;
   ctx->peer_step = 0;
+  reset_bcast(ctx);  // the local flag counts steps too
   return CGE_OK;
 }
 
@@ -1012,6 +1030,7 @@ extern "C" int cge_internal_peer_attach(cge_context *ctx, int rank, int world,
   ctx->peer_rank = rank;
   ctx->peer_world = world;
   ctx->peer_step = 0;
+  reset_bcast(ctx);  // the local flag counts steps too
   ctx->peer_ipc = false;
   ctx->peer_on = true;
   return CGE_OK;
