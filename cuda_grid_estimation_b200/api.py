@@ -29,6 +29,7 @@ VARIANT_LOG_F64 = 5
 VARIANT_PAIRED3 = 8
 VARIANT_SLOPE = 9
 VARIANT_SLOPE_WIDE = 10
+VARIANT_SLOPE_TALL = 11
 VARIANT_UNFUSED = 7
 
 OK, ERR_BAD_ARG, ERR_NO_DEVICE, ERR_CUDA, ERR_DEGENERATE, ERR_PEER, ERR_SIZE = range(7)
@@ -393,7 +394,8 @@ def _scale_info(self, stream=None) -> dict:
     # product_path: "slope8" when the whole grid ran the 8-column wide policy; otherwise the
     # arithmetic of the most demanding column band (the one at the smallest sigma) -- bands at
     # larger sigma may run a cheaper policy (see band_paths)
-    d["product_path"] = "slope8" if d["wide"] else _product_path(d, d["umax"], d["slope_eps"])
+    d["product_path"] = ("slope8x7" if d["wide"] == 2 else "slope8" if d["wide"] else
+                         _product_path(d, d["umax"], d["slope_eps"]))
     return d
 
 
@@ -429,7 +431,7 @@ def band_paths(info: dict, sigma: np.ndarray) -> list:
     mirrors cge::strip_umax (|a_j| = 0.5*log2(e)/sigma_j^2 at the band's two ends) and
     cge::strip_sigma_step (the column step over the band's smallest sigma)."""
     if info.get("wide"):
-        return ["slope8"] * ((len(sigma) + 127) // 128)
+        return ["slope8x7" if info["wide"] == 2 else "slope8"] * ((len(sigma) + 127) // 128)
     out = []
     n = len(sigma)
     band_cols = band_columns(n)

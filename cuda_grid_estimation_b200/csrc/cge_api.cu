@@ -132,7 +132,8 @@ struct cge_context {
   int knob_grid_mult = 1;    // CGE_GRID_MULT: CTAs per resident slot (1 = persistent)
   int knob_chunk = 0;        // CGE_ITEM_STEPS: CTA steps per claimed item
   int knob_cta_warps = 0;    // CGE_CTA_WARPS: 8 or 24 warps per CTA of the product kernel
-  bool knob_no_wide = false;     // CGE_NO_WIDE: never take the 8-column wide product policy
+  bool knob_no_wide = false;     // CGE_NO_WIDE: never take the 8-column product policies
+  bool knob_no_tall = false;     // CGE_NO_TALL: never take the 7-row one of them
   bool knob_no_cluster = false;  // CGE_NO_CLUSTER: small grids without the cluster launch
   bool knob_no_pdl = false;      // CGE_NO_PDL: ordinary stream-ordered launches
   // resident CTAs per SM of each likelihood kernel at its shared-memory size (occupancy query)
@@ -182,7 +183,7 @@ int check_params(const cge_params *p, int *rb, int *re) {
   switch (p->variant) {
     case CGE_VARIANT_DEFAULT: case CGE_VARIANT_UNFUSED: break;
     case CGE_VARIANT_MUFU_ONLY: case CGE_VARIANT_PAIRED: case CGE_VARIANT_PAIRED3: case CGE_VARIANT_HYBRID:
-    case CGE_VARIANT_SLOPE: case CGE_VARIANT_SLOPE_WIDE:
+    case CGE_VARIANT_SLOPE: case CGE_VARIANT_SLOPE_WIDE: case CGE_VARIANT_SLOPE_TALL:
       if (p->mode != CGE_MODE_PRODUCT_F32)
         return set_error(CGE_ERR_BAD_ARG, "variant %d belongs to the product mode", p->variant);
       break;
@@ -410,7 +411,8 @@ int fill_like_args(cge_context *ctx, const cge_params *p, const Plan &pl, const 
   args->vec4 = pl.vec4 ? 1 : 0;
   args->keep_l2 = pl.keep_l2 ? 1 : 0;
   args->vec8 = (N % 8 == 0) && ((reinterpret_cast<uintptr_t>(posterior_dev) & 31u) == 0) ? 1 : 0;
-  args->wide = p->variant == CGE_VARIANT_SLOPE_WIDE ? 1 : ctx->knob_no_wide ? -1 : 0;
+  args->wide = p->variant == CGE_VARIANT_SLOPE_WIDE ? 1 : p->variant == CGE_VARIANT_SLOPE_TALL ? 2
+               : ctx->knob_no_wide ? -1 : ctx->knob_no_tall ? -2 : 0;
 #ifdef CGE_DEBUG_TIMES
   CKRC(ctx->debug_times.reserve((size_t)(4 + 32) * pl.nctas));
   CK(cudaMemset(ctx->debug_times.ptr, 0, (size_t)(4 + 32) * pl.nctas * sizeof(unsigned long long)));
@@ -592,6 +594,7 @@ CGE_EXPORT int cge_create(int device, cge_context **out) {
   if (const char *v = std::getenv("CGE_ITEM_STEPS")) ctx->knob_chunk = std::atoi(v);
   if (const char *v = std::getenv("CGE_CTA_WARPS")) ctx->knob_cta_warps = std::atoi(v);
   ctx->knob_no_wide = std::getenv("CGE_NO_WIDE") != nullptr;
+  ctx->knob_no_tall = std::getenv("CGE_NO_TALL") != nullptr;
   ctx->knob_no_cluster = std::getenv("CGE_NO_CLUSTER") != nullptr;
   ctx->knob_no_pdl = std::getenv("CGE_NO_PDL") != nullptr;
   cudaError_t se = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);

@@ -72,7 +72,7 @@ struct ScaleInfo {
   double umax;   // bound on |t_(i+1,j,k) - t_(i,j,k)| over adjacent mu rows, whole grid
   double ustep;  // the same bound per unit |a_j|: umax of a column band = max |a_j| in it * ustep
   double seps;   // relative sigma step |dsigma| / min |sigma| of the whole grid (slope policies' eligibility)
-  double wide;   // 1 when the step ran the 8-column wide product policy (reporting only)
+  double wide;   // 1 / 2 when the step ran the 8-column wide / tall product policy (reporting only)
 };
 
 struct RangeArgs {
@@ -146,7 +146,8 @@ struct LikeArgs {
   int vec4;            // N % 4 == 0 and the shard base is 16-byte aligned: float4 stores
   int keep_l2;         // the shard fits in L2: store with the default policy instead of .cs
   int vec8;            // N % 8 == 0 and the shard base is 32-byte aligned: 32-byte stores (wide policy)
-  int wide;            // the 8-column policy of the product kernel: 0 = where eligible, -1 = never, 1 = forced
+  int wide;            // the 8-column policies of the product kernel: 0 = where eligible (tall, else wide),
+                       // -1 = never, -2 = never the tall one, 1 = wide forced, 2 = tall forced
 #ifdef CGE_DEBUG_TIMES
   unsigned long long *debug;  // per CTA: {start ns, end ns, smid, set-up done ns}, then 32 slots per CTA: warp end ns
 #endif
@@ -1026,6 +1027,113 @@ using ProductSlope = ProductSlopeT<4>;
 using ProductSlopeWide = ProductSlopeT<8>;
 
 // ---------------------------------------------------------------------------------------
+// float32 product path, TALL shared-slope policy (the finest grids): 7 rows x 8 adjacent columns
+// per thread, ONE MUFU row (the middle one) and six derived rows at distances 1, 2 and 3 -- the
+// same arithmetic as ProductSlopeWide with a longer neighbour chain:
+//   per (observation, column pair): FFMA2 (exponent), 2 MUFU.EX2, FMUL2 (product), FMUL2 (ea = e a_j),
+//                                   then FFMA2 (f = ea H_r + e) + FMUL2 (product) per derived row
+//   per observation              : d, d^2 and six Horner quadratics H_r(d) (scalar FMAs)
+// i.e. 60 packed + 14 scalar FMA-pipe instructions and 8 MUFU.EX2 per 56 evals: 0.143 MUFU and 2.39
+// FP32 lane-ops per eval against 0.333 / 2.58 for the wide policy -- 150 issue cycles per 56 evals
+// instead of 158 per 48.  The exponent offset of a row three away is three times as large, so the
+// bounds are those of the wide policy with U -> 3 U: 3 umax <= kPairedUmax (cubic term of the
+// degree-2 polynomial) and k2 (3 U)^2 eps(3.5 columns) <= 2^-24 -- README ranges: N >= ~9400.
+// Every pdf-eval still forms its own factor and multiplies it into its own running product.
+// ---------------------------------------------------------------------------------------
+struct ProductSlopeTall {
+  static constexpr double kUmax = kPairedUmax / 3.0;
+  static __device__ __forceinline__ bool eligible(double umax, double rstep) {
+    const double x = 3.5 * rstep * 1.01, u3 = 3.0 * umax;
+    return u3 <= kPairedUmax && 0.2402265069591007 * u3 * u3 * (2.0 * x * (1.0 + 1.5 * x)) <= kSlopeErr;
+  }
+  static constexpr bool kColSmem = true;
+  static constexpr bool kAdjacent = true;
+  static constexpr int kRows = 7;
+  static constexpr int kMid = 3;  // the MUFU row
+  static constexpr int kCols = 8;
+  static constexpr int kSmemDoubles = 0;
+  static constexpr int kPairs = kCols / 2;
+  f32x2 a2[kPairs], c2[kPairs];
+  float k1, a0k2;
+  f32x2 p2[kRows][kPairs];
+
+  template <int NT>
+  __device__ __forceinline__ void load_columns(const LikeArgs &g, int j0, const ScaleInfo &sc,
+                                               const ColumnCoefs<kCols, true> &cf, double *) {
+    const double U = 3.0 * sc.umax;  // the rows furthest from the MUFU row
+    const double k2 = 0.24022650695910071233;
+    k1 = (float)(0.69314718055994530942 + 0.0555041086648215799 * 0.75 * U * U);
+    const double s1 = (double)range_value(min(j0 + kCols / 2 - 1, g.N - 1), g.N, g.range.sg0, g.range.sg1);
+    const double s2 = (double)range_value(min(j0 + kCols / 2, g.N - 1), g.N, g.range.sg0, g.range.sg1);
+    a0k2 = (float)(0.5 * (coef_a(s1) + coef_a(s2)) * k2);
+#pragma unroll
+    for (int h = 0; h < kPairs; ++h) {
+      float av[2], cv[2];
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int j = j0 + 2 * h + e;
+        av[e] = (float)cf.a[2 * h + e];
+        cv[e] = j < g.N ? (float)(cf.c0[2 * h + e] + sc.log2s) : 0.0f;
+      }
+      a2[h] = pack2(av[0], av[1]);
+      c2[h] = pack2(cv[0], cv[1]);
+    }
+  }
+  __device__ __forceinline__ void begin_rows() {
+    const f32x2 one = pack2(1.0f, 1.0f);
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+#pragma unroll
+      for (int h = 0; h < kPairs; ++h) p2[r][h] = one;
+  }
+  // per-row scalars of a group: H_r(d) = qa d^2 + qb d + qc (ProductSlopeT::rows), d = x - mu_mid
+  struct Rows {
+    float mid, qa[kRows], qb[kRows], qc[kRows];  // (index kMid unused)
+  };
+  __device__ __forceinline__ Rows rows(const float (&mu)[kRows]) const {
+    Rows rs;
+    rs.mid = mu[kMid];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r) {
+      const float delta = __fsub_rn(mu[r], mu[kMid]);  // exact (nearby range values)
+      const float kd2 = a0k2 * delta * delta;
+      rs.qa[r] = 4.0f * kd2;
+      rs.qb[r] = -2.0f * delta * fmaf(2.0f, kd2, k1);
+      rs.qc[r] = delta * delta * (k1 + kd2);
+    }
+    return rs;
+  }
+  __device__ __forceinline__ void step(float x, const Rows &rs) {
+    const float d = x - rs.mid;  // same f32 rounding as the reference's (x - mu)
+    const float dd = d * d;
+    float hv[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+      if (r != kMid) hv[r] = fmaf(fmaf(d, rs.qa[r], rs.qb[r]), d, rs.qc[r]);
+    const f32x2 dd2 = pack2(dd, dd);  // (scalar-broadcast operands of the packed instructions)
+#pragma unroll
+    for (int h = 0; h < kPairs; ++h) {
+      const f32x2 e2 = ex2_mufu2(fma2(dd2, a2[h], c2[h]));
+      p2[kMid][h] = mul2(p2[kMid][h], e2);
+      const f32x2 ea2 = mul2(e2, a2[h]);
+#pragma unroll
+      for (int r = 0; r < kRows; ++r)
+        if (r != kMid) p2[r][h] = mul2(p2[r][h], fma2(ea2, pack2(hv[r], hv[r]), e2));
+    }
+  }
+  template <int NT>
+  __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx, const double *) const {
+    float lo, hi;
+    unpack2(p2[r][cidx >> 1], lo, hi);
+    return (cidx & 1) ? hi : lo;
+  }
+  static __device__ __forceinline__ void consume(ProductSlopeTall &pol, const float *xs, int count,
+                                                 const float (&mu)[kRows]) {
+    neighbour_consume(pol, xs, count, mu);
+  }
+};
+
+// ---------------------------------------------------------------------------------------
 // Shared-memory layout of the likelihood kernels (dynamic):
 //   [0, 16)    two mbarriers (streamed observations only)
 //   [16, 112)  ScaleInfo of this step (written once per CTA by the set-up)
@@ -1044,7 +1152,7 @@ __host__ __device__ __forceinline__ size_t stage_bytes(int n_pad) {
 // bytes per thread behind the observation stage
 template <class Policy>
 constexpr int policy_smem_bytes() {
-  return Policy::kCols * 8 + Policy::kCols * 4 + Policy::kSmemDoubles * 8 + Policy::kRows * 4;
+  return Policy::kCols * 8 + Policy::kCols * 4 + Policy::kSmemDoubles * 8 + (Policy::kRows == 7 ? 8 : Policy::kRows) * 4;
 }
 
 // thread 0 only: start the bulk copy of chunk `ch` of the streamed observations into stage `st`
@@ -1087,8 +1195,10 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
   constexpr bool kAdj = Policy::kAdjacent;
   // float offset between a thread's successive 4-column groups: adjacent, or 128 columns apart
   constexpr int kGroupStride = kAdj ? kRN : kGroupCols;
-  static_assert(kRows == 4 || kRows == 6, "the epilogue is written for 4- and 6-row patches");
-  static_assert(!kAdj || (kCols == 8 && kRows == 6 && !STREAMED), "the adjacent layout is the wide product policy's");
+  static_assert(kRows == 4 || kRows == 6 || kRows == 7, "the epilogue is written for 4-, 6- and 7-row patches");
+  static_assert(!kAdj || (kCols == 8 && kRows >= 6 && !STREAMED), "the adjacent layout is the wide product policies'");
+  static_assert(kRows != 7 || kAdj, "7-row patches: the tall policy");
+  constexpr int kBufRows = kRows == 7 ? 8 : kRows;  // rows of the transposition buffer
   const int tid = threadIdx.x;
   const int lane = tid & 31, warp = tid >> 5;
   // first column; group g starts 128*g further (adjacent layout: all kCols columns in a row)
@@ -1105,7 +1215,7 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
   float2 *colscale_s = reinterpret_cast<float2 *>(tsm_raw + (size_t)kCols * 8 * NT) + tid;
   double *own = reinterpret_cast<double *>(tsm_raw + (size_t)kCols * 12 * NT) + tid;
   float *rowbuf = reinterpret_cast<float *>(tsm_raw + (size_t)(kCols * 12 + Policy::kSmemDoubles * 8) * NT) +
-                  warp * (kRows * 32);  // this warp's [kRows][32] transposition buffer
+                  warp * (kBufRows * 32);  // this warp's [kBufRows][32] transposition buffer
 
   Policy pol;
   {
@@ -1254,7 +1364,8 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
     // column sums over the patch rows (float32, pairwise), scaled by 2^s_j and added as integers
     auto colsum = [&](int cidx) {
       float t = (v[0][cidx] + v[1][cidx]) + (v[2][cidx] + v[3][cidx]);
-      if (kRows == 6) t += v[kRows - 2][cidx] + v[kRows - 1][cidx];
+      if (kRows >= 6) t += v[4][cidx] + v[5][cidx];
+      if (kRows == 7) t += v[6][cidx];
       return t;
     };
 #pragma unroll
@@ -1277,10 +1388,13 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
       if (kCols == 8) t += (v[r][4] + v[r][5]) + (v[r][6] + v[r][7]);
       rowbuf[r * 32 + lane] = t;
     }
+    if (kRows == 7) rowbuf[7 * 32 + lane] = 0.0f;  // (rows 4..7 go through the 4-row path again)
     __syncwarp();
     const float4 q = *reinterpret_cast<const float4 *>(rowbuf + lane * 4);  // row lane/8, lanes 4*(lane%8)..+3
     float2 w = make_float2(0.0f, 0.0f);
+    float4 q7 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     if (kRows == 6) w = *reinterpret_cast<const float2 *>(rowbuf + 128 + lane * 2);  // row 4 + lane/16
+    if (kRows == 7) q7 = *reinterpret_cast<const float4 *>(rowbuf + 128 + lane * 4);  // row 4 + lane/8
     __syncwarp();
     double tot = ((double)q.x + (double)q.y) + ((double)q.z + (double)q.w);
     // (adjacent layout: the warp's 256 columns are two row-partial slots of 128 columns, lanes
@@ -1296,6 +1410,15 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
       const int slot = 2 * cw + ((lane >> 2) & 1);  // (lanes 0, 4 of every 8)
       if ((lane & 3) == 0 && rq >= g.row_begin && rq < g.row_end && slot < g.ncw)
         g.rowpart[(size_t)(rq - g.row_begin) * (size_t)g.ncw + slot] = tot;
+    }
+    if constexpr (kRows == 7) {  // rows 4..6 exactly as rows 0..2 (adjacent layout: two slots)
+      double tot7 = ((double)q7.x + (double)q7.y) + ((double)q7.z + (double)q7.w);
+      tot7 += __shfl_xor_sync(0xffffffffu, tot7, 2);
+      tot7 += __shfl_xor_sync(0xffffffffu, tot7, 1);
+      const int rq7 = row + 4 + (lane >> 3);
+      const int slot = 2 * cw + ((lane >> 2) & 1);
+      if ((lane & 3) == 0 && (lane >> 3) < 3 && rq7 >= g.row_begin && rq7 < g.row_end && slot < g.ncw)
+        g.rowpart[(size_t)(rq7 - g.row_begin) * (size_t)g.ncw + slot] = tot7;
     }
     if (kRows == 6) {
       double tot2 = (double)w.x + (double)w.y;
@@ -1434,21 +1557,26 @@ __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char 
   const int tid = threadIdx.x, lane = tid & 31;
   unsigned char *after_stage = smem_raw + kSmemHeader + stage_bytes(g.n_pad);
 
-  // WIDE: the whole grid runs ProductSlopeWide (strips of 256 columns) when the grid-level bounds
-  // allow it -- a function of (ranges, N, observations) only, like the per-strip choice below
-  bool wide = false;
+  // WIDE: the whole grid runs ProductSlopeTall or ProductSlopeWide (strips of 256 columns) when
+  // the grid-level bounds allow it -- a function of (ranges, N, observations) only, like the
+  // per-strip choice below.  0: no, 1: wide (6 rows x 8 columns), 2: tall (7 x 8)
+  int wide = 0;
   if (!PRELOADED) {
     if (!STREAMED) {
       // fused set-up: this CTA's own copy of the observations and of the statistics
       const ScaleInfo sc = setup_scale(g.range, g.obs, obs_s, g.n, g.n_pad, g.centred,
                                        g.reorder ? reinterpret_cast<float *>(after_stage) : nullptr,
                                        scratch);
-      if (WIDE) wide = g.wide > 0 || (g.wide == 0 && ProductSlopeWide::eligible(sc.umax, sc.seps));
+      if (WIDE) {
+        if (g.wide > 0) wide = g.wide;  // forced
+        else if (g.wide == 0 && ProductSlopeTall::eligible(sc.umax, sc.seps)) wide = 2;
+        else if (g.wide != -1 && ProductSlopeWide::eligible(sc.umax, sc.seps)) wide = 1;
+      }
       if (tid == 0) {
         *sc_s = sc;
         if (cta == 0) {
           *g.scale_out = sc;
-          g.scale_out->wide = wide ? 1.0 : 0.0;
+          g.scale_out->wide = (double)wide;
         }
       }
     } else {
@@ -1462,7 +1590,12 @@ __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char 
   }
   // this CTA's pool: an equal contiguous share of the groups, strip-major
   const int ncw_run = wide ? (g.N + 32 * ProductSlopeWide::kCols - 1) / (32 * ProductSlopeWide::kCols) : g.ncw;
-  const long long units = (long long)ncw_run * g.groups;
+  // (the tall policy's groups are 7 rows, anchored at global multiples of 7)
+  const int groups_run =
+      wide == 2 ? (g.row_end - (g.row_begin - g.row_begin % ProductSlopeTall::kRows) + ProductSlopeTall::kRows - 1) /
+                      ProductSlopeTall::kRows
+                : g.groups;
+  const long long units = (long long)ncw_run * groups_run;
   const int pool_begin = (int)(units * cta / nctas), pool_end = (int)(units * (cta + 1) / nctas);
   if (tid == 0) claim[4] = pool_begin;
   __syncthreads();
@@ -1491,12 +1624,27 @@ __device__ __forceinline__ void likelihood_cta(const LikeArgs &g, unsigned char 
   };
 
   if (!STREAMED) {
+    // a claim covers at most 32 rows (run_strip: one range value per lane)
+    const int chunk_run = wide == 2 ? min(g.chunk, 32 / ProductSlopeTall::kRows) : g.chunk;
     int u0 = 0;
-    if (lane == 0) u0 = atomicAdd(const_cast<int *>(claim) + 4, g.chunk);
+    if (lane == 0) u0 = atomicAdd(const_cast<int *>(claim) + 4, chunk_run);
     u0 = __shfl_sync(0xffffffffu, u0, 0);
-    int u1 = min(u0 + g.chunk, pool_end);
+    int u1 = min(u0 + chunk_run, pool_end);
     if constexpr (WIDE) {
-      if (wide) {
+      if (wide == 2) {
+        LikeArgs gt = g;
+        gt.groups = groups_run;
+        gt.chunk = chunk_run;
+        while (u0 < pool_end) {
+          const int cw = u0 / gt.groups;
+          ScaleInfo sc = *sc_s;
+          sc.umax = strip_umax(g.range, cw, 32 * ProductSlopeTall::kCols, sc.ustep);
+          run_strip<ProductSlopeTall, false, NT>(gt, sc, cw, u0, u1, pool_end, bars, obs_s, after_stage, claim,
+                                                 claim_par, streams);
+        }
+        return;
+      }
+      if (wide == 1) {
         while (u0 < pool_end) {
           const int cw = u0 / g.groups;
           ScaleInfo sc = *sc_s;

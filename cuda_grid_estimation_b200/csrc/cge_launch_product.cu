@@ -10,6 +10,8 @@ static KernelChoice pick() {
   kc.smem_bytes = smem_bytes4<Finest, Fine, Mid, Coarse>();
   if (WIDE && cge::policy_smem_bytes<cge::ProductSlopeWide>() > kc.smem_bytes)
     kc.smem_bytes = cge::policy_smem_bytes<cge::ProductSlopeWide>();
+  if (WIDE && cge::policy_smem_bytes<cge::ProductSlopeTall>() > kc.smem_bytes)
+    kc.smem_bytes = cge::policy_smem_bytes<cge::ProductSlopeTall>();
   kc.kcols = Fine::kCols;
   kc.threads = WARPS * 32;
   kc.fn = (const void *)cge::grid_likelihood_kernel<Finest, Fine, Mid, Coarse, SELECT, MINB, false, WARPS, WIDE>;

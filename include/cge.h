@@ -107,6 +107,8 @@ enum {
   CGE_VARIANT_SLOPE_WIDE = 10, /* the same with eight adjacent columns per thread (32-byte stores),
                                 forced; the default kernel takes it for the whole grid when the
                                 grid-level bounds allow it */
+  CGE_VARIANT_SLOPE_TALL = 11, /* seven rows x eight adjacent columns per thread, one exponential
+                                per seven rows, forced; the default on the finest grids */
   CGE_VARIANT_LOG_F64 = 5,   /* log-space mode only: float64 accumulation, one DFMA per pdf-eval (the
                                 default log-space kernel sums centred terms in float32x2 tiles of 256
                                 observations and folds the tiles into float64) */
@@ -330,7 +332,8 @@ int cge_quantiles(cge_context *ctx, const double *marginal_dev, int n, const dou
  * kernel runs with its degree-2 and degree-3 polynomial, ustep (umax per unit |a_j|: a column
  * band's own bound is max |a_j| over the band times ustep -- the kernel chooses per band),
  * out[12..14] = the grid's relative sigma step |dsigma| / min |sigma|, the largest shared-slope
- * error term the slope policies accept (2^-24), and 1 when the step ran the 8-column wide policy. */
+ * error term the slope policies accept (2^-24), and 1 / 2 when the step ran the 8-column wide /
+ * tall policy. */
 int cge_scale_info(cge_context *ctx, double *out, int count, void *stream);
 
 /* ---- roofline micro-benchmarks (bench.py): measured pipe peaks on this device ------------

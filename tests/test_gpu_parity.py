@@ -397,7 +397,7 @@ def test_default_picks_the_path_on_the_device(ctx, readme_obs):
     variant and differs from the others.  A far-out observation raises |u| and moves N=4096 to
     the degree-3 polynomial."""
     forced = {"hybrid": api.VARIANT_HYBRID, "paired3": api.VARIANT_PAIRED3, "paired": api.VARIANT_PAIRED,
-              "slope": api.VARIANT_SLOPE, "slope8": api.VARIANT_SLOPE_WIDE}
+              "slope": api.VARIANT_SLOPE, "slope8": api.VARIANT_SLOPE_WIDE, "slope8x7": api.VARIANT_SLOPE_TALL}
     bw = api.band_columns(0)
     for N, sg_r, want in ((512, (1, 3), "hybrid"), (1024, (1, 3), "paired3"), (3300, (1, 4), "paired"),
                           (3300, (1, 3), "slope"), (4096, (1, 3), "slope8")):
@@ -456,8 +456,9 @@ def test_paired_rows_on_small_fine_grids(ctx, readme_obs, N):
     d = ctx.grid_posterior(readme_obs, N, mu_r, sg_r)
     info = ctx.scale_info()
     took = info["product_path"]
-    assert took in ("slope8", "slope", "paired")   # (small N: the sigma columns are too far apart for "slope")
-    variants = {"slope8": api.VARIANT_SLOPE_WIDE, "slope": api.VARIANT_SLOPE, "paired": api.VARIANT_PAIRED}
+    assert took in ("slope8x7", "slope8", "slope", "paired")   # (small N: the sigma columns are too far apart for "slope")
+    variants = {"slope8x7": api.VARIANT_SLOPE_TALL, "slope8": api.VARIANT_SLOPE_WIDE, "slope": api.VARIANT_SLOPE,
+                "paired": api.VARIANT_PAIRED}
     paths = api.band_paths(info, oracle.linspace(N, *sg_r))
     assert set(paths) <= set(variants)
     if len(set(paths)) == 1:
@@ -488,10 +489,10 @@ def test_paired_rows_observation_counts(ctx, n):
         sg_r = (1.6, 2.4)
         ref = oracle.grid_posterior(obs, N, *mu_r, *sg_r, oracle.NUM_F64)
         res = ctx.grid_posterior(obs, N, mu_r, sg_r)
-        # (the single launch at N = 200 has the 4-column policies only; N = 1100 runs the wide one)
-        assert ctx.scale_info()["product_path"] == ("slope" if N == 200 else "slope8")
+        # (the single launch at N = 200 has the 4-column policies only; N = 1100 runs the tall one)
+        assert ctx.scale_info()["product_path"] == ("slope" if N == 200 else "slope8x7")
         check_against(res, ref, what=f"default n={n} N={N}")
-        for variant in (api.VARIANT_PAIRED, api.VARIANT_SLOPE, api.VARIANT_SLOPE_WIDE):
+        for variant in (api.VARIANT_PAIRED, api.VARIANT_SLOPE, api.VARIANT_SLOPE_WIDE, api.VARIANT_SLOPE_TALL):
             res = ctx.grid_posterior(obs, N, mu_r, sg_r, variant=variant)
             check_against(res, ref, what=f"variant {variant} n={n} N={N}")
 
@@ -508,7 +509,7 @@ def test_descending_and_sign_crossing_ranges(ctx):
                 ref = oracle.grid_posterior(obs, N, *mu_r, *sg_r, num)
                 check_against(res, ref, what=f"N={N} mu={mu_r} sigma={sg_r} mode={mode}")
     res = ctx.grid_posterior(obs, 2048, (0.6, -0.4), (0.7, 1.5))
-    assert ctx.scale_info()["product_path"] in ("slope8", "slope", "paired", "paired3")
+    assert ctx.scale_info()["product_path"] in ("slope8x7", "slope8", "slope", "paired", "paired3")
 
 
 def test_paired_rows_at_the_eligibility_bound(ctx, readme_obs):
@@ -526,6 +527,15 @@ def test_paired_rows_at_the_eligibility_bound(ctx, readme_obs):
         for variant in (api.VARIANT_SLOPE, api.VARIANT_SLOPE_WIDE):
             res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=variant)
             check_against(res, ref, post_rel=rel_max, what=f"forced variant {variant} N={N}")
+    # tall policy (one exponential per 7 rows): eligible from N ~ 9400 on the README ranges
+    # (3|u| <= 0.011, slope term 9 x the wide policy's); forced at N = 7000: 3|u| = 0.0147, 1.05e-7
+    for N, rel_max, want in ((9600, 3e-5, "slope8x7"), (7000, 1e-4, "slope8")):
+        ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_F64)
+        res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3))
+        assert ctx.scale_info()["product_path"] == want
+        check_against(res, ref, post_rel=3e-5, what=f"default N={N}")
+        res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_SLOPE_TALL)
+        check_against(res, ref, post_rel=rel_max, what=f"forced tall N={N}")
     for N, rel_max in ((700, 3e-5), (560, 1e-4)):  # degree 3: |u| <= 0.0495, 0.062
         res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=api.VARIANT_PAIRED3)
         ref = oracle.grid_posterior(readme_obs, N, 18, 22, 1, 3, oracle.NUM_F64)
@@ -607,7 +617,7 @@ def test_65536_product_properties(ctx, readme_obs):
     dev = torch.device("cuda", 0)
     ranges = (18.0, 22.0, 1.0, 3.0)
     res = ctx.grid_posterior(readme_obs, N, ranges[:2], ranges[2:], posterior="device")
-    assert ctx.scale_info()["product_path"] == "slope8"
+    assert ctx.scale_info()["product_path"] == "slope8x7"
     ptr, cnt = ctx.posterior_ptr()
     post = cge.device_tensor(ptr, cnt, "float32", 0).view(N, N)
     mu = torch.from_numpy(oracle.linspace(N, *ranges[:2]).astype(np.float64)).to(dev)

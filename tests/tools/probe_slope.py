@@ -20,7 +20,8 @@ with cge.Context(0) as ctx:
         Q = ref["posterior"]
         big = Q >= 1e-20 * Q.max()
         row = {"N": N}
-        for name, variant in (("default", 0), ("slope", api.VARIANT_SLOPE), ("paired", api.VARIANT_PAIRED)):
+        for name, variant in (("default", 0), ("slope", api.VARIANT_SLOPE), ("paired", api.VARIANT_PAIRED),
+                              ("wide", api.VARIANT_SLOPE_WIDE), ("tall", api.VARIANT_SLOPE_TALL)):
             res = ctx.grid_posterior(obs, N, mu_r, sg_r, variant=variant)
             info = ctx.scale_info()
             P = res.posterior.astype(np.float64)
