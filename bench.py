@@ -59,7 +59,7 @@ TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
 # loop (profiles/r02_sass_inner_loop_*.txt): MUFU.EX2 per eval, FMA-pipe lane-ops per eval
 PIPE_OPS = {
     # per thread and observation (6 rows x 4 columns = 24 evals): 8 MUFU.EX2 and
-    "slope8x7": (8 / 56, (2 * 60 + 14) / 56),  # tall: 7 rows x 8 columns: 8 MUFU.EX2 + 60 packed + 14 scalar
+    "slope8x7": (8 / 56, 2 * 67 / 56),  # tall: 7 rows x 8 columns = 56 evals: 8 MUFU.EX2 + 67 packed
     "slope8": (16 / 48, 2 * 62 / 48),  # wide: 6 rows x 8 columns = 48 evals: 16 MUFU.EX2 + 62 packed
     "slope": (8 / 24, 2 * 34 / 24),    # 34 packed f32x2 instructions (2 lane-ops each)
     "paired": (8 / 24, 2 * 44 / 24),   # 44 packed (the polynomial per cell instead of per row)

@@ -1032,9 +1032,9 @@ using ProductSlopeWide = ProductSlopeT<8>;
 // same arithmetic as ProductSlopeWide with a longer neighbour chain:
 //   per (observation, column pair): FFMA2 (exponent), 2 MUFU.EX2, FMUL2 (product), FMUL2 (ea = e a_j),
 //                                   then FFMA2 (f = ea H_r + e) + FMUL2 (product) per derived row
-//   per observation              : d, d^2 and six Horner quadratics H_r(d) (scalar FMAs)
-// i.e. 60 packed + 14 scalar FMA-pipe instructions and 8 MUFU.EX2 per 56 evals: 0.143 MUFU and 2.39
-// FP32 lane-ops per eval against 0.333 / 2.58 for the wide policy -- 150 issue cycles per 56 evals
+//   per pair of observations     : d, d^2 and six Horner quadratics H_r(d) of both, packed
+// i.e. 67 packed FMA-pipe instructions and 8 MUFU.EX2 per 56 evals: 0.143 MUFU and 2.39 FP32
+// lane-ops per eval against 0.333 / 2.58 for the wide policy -- 150 issue cycles per 56 evals
 // instead of 158 per 48.  The exponent offset of a row three away is three times as large, so the
 // bounds are those of the wide policy with U -> 3 U: 3 umax <= kPairedUmax (cubic term of the
 // degree-2 polynomial) and k2 (3 U)^2 eps(3.5 columns) <= 2^-24 -- README ranges: N >= ~9400.
@@ -1121,6 +1121,37 @@ struct ProductSlopeTall {
         if (r != kMid) p2[r][h] = mul2(p2[r][h], fma2(ea2, pack2(hv[r], hv[r]), e2));
     }
   }
+  // two observations: the row scalars of both as packed FMAs -- an all-packed instruction stream
+  // (measured 1.173 against 1.229 ms for the scalar form at 16384^2 x 50: mixing scalar and packed
+  // FMAs costs issue slots)
+  __device__ __forceinline__ void step2(f32x2 x2, const Rows &rs) {
+    const f32x2 d2 = sub2(x2, pack2(rs.mid, rs.mid));
+    float dd0, dd1;
+    unpack2(mul2(d2, d2), dd0, dd1);
+    float h0[kRows], h1[kRows];
+#pragma unroll
+    for (int r = 0; r < kRows; ++r)
+      if (r != kMid)
+        unpack2(fma2(fma2(d2, pack2(rs.qa[r], rs.qa[r]), pack2(rs.qb[r], rs.qb[r])), d2, pack2(rs.qc[r], rs.qc[r])),
+                h0[r], h1[r]);
+#pragma unroll
+    for (int o = 0; o < 2; ++o) {
+      const float dd = o ? dd1 : dd0;
+      const f32x2 dd2 = pack2(dd, dd);
+#pragma unroll
+      for (int h = 0; h < kPairs; ++h) {
+        const f32x2 e2 = ex2_mufu2(fma2(dd2, a2[h], c2[h]));
+        p2[kMid][h] = mul2(p2[kMid][h], e2);
+        const f32x2 ea2 = mul2(e2, a2[h]);
+#pragma unroll
+        for (int r = 0; r < kRows; ++r)
+          if (r != kMid) {
+            const float hv = o ? h1[r] : h0[r];
+            p2[r][h] = mul2(p2[r][h], fma2(ea2, pack2(hv, hv), e2));
+          }
+      }
+    }
+  }
   template <int NT>
   __device__ __forceinline__ float value(const LikeArgs &, int r, int cidx, const double *) const {
     float lo, hi;
@@ -1129,7 +1160,20 @@ struct ProductSlopeTall {
   }
   static __device__ __forceinline__ void consume(ProductSlopeTall &pol, const float *xs, int count,
                                                  const float (&mu)[kRows]) {
-    neighbour_consume(pol, xs, count, mu);
+    const Rows rs = pol.rows(mu);
+    const float4 *xs4 = reinterpret_cast<const float4 *>(xs);
+    const int n4 = count >> 2;
+#pragma unroll 1
+    for (int q = 0; q < n4; ++q) {
+      const float4 x = xs4[q];
+      pol.step2(pack2(x.x, x.y), rs);
+      pol.step2(pack2(x.z, x.w), rs);
+    }
+    if (count & 2) {
+      const float2 x = *reinterpret_cast<const float2 *>(xs + (n4 << 2));
+      pol.step2(pack2(x.x, x.y), rs);
+    }
+    if (count & 1) pol.step(xs[count - 1], rs);
   }
 };
 
