@@ -1431,6 +1431,13 @@ extern "C" int cge_internal_stream(cge_context *ctx, void **stream, int *sm_coun
   return CGE_OK;
 }
 extern "C" int cge_internal_error(int code, const char *msg) { return set_error(code, "%s", msg); }
+// `count` doubles of context-owned device scratch (grow-only; valid until the next call that asks)
+extern "C" int cge_internal_scratch(cge_context *ctx, size_t count, double **ptr) {
+  CKRC(bind(ctx));
+  CKRC(ctx->tmp.reserve(count));
+  *ptr = ctx->tmp.ptr;
+  return CGE_OK;
+}
 #ifdef CGE_DEBUG_TIMES
 // diagnostic build only: per-CTA {start ns, end ns, smid, set-up done ns} of the last likelihood
 // launch, followed by the end time of each of its warps (32 slots per CTA, unused ones zero);

@@ -15,6 +15,7 @@
 
 extern "C" int cge_internal_stream(cge_context *ctx, void **stream, int *sm_count);
 extern "C" int cge_internal_error(int code, const char *msg);
+extern "C" int cge_internal_scratch(cge_context *ctx, size_t count, double **ptr);
 
 namespace {
 
@@ -39,38 +40,48 @@ __global__ void generate_normal_kernel(float *out, unsigned n, float mu, float s
 }
 
 // inclusive prefix sum of `n` doubles by one CTA in a fixed order (thread t owns a contiguous
-// chunk, chunk totals are scanned by warp 0), then the first index whose cumulative mass exceeds
+// chunk; the 1024 chunk totals are scanned by shuffles inside each warp and then across the 32
+// warp totals -- a fixed tree, no serial pass), then the first index whose cumulative mass exceeds
 // each probability -- notebooks/quick-prototyping.ipynb cell 5 (credible_interval_90).
+struct QuantileProbs {
+  double p[16];
+};
 __global__ void __launch_bounds__(1024)
-    quantile_kernel(const double *__restrict__ marginal, int n, const double *__restrict__ probs,
-                    int nprobs, int *__restrict__ idx_out, double *__restrict__ cdf_out) {
-  __shared__ double chunk_total[1024];
-  __shared__ double chunk_base[1024];
-  const int tid = threadIdx.x, nt = blockDim.x;
+    quantile_kernel(const double *__restrict__ marginal, int n, const QuantileProbs probs, int nprobs,
+                    int *__restrict__ idx_out, double *__restrict__ cdf_out) {
+  __shared__ double warp_total[32];
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
   const int per = (n + nt - 1) / nt;
   const int b = tid * per, e = min(n, b + per);
   double s = 0.0;
   for (int i = b; i < e; ++i) s += marginal[i];
-  chunk_total[tid] = s;
+  double incl = s;  // inclusive scan of the chunk totals inside the warp
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const double up = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += up;
+  }
+  if (lane == 31) warp_total[warp] = incl;
+  if (tid < nprobs) idx_out[tid] = n;  // "never exceeded"
   __syncthreads();
-  if (tid == 0) {
-    double run = 0.0;
-    for (int t = 0; t < nt; ++t) {
-      chunk_base[t] = run;
-      run += chunk_total[t];
+  if (warp == 0) {  // exclusive scan of the warp totals
+    const double w = warp_total[lane];
+    double wi = w;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const double up = __shfl_up_sync(0xffffffffu, wi, off);
+      if (lane >= off) wi += up;
     }
+    warp_total[lane] = wi - w;
   }
   __syncthreads();
-  for (int q = 0; q < nprobs; ++q)
-    if (tid == 0) idx_out[q] = n;  // "never exceeded"
-  __syncthreads();
-  double run = chunk_base[tid];
+  double run = warp_total[warp] + (incl - s);  // mass before this thread's chunk
   for (int i = b; i < e; ++i) {
     const double prev = run;
     run += marginal[i];
     if (cdf_out) cdf_out[i] = run;
     for (int q = 0; q < nprobs; ++q)
-      if (prev <= probs[q] && run > probs[q]) atomicMin(&idx_out[q], i);
+      if (prev <= probs.p[q] && run > probs.p[q]) atomicMin(&idx_out[q], i);
   }
 }
 
@@ -102,21 +113,17 @@ CGE_EXPORT int cge_quantiles(cge_context *ctx, const double *marginal_dev, int n
   if (!marginal_dev || n < 1 || !probs_host || nprobs < 1 || nprobs > 16 || !indices_host)
     return cge_internal_error(CGE_ERR_BAD_ARG, "quantiles: bad argument");
   cudaStream_t stream = (cudaStream_t)st;
-  double *probs_dev = nullptr;
-  int *idx_dev = nullptr;
-  cudaError_t e = cudaMalloc(&probs_dev, nprobs * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&idx_dev, nprobs * sizeof(int));
-  if (e == cudaSuccess)
-    e = cudaMemcpyAsync(probs_dev, probs_host, nprobs * sizeof(double), cudaMemcpyHostToDevice, stream);
-  if (e == cudaSuccess) {
-    quantile_kernel<<<1, 1024, 0, stream>>>(marginal_dev, n, probs_dev, nprobs, idx_dev, cdf_dev);
-    e = cudaGetLastError();
-  }
+  double *scratch = nullptr;  // context-owned: no allocation on the call path
+  rc = cge_internal_scratch(ctx, 16, &scratch);
+  if (rc != CGE_OK) return rc;
+  int *idx_dev = reinterpret_cast<int *>(scratch);
+  QuantileProbs probs = {};
+  for (int q = 0; q < nprobs; ++q) probs.p[q] = probs_host[q];
+  quantile_kernel<<<1, 1024, 0, stream>>>(marginal_dev, n, probs, nprobs, idx_dev, cdf_dev);
+  cudaError_t e = cudaGetLastError();
   if (e == cudaSuccess)
     e = cudaMemcpyAsync(indices_host, idx_dev, nprobs * sizeof(int), cudaMemcpyDeviceToHost, stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
-  cudaFree(probs_dev);
-  cudaFree(idx_dev);
   if (e != cudaSuccess) return cge_internal_error(CGE_ERR_CUDA, cudaGetErrorString(e));
   return CGE_OK;
 }

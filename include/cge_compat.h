@@ -33,15 +33,17 @@ namespace cge_compat {
 /* One lazily created context on the current device, like the reference's implicit use of the
  * default device/stream.  Failure to create it (no sm_100 GPU) is fatal: there is no CPU path. */
 inline cge_context *context() {
-  static cge_context *ctx = nullptr;
-  if (!ctx) {
+  // (function-local static: initialised once, thread-safe since C++11)
+  static cge_context *ctx = [] {
+    cge_context *c = nullptr;
     int dev = 0;
     cudaGetDevice(&dev);
-    if (cge_create(dev, &ctx) != CGE_OK) {
+    if (cge_create(dev, &c) != CGE_OK) {
       std::fprintf(stderr, "libcge: %s\n", cge_last_error());
       std::abort();
     }
-  }
+    return c;
+  }();
   return ctx;
 }
 
