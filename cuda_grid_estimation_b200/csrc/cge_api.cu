@@ -131,7 +131,6 @@ struct cge_context {
   int knob_ctas_per_sm = 0;  // CGE_CTAS_PER_SM: cap the persistent grid
   int knob_grid_mult = 1;    // CGE_GRID_MULT: CTAs per resident slot (1 = persistent)
   int knob_chunk = 0;        // CGE_ITEM_STEPS: CTA steps per claimed item
-  int knob_cta_warps = 0;    // CGE_CTA_WARPS: 8 or 24 warps per CTA of the product kernel
   bool knob_no_wide = false;     // CGE_NO_WIDE: never take the 8-column product policies
   bool knob_no_tall = false;     // CGE_NO_TALL: never take the 7-row one of them
   bool knob_no_cluster = false;  // CGE_NO_CLUSTER: small grids without the cluster launch
@@ -251,10 +250,6 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   pl->streamed = pl->n_pad > cge::kObsSingleMax;
   pl->reorder = p->mode == CGE_MODE_PRODUCT_F32 && pl->n <= cge::kReorderMax;
   pl->cluster = false;
-  // one CTA per SM whose warps share a single pool (product: 20 warps, log-space: 16), or with
-  // CGE_CTA_WARPS=8 the earlier shape of several 8-warp CTAs per SM with a pool each (A/B runs;
-  // measured at 16384^2 x 50: 1.60 vs 1.50 ms, log-space 16384^2 x 10k: 112.5 vs 107.6 ms)
-  pl->cta_warps = ctx->knob_cta_warps > 0 ? ctx->knob_cta_warps : 0;
   pl->nctas = 0;
 }
 
@@ -592,7 +587,6 @@ CGE_EXPORT int cge_create(int device, cge_context **out) {
   if (const char *v = std::getenv("CGE_CTAS_PER_SM")) ctx->knob_ctas_per_sm = std::atoi(v);
   if (const char *v = std::getenv("CGE_GRID_MULT")) ctx->knob_grid_mult = std::atoi(v) > 0 ? std::atoi(v) : 1;
   if (const char *v = std::getenv("CGE_ITEM_STEPS")) ctx->knob_chunk = std::atoi(v);
-  if (const char *v = std::getenv("CGE_CTA_WARPS")) ctx->knob_cta_warps = std::atoi(v);
   ctx->knob_no_wide = std::getenv("CGE_NO_WIDE") != nullptr;
   ctx->knob_no_tall = std::getenv("CGE_NO_TALL") != nullptr;
   ctx->knob_no_cluster = std::getenv("CGE_NO_CLUSTER") != nullptr;

@@ -42,7 +42,6 @@ struct Plan {
   int nb_col = 0, nb_row = 0, nb_res = 0;
   bool vec4 = false, keep_l2 = false, streamed = false, reorder = false;
   bool cluster = false;    // small-grid path: launch the grid as one thread-block cluster
-  int cta_warps = 0;       // CGE_CTA_WARPS knob (0 = the default CTA shape)
   size_t smem = 0;         // dynamic shared memory of the likelihood kernel
 };
 
@@ -60,12 +59,9 @@ using DefaultFinest = cge::ProductSlope;       // shared-slope neighbours: the f
 using DefaultFine = cge::ProductNeighbour<2>;  // degree-2 polynomial, strip umax <= 0.011
 using DefaultMid = cge::ProductNeighbour<3>;   // degree-3 polynomial, strip umax <= 0.05
 using DefaultCoarse = cge::ProductHybrid;
-constexpr int kDefaultMinB = 3;  // <= 80 registers: three 256-thread CTAs (24 warps) per SM
-#ifndef CGE_WIDE_WARPS
-#define CGE_WIDE_WARPS 16
-#endif
-constexpr int kWideWarps = CGE_WIDE_WARPS;   // ... or one CTA per SM: one pool for all its warps, and up to
-                                             // 102 registers per thread for the 8-column wide policy
+constexpr int kDefaultMinB = 3;  // forced 4-column policies: <= 80 registers, three 256-thread CTAs per SM
+constexpr int kWideWarps = 16;   // default kernel: one 512-thread CTA per SM -- one pool for all its
+                                 // warps, and 128 registers per thread for the 8-column policies
 
 template <class A, class B, class C, class D>
 constexpr int smem_bytes4() {

@@ -719,10 +719,7 @@ struct ProductHybrid {
 // (row % 3 == 1).  Four observations per loop iteration (one LDS.128), the per-row scalars of the
 // two triples packed.
 // ---------------------------------------------------------------------------------------
-#ifndef CGE_Q_UNROLL
-#define CGE_Q_UNROLL 1
-#endif
-constexpr int kObsLoopUnroll = CGE_Q_UNROLL;  // iterations (of 4 observations) per unrolled loop body
+constexpr int kObsLoopUnroll = 1;  // iterations (of 4 observations) per unrolled loop body
 constexpr double kPairedUmax = 0.011;
 constexpr double kPairedUmax3 = 0.05;
 

@@ -1,10 +1,9 @@
 // cge_launch_logspace.cu -- instantiations of the log-space likelihood kernels
 #include "cge_host.cuh"
 
-#ifndef CGE_LOG_WARPS
-#define CGE_LOG_WARPS 16
-#endif
 namespace cge_host {
+
+constexpr int kLogWarps = 16;
 
 template <class P, int MINB, bool STREAMED, int WARPS = cge::kWarps>
 static KernelChoice pick() {
@@ -24,11 +23,11 @@ int choose_logspace(const Plan &pl, KernelChoice *out) {
   if (pl.variant == CGE_VARIANT_LOG_F64)
     *out = pl.streamed ? pick<cge::LogSpaceF64, 1, true>() : pick<cge::LogSpaceF64, 1, false>();
   else
-    // (<= 128 registers either way: two 8-warp CTAs per SM, or -- like the product kernel -- one
-    // 16-warp CTA whose warps share a single pool)
+    // (<= 128 registers: like the product kernel, one 16-warp CTA per SM whose warps share a
+    // single pool -- 107.6 ms against 112.5 for two 8-warp CTAs with a pool each; the streamed form
+    // moves as a CTA and keeps two 8-warp CTAs per SM)
     *out = pl.streamed ? pick<cge::LogSpaceTiled<256>, 2, true>()
-           : pl.cta_warps != 8 ? pick<cge::LogSpaceTiled<256>, 1, false, CGE_LOG_WARPS>()
-                                        : pick<cge::LogSpaceTiled<256>, 2, false>();
+                       : pick<cge::LogSpaceTiled<256>, 1, false, kLogWarps>();
   return CGE_OK;
 }
 

@@ -44,12 +44,9 @@ int choose_product(const Plan &pl, KernelChoice *out) {
       *out = pick<DefaultCoarse, DefaultCoarse, DefaultCoarse, DefaultCoarse, false, 1>();
       break;
     default:
-      // one CTA per SM (a single pool for all its warps) that also holds the 8-column wide policy;
-      // CGE_CTA_WARPS=8: the three-CTA shape without it (A/B runs)
-      if (pl.cta_warps == 8)
-        *out = pick<DefaultFinest, DefaultFine, DefaultMid, DefaultCoarse, true, kDefaultMinB>();
-      else
-        *out = pick<DefaultFinest, DefaultFine, DefaultMid, DefaultCoarse, true, 1, kWideWarps, true>();
+      // one 16-warp CTA per SM (a single pool for all its warps) that also holds the 8-column
+      // tall and wide policies
+      *out = pick<DefaultFinest, DefaultFine, DefaultMid, DefaultCoarse, true, 1, kWideWarps, true>();
       break;
   }
   return CGE_OK;

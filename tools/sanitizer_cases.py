@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """GPU: a small tour of every likelihood path for compute-sanitizer (memcheck), sizes kept tiny:
-single-launch kernel, five-launch path with each product policy, log-space tiled and float64,
+single-launch kernel, three-launch path with each product policy, log-space tiled and float64,
 streamed observations, row shards with odd edges, grids that are not multiples of 4 or 128."""
 import sys
 
@@ -20,7 +20,8 @@ with cge.Context(0) as ctx:
             assert abs(float(r.posterior.astype(np.float64).sum()) - 1) < 1e-6, (N, mode)
     for N, mu_r in ((130, (19.9, 20.1)), (1030, (19.6, 20.4)), (1030, (18, 22)), (520, (18, 22))):
         for variant in (0, api.VARIANT_UNFUSED, api.VARIANT_PAIRED, api.VARIANT_PAIRED3,
-                        api.VARIANT_HYBRID, api.VARIANT_MUFU_ONLY):
+                        api.VARIANT_HYBRID, api.VARIANT_MUFU_ONLY, api.VARIANT_SLOPE,
+                        api.VARIANT_SLOPE_WIDE, api.VARIANT_SLOPE_TALL):
             r = ctx.grid_posterior(obs, N, mu_r, (1.6, 2.4), variant=variant)
             assert np.isfinite(r.expectations).all()
     for variant in (0, api.VARIANT_LOG_F64):
@@ -36,4 +37,9 @@ with cge.Context(0) as ctx:
     ctx.grid_posterior(obs, 130, (18, 22), (1, 3))
     ctx.grid_posterior(obs, 130, (18, 22), (1, 3), variant=api.VARIANT_UNFUSED)
     ctx.set_prior()
+    # several shards on one device through the peer exchange (publish flag, poll, local broadcast)
+    with cge.MultiContext([0, 0, 0]) as mc:
+        for _ in range(3):
+            r = mc.grid_posterior(obs, 301, (19.4, 19.7), (1.7, 2.1))
+            assert np.isfinite(r.expectations).all()
 print("sanitizer tour done")
