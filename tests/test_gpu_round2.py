@@ -187,3 +187,32 @@ def test_host_posterior_is_copied_in_row_chunks(ctx, readme_obs, N, dtype):
     assert dev.cpu().numpy().tobytes() == host.posterior.tobytes()
     assert res.expectations.tobytes() == host.expectations.tobytes()
     assert abs(host.posterior.astype(np.float64).sum() - 1.0) <= 1e-6
+
+
+@pytest.mark.parametrize("variant,path", [(0, "slope8x7"), (api.VARIANT_SLOPE_WIDE, "slope8"),
+                                           (api.VARIANT_SLOPE, "slope")])
+@pytest.mark.parametrize("N,shards", [(1100, 3), (1031, 4)])
+def test_shards_take_the_neighbour_row_policies(ctx, readme_obs, variant, path, N, shards):
+    """Row shards whose edges are multiples of neither 6 nor 7 rows, on a grid fine enough for the
+    8-column policies (the benchmark's path): the tall policy's 7-row groups and the others' 6-row
+    groups are anchored at GLOBAL rows, so every shard computes bit-identical cells to the
+    unsharded call; N = 1031 is not a multiple of 8 either (scalar store path at the last strip).
+    float64 output goes through the same kernels."""
+    mu_r, sg_r = (19.6, 20.4), (1.6, 2.4)
+    full = ctx.grid_posterior(readme_obs, N, mu_r, sg_r, variant=variant)
+    assert ctx.scale_info()["product_path"] == path
+    check_against(full, oracle.grid_posterior(readme_obs, N, *mu_r, *sg_r, oracle.NUM_F64),
+                  what=f"{path} N={N}")
+    with cge.MultiContext([0] * shards) as mc:
+        for step in range(2):
+            res = mc.grid_posterior(readme_obs, N, mu_r, sg_r, variant=variant)
+            assert res.posterior.tobytes() == full.posterior.tobytes(), f"step {step}"
+            assert np.abs(res.expectations - full.expectations).max() < 1e-9
+            assert np.abs(res.marg_sigma - full.marg_sigma).max() < 2e-8 * full.marg_sigma.max()
+            assert np.abs(res.marg_mu - full.marg_mu).max() < 1e-9 * full.marg_mu.max()
+        res64 = mc.grid_posterior(readme_obs, N, mu_r, sg_r, variant=variant,
+                                  posterior_dtype=api.POSTERIOR_F64)
+        assert abs(res64.posterior.sum() - 1.0) <= 5e-9
+        nz = res64.posterior > 1e-30
+        assert (np.abs(full.posterior.astype(np.float64)[nz] - res64.posterior[nz]) /
+                res64.posterior[nz]).max() <= 1.3e-7
