@@ -241,7 +241,7 @@ void make_plan(const cge_context *ctx, const cge_params *p, int rb, int re, cons
   while ((1ll << lc) < (long long)groups + 1) ++lc;
   pl->fixed_bits = 58 - lc - (pl->krows > 4 ? 1 : 0);
   pl->nb_col = (pl->N + 255) / 256;
-  pl->nb_row = (pl->rows_local + 7) / 8;
+  pl->nb_row = (pl->rows_local + 31) / 32;
   pl->nb_res = (pl->N + 255) / 256;
   pl->vec4 = (pl->N % 4 == 0) && ((reinterpret_cast<uintptr_t>(post) & 15u) == 0);
   // a shard that fits in L2 with room to spare is stored with the default cache policy, so the

@@ -21,7 +21,10 @@
 //
 // Data layout in HBM
 //   posterior  float32 [rows_local][N], sigma fastest (the reference layout, kernels.h:92)
-//   rowpart    float64 [rows_local][ncw]    per (row, warp column strip) partial row sums
+//   rowpart    float64 [ncw][rows_local]    per (128-column slot, row) partial row sums: the rows a warp
+//                                       walks down are contiguous, so L2 merges its 8-byte stores
+//                                       into full sectors (the [row][slot] layout cost a read-modify-
+//                                       write of every sector: 1.09 GB of DRAM reads at 65536^2)
 //   colacc     int64   [N]      column sums in per-column fixed point (exact, order-independent)
 //   partials   float64 [N+2]    {Z, sum_i mu_i*rowsum_i, colsum[0..N)}  <- the exchange payload
 //   results    float64 [4+2N]   {E[mu], E[sigma], Z, 1/Z}, marg_sigma[N], marg_mu[N]
@@ -130,7 +133,7 @@ struct LikeArgs {
   const float *prior_full;
   float prior_log2max;  // log2 of the largest |prior factor product| (0 for the flat prior)
   float *post;      // shard base (row `row_begin` at offset 0)
-  double *rowpart;  // [rows_local][ncw]
+  double *rowpart;  // [ncw][rows_local]
   unsigned long long *colacc;  // [N] fixed-point column sums (zero at launch; the fold kernel clears them)
   int *strip_next;  // streamed only: [ncw] next unclaimed item of each strip (zero at launch; the fold
                     // kernel clears them)
@@ -1248,6 +1251,7 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
   // register patch (hence which exponential path it takes) depends on its GLOBAL row only: a row
   // shard computes bit-identical unnormalised cells to the single-GPU run
   const int row_base = g.row_begin - g.row_begin % kRows;
+  const size_t rows_loc = (size_t)(g.row_end - g.row_begin);  // rowpart is [slot][row]: a warp's rows are contiguous
 
   // per-thread shared-memory slots, element k of thread t at [k * NT + t]
   // (the column accumulators and scales are kept as pairs: one 16-byte / 8-byte access per pair)
@@ -1446,11 +1450,11 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
     const int rq = row + (lane >> 3);  // lanes 0, 8, 16, 24 publish rows 0..3 of the patch
     if (!kAdj) {
       if ((lane & 7) == 0 && rq >= g.row_begin && rq < g.row_end)
-        g.rowpart[(size_t)(rq - g.row_begin) * (size_t)g.ncw + cw] = tot;
+        g.rowpart[(size_t)cw * rows_loc + (size_t)(rq - g.row_begin)] = tot;
     } else {
       const int slot = 2 * cw + ((lane >> 2) & 1);  // (lanes 0, 4 of every 8)
       if ((lane & 3) == 0 && rq >= g.row_begin && rq < g.row_end && slot < g.ncw)
-        g.rowpart[(size_t)(rq - g.row_begin) * (size_t)g.ncw + slot] = tot;
+        g.rowpart[(size_t)slot * rows_loc + (size_t)(rq - g.row_begin)] = tot;
     }
     if constexpr (kRows == 7) {  // rows 4..6 exactly as rows 0..2 (adjacent layout: two slots)
       double tot7 = ((double)q7.x + (double)q7.y) + ((double)q7.z + (double)q7.w);
@@ -1459,7 +1463,7 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
       const int rq7 = row + 4 + (lane >> 3);
       const int slot = 2 * cw + ((lane >> 2) & 1);
       if ((lane & 3) == 0 && (lane >> 3) < 3 && rq7 >= g.row_begin && rq7 < g.row_end && slot < g.ncw)
-        g.rowpart[(size_t)(rq7 - g.row_begin) * (size_t)g.ncw + slot] = tot7;
+        g.rowpart[(size_t)slot * rows_loc + (size_t)(rq7 - g.row_begin)] = tot7;
     }
     if (kRows == 6) {
       double tot2 = (double)w.x + (double)w.y;
@@ -1470,11 +1474,11 @@ __device__ __forceinline__ void run_strip(const LikeArgs &g, const ScaleInfo &sc
       const int rq2 = row + 4 + (lane >> 4);  // lanes 0, 16 publish rows 4, 5
       if (!kAdj) {
         if ((lane & 15) == 0 && rq2 >= g.row_begin && rq2 < g.row_end)
-          g.rowpart[(size_t)(rq2 - g.row_begin) * (size_t)g.ncw + cw] = tot2;
+          g.rowpart[(size_t)cw * rows_loc + (size_t)(rq2 - g.row_begin)] = tot2;
       } else {
         const int slot = 2 * cw + ((lane >> 3) & 1);  // (lanes 0, 8 of every 16)
         if ((lane & 7) == 0 && rq2 >= g.row_begin && rq2 < g.row_end && slot < g.ncw)
-          g.rowpart[(size_t)(rq2 - g.row_begin) * (size_t)g.ncw + slot] = tot2;
+          g.rowpart[(size_t)slot * rows_loc + (size_t)(rq2 - g.row_begin)] = tot2;
       }
     }
   };
@@ -1854,7 +1858,7 @@ __global__ void __launch_bounds__(kThreads)
   double z = 0.0, smu = 0.0;
   for (int i = tid; i < N; i += nt) {
     double s = 0.0;
-    for (int w = 0; w < g.ncw; ++w) s += __ldcg(g.rowpart + (size_t)i * g.ncw + w);
+    for (int w = 0; w < g.ncw; ++w) s += __ldcg(g.rowpart + (size_t)w * N + i);  // [slot][row], rows_local = N
     if (writer) a.rowsum[i] = s;
     z += s;
     smu += s * (double)range_value(i, N, g.range.mu0, g.range.mu1);

@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(256)
 //                       the likelihood kernel accumulated, scaled back with the same per-column
 //                       exponent (col_fixed_shift); the accumulators and the claim counters are
 //                       cleared for the next step
-//   blocks [nb_col, ..): warp per row, lanes stride the ncw strips, shuffle tree  -> rowsum;
+//   blocks [nb_col, ..): 32 rows each, 8 warps share the slots of a row (fixed tree) -> rowsum;
 //                        per-block partials of Z and sum mu_i*rowsum_i
 //   the last block to finish (threadfence + ticket) adds the block partials in index order:
 //                        out[0] = Z, out[1] = sum_i mu_i*rowsum_i
@@ -69,31 +69,32 @@ __global__ void __launch_bounds__(256) fold_publish_kernel(const FoldArgs f) {
     if (blockIdx.x == 0)
       for (int b = tid; b < f.ncw; b += 256) f.strip_next[b] = 0;
   } else {
+    // 32 rows per block: rowpart is [slot][row], so a warp's loads are coalesced along the rows;
+    // warp q adds the slots q, q + 8, ... of its 32 rows, warp 0 then adds the 8 partial sums of a
+    // row in index order (a fixed tree, and 8 x the loads in flight of a thread per row)
     const int rb = blockIdx.x - f.nb_col;
-    const int il = rb * 8 + warp;
-    double s = 0.0;
+    const int il = rb * 32 + lane;
+    double part = 0.0;
     if (il < f.rows_local) {
-      const double *src = f.rowpart + (size_t)il * f.ncw;
-      for (int w = lane; w < f.ncw; w += 32) s += src[w];
+      const double *src = f.rowpart + il;
+#pragma unroll 4
+      for (int w = warp; w < f.ncw; w += 8) part += src[(size_t)w * f.rows_local];
     }
-    s = warp_sum(s);
-    if (lane == 0) {
-      if (il < f.rows_local) f.rowsum[il] = s;
-      sh[0][warp] = s;
-      sh[1][warp] = il < f.rows_local
-                        ? s * (double)range_value(f.row_begin + il, N, f.range.mu0, f.range.mu1)
-                        : 0.0;
-    }
+    sh[warp][lane] = part;
     __syncthreads();
-    if (tid == 0) {
-      double z = 0.0, m = 0.0;
+    if (warp == 0) {
+      double s = 0.0;
 #pragma unroll
-      for (int w = 0; w < 8; ++w) {
-        z += sh[0][w];
-        m += sh[1][w];
+      for (int q = 0; q < 8; ++q) s += sh[q][lane];
+      if (il < f.rows_local) f.rowsum[il] = s;
+      const double z = warp_sum(s);
+      const double m = warp_sum(il < f.rows_local
+                                    ? s * (double)range_value(f.row_begin + il, N, f.range.mu0, f.range.mu1)
+                                    : 0.0);
+      if (lane == 0) {
+        f.zpart[rb] = z;
+        f.smupart[rb] = m;
       }
-      f.zpart[rb] = z;
-      f.smupart[rb] = m;
     }
   }
   // ---- last block: Z and sum mu*rowsum over the row-block partials, in index order
