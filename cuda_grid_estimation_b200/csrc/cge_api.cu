@@ -123,6 +123,7 @@ struct cge_context {
   PinnedBuf<float> host_obs;       // staging for host observations
   PinnedBuf<double> host_results;  // staging for {E, Z, 1/Z}, both marginals
   bool host_results_valid = false;  // the last step's kernel wrote host_results itself
+  bool want_host_results = false;   // set by cge_grid_posterior around its finalize call
   Plan plan;
   cge_host::KernelChoice kernel;   // the likelihood kernel of the current plan
   cge_timing timing = {};
@@ -823,6 +824,12 @@ static int finalize_impl(cge_context *ctx, const cge_params *p, void *posterior_
   a.partials = ctx->partials.ptr;
   a.rowsum = ctx->rowsum.ptr;
   a.results = ctx->results.ptr;
+  a.results_host = nullptr;
+  if (ctx->want_host_results) {  // cge_grid_posterior with host outputs: written in place over PCIe
+    CKRC(ctx->host_results.reserve(4 + 2 * (size_t)N));
+    a.results_host = ctx->host_results.ptr;
+    ctx->host_results_valid = true;
+  }
   a.espart = ctx->espart.ptr;
   a.ticket = ctx->tickets.ptr + 1;
   a.bcast = ctx->zbcast.ptr;
@@ -1199,8 +1206,15 @@ CGE_EXPORT int cge_grid_posterior(cge_context *ctx, const cge_params *p, const f
     rc = small_grid_step(ctx, p, obs_dev, static_cast<float *>(post_dev), st, host_out);
   } else {
     rc = cge_likelihood_partials(ctx, p, obs_dev, post_dev, st);
-    if (rc == CGE_OK)
+    if (rc == CGE_OK) {
+      // host destinations for the results: the finish kernel writes them into the mapped staging
+      // block itself (no D2H copy after it)
+      ctx->want_host_results = !(marg_mu && is_device_pointer(marg_mu)) &&
+                               !(marg_sigma && is_device_pointer(marg_sigma)) &&
+                               !(expectations && is_device_pointer(expectations));
       rc = post_to_host ? finalize_to_host(ctx, p, post_dev, posterior, st) : cge_finalize(ctx, p, post_dev, st);
+      ctx->want_host_results = false;
+    }
   }
   if (rc != CGE_OK) {
     if (!was_on) ctx->prof_on = false;

@@ -171,6 +171,8 @@ struct FinishArgs {
   double *partials;        // N+2: local / all-reduced vector in; summed vector out
   const double *rowsum;    // rows_local
   double *results;         // 4 + 2N
+  double *results_host;    // optional mapped pinned copy of `results` (saves the D2H copy of the
+                           // synchronous host-buffer entry point)
   double *espart;          // nb_res
   unsigned int *ticket;
   unsigned long long *bcast;  // peer exchange: {step flag, Z bits, Smu bits} block 0 publishes locally
@@ -327,7 +329,12 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishArgs a) {
       const double m = c * inv;
       marg_sigma[idx] = m;
       es = m * (double)range_value(idx, N, a.range.sg0, a.range.sg1);
-      marg_mu[idx] = (idx >= a.row_begin && idx < a.row_end) ? a.rowsum[idx - a.row_begin] * inv : 0.0;
+      const double mm = (idx >= a.row_begin && idx < a.row_end) ? a.rowsum[idx - a.row_begin] * inv : 0.0;
+      marg_mu[idx] = mm;
+      if (a.results_host) {
+        a.results_host[4 + idx] = m;
+        a.results_host[4 + N + idx] = mm;
+      }
     }
     es = block_sum(es, scratch);
     if (tid == 0) a.espart[blockIdx.x] = es;
@@ -349,6 +356,12 @@ __global__ void __launch_bounds__(256) finish_kernel(const FinishArgs a) {
         a.results[1] = e;
         a.results[2] = z;
         a.results[3] = inv;
+        if (a.results_host) {
+          a.results_host[0] = smu * inv;
+          a.results_host[1] = e;
+          a.results_host[2] = z;
+          a.results_host[3] = inv;
+        }
         *a.ticket = 0u;
       }
     }
