@@ -7,7 +7,7 @@ summed over ranks (one all-reduce); after it every rank knows Z, E[mu], the sigm
 E[sigma], and scales its own rows by 1/Z.  No posterior data ever moves between GPUs.
 
 ``pack_partials`` / ``finalize_from_partials`` restate, in numpy, exactly what the device
-kernels fold_partials_kernel / results_kernel compute, so the multi-rank host logic can be
+kernels fold_publish_kernel / finish_kernel compute, so the multi-rank host logic can be
 exercised on CPU with the gloo backend (tests/test_sharding_gloo.py).
 """
 from __future__ import annotations
@@ -40,7 +40,7 @@ def pack_partials(unnormalised_rows: np.ndarray, mu_rows: np.ndarray) -> np.ndar
 
 def finalize_from_partials(partials: np.ndarray, rowsum_local: np.ndarray, sigma: np.ndarray,
                            row_begin: int, row_end: int):
-    """Marginals and expectations from the all-reduced partial vector (results_kernel)."""
+    """Marginals and expectations from the all-reduced partial vector (finish_kernel)."""
     partials = np.asarray(partials, np.float64)
     N = partials.size - 2
     inv = 1.0 / partials[0]
@@ -138,7 +138,7 @@ class ShardedGridPosterior:
         from .api import device_tensor
         stream = self.torch.cuda.current_stream().cuda_stream
         if self.world == 1:
-            # no exchange: the fused asynchronous entry (one launch for small grids, five otherwise)
+            # no exchange: the fused asynchronous entry (one launch for small grids, three otherwise)
             self.ctx.grid_posterior_async(self.params, obs_dev, posterior_dev, stream)
             return
         self.ctx.likelihood_partials(self.params, obs_dev, posterior_dev, stream)

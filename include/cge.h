@@ -92,16 +92,19 @@ typedef struct cge_params {
 
 /* likelihood-kernel variants for cge_params.variant */
 enum {
-  CGE_VARIANT_DEFAULT = 0,   /* paired rows on fine grids -- degree-2 polynomial, or degree-3 on
-                                grids up to 4.5x coarser -- hybrid otherwise; chosen on the device,
-                                per CTA column band of up to 1024 sigma columns, from the ranges
-                                and the observations */
+  CGE_VARIANT_DEFAULT = 0,   /* neighbour rows on fine grids (one exponential on MUFU.EX2 per 7 or
+                                3 rows, the others derived from it on the FMA pipe: the tall /
+                                wide 8-column policies for a whole grid, the 4-column shared-slope
+                                one or a per-cell degree-2 / degree-3 polynomial per 128-column
+                                strip), hybrid otherwise; chosen on the device from the ranges and
+                                the observations */
   CGE_VARIANT_MUFU_ONLY = 1, /* scalar arithmetic, every 2^t on MUFU.EX2 (the MUFU roofline case) */
-  CGE_VARIANT_PAIRED = 3,    /* paired rows, forced: packed f32x2 arithmetic; of two vertically
-                                adjacent cells one factor is 2^t on MUFU.EX2, the other is derived
-                                from it, e * 2^u with 2^u - 1 a degree-2 FMA-pipe polynomial (only
-                                accurate while the row spacing keeps |u| <= 0.011) */
-  CGE_VARIANT_PAIRED3 = 8,   /* paired rows with the degree-3 polynomial, forced (|u| <= 0.05) */
+  CGE_VARIANT_PAIRED = 3,    /* neighbour rows with a per-cell polynomial, forced: packed f32x2
+                                arithmetic; of three vertically adjacent cells the middle one's
+                                factor is 2^t on MUFU.EX2, the two others are derived from it,
+                                e * 2^u with 2^u - 1 a degree-2 FMA-pipe polynomial (only accurate
+                                while the row spacing keeps |u| <= 0.011) */
+  CGE_VARIANT_PAIRED3 = 8,   /* the same with the degree-3 polynomial, forced (|u| <= 0.05) */
   CGE_VARIANT_SLOPE = 9,     /* neighbour rows with the polynomial shared by a thread's four adjacent
                                 columns, forced (only accurate on the finest grids) */
   CGE_VARIANT_SLOPE_WIDE = 10, /* the same with eight adjacent columns per thread (32-byte stores),

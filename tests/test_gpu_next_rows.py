@@ -79,7 +79,7 @@ def test_sequential_update_equals_batch(readme_obs, N):
     """The prior row used the way Bayes updating uses it: the posterior of the first 20
     observations, left on the device, becomes the full prior table for the other 30; the result
     must be the posterior of all 50 (flat prior).  N=200 goes through the single-launch kernel,
-    N=1500 through the five-launch path."""
+    N=1500 through the three-launch path."""
     import torch
     dev = torch.device("cuda", 0)
     with cge.Context(0) as ctx:

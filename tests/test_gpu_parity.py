@@ -62,7 +62,7 @@ def test_readme_product_vs_oracle(ctx, readme_obs):
 @pytest.mark.parametrize("variant", [api.VARIANT_MUFU_ONLY, api.VARIANT_HYBRID, api.VARIANT_UNFUSED])
 def test_product_kernel_variants(ctx, readme_obs, variant):
     """The MUFU-only scalar kernel, the forced hybrid (MUFU + degree-5 FMA polynomial) and the
-    default through the five-launch path meet the same tolerances; N=1024 uses the wide tile
+    default through the three-launch path meet the same tolerances; N=1024 uses the wide tile
     shape, N=101 the narrow one."""
     for N in (101, 1024):
         res = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), variant=variant)
@@ -198,7 +198,7 @@ def test_logspace_kernel_variants(ctx, variant):
 @pytest.mark.parametrize("N", [1, 2, 3, 5, 64, 101, 128, 129, 200, 255, 256, 257])
 def test_single_launch_small_grids(ctx, readme_obs, N):
     """Grids up to 256 points per axis run as one launch (tables, likelihood, fold, results and
-    scale in small_grid_kernel).  Same cells as the five-launch path bit for bit before the 1/Z
+    scale in small_grid_kernel).  Same cells as the three-launch path bit for bit before the 1/Z
     scale; sums agree to float64 rounding; both against the oracle; repeatable bit for bit."""
     for mode, num in ((cge.MODE_PRODUCT_F32, oracle.NUM_REF), (cge.MODE_LOGSPACE, oracle.NUM_F64)):
         one = ctx.grid_posterior(readme_obs, N, (18, 22), (1, 3), mode=mode)
@@ -269,7 +269,7 @@ def test_error_behaviour(ctx, readme_obs):
 # ---------------------------------------------------------------------------------------
 # device-pointer phase API + row shards on one GPU (the multi-GPU data path, minus NCCL)
 # ---------------------------------------------------------------------------------------
-@pytest.mark.parametrize("N", [257, 4100])  # 257: hybrid path; 4100: paired rows, odd shard edges
+@pytest.mark.parametrize("N", [257, 4100])  # 257: hybrid path; 4100: neighbour rows, odd shard edges
 def test_phase_api_with_row_shards(ctx, readme_obs, N):
     import torch
     dev = torch.device("cuda", 0)
@@ -314,7 +314,7 @@ def test_phase_api_with_row_shards(ctx, readme_obs, N):
 
 def test_async_fused_entry(ctx, readme_obs):
     """cge_grid_posterior_async: device buffers on the caller's stream, nothing waited for until
-    read_results; same bits as the synchronous call (one launch at N=101, five at N=1000)."""
+    read_results; same bits as the synchronous call (one launch at N=101, three at N=1000)."""
     import torch
     dev = torch.device("cuda", 0)
     obs_t = torch.from_numpy(readme_obs).to(dev)
@@ -440,7 +440,7 @@ def test_default_picks_the_path_on_the_device(ctx, readme_obs):
             assert same == (want == name) or (want == name and np.ptp(ratio) < 3e-7), (b, name)
     ref = oracle.grid_posterior(far, 4096, 18, 22, 1, 3, oracle.NUM_F64)
     check_against(d, ref, what="far observation, N=4096")
-    # a wide sigma range: hybrid only where sigma is small, paired rows in the other bands
+    # a wide sigma range: hybrid only where sigma is small, neighbour rows in the other bands
     d = ctx.grid_posterior(readme_obs, 4096, (18, 22), (0.4, 3))
     paths = api.band_paths(ctx.scale_info(), oracle.linspace(4096, 0.4, 3))
     assert paths[0] not in ("paired", "slope") and paths[-1] == "slope", paths

@@ -1,6 +1,6 @@
 """CPU, world_size 2 over gloo: the multi-rank host logic of the path -- row sharding, the
 packed partial vector, its all-reduce, and the finalisation -- with the oracle standing in for
-the per-rank likelihood kernel.  The device kernels fold_partials_kernel / results_kernel compute
+the per-rank likelihood kernel.  The device kernels fold_publish_kernel / finish_kernel compute
 exactly what pack_partials / finalize_from_partials state."""
 import os
 

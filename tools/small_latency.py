@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """GPU: end-to-end latency of cge_grid_posterior on small grids (host observations in;
 expectations and marginals to the host; posterior left on the device), single-launch path
-against the five-launch path."""
+against the three-launch path."""
 import json
 import sys
 import time
