@@ -181,3 +181,39 @@ def test_reference_main_unchanged_on_libcge():
     assert a.returncode == 0 and b.returncode == 0, (a.stdout, a.stderr, b.stdout, b.stderr)
     assert "Inferred mu" in a.stdout
     assert a.stdout.strip().splitlines()[-2:] == b.stdout.strip().splitlines()[-2:], (a.stdout, b.stdout)
+
+
+@pytest.mark.parametrize("variant", [0, 10, 9])   # default (tall, 7 x 8), wide (6 x 8), 4-column slope
+def test_non_flat_prior_on_the_neighbour_row_policies(readme_obs, variant):
+    """The prior is multiplied in the likelihood kernel's epilogue: the same check on a grid fine
+    enough for the 8-column policies (the prior path stores from the unpacked cells, N = 1100 is
+    not a multiple of 8 at the last strip)."""
+    import torch
+    N, mu_r, sg_r = 1100, (19.6, 20.4), (1.6, 2.4)
+    mu = oracle.linspace(N, *mu_r).astype(np.float64)
+    sg = oracle.linspace(N, *sg_r).astype(np.float64)
+    pm = np.exp(-0.5 * ((mu - 20.2) / 0.1) ** 2).astype(np.float32)
+    ps = (1.0 / sg).astype(np.float32)
+    pf = np.random.default_rng(6).uniform(0.5, 1.5, size=(N, N)).astype(np.float32)
+    likes = oracle.grid_likes(readme_obs, N, *mu_r, *sg_r, oracle.NUM_F64)
+
+    def ref(prior):
+        post = likes * prior
+        post /= post.sum()
+        return dict(posterior=post, marg_mu=post.sum(axis=1), marg_sigma=post.sum(axis=0),
+                    expectations=np.array([np.sum(mu * post.sum(axis=1)), np.sum(sg * post.sum(axis=0))]))
+
+    with cge.Context(0) as ctx:
+        flat = ctx.grid_posterior(readme_obs, N, mu_r, sg_r, variant=variant)
+        if variant == 0:
+            assert ctx.scale_info()["product_path"] == "slope8x7"
+        ctx.set_prior(pm, ps, N)
+        res = ctx.grid_posterior(readme_obs, N, mu_r, sg_r, variant=variant)
+        _check(res, ref(pm.astype(np.float64)[:, None] * ps.astype(np.float64)[None, :]))
+        assert abs(res.expectations[0] - flat.expectations[0]) > 0.01
+        ctx.set_prior(None, ps, N, torch.from_numpy(pf).cuda())
+        _check(ctx.grid_posterior(readme_obs, N, mu_r, sg_r, variant=variant),
+               ref(pf.astype(np.float64) * ps.astype(np.float64)[None, :]))
+        ctx.set_prior()
+        again = ctx.grid_posterior(readme_obs, N, mu_r, sg_r, variant=variant)
+        assert again.posterior.tobytes() == flat.posterior.tobytes()
