@@ -176,21 +176,94 @@ __device__ __forceinline__ int col_fixed_shift(double a, double c0, const ScaleI
   return max(-120, min(120, fixed_bits - e - 2));
 }
 
-// per-thread column coefficients in float64: a_j = -0.5*log2(e)/sigma_j^2, c0_j = -log2(sigma_j*sqrt(2 pi)),
-// sigma_j from the reference's float32 range formula
+// Column coefficients in float64: a_j = -0.5*log2(e)/sigma_j^2, c0_j = -log2(sigma_j*sqrt(2 pi)),
+// sigma_j from the reference's float32 range formula.  A float64 divide and log2 per column made a
+// strip set-up ~1700 instructions per warp (1.4 % of the 16384^2 kernel, 11 % on a 2048-row shard,
+// 22 % at 4096^2), so columns come in GROUPS of G neighbours (4, or 8 for the adjacent layouts):
+// the group's first column is evaluated exactly and the others from it,
+//   sigma_k = sigma_0 (1 + d):  1/sigma_k = (1/sigma_0) / (1 + d),  log2 sigma_k = log2 sigma_0 + log2(1 + d)
+// with 8-term series in d (|d| <= 0.01: truncation below 1e-19; coarser groups take the exact
+// path).  Every kernel that needs a column's coefficients (the likelihood kernel, and the fold
+// kernels for the fixed-point exponent) calls these same functions with the same G, and every
+// operation is an explicit intrinsic, so they all get the same bits.
+struct ColumnBase {
+  double sd, rinv, l2;  // sigma_0, 1/sigma_0, log2(sigma_0 sqrt(2 pi))
+};
+__device__ __forceinline__ ColumnBase column_base(const RangeArgs &r, int jb) {
+  ColumnBase b;
+  b.sd = (double)range_value(min(jb, r.N - 1), r.N, r.sg0, r.sg1);
+  b.rinv = __ddiv_rn(1.0, b.sd);
+  b.l2 = log2(__dmul_rn(b.sd, 2.5066282746310005024));
+  return b;
+}
+__device__ __forceinline__ void column_from_base(const RangeArgs &r, int j, const ColumnBase &b,
+                                                 double &a, double &c0) {
+  const double sd = (double)range_value(min(j, r.N - 1), r.N, r.sg0, r.sg1);
+  const double d = __fma_rn(sd, b.rinv, -1.0);
+  double rinv, l2;
+  if (fabs(d) <= 0.01) {
+    // 1/(1+d) = 1 - d + d^2 - ... + d^8;  ln(1+d) = d (1 - d/2 + d^2/3 - ... - d^7/8)
+    double q = 1.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) q = __fma_rn(-d, q, 1.0);
+    rinv = __dmul_rn(b.rinv, q);
+    double p = -1.0 / 8.0;
+    p = __fma_rn(p, d, 1.0 / 7.0);
+    p = __fma_rn(p, d, -1.0 / 6.0);
+    p = __fma_rn(p, d, 1.0 / 5.0);
+    p = __fma_rn(p, d, -1.0 / 4.0);
+    p = __fma_rn(p, d, 1.0 / 3.0);
+    p = __fma_rn(p, d, -1.0 / 2.0);
+    p = __fma_rn(p, d, 1.0);
+    l2 = __fma_rn(__dmul_rn(p, d), 1.4426950408889634074, b.l2);
+  } else {
+    rinv = __ddiv_rn(1.0, sd);
+    l2 = log2(__dmul_rn(sd, 2.5066282746310005024));
+  }
+  a = __dmul_rn(-0.5 * 1.4426950408889634074, __dmul_rn(rinv, rinv));
+  c0 = -l2;
+}
+// one column on its own (fold kernels): G = neighbours per group of the policy that ran
+__device__ __forceinline__ void column_coef(const RangeArgs &r, int j, int G, double &a, double &c0) {
+  const ColumnBase b = column_base(r, j - j % G);
+  column_from_base(r, j, b, a, c0);
+}
+
+// per-thread coefficients of a policy's columns (groups of 4 neighbours 128 columns apart, or KC
+// adjacent columns)
 template <int KC, bool ADJ = false>
 struct ColumnCoefs {
+  static constexpr int kGroup = ADJ ? KC : 4;
   double a[KC], c0[KC];
   __device__ __forceinline__ void compute(const RangeArgs &r, int j0) {
 #pragma unroll
-    for (int cidx = 0; cidx < KC; ++cidx) {
-      const int j = col_at<ADJ>(j0, cidx);
-      const double sd = (double)range_value(min(j, r.N - 1), r.N, r.sg0, r.sg1);
-      a[cidx] = j < r.N ? coef_a(sd) : 0.0;
-      c0[cidx] = j < r.N ? coef_c0(sd) : 0.0;
+    for (int gb = 0; gb < KC; gb += kGroup) {
+      const ColumnBase b = column_base(r, col_at<ADJ>(j0, gb));  // (j0 is a multiple of kGroup)
+#pragma unroll
+      for (int k = 0; k < kGroup; ++k) {
+        const int j = col_at<ADJ>(j0, gb + k);
+        double av, cv;
+        column_from_base(r, j, b, av, cv);
+        a[gb + k] = j < r.N ? av : 0.0;
+        c0[gb + k] = j < r.N ? cv : 0.0;
+      }
     }
   }
 };
+
+// mean a_j of the two middle columns of a thread's KC neighbouring columns (layouts whose columns
+// are j0 .. j0 + KC - 1), each replaced by the last column inside the grid when it lies outside
+template <int KC, bool ADJ>
+__device__ __forceinline__ double middle_slope(const ColumnCoefs<KC, ADJ> &cf, int j0, int N) {
+  double lo = cf.a[0], hi = cf.a[0];
+#pragma unroll
+  for (int cidx = 1; cidx <= KC / 2; ++cidx) {
+    const bool in = j0 + cidx < N;
+    if (cidx <= KC / 2 - 1 && in) lo = cf.a[cidx];
+    if (in) hi = cf.a[cidx];
+  }
+  return 0.5 * (lo + hi);
+}
 
 // ---------------------------------------------------------------------------------------
 // setup_scale: block-wide (every thread of the block calls it, every thread gets the result).
@@ -931,11 +1004,9 @@ struct ProductSlopeT {
     const double U = sc.umax;
     const double k2 = 0.24022650695910071233;
     k1 = (float)(0.69314718055994530942 + 0.0555041086648215799 * 0.75 * U * U);
-    // slope of the thread's columns: the mean of the two middle ones (clamped to the grid, so a
-    // thread that straddles the last column still gets a slope of its own columns)
-    const double s1 = (double)range_value(min(j0 + kCols / 2 - 1, g.N - 1), g.N, g.range.sg0, g.range.sg1);
-    const double s2 = (double)range_value(min(j0 + kCols / 2, g.N - 1), g.N, g.range.sg0, g.range.sg1);
-    a0k2 = (float)(0.5 * (coef_a(s1) + coef_a(s2)) * k2);
+    // slope of the thread's columns: the mean of the two middle ones (of the last one inside the
+    // grid for a thread that straddles its edge, so it is always a slope of its own columns)
+    a0k2 = (float)(middle_slope(cf, j0, g.N) * k2);
 #pragma unroll
     for (int h = 0; h < kPairs; ++h) {
       float av[2], cv[2];
@@ -1063,9 +1134,7 @@ struct ProductSlopeTall {
     const double U = 3.0 * sc.umax;  // the rows furthest from the MUFU row
     const double k2 = 0.24022650695910071233;
     k1 = (float)(0.69314718055994530942 + 0.0555041086648215799 * 0.75 * U * U);
-    const double s1 = (double)range_value(min(j0 + kCols / 2 - 1, g.N - 1), g.N, g.range.sg0, g.range.sg1);
-    const double s2 = (double)range_value(min(j0 + kCols / 2, g.N - 1), g.N, g.range.sg0, g.range.sg1);
-    a0k2 = (float)(0.5 * (coef_a(s1) + coef_a(s2)) * k2);
+    a0k2 = (float)(middle_slope(cf, j0, g.N) * k2);
 #pragma unroll
     for (int h = 0; h < kPairs; ++h) {
       float av[2], cv[2];
@@ -1867,8 +1936,9 @@ __global__ void __launch_bounds__(kThreads)
                  // accumulators and claim counters left at zero for the next call
     const ScaleInfo sc = *reinterpret_cast<const ScaleInfo *>(smem_raw + 16);
     for (int j = tid; j < N; j += nt) {
-      const double sd = (double)range_value(j, N, g.range.sg0, g.range.sg1);
-      const int s = col_fixed_shift(coef_a(sd), coef_c0(sd), sc, g.n, g.prior_log2max, g.fixed_bits);
+      double ca, cc;
+      column_coef(g.range, j, 4, ca, cc);  // (the single-launch kernel has the 4-neighbour layouts only)
+      const int s = col_fixed_shift(ca, cc, sc, g.n, g.prior_log2max, g.fixed_bits);
       a.partials[2 + j] = scalbn((double)(long long)__ldcg(g.colacc + j), -s);
       g.colacc[j] = 0ull;
     }

@@ -61,8 +61,11 @@ __global__ void __launch_bounds__(256) fold_publish_kernel(const FoldArgs f) {
     const int j = blockIdx.x * 256 + tid;
     if (j < N) {
       const ScaleInfo sc = *f.scale;
-      const double sd = (double)range_value(j, N, f.range.sg0, f.range.sg1);
-      const int s = col_fixed_shift(coef_a(sd), coef_c0(sd), sc, f.n, f.prior_log2max, f.fixed_bits);
+      // the same coefficient functions, with the same neighbour-group size, as the likelihood
+      // kernel that scaled the sums (8 adjacent columns for the wide / tall policies, else 4)
+      double ca, cc;
+      column_coef(f.range, j, sc.wide != 0.0 ? 8 : 4, ca, cc);
+      const int s = col_fixed_shift(ca, cc, sc, f.n, f.prior_log2max, f.fixed_bits);
       f.out[2 + j] = scalbn((double)(long long)f.colacc[j], -s);
       f.colacc[j] = 0ull;
     }
