@@ -92,3 +92,36 @@ def test_product_does_not_import_oracle():
             assert m.group(1) in ("cpu_rate_sample", "run_reference", "oracle_all_cores"), m.group(1)
         if "oracle_all_cores()" in m.group(0):
             assert m.group(1) in ("cpu_rate_sample", "run_reference", "oracle_all_cores"), m.group(1)
+
+
+def test_policy_mirror_matches_the_documented_bounds():
+    """api.slope_error_bound / api._product_path / api.band_paths restate the device-side choice
+    of the product policy (cge::ProductSlopeT::eligible, likelihood_cta); the numbers DESIGN.md
+    quotes for the README ranges follow from them (no GPU needed)."""
+    import numpy as np
+
+    from cuda_grid_estimation_b200 import api
+    info = dict(paired_umax=0.011, paired3_umax=0.05, slope_err_max=2.0 ** -24, wide=0.0)
+
+    def readme(N):   # umax and relative sigma step of the README ranges (mu 18..22, sigma 1..3)
+        return 0.008386777734265279 * 4096 / N, (2.0 / (N - 1)) / 1.0
+
+    u, r = readme(4096)
+    assert abs(api.slope_error_bound(u, r, 1.5) - 2.503e-8) < 1e-10      # 4 columns
+    assert abs(api.slope_error_bound(u, r, 3.5) - 5.850e-8) < 1e-10      # 8 columns: just inside 2^-24
+    assert api.slope_error_bound(u, r, 3.5) <= info["slope_err_max"]
+    u, r = readme(3300)
+    assert api._product_path(info, u, r) == "slope"
+    assert api._product_path(info, u, (3.0 / 3299) / 1.0) == "paired"    # sigma in [1, 4]: columns too far apart
+    assert api._product_path(info, *readme(1024)) == "paired3"
+    assert api._product_path(info, *readme(512)) == "hybrid"
+    # the tall policy's bound: 3 umax <= 0.011 and 9 x the 8-column slope term <= 2^-24
+    u, r = readme(9600)
+    assert 3 * u <= 0.011 and 9 * api.slope_error_bound(u, r, 3.5) <= 2.0 ** -24
+    u, r = readme(9000)
+    assert 3 * u > 0.011
+    # per-band choice on a wide sigma range: costlier arithmetic only where sigma is small
+    sigma = np.linspace(0.4, 3.0, 4096).astype(np.float32)
+    paths = api.band_paths(dict(info, ustep=u * 9000 / 4096 / 0.7213475204444817), sigma)
+    assert len(paths) == 32 and paths[0] != "slope" and paths[-1] == "slope"
+    assert api.band_paths(dict(info, wide=2.0, ustep=0.0), sigma) == ["slope8x7"] * 32
