@@ -19,6 +19,9 @@ OBJ_DIR = os.path.join(PKG_DIR, "_obj")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
+    # the SASS + line tables of ~40 kernel instantiations: 10.2 MB uncompressed, 4.0 MB compressed
+    # (the driver inflates a kernel's image when the module is first loaded, not per launch)
+    "-Xfatbin=-compress-all",
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
 ] + os.environ.get("CGE_BUILD_DEFINES", "").split()   # e.g. -DCGE_DEBUG_TIMES (diagnostic builds)
 
