@@ -56,11 +56,11 @@ TRAFFIC_FILE = os.path.join(ROOT, "profiles", "r02_dram_traffic.json")
 
 # instructions the likelihood kernel issues per pdf-eval on the two pipes that bound it, by the
 # arithmetic policy that ran (cge_scale_info "product_path"); counted from the SASS of the inner
-# loop (profiles/r02_sass_inner_loop_*.txt): MUFU.EX2 per eval, FMA-pipe lane-ops per eval
+# loop (profiles/r02_sass_inner_loop_*.txt, written by tools/sass_inner_loop.py): MUFU.EX2 per eval, FMA-pipe lane-ops per eval
 PIPE_OPS = {
-    # per thread and observation (6 rows x 4 columns = 24 evals): 8 MUFU.EX2 and
     "slope8x7": (8 / 56, 2 * 67 / 56),  # tall: 7 rows x 8 columns = 56 evals: 8 MUFU.EX2 + 67 packed
     "slope8": (16 / 48, 2 * 62 / 48),  # wide: 6 rows x 8 columns = 48 evals: 16 MUFU.EX2 + 62 packed
+    # 4-column policies, per thread and observation (6 rows x 4 columns = 24 evals): 8 MUFU.EX2 and
     "slope": (8 / 24, 2 * 34 / 24),    # 34 packed f32x2 instructions (2 lane-ops each)
     "paired": (8 / 24, 2 * 44 / 24),   # 44 packed (the polynomial per cell instead of per row)
     "paired3": (8 / 24, 2 * 52 / 24),  # + 8 packed for the cubic term
