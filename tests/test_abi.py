@@ -125,3 +125,41 @@ def test_policy_mirror_matches_the_documented_bounds():
     paths = api.band_paths(dict(info, ustep=u * 9000 / 4096 / 0.7213475204444817), sigma)
     assert len(paths) == 32 and paths[0] != "slope" and paths[-1] == "slope"
     assert api.band_paths(dict(info, wide=2.0, ustep=0.0), sigma) == ["slope8x7"] * 32
+
+
+def test_argument_errors_need_no_device():
+    """The error behaviour of the boundary (include/cge.h: int status + cge_last_error(), never
+    exit, never print) for the mistakes that are caught before any CUDA call -- so it can be checked
+    in the build container too."""
+    import threading
+
+    lib = cge.load_library()
+    null = C.c_void_p()
+    params = api.Params()
+    assert lib.cge_destroy(None) == api.OK
+    assert lib.cge_destroy_multi(None) == api.OK
+    assert lib.cge_create(0, None) == api.ERR_BAD_ARG
+    assert b"NULL" in lib.cge_last_error()
+    out = C.c_void_p()
+    for n_gpus in (0, -1, 1000):
+        assert lib.cge_create_multi(n_gpus, None, C.byref(out)) == api.ERR_BAD_ARG
+        assert b"n_gpus" in lib.cge_last_error() and not out.value
+    assert lib.cge_grid_posterior(None, C.byref(params), None, None, None, None, None, None) == api.ERR_BAD_ARG
+    assert b"context is NULL" in lib.cge_last_error()
+    assert lib.cge_grid_posterior_multi(None, C.byref(params), None, None, None, None, None, None) == api.ERR_BAD_ARG
+    assert lib.cge_multi_size(None, None) == api.ERR_BAD_ARG
+    assert lib.cge_results(None, C.byref(null), None) == api.ERR_BAD_ARG
+    # the message belongs to the calling thread (cge.h: one context per host thread)
+    seen = {}
+
+    def other():
+        seen["before"] = lib.cge_last_error()
+        lib.cge_multi_size(None, None)
+        seen["after"] = lib.cge_last_error()
+
+    lib.cge_create(0, None)
+    t = threading.Thread(target=other)
+    t.start()
+    t.join()
+    assert seen["before"] == b"" and seen["after"] != b""
+    assert b"out is NULL" in lib.cge_last_error()
