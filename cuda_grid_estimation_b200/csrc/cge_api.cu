@@ -1061,6 +1061,17 @@ extern "C" int cge_internal_share_stream(cge_context *ctx, void *stream) {
   return CGE_OK;
 }
 
+// cge_multi.cu, host outputs: `on` makes the finish kernel of the following cge_finalize write the
+// result block into this context's pinned staging block as well (what cge_grid_posterior does for
+// host destinations: no device-to-host copy afterwards); `block` receives that staging block once
+// such a finish kernel has been issued (valid after the stream has been synchronised)
+extern "C" int cge_internal_host_results(cge_context *ctx, int on, const double **block) {
+  if (!ctx) return set_error(CGE_ERR_BAD_ARG, "context is NULL");
+  ctx->want_host_results = on != 0;
+  if (block) *block = ctx->host_results_valid ? ctx->host_results.ptr : nullptr;
+  return CGE_OK;
+}
+
 CGE_EXPORT int cge_results(cge_context *ctx, double **results_dev, size_t *count) {
   if (!ctx) return set_error(CGE_ERR_BAD_ARG, "context is NULL");
   if (!ctx->plan.valid) return set_error(CGE_ERR_BAD_ARG, "no likelihood call has been made");

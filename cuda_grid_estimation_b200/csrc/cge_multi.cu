@@ -28,6 +28,7 @@ extern "C" int cge_internal_peer_attach(cge_context *ctx, int rank, int world,
                                         unsigned char *const *blocks);
 extern "C" int cge_internal_peer_detach(cge_context *ctx);
 extern "C" int cge_internal_share_stream(cge_context *ctx, void *stream);
+extern "C" int cge_internal_host_results(cge_context *ctx, int on, const double **block);
 
 using cge_host::set_error;
 
@@ -47,8 +48,8 @@ struct cge_multi {
   std::vector<size_t> obs_cap;
   float *obs_pinned = nullptr;       // portable mapped pinned staging of the observations
   size_t obs_pinned_cap = 0;
-  double *res_pinned = nullptr;      // {head[4], marg_sigma[N], marg_mu[N]}
-  size_t res_pinned_cap = 0;
+  std::vector<const double *> res_host;  // each context's pinned result block {head[4],
+                                         // marg_sigma[N], marg_mu[N]}, written by its finish kernel
   std::vector<cudaEvent_t> ev0, ev1;
   int last_dtype = 0, last_N = 0;
 };
@@ -113,8 +114,9 @@ int prepare(cge_multi *m, const cge_params *p) {
   return connect_peers(m, p->grid_size);
 }
 
-// both phases on every device; obs[i] is readable from device i
-int issue_step(cge_multi *m, const cge_params *p, const float *const *obs) {
+// both phases on every device; obs[i] is readable from device i.  host_results: every finish
+// kernel also writes its result block into its context's pinned staging block (m->res_host[i])
+int issue_step(cge_multi *m, const cge_params *p, const float *const *obs, bool host_results) {
   cge_params q = *p;
   for (int i = 0; i < m->n; ++i) {  // phase 1 everywhere first: every flag is on its way before any
     q.row_begin = m->rb[i];         // finish kernel starts to poll
@@ -124,7 +126,12 @@ int issue_step(cge_multi *m, const cge_params *p, const float *const *obs) {
   for (int i = 0; i < m->n; ++i) {
     q.row_begin = m->rb[i];
     q.row_end = m->re[i];
-    CKRC(cge_finalize(m->ctx[i], &q, m->post[i], m->stream[i]));
+    if (host_results) CKRC(cge_internal_host_results(m->ctx[i], 1, nullptr));
+    const int rc = cge_finalize(m->ctx[i], &q, m->post[i], m->stream[i]);
+    if (host_results) cge_internal_host_results(m->ctx[i], 0, &m->res_host[i]);
+    if (rc != CGE_OK) return rc;
+    if (host_results && !m->res_host[i])
+      return set_error(CGE_ERR_CUDA, "shard %d: the finish kernel has no host result block", i);
   }
   return CGE_OK;
 }
@@ -152,6 +159,7 @@ CGE_EXPORT int cge_create_multi(int n_gpus, const int *devices, cge_multi **out)
   m->post_bytes.assign(n_gpus, 0);
   m->obs_dev.assign(n_gpus, nullptr);
   m->obs_cap.assign(n_gpus, 0);
+  m->res_host.assign(n_gpus, nullptr);
   m->ev0.assign(n_gpus, nullptr);
   m->ev1.assign(n_gpus, nullptr);
   auto fail = [&](int rc) {
@@ -231,7 +239,6 @@ CGE_EXPORT int cge_destroy_multi(cge_multi *m) {
     cudaStreamDestroy(m->shared);
   }
   if (m->obs_pinned) cudaFreeHost(m->obs_pinned);
-  if (m->res_pinned) cudaFreeHost(m->res_pinned);
   cudaGetLastError();
   delete m;
   return CGE_OK;
@@ -257,7 +264,7 @@ CGE_EXPORT int cge_multi_step_async(cge_multi *m, const cge_params *p, const flo
   CKRC(check_multi_params(m, p));
   if (!obs_dev) return set_error(CGE_ERR_BAD_ARG, "obs_dev is NULL");
   CKRC(prepare(m, p));
-  return issue_step(m, p, obs_dev);
+  return issue_step(m, p, obs_dev, false);
 }
 
 CGE_EXPORT int cge_multi_synchronize(cge_multi *m) {
@@ -289,14 +296,6 @@ CGE_EXPORT int cge_grid_posterior_multi(cge_multi *m, const cge_params *p, const
     m->obs_pinned_cap = (size_t)n + 64;
   }
   std::memcpy(m->obs_pinned, obs, (size_t)n * sizeof(float));
-  const size_t res_count = 4 + 2 * (size_t)N;
-  if (res_count > m->res_pinned_cap) {
-    if (m->res_pinned) CK(cudaFreeHost(m->res_pinned));
-    m->res_pinned = nullptr;
-    m->res_pinned_cap = 0;
-    CK(cudaHostAlloc(&m->res_pinned, res_count * sizeof(double), cudaHostAllocPortable));
-    m->res_pinned_cap = res_count;
-  }
   std::vector<const float *> obs_ptr(m->n, nullptr);
   const bool in_place = n <= kZeroCopyObsMax;
   for (int i = 0; i < m->n; ++i) {
@@ -317,35 +316,33 @@ CGE_EXPORT int cge_grid_posterior_multi(cge_multi *m, const cge_params *p, const
       obs_ptr[i] = m->obs_dev[i];
     }
   }
-  CKRC(issue_step(m, p, obs_ptr.data()));
-
-  // results: head and sigma marginal from shard 0 (identical on every shard), each shard's own
-  // rows of the mu marginal; optionally the posterior shards, each over its own stream
+  // results: every finish kernel writes its result block straight into its context's pinned
+  // host block (no device-to-host copies to issue); optionally the posterior shards are copied,
+  // each over its own stream
+  CKRC(issue_step(m, p, obs_ptr.data(), true));
   const size_t cell = p->posterior_dtype == CGE_POSTERIOR_F64 ? sizeof(double) : sizeof(float);
-  for (int i = 0; i < m->n; ++i) {
-    CK(cudaSetDevice(m->devices[i]));
-    double *res = nullptr;
-    CKRC(cge_results(m->ctx[i], &res, nullptr));
-    if (i == 0)
-      CK(cudaMemcpyAsync(m->res_pinned, res, (4 + (size_t)N) * sizeof(double), cudaMemcpyDeviceToHost,
-                         m->stream[i]));
-    CK(cudaMemcpyAsync(m->res_pinned + 4 + N + m->rb[i], res + 4 + N + m->rb[i],
-                       (size_t)(m->re[i] - m->rb[i]) * sizeof(double), cudaMemcpyDeviceToHost,
-                       m->stream[i]));
-    if (timing) CK(cudaEventRecord(m->ev1[i], m->stream[i]));
-    if (posterior_host)
-      CK(cudaMemcpyAsync(static_cast<unsigned char *>(posterior_host) + (size_t)m->rb[i] * N * cell,
-                         m->post[i], (size_t)(m->re[i] - m->rb[i]) * N * cell, cudaMemcpyDeviceToHost,
-                         m->stream[i]));
-  }
+  if (timing || posterior_host)
+    for (int i = 0; i < m->n; ++i) {
+      CK(cudaSetDevice(m->devices[i]));
+      if (timing) CK(cudaEventRecord(m->ev1[i], m->stream[i]));
+      if (posterior_host)
+        CK(cudaMemcpyAsync(static_cast<unsigned char *>(posterior_host) + (size_t)m->rb[i] * N * cell,
+                           m->post[i], (size_t)(m->re[i] - m->rb[i]) * N * cell, cudaMemcpyDeviceToHost,
+                           m->stream[i]));
+    }
   CKRC(cge_multi_synchronize(m));
-  const double *h = m->res_pinned;
+  // head and sigma marginal from shard 0 (identical on every shard: the same rank-ordered sums),
+  // each shard's own rows of the mu marginal
+  const double *h = m->res_host[0];
   if (expectations) {
     expectations[0] = h[0];
     expectations[1] = h[1];
   }
   if (marg_sigma) std::memcpy(marg_sigma, h + 4, (size_t)N * sizeof(double));
-  if (marg_mu) std::memcpy(marg_mu, h + 4 + N, (size_t)N * sizeof(double));
+  if (marg_mu)
+    for (int i = 0; i < m->n; ++i)
+      std::memcpy(marg_mu + m->rb[i], m->res_host[i] + 4 + N + m->rb[i],
+                  (size_t)(m->re[i] - m->rb[i]) * sizeof(double));
   if (timing) {
     cge_timing t = {};
     for (int i = 0; i < m->n; ++i) {
